@@ -1,0 +1,123 @@
+"""CPU: the oracle (oracle/vf_oracle.py) against the committed REFERENCE outputs in tests/golden/.
+
+The fixtures were produced by oracle/make_golden.py from the unmodified reference modules; these tests
+make sure the restatement still reproduces them wherever the suite runs (the reference itself cannot travel).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import vf_oracle as O
+
+torch.set_num_threads(max(1, os.cpu_count() or 1))
+
+
+def _load(golden_dir, name):
+    d = np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=False)
+    return {k: (torch.from_numpy(d[k]) if d[k].dtype.kind in "fi" and d[k].ndim > 0 else d[k]) for k in d.files}
+
+
+def rel(a, b):
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def test_schedule_bit_exact(golden_dir):
+    g = _load(golden_dir, "schedule_train")
+    s = O.make_schedule(**O.BETA_TRAIN)
+    assert set(s) == set(g)
+    for k in s:
+        assert torch.equal(s[k], g[k]), k
+    assert s["gammas"].shape == (2000,)
+
+
+def test_layout_matches_survey_appendix():
+    shapes = O.param_shapes(O.SMALL_V100)
+    assert len(shapes) == 400
+    assert sum(int(np.prod(s)) for _, s, _ in shapes) == 33_947_206
+
+
+@pytest.mark.parametrize("tag,cfg", [("tiny", O.TINY), ("small", O.SMALL_V100)])
+def test_unet_forward(golden_dir, tag, cfg):
+    g = _load(golden_dir, f"unet_{tag}")
+    sd = O.init_state_dict(cfg, int(g["seed"]))
+    chk = sum(float(v.double().sum()) for v in sd.values())
+    assert abs(chk - float(g["w_checksum"])) < 1e-9 * max(1.0, abs(chk)), "weight init is not reproducible on this box"
+    with torch.no_grad():
+        out = O.unet_forward(sd, cfg, g["x"], g["angle"], g["time"])
+    assert rel(out, g["out"]) < 5e-6
+
+
+@pytest.mark.parametrize("tag,weighting", [("ragged", True), ("full6", True), ("mean", False)])
+def test_compose_ddpm(golden_dir, tag, weighting):
+    g = _load(golden_dir, f"compose_{tag}")
+    sched = O.make_schedule(**O.BETA_TRAIN)
+    eps, logits, w = O.compose(g["out"], g["view_count"], weighting)
+    assert rel(eps, g["eps"]) < 1e-6
+    if weighting:
+        assert rel(w, g["weights"]) < 1e-6
+        # padded slots carry exactly zero weight, real slots sum to one
+        vc = g["view_count"].tolist()
+        for b, v in enumerate(vc):
+            assert float(w[b, v:].abs().sum()) == 0.0
+        assert torch.allclose(w.sum(dim=1), torch.ones_like(w.sum(dim=1)), atol=1e-6)
+    for tn in ("hi", "mid", "one", "zero"):
+        y = O.ddpm_update(sched, g["y_t"], eps, g[f"t_{tn}"], g["z"])
+        assert rel(y, g[f"y_prev_{tn}"]) < 1e-6, tn
+
+
+def test_psample_tiny_trajectory(golden_dir):
+    g = _load(golden_dir, "psample_tiny_ragged")
+    cfg = O.TINY
+    sd = O.init_state_dict(cfg, int(g["seed"]), prefix="denoise_fn.")
+    sched = O.make_schedule(**O.BETA_TRAIN)
+    y = g["y_T"]
+    with torch.no_grad():
+        for j, i in enumerate(g["steps"].tolist()):
+            t = torch.full((y.shape[0],), i, dtype=torch.long)
+            y, eps, logits, w = O.p_sample(sd, cfg, sched, y, g["y_cond"], g["view_count"], g["angle"], t, g["z"][j])
+            assert rel(y, g["y"][j]) < 1e-5, i
+    assert rel(w, g["weights_last"]) < 1e-5
+    assert rel(logits, g["logits_last"]) < 1e-5
+
+
+def test_train_tiny_loss_and_grads(golden_dir):
+    g = _load(golden_dir, "train_tiny_ragged")
+    cfg = O.TINY
+    sd = O.init_state_dict(cfg, int(g["seed"]), prefix="denoise_fn.")
+    sd = {k: v.requires_grad_(True) for k, v in sd.items()}
+    sched = O.make_schedule(**O.BETA_TRAIN)
+    loss, eps = O.train_loss(sd, cfg, sched, g["y_0"], g["y_cond"], g["view_count"], g["angle"], g["t"], g["u"], g["noise"])
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g["loss"])) < 2e-6
+    assert rel(eps.detach(), g["eps"]) < 1e-5
+    names = [str(n) for n in g["grad_names"]]
+    norms = g["grad_norms"]
+    big = float(norms.max())
+    for n, ref in zip(names, norms.tolist()):
+        mine = float(sd["denoise_fn." + n].grad.norm())
+        if ref < 1e-6 * big:          # mathematically-zero gradients (bias in front of a 1-channel-per-group GN)
+            assert mine < 1e-6 * big, n
+        else:
+            assert abs(mine - ref) < 1e-4 * ref, n
+    for k in g:
+        if k.startswith("grad:"):
+            full = sd["denoise_fn." + k[5:]].grad.reshape(-1)
+            stride = max(1, (full.numel() + 8191) // 8192)
+            assert rel(full[::stride], g[k]) < 1e-4, k
+
+
+def test_generate_contract_shapes():
+    """generate() return tuple shapes of view_fusion.py:208-214 on a 16-step toy schedule."""
+    cfg = O.TINY
+    sd = O.init_state_dict(cfg, 3, prefix="denoise_fn.")
+    sched = O.make_schedule(schedule="linear", num_timesteps=16, linear_start=1e-4, linear_end=0.09)
+    bt = O.synthetic_batch(2, 3, 16, seed=5, ragged=True)
+    zs = O.normal_draws(16, (2, 3, 16, 16), seed=6)
+    y_T = O.normal_draws(1, (2, 3, 16, 16), seed=7)[0]
+    with torch.no_grad():
+        y, ret, la, wa, last = O.generate(sd, cfg, sched, bt["y_cond"], bt["view_count"], bt["angle"], y_T, zs)
+    sv, mv = int(bt["view_count"].sum()), int(bt["view_count"].max())
+    assert ret.shape == (2, 9, 3, 16, 16) and la.shape == (sv, 8, 3, 16, 16) and wa.shape == (2, 8, mv, 3, 16, 16)
+    assert torch.equal(last, y)
