@@ -1,0 +1,244 @@
+/*
+ * viewfusion_b200 — C ABI of the B200-native (sm_100a) ViewFusion hot path.
+ *
+ * This is the drop-in boundary: everything the reference computes on the path
+ *     ViewFusion.forward / generate / p_sample / p_mean_variance   (model/view_fusion.py:86-300)
+ *     UNet.forward and the blocks it calls                          (model/unet.py:114-303)
+ * is reachable through the entry points below with plain pointers and sizes.  The reference has no FFI of
+ * its own (it is pure PyTorch); the host side that binds these symbols is `view_fusion_b200/_lib.py` (ctypes),
+ * and INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative vf_status; the message is in vf_last_error()
+ *    (thread-local).  Nothing throws, prints or exits.
+ *  - every pointer is a DEVICE pointer unless the name ends in `_host`.  The library never allocates or
+ *    frees device memory: buffers, workspaces and packed weights are owned by the caller (PyTorch).
+ *  - every launch is asynchronous on the `stream` argument (a cudaStream_t), performs no host sync and is
+ *    CUDA-graph capturable.
+ *  - activations inside the library are NHWC ("pixel-major") in fp32 (VF_F32, CUDA-core reference-precision
+ *    mode) or bf16 (VF_BF16, tcgen05 tensor-core mode); the reference's NCHW fp32 tensors are converted at
+ *    the edges by vf_pack_views / vf_nhwc_to_nchw.
+ */
+#ifndef VIEWFUSION_B200_H_
+#define VIEWFUSION_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VF_ABI_VERSION 1
+
+typedef enum vf_status {
+  VF_OK = 0,
+  VF_ERR_ARG = -1,    /* bad shape / alignment / null pointer */
+  VF_ERR_CUDA = -2,   /* a CUDA runtime or driver call failed */
+  VF_ERR_ARCH = -3,   /* device is not sm_100 */
+  VF_ERR_STATE = -4   /* call order (e.g. forward before weights were packed) */
+} vf_status;
+
+typedef enum vf_dtype { VF_F32 = 0, VF_BF16 = 1 } vf_dtype;
+
+typedef void* vf_stream; /* cudaStream_t */
+
+const char* vf_last_error(void);
+int vf_abi_version(void);
+/* 0 when the current device is sm_100 (B200); VF_ERR_ARCH / VF_ERR_CUDA otherwise. */
+int vf_device_check(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * UNet description — mirrors the constructor of model/unet.py:9-21 (dropout is always 0 in the reference
+ * configs and is not supported; with_noise_level_emb is always true).
+ * ---------------------------------------------------------------------------------------------------- */
+#define VF_MAX_LEVELS 8
+typedef struct vf_unet_config {
+  int in_channel;
+  int out_channel;
+  int inner_channel;
+  int norm_groups;
+  int n_mults;
+  int channel_mults[VF_MAX_LEVELS];
+  int n_attn_res;
+  int attn_res[VF_MAX_LEVELS];
+  int res_blocks;
+  int image_size;
+} vf_unet_config;
+
+typedef struct vf_unet vf_unet; /* opaque host-side plan; owns no device memory */
+
+/* Builds the layer table of unet.py:38-112 for `cfg`. `act_dtype` selects the arithmetic:
+ * VF_F32 = fp32 activations + CUDA-core FFMA GEMMs (reference-precision mode, 1e-4 bar),
+ * VF_BF16 = bf16 activations + tcgen05/TMEM implicit-GEMM (performance mode, 1e-2 bar). */
+int vf_unet_create(const vf_unet_config* cfg, int act_dtype, vf_unet** out);
+void vf_unet_destroy(vf_unet* u);
+
+/* Parameter table in the reference's state_dict order (no prefix). */
+int vf_unet_num_params(const vf_unet* u);
+/* name is written NUL-terminated into name_buf; shape gets up to 4 dims, *ndim their count. */
+int vf_unet_param_info(const vf_unet* u, int index, char* name_buf, int name_cap, int64_t shape[4], int* ndim);
+
+/* Total channel count of the per-block additive embeddings (sum of Cout over all ResnetBlocks). */
+int vf_unet_emb_channels(const vf_unet* u);
+
+/* Packed (GEMM-ready) weights: K-major [Cout][tap][Cin] in the activation dtype, fused fp32 biases, the
+ * concatenated embedding matrix.  `params` is an array of vf_unet_num_params() device pointers to the fp32
+ * master tensors in table order.  Re-run after every optimizer step / state_dict load. */
+size_t vf_unet_packed_bytes(const vf_unet* u);
+int vf_unet_pack_weights(vf_unet* u, const float* const* params_host, void* packed, vf_stream stream);
+
+/* Scratch for one forward over up to `max_images` view-images (activations are not recycled, so the same
+ * workspace doubles as the activation stash of the training backward). */
+size_t vf_unet_workspace_bytes(const vf_unet* u, int max_images);
+
+/* UNet.forward (unet.py:114-138) on pre-packed input.
+ *   x0       : [images*H*W, K0] activation dtype, the im2col'd first-layer input written by vf_pack_views
+ *              (K0 = vf_unet_k0()).
+ *   level/angle : [rows] fp32 — the noise level ("time") and target angle of each embedding row
+ *   img_row  : [images] int32 — embedding row used by each view-image (views of one sample share a row)
+ *   out      : [images*H*W, 8] fp32, channels 0..out_channel-1 valid (NHWC, padded to 8)
+ */
+int vf_unet_k0(const vf_unet* u);
+int vf_unet_forward(vf_unet* u, const void* packed, void* workspace, size_t workspace_bytes, int images,
+                    const void* x0, const float* level, const float* angle, int rows, const int* img_row,
+                    float* out, vf_stream stream);
+
+/* Number of kernels enqueued by the last vf_unet_forward on this plan (bench.py's gpu_launches claim). */
+int vf_unet_last_launches(const vf_unet* u);
+
+/* Debug/parity tap: copies the output activation of module `name` ("downs.3", "mid.0", "ups.17", ...) of the
+ * LAST vf_unet_forward on this plan into `dst` as NCHW fp32.  dst must hold images*C*H*W floats. */
+int vf_unet_read_tap(vf_unet* u, const void* workspace, const char* name, float* dst, int64_t* chw, vf_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * View stacking (view_fusion.py:95-115 / :244-263) fused with the first layer's im2col.
+ *   y_cond      : (B, Nmax, Cc, H, W) fp32 NCHW;   y_t : (B, 3, H, W) fp32
+ *   view_offset : [B+1] int32 prefix sum of view_count;  only the first V_b views of sample b are used
+ *   x0          : [images*H*W, K0] in `x0_dtype`, k = (kh*3+kw)*(Cc+3) + c, zero padded (pad 1 halo and K tail)
+ *   img_sample  : [images] int32 out — sample index of each stacked view (the `img_row` of vf_unet_forward)
+ * ---------------------------------------------------------------------------------------------------- */
+int vf_pack_views(const float* y_cond, const float* y_t, const int* view_offset, int B, int n_max, int cond_channels,
+                  int H, int W, int images, int k0, int x0_dtype, void* x0, int* img_sample, vf_stream stream);
+
+/* Generic NCHW fp32 (R,C,H,W) -> im2col'd first-layer input, for the stand-alone UNet.forward API. */
+int vf_pack_nchw(const float* x, int R, int C, int H, int W, int k0, int x0_dtype, void* x0, vf_stream stream);
+
+/* [R*H*W, ld] fp32 NHWC -> (R, C, H, W) fp32 NCHW (first C channels). */
+int vf_nhwc_to_nchw(const float* src, int ld, int R, int C, int H, int W, float* dst, vf_stream stream);
+
+/* q_sample (view_fusion.py:162-164): y = sqrt(g_b) * y0 + sqrt(1 - g_b) * noise, g per sample. */
+int vf_q_sample(const float* y0, const float* noise, const float* gammas, int B, int chw, float* y, vf_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Composition + DDPM update (view_fusion.py:116-160 + :70-84 + :166-177), one pass over HBM.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct vf_schedule {       /* the six (T,) fp32 buffers of set_new_noise_schedule (view_fusion.py:50-68) */
+  const float* gammas;
+  const float* sqrt_recip_gammas;
+  const float* sqrt_recipm1_gammas;
+  const float* posterior_log_variance_clipped;
+  const float* posterior_mean_coef1;
+  const float* posterior_mean_coef2;
+  int num_timesteps;
+} vf_schedule;
+
+typedef struct vf_compose_args {
+  const float* unet_out;     /* [images*H*W, 8] fp32: eps in 0..2, logits in 3..5 */
+  const int* view_offset;    /* [B+1] */
+  const int* t;              /* [B] int32 time-step of each sample */
+  const float* y_t;          /* (B,3,H,W) fp32 NCHW */
+  float* y_prev;             /* (B,3,H,W) out; may alias y_t */
+  const float* z;            /* (B,3,H,W) injected N(0,1) draw, or NULL -> Philox(seed, offset) in-kernel */
+  uint64_t seed;
+  uint64_t offset;
+  int add_noise;             /* the reference's `any(t > 0)` (view_fusion.py:176), decided by the caller */
+  int clip_denoised;
+  int weighting;             /* 1: softmax over views (6-channel UNet); 0: plain mean (ablation, :141-150) */
+  int B, H, W;
+  float* eps_out;            /* optional (B,3,H,W): the composed noise prediction */
+  float* weights_out;        /* optional (B,max_v,3,H,W): softmax weights, zero in padded slots */
+  int max_v;
+  float* logits_out;         /* optional (images,3,H,W): un-padded logits (p_sample's 2nd return value) */
+} vf_compose_args;
+
+int vf_compose_ddpm_step(const vf_compose_args* a, const vf_schedule* s, vf_stream stream);
+
+/* Training tail (view_fusion.py:265-298): composition + MSE loss + gradient w.r.t. the UNet output.
+ *   loss_acc : [1] fp32, must be zero on entry; receives mean((noise - eps_hat)^2)
+ *   grad_out : [images*H*W, 8] fp32 or NULL: dL/d(unet_out) scaled by `grad_scale` */
+int vf_compose_mse(const float* unet_out, const int* view_offset, const float* noise, int B, int H, int W,
+                   int weighting, float* loss_acc, float* eps_out, float* grad_out, float grad_scale,
+                   vf_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Stage-level operators (used by the plan above; exported for unit parity tests and ncu captures).
+ * All activations [images*H*W, C] NHWC in `dtype`.
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* PositionalEncoding + noise_level_mlp + all per-block Linear(inner->Cout) (unet.py:115-116,:147-157,:160-177).
+ *   w0 [4*ic, ic], b0, w2 [ic, 4*ic], b2 : the MLP;  emb_w [E, ic], emb_b [E]: concatenated block linears
+ *   out [rows, E] fp32 */
+int vf_embed(const float* level, const float* angle, int rows, int inner_channel, const float* w0, const float* b0,
+             const float* w2, const float* b2, const float* emb_w, const float* emb_b, int E, float* out,
+             vf_stream stream);
+
+/* GroupNorm statistics: per (image, channel) sum and sum of squares over H*W of the channel-concatenation of
+ * src0 [.,C0] and src1 [.,C1] (src1 may be NULL).  stats [images, C0+C1, 2] fp32 must be zero on entry. */
+int vf_gn_stats(const void* src0, int C0, const void* src1, int C1, int dtype, int images, int HW, float* stats,
+                vf_stream stream);
+
+/* GroupNorm(groups, eps=1e-5, affine) + optional Swish (unet.py:207-218,:254) -> dst [., C0+C1]. */
+int vf_gn_apply(const void* src0, int C0, const void* src1, int C1, int dtype, int images, int HW, int groups,
+                const float* stats, const float* gamma, const float* beta, int swish, void* dst, vf_stream stream);
+
+/* Nearest-neighbour x2 up-sampling (unet.py:188). */
+int vf_upsample2x(const void* src, int dtype, int images, int H, int W, int C, void* dst, vf_stream stream);
+
+/* Implicit-GEMM convolution, out[m, n] = sum_seg sum_tap sum_c A_seg[pix(m, tap), c] * Wt[n, koff + tap*C_seg + c]
+ * with the fused epilogue  + bias[n] + emb[img_row[img(m)]*emb_ld + n] + residual[m, n].
+ * ksize 3 uses padding 1; stride 2 only with ksize 3 (Downsample, unet.py:195-201). */
+typedef struct vf_conv_args {
+  int dtype;                 /* VF_F32 -> CUDA-core kernel, VF_BF16 -> tcgen05 kernel */
+  int images, H, W;          /* OUTPUT spatial size */
+  int n_seg;                 /* 1..3 K-segments accumulated into the same output tile */
+  const void* src[3];        /* [images*Hin*Win, src_c[i]] */
+  int src_c[3];
+  int ksize[3];              /* 1 or 3 */
+  int stride;                /* 1 or 2 (applies to segment 0 only; others must be ksize 1) */
+  const void* weight;        /* [Cout_pad, K_total] K-major in `dtype`; K_total = sum ksize^2 * src_c */
+  int cout;                  /* logical output channels */
+  int cout_pad;              /* rows of `weight` (multiple of 16) */
+  const float* bias;         /* [cout] or NULL */
+  const float* emb;          /* [rows, emb_ld] or NULL; column offset already applied */
+  const int* img_row;        /* [images] */
+  int emb_ld;
+  const void* residual;      /* [images*H*W, cout] in `dtype` or NULL */
+  void* out;                 /* [images*H*W, out_ld] */
+  int out_dtype;             /* `dtype`, or VF_F32 for the final layer */
+  int out_ld;
+  int qkv_split;             /* >0: C of an attention block; columns [2C,3C) are written transposed to out_vt */
+  void* out_vt;              /* [images, C, H*W] (keys contiguous) when qkv_split */
+  float* stats;              /* optional [images, cout, 2]: GroupNorm partial sums of the OUTPUT (pre-zeroed) */
+} vf_conv_args;
+
+int vf_conv2d(const vf_conv_args* a, vf_stream stream);
+
+/* Test hook: route VF_BF16 vf_conv2d / vf_attention through the CUDA-core kernels (same bf16 storage, fp32
+ * accumulation) so the tcgen05 kernels can be cross-checked on the device.  Never enabled by the product path. */
+void vf_debug_force_simt(int on);
+
+/* Single-head self-attention core (unet.py:267-274): O = softmax(Q K^T / sqrt(C)) V per image.
+ *   qk  : [images*L, 3C] rows hold q in [0,C), k in [C,2C) (v columns unused when vt != NULL)
+ *   vt  : [images, C, L] V transposed (bf16 tensor-core path) or NULL (fp32 path reads v from qk)
+ *   out : [images*L, C] */
+int vf_attention(const void* qk, const void* vt, int dtype, int images, int L, int C, void* out, vf_stream stream);
+
+/* fp32 OIHW conv weight -> K-major [cout_pad][k_off + tap*cin + c] rows of length k_total in `dtype`. */
+int vf_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, int dtype, void* dst, int cout_pad,
+                        int k_total, int k_off, vf_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIEWFUSION_B200_H_ */

@@ -1,0 +1,39 @@
+"""Helpers shared by the -m gpu tests."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import torch
+
+import vf_oracle as O
+
+BETA = {"train": dict(O.BETA_TRAIN)}
+# bf16-capable toy config (every level a multiple of 64 channels; attention at L=64 and in mid at L=16 is avoided)
+TOY64 = dict(in_channel=6, out_channel=6, inner_channel=64, norm_groups=32, channel_mults=(1, 2), attn_res=(8,),
+             res_blocks=1, image_size=16)
+
+
+def load(golden_dir, name):
+    d = np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=False)
+    return {k: (torch.from_numpy(d[k]) if d[k].dtype.kind in "fi" and d[k].ndim > 0 else d[k]) for k in d.files}
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def build_model(cfg, seed, precision, weighting=True):
+    from view_fusion_b200 import UNet, ViewFusion
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ViewFusion(UNet(**cfg, precision=precision), BETA, weighting_train=weighting, weighting_inference=weighting)
+    m.set_new_noise_schedule(device="cpu", phase="train")
+    sd = O.init_state_dict(cfg, seed, prefix="denoise_fn.")
+    sd.update(O.make_schedule(**O.BETA_TRAIN))
+    m.load_state_dict(sd, strict=True)
+    return m.cuda(), {k: v for k, v in sd.items()}
+
+
+def bf16r(x):
+    return x.to(torch.bfloat16).float()

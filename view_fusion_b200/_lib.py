@@ -1,0 +1,152 @@
+"""ctypes binding of the C ABI declared in include/viewfusion_b200.h.
+
+There is exactly one implementation behind these symbols — the sm_100a CUDA library built in-tree by
+`view_fusion_b200.build`.  If it is missing, loading fails loudly; there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libviewfusion_b200.so")
+
+VF_F32, VF_BF16 = 0, 1
+VF_MAX_LEVELS = 8
+
+# every symbol include/viewfusion_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "vf_last_error", "vf_abi_version", "vf_device_check",
+    "vf_unet_create", "vf_unet_destroy", "vf_unet_num_params", "vf_unet_param_info", "vf_unet_emb_channels",
+    "vf_unet_packed_bytes", "vf_unet_pack_weights", "vf_unet_workspace_bytes", "vf_unet_k0", "vf_unet_forward",
+    "vf_unet_last_launches", "vf_unet_read_tap",
+    "vf_pack_views", "vf_pack_nchw", "vf_nhwc_to_nchw", "vf_q_sample",
+    "vf_compose_ddpm_step", "vf_compose_mse",
+    "vf_embed", "vf_gn_stats", "vf_gn_apply", "vf_upsample2x", "vf_conv2d", "vf_debug_force_simt", "vf_attention",
+    "vf_pack_conv_weight",
+]
+
+
+class UnetConfig(C.Structure):
+    _fields_ = [
+        ("in_channel", C.c_int), ("out_channel", C.c_int), ("inner_channel", C.c_int), ("norm_groups", C.c_int),
+        ("n_mults", C.c_int), ("channel_mults", C.c_int * VF_MAX_LEVELS),
+        ("n_attn_res", C.c_int), ("attn_res", C.c_int * VF_MAX_LEVELS),
+        ("res_blocks", C.c_int), ("image_size", C.c_int),
+    ]
+
+
+class Schedule(C.Structure):
+    _fields_ = [
+        ("gammas", C.c_void_p), ("sqrt_recip_gammas", C.c_void_p), ("sqrt_recipm1_gammas", C.c_void_p),
+        ("posterior_log_variance_clipped", C.c_void_p), ("posterior_mean_coef1", C.c_void_p),
+        ("posterior_mean_coef2", C.c_void_p), ("num_timesteps", C.c_int),
+    ]
+
+
+class ComposeArgs(C.Structure):
+    _fields_ = [
+        ("unet_out", C.c_void_p), ("view_offset", C.c_void_p), ("t", C.c_void_p), ("y_t", C.c_void_p),
+        ("y_prev", C.c_void_p), ("z", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64),
+        ("add_noise", C.c_int), ("clip_denoised", C.c_int), ("weighting", C.c_int),
+        ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("eps_out", C.c_void_p), ("weights_out", C.c_void_p), ("max_v", C.c_int), ("logits_out", C.c_void_p),
+    ]
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int), ("images", C.c_int), ("H", C.c_int), ("W", C.c_int), ("n_seg", C.c_int),
+        ("src", C.c_void_p * 3), ("src_c", C.c_int * 3), ("ksize", C.c_int * 3), ("stride", C.c_int),
+        ("weight", C.c_void_p), ("cout", C.c_int), ("cout_pad", C.c_int), ("bias", C.c_void_p),
+        ("emb", C.c_void_p), ("img_row", C.c_void_p), ("emb_ld", C.c_int), ("residual", C.c_void_p),
+        ("out", C.c_void_p), ("out_dtype", C.c_int), ("out_ld", C.c_int), ("qkv_split", C.c_int),
+        ("out_vt", C.c_void_p), ("stats", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library (no GPU needed for this) and declare the signatures."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m view_fusion_b200.build` "
+            "(view_fusion_b200 has no CPU / PyTorch fallback)")
+    lib = C.CDLL(LIB_PATH)
+    p, i, f, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+    sig = {
+        "vf_last_error": (C.c_char_p, []),
+        "vf_abi_version": (i, []),
+        "vf_device_check": (i, []),
+        "vf_unet_create": (i, [C.POINTER(UnetConfig), i, C.POINTER(p)]),
+        "vf_unet_destroy": (None, [p]),
+        "vf_unet_num_params": (i, [p]),
+        "vf_unet_param_info": (i, [p, i, C.c_char_p, i, C.POINTER(C.c_int64), C.POINTER(i)]),
+        "vf_unet_emb_channels": (i, [p]),
+        "vf_unet_packed_bytes": (sz, [p]),
+        "vf_unet_pack_weights": (i, [p, C.POINTER(p), p, p]),
+        "vf_unet_workspace_bytes": (sz, [p, i]),
+        "vf_unet_k0": (i, [p]),
+        "vf_unet_forward": (i, [p, p, p, sz, i, p, p, p, i, p, p, p]),
+        "vf_unet_last_launches": (i, [p]),
+        "vf_unet_read_tap": (i, [p, p, C.c_char_p, p, C.POINTER(C.c_int64), p]),
+        "vf_pack_views": (i, [p, p, p, i, i, i, i, i, i, i, i, p, p, p]),
+        "vf_pack_nchw": (i, [p, i, i, i, i, i, i, p, p]),
+        "vf_nhwc_to_nchw": (i, [p, i, i, i, i, i, p, p]),
+        "vf_q_sample": (i, [p, p, p, i, i, p, p]),
+        "vf_compose_ddpm_step": (i, [C.POINTER(ComposeArgs), C.POINTER(Schedule), p]),
+        "vf_compose_mse": (i, [p, p, p, i, i, i, i, p, p, p, f, p]),
+        "vf_embed": (i, [p, p, i, i, p, p, p, p, p, p, i, p, p]),
+        "vf_gn_stats": (i, [p, i, p, i, i, i, i, p, p]),
+        "vf_gn_apply": (i, [p, i, p, i, i, i, i, i, p, p, p, i, p, p]),
+        "vf_upsample2x": (i, [p, i, i, i, i, i, p, p]),
+        "vf_conv2d": (i, [C.POINTER(ConvArgs), p]),
+        "vf_debug_force_simt": (None, [i]),
+        "vf_attention": (i, [p, p, i, i, i, i, p, p]),
+        "vf_pack_conv_weight": (i, [p, i, i, i, i, p, i, i, i, p]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.vf_abi_version() != 1:
+        raise RuntimeError("libviewfusion_b200.so: ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().vf_last_error().decode(errors="replace")
+        raise RuntimeError(f"viewfusion_b200 {what} failed ({rc}): {msg}")
+
+
+def ptr(t) -> int:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return 0 if t is None else t.data_ptr()
+
+
+def stream_handle() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+_checked = False
+
+
+def require_device() -> C.CDLL:
+    """The product path: library present AND an sm_100 device.  Raises otherwise."""
+    global _checked
+    lib = load()
+    if not _checked:
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("view_fusion_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        check(lib.vf_device_check(), "device check")
+        _checked = True
+    return lib

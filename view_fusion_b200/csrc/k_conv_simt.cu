@@ -1,0 +1,154 @@
+// CUDA-core implicit-GEMM convolution: the fp32 "reference-precision" mode of vf_conv2d (1e-4 parity bar, no
+// TF32/bf16 rounding anywhere) and the on-device cross-check for the tcgen05 kernel.  Same contract as the
+// tensor-core path: NHWC activations, K-major weights, up to three K-segments (3x3 main conv + 1x1 res_conv over
+// one or two sources) accumulated into one tile, fused bias + embedding + residual epilogue.
+// Reference: nn.Conv2d call sites model/unet.py:42,189,198,214,238,255,256.
+#include "vf_common.cuh"
+
+namespace vf {
+
+constexpr int SBM = 64, SBN = 64, SBK = 16;
+
+struct SimtConvParams {
+  const void* src[3];
+  int src_c[3];
+  int ksize[3];
+  int n_seg;
+  int stride;
+  int images, H, W;      // output spatial
+  const void* weight;
+  int k_total;
+  int cout, cout_pad;
+  const float* bias;
+  const float* emb;
+  const int* img_row;
+  int emb_ld;
+  const void* residual;
+  void* out;
+  int out_ld;
+  int qkv_split;
+  void* out_vt;
+};
+
+__device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
+  float4 t = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load4(const __nv_bfloat16* p, float (&v)[4]) {
+  uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+  float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+template <typename TA, typename TO>
+__global__ void __launch_bounds__(256) conv_simt_kernel(const SimtConvParams p) {
+  __shared__ float As[SBK][SBM + 4];
+  __shared__ float Bs[SBK][SBN + 4];
+  const int HW = p.H * p.W;
+  const int M = p.images * HW;
+  const int m0 = blockIdx.x * SBM, n0 = blockIdx.y * SBN;
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;          // 16x16 threads, each 4 rows x 4 cols
+  // loader roles
+  const int lrow = tid / 4, lk = (tid % 4) * 4;
+  const int lm = m0 + lrow;
+  int limg = 0, ly = 0, lx = 0;
+  if (lm < M) { limg = lm / HW; int r = lm % HW; ly = r / p.W; lx = r % p.W; }
+  const int ln = n0 + lrow;
+  const TA* wt = reinterpret_cast<const TA*>(p.weight);
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  int koff = 0;
+  for (int s = 0; s < p.n_seg; ++s) {
+    const int C = p.src_c[s];
+    const int ks = p.ksize[s];
+    const int st = (s == 0) ? p.stride : 1;
+    const int Hin = p.H * st, Win = p.W * st;
+    const TA* src = reinterpret_cast<const TA*>(p.src[s]);
+    for (int tap = 0; tap < ks * ks; ++tap) {
+      const int dy = ks == 3 ? tap / 3 - 1 : 0, dx = ks == 3 ? tap % 3 - 1 : 0;
+      const int yy = ly * st + dy, xx = lx * st + dx;
+      const bool inb = lm < M && yy >= 0 && yy < Hin && xx >= 0 && xx < Win;
+      const TA* arow = src + (((size_t)limg * Hin + (inb ? yy : 0)) * Win + (inb ? xx : 0)) * C;
+      for (int c0 = 0; c0 < C; c0 += SBK) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+        if (inb) load4(arow + c0 + lk, a);
+        if (ln < p.cout_pad) load4(wt + (size_t)ln * p.k_total + koff + tap * C + c0 + lk, b);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { As[lk + j][lrow] = a[j]; Bs[lk + j][lrow] = b[j]; }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SBK; ++k) {
+          float av[4], bv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { av[i] = As[k][ty * 4 + i]; bv[i] = Bs[k][tx * 4 + i]; }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
+        }
+      }
+    }
+    koff += ks * ks * C;
+  }
+
+  // epilogue
+  TO* out = reinterpret_cast<TO*>(p.out);
+  const TA* res = reinterpret_cast<const TA*>(p.residual);
+  TA* vt = reinterpret_cast<TA*>(p.out_vt);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const int img = m / HW;
+    const float* erow = p.emb ? p.emb + (size_t)__ldg(p.img_row + img) * p.emb_ld : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= p.cout) continue;
+      float v = acc[i][j];
+      if (p.bias) v += __ldg(p.bias + n);
+      if (erow) v += __ldg(erow + n);
+      if (res) v += to_f(res[(size_t)m * p.cout + n]);
+      if (p.qkv_split > 0 && n >= 2 * p.qkv_split)
+        vt[((size_t)img * p.qkv_split + (n - 2 * p.qkv_split)) * HW + (m % HW)] = from_f<TA>(v);
+      else
+        out[(size_t)m * p.out_ld + n] = from_f<TO>(v);
+    }
+  }
+}
+
+int conv2d_simt(const vf_conv_args* a, cudaStream_t st) {
+  SimtConvParams p{};
+  int k_total = 0;
+  for (int s = 0; s < a->n_seg; ++s) {
+    p.src[s] = a->src[s]; p.src_c[s] = a->src_c[s]; p.ksize[s] = a->ksize[s];
+    VF_REQUIRE(a->src_c[s] % SBK == 0, "vf_conv2d(simt): segment channels %d not a multiple of %d", a->src_c[s], SBK);
+    k_total += a->ksize[s] * a->ksize[s] * a->src_c[s];
+  }
+  p.n_seg = a->n_seg; p.stride = a->stride; p.images = a->images; p.H = a->H; p.W = a->W;
+  p.weight = a->weight; p.k_total = k_total; p.cout = a->cout; p.cout_pad = a->cout_pad;
+  p.bias = a->bias; p.emb = a->emb; p.img_row = a->img_row; p.emb_ld = a->emb_ld; p.residual = a->residual;
+  p.out = a->out; p.out_ld = a->out_ld; p.qkv_split = a->qkv_split; p.out_vt = a->out_vt;
+  const int M = a->images * a->H * a->W;
+  dim3 grid(cdiv(M, SBM), cdiv(a->cout, SBN));
+  if (a->dtype == VF_F32) {
+    VF_REQUIRE(a->out_dtype == VF_F32, "vf_conv2d(simt): fp32 activations need fp32 output");
+    conv_simt_kernel<float, float><<<grid, 256, 0, st>>>(p);
+  } else if (a->out_dtype == VF_F32) {
+    conv_simt_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(p);
+  } else {
+    conv_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(p);
+  }
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}
+
+}  // namespace vf

@@ -1,0 +1,169 @@
+// Layout kernels at the edges of the hot path.
+//  - vf_pack_views: view stacking of model/view_fusion.py:95-115 / :244-263 (first V_b views, target repeated per
+//    view, channel concat) fused with the im2col of the first 3x3 convolution (unet.py:42), so that layer runs as
+//    a plain K=K0 GEMM.  Bandwidth-trivial: reads 12-24 B and writes K0*sizeof(T) per view-pixel.
+//  - vf_pack_nchw / vf_nhwc_to_nchw: the NCHW fp32 <-> NHWC conversions of the stand-alone UNet.forward API.
+//  - vf_pack_conv_weight: fp32 OIHW masters -> K-major GEMM rows.
+#include "vf_common.cuh"
+
+namespace vf {
+
+__global__ void img_sample_kernel(const int* __restrict__ voff, int B, int images, int* __restrict__ img_sample) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= images) return;
+  int b = 0;
+  while (b + 1 < B && __ldg(voff + b + 1) <= i) ++b;
+  img_sample[i] = b;
+}
+
+// one thread per (image, pixel, 16-byte chunk of the K0 row)
+template <typename T>
+__global__ void __launch_bounds__(256) pack_views_kernel(const float* __restrict__ y_cond, const float* __restrict__ y_t,
+                                                         const int* __restrict__ voff, const int* __restrict__ img_sample,
+                                                         int n_max, int Cc, int H, int W, int images, int K0,
+                                                         T* __restrict__ x0) {
+  constexpr int VEC = VecOf<T>::N;
+  const int chunks = K0 / VEC;
+  const size_t total = (size_t)images * H * W * chunks;
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int ch = (int)(gid % chunks);
+  const size_t ip = gid / chunks;
+  const int pix = (int)(ip % (H * W));
+  const int img = (int)(ip / (H * W));
+  const int y = pix / W, x = pix % W;
+  const int b = __ldg(img_sample + img);
+  const int view = img - __ldg(voff + b);
+  const int Cin = Cc + 3;
+  const float* cond = y_cond + ((size_t)b * n_max + view) * Cc * H * W;
+  const float* tgt = y_t + (size_t)b * 3 * H * W;
+  float v[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int k = ch * VEC + j;
+    float val = 0.f;
+    if (k < 9 * Cin) {
+      const int tap = k / Cin, c = k % Cin;
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+        val = c < Cc ? __ldg(cond + ((size_t)c * H + yy) * W + xx) : __ldg(tgt + ((size_t)(c - Cc) * H + yy) * W + xx);
+    }
+    v[j] = val;
+  }
+  store_vec(x0 + gid * VEC, v);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) pack_nchw_kernel(const float* __restrict__ x, int C, int H, int W, int R, int K0,
+                                                        T* __restrict__ x0) {
+  constexpr int VEC = VecOf<T>::N;
+  const int chunks = K0 / VEC;
+  const size_t total = (size_t)R * H * W * chunks;
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int ch = (int)(gid % chunks);
+  const size_t ip = gid / chunks;
+  const int pix = (int)(ip % (H * W));
+  const int img = (int)(ip / (H * W));
+  const int y = pix / W, xq = pix % W;
+  const float* src = x + (size_t)img * C * H * W;
+  float v[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int k = ch * VEC + j;
+    float val = 0.f;
+    if (k < 9 * C) {
+      const int tap = k / C, c = k % C;
+      const int yy = y + tap / 3 - 1, xx = xq + tap % 3 - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = __ldg(src + ((size_t)c * H + yy) * W + xx);
+    }
+    v[j] = val;
+  }
+  store_vec(x0 + gid * VEC, v);
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, int ld, int C, int HW, size_t total,
+                                    float* __restrict__ dst) {
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // over (r, c, pix): coalesced writes
+  if (gid >= total) return;
+  const int pix = (int)(gid % HW);
+  const size_t rc = gid / HW;
+  const int c = (int)(rc % C);
+  const size_t r = rc / C;
+  dst[gid] = __ldg(src + (r * HW + pix) * ld + c);
+}
+
+template <typename T>
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int kk, T* __restrict__ dst,
+                                        int cout_pad, int k_total, int k_off) {
+  const int per_row = kk * cin;
+  const size_t total = (size_t)cout_pad * per_row;
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int n = (int)(gid / per_row);
+  const int r = (int)(gid % per_row);
+  const int tap = r / cin, c = r % cin;
+  float v = n < cout ? __ldg(w + ((size_t)n * cin + c) * kk + tap) : 0.f;   // OIHW: ((n*cin + c)*k + kh)*k + kw
+  dst[(size_t)n * k_total + k_off + r] = from_f<T>(v);
+}
+
+}  // namespace vf
+
+extern "C" __attribute__((visibility("default"))) int vf_pack_views(const float* y_cond, const float* y_t, const int* view_offset, int B, int n_max,
+                             int cond_channels, int H, int W, int images, int k0, int x0_dtype, void* x0,
+                             int* img_sample, vf_stream stream) {
+  using namespace vf;
+  VF_REQUIRE(y_cond && y_t && view_offset && x0 && img_sample, "vf_pack_views: null tensor");
+  VF_REQUIRE(B > 0 && images > 0 && H > 0 && W > 0 && n_max > 0, "vf_pack_views: bad shape");
+  VF_REQUIRE(k0 % 8 == 0 && k0 >= 9 * (cond_channels + 3), "vf_pack_views: k0=%d too small for %d channels", k0,
+             cond_channels + 3);
+  cudaStream_t st = as_stream(stream);
+  img_sample_kernel<<<cdiv(images, 128), 128, 0, st>>>(view_offset, B, images, img_sample);
+  VF_LAUNCH_CHECK();
+  const size_t vec = x0_dtype == VF_BF16 ? 8 : 4;
+  const size_t total = (size_t)images * H * W * (k0 / vec);
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (x0_dtype == VF_BF16)
+    pack_views_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(y_cond, y_t, view_offset, img_sample, n_max, cond_channels, H, W, images, k0, (__nv_bfloat16*)x0);
+  else
+    pack_views_kernel<float><<<grid, 256, 0, st>>>(y_cond, y_t, view_offset, img_sample, n_max, cond_channels, H, W, images, k0, (float*)x0);
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int vf_pack_nchw(const float* x, int R, int C, int H, int W, int k0, int x0_dtype, void* x0, vf_stream stream) {
+  using namespace vf;
+  VF_REQUIRE(x && x0 && R > 0 && C > 0 && H > 0 && W > 0, "vf_pack_nchw: bad args");
+  VF_REQUIRE(k0 % 8 == 0 && k0 >= 9 * C, "vf_pack_nchw: k0=%d too small for C=%d", k0, C);
+  const size_t vec = x0_dtype == VF_BF16 ? 8 : 4;
+  const size_t total = (size_t)R * H * W * (k0 / vec);
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (x0_dtype == VF_BF16) pack_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(x, C, H, W, R, k0, (__nv_bfloat16*)x0);
+  else pack_nchw_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(x, C, H, W, R, k0, (float*)x0);
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int vf_nhwc_to_nchw(const float* src, int ld, int R, int C, int H, int W, float* dst, vf_stream stream) {
+  using namespace vf;
+  VF_REQUIRE(src && dst && R > 0 && C > 0 && C <= ld && H > 0 && W > 0, "vf_nhwc_to_nchw: bad args");
+  const size_t total = (size_t)R * C * H * W;
+  nhwc_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(src, ld, C, H * W, total, dst);
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int vf_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, int dtype, void* dst, int cout_pad,
+                                   int k_total, int k_off, vf_stream stream) {
+  using namespace vf;
+  VF_REQUIRE(w_oihw && dst && cout > 0 && cin > 0 && (ksize == 1 || ksize == 3), "vf_pack_conv_weight: bad args");
+  VF_REQUIRE(cout_pad >= cout && k_off + ksize * ksize * cin <= k_total, "vf_pack_conv_weight: row overflow");
+  const size_t total = (size_t)cout_pad * ksize * ksize * cin;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (dtype == VF_BF16)
+    pack_conv_weight_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(w_oihw, cout, cin, ksize * ksize, (__nv_bfloat16*)dst, cout_pad, k_total, k_off);
+  else
+    pack_conv_weight_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(w_oihw, cout, cin, ksize * ksize, (float*)dst, cout_pad, k_total, k_off);
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}

@@ -1,0 +1,584 @@
+// Host-side UNet plan: the layer table of model/unet.py:38-112 and the launch sequence of UNet.forward
+// (unet.py:114-138) expressed over the stage-level operators of this library.  Owns no device memory: the
+// caller passes master parameter pointers, the packed-weight buffer and the workspace.
+//
+// Fusions relative to the reference module graph:
+//   * torch.cat((x, skip)) (unet.py:134) is never materialised: GroupNorm reads both sources, res_conv is two
+//     extra K-segments of the block's second convolution;
+//   * res_conv (1x1, unet.py:238) + "h + res_conv(x)" (:245) ride in conv2's accumulator (K-concatenation);
+//   * FeatureWiseAffine (:160-177): all 30 Linear layers are one table computed per sample by vf_embed and added
+//     in conv1's epilogue; conv bias, identity residual and the attention residual (:277) are epilogue adds;
+//   * the first 3x3 conv runs as a K=64 GEMM over the im2col rows written by vf_pack_views.
+#include <map>
+#include <string>
+#include <vector>
+
+#include "vf_common.cuh"
+
+namespace vf {
+
+struct ParamInfo {
+  std::string name;
+  int64_t shape[4];
+  int ndim;
+};
+
+struct ResBlock {
+  std::string name;
+  int c0 = 0, c1 = 0;   // channels of x and of the skip tensor (0 when none)
+  int cout = 0;
+  bool attn = false;
+  // parameter indices
+  int nf_w, nf_b, g1_w, g1_b, c1_w, c1_b, g2_w, g2_b, c2_w, c2_b, rs_w = -1, rs_b = -1;
+  int an_w = -1, an_b = -1, qkv_w = -1, ao_w = -1, ao_b = -1;
+  // packed offsets (bytes from the start of the packed buffer)
+  size_t w1 = 0, w2 = 0, wqkv = 0, wout = 0, bias2 = 0;
+  int emb_col = 0;
+};
+
+struct Layer {
+  int kind;  // 0 conv0, 1 resblock, 2 down, 3 up
+  int rb = -1;
+  std::string name;
+  int c = 0;
+  int w_idx = -1, b_idx = -1;
+  size_t w = 0;
+};
+
+}  // namespace vf
+
+struct vf_unet {
+  vf_unet_config cfg;
+  int dtype;
+  std::vector<vf::ParamInfo> params;
+  std::vector<vf::ResBlock> blocks;
+  std::vector<vf::Layer> downs, mid, ups;
+  int final_c = 0, fin_gw = -1, fin_gb = -1, fin_w = -1, fin_b = -1;
+  size_t final_w = 0;
+  int mlp_w0, mlp_b0, mlp_w2, mlp_b2;
+  int E = 0;
+  int k0 = 0;
+  size_t packed_bytes = 0, emb_w_off = 0, emb_b_off = 0, conv0_w = 0;
+  std::vector<const float*> master;   // device pointers of the fp32 masters (valid after pack_weights)
+  bool packed = false;
+  int launches = 0;                   // kernels enqueued by the last forward
+  struct Tap { size_t off; int C, H, W; int dtype; int ld; };
+  std::map<std::string, Tap> taps;
+  int last_images = 0;
+};
+
+namespace vf {
+
+static int add_param(vf_unet* u, const std::string& name, std::initializer_list<int64_t> shape) {
+  ParamInfo p;
+  p.name = name;
+  p.ndim = (int)shape.size();
+  int i = 0;
+  for (auto s : shape) p.shape[i++] = s;
+  for (; i < 4; ++i) p.shape[i] = 1;
+  u->params.push_back(p);
+  return (int)u->params.size() - 1;
+}
+
+static void add_resblock(vf_unet* u, std::vector<Layer>& sec, const std::string& name, int c0, int c1, int cout, bool attn) {
+  const int ic = u->cfg.inner_channel;
+  const int cin = c0 + c1;
+  ResBlock b;
+  b.name = name; b.c0 = c0; b.c1 = c1; b.cout = cout; b.attn = attn;
+  const std::string r = name + ".res_block";
+  // registration order of ResnetBlock.__init__ (unet.py:232-238): noise_func, block1, block2, res_conv
+  b.nf_w = add_param(u, r + ".noise_func.noise_func.0.weight", {cout, ic});
+  b.nf_b = add_param(u, r + ".noise_func.noise_func.0.bias", {cout});
+  b.g1_w = add_param(u, r + ".block1.block.0.weight", {cin});
+  b.g1_b = add_param(u, r + ".block1.block.0.bias", {cin});
+  b.c1_w = add_param(u, r + ".block1.block.3.weight", {cout, cin, 3, 3});
+  b.c1_b = add_param(u, r + ".block1.block.3.bias", {cout});
+  b.g2_w = add_param(u, r + ".block2.block.0.weight", {cout});
+  b.g2_b = add_param(u, r + ".block2.block.0.bias", {cout});
+  b.c2_w = add_param(u, r + ".block2.block.3.weight", {cout, cout, 3, 3});
+  b.c2_b = add_param(u, r + ".block2.block.3.bias", {cout});
+  if (cin != cout) {
+    b.rs_w = add_param(u, r + ".res_conv.weight", {cout, cin, 1, 1});
+    b.rs_b = add_param(u, r + ".res_conv.bias", {cout});
+  }
+  if (attn) {
+    b.an_w = add_param(u, name + ".attn.norm.weight", {cout});
+    b.an_b = add_param(u, name + ".attn.norm.bias", {cout});
+    b.qkv_w = add_param(u, name + ".attn.qkv.weight", {3 * cout, cout, 1, 1});
+    b.ao_w = add_param(u, name + ".attn.out.weight", {cout, cout, 1, 1});
+    b.ao_b = add_param(u, name + ".attn.out.bias", {cout});
+  }
+  b.emb_col = u->E;
+  u->E += cout;
+  u->blocks.push_back(b);
+  Layer l;
+  l.kind = 1; l.rb = (int)u->blocks.size() - 1; l.name = name; l.c = cout;
+  sec.push_back(l);
+}
+
+static void add_resample(vf_unet* u, std::vector<Layer>& sec, const std::string& name, int kind, int c) {
+  Layer l;
+  l.kind = kind; l.name = name; l.c = c;
+  l.w_idx = add_param(u, name + ".conv.weight", {c, c, 3, 3});
+  l.b_idx = add_param(u, name + ".conv.bias", {c});
+  sec.push_back(l);
+}
+
+// ---- execution context: the same walk either sizes the workspace (dry) or enqueues the kernels -----------
+struct Exec {
+  bool dry;
+  uint8_t* base;
+  size_t off = 0;
+  size_t cap = 0;
+  cudaStream_t st;
+  int rc = VF_OK;
+  int launches = 0;
+  void* alloc(size_t bytes) {
+    off = align_up(off, 256);
+    void* p = dry ? nullptr : base + off;
+    off += bytes;
+    return p;
+  }
+};
+
+#define VF_RUN(ex, n, call)               \
+  do {                                    \
+    if (!(ex).dry && (ex).rc == VF_OK) {  \
+      (ex).rc = (call);                   \
+      (ex).launches += (n);               \
+    }                                     \
+  } while (0)
+
+template <typename T>
+__global__ void tap_to_nchw_kernel(const T* __restrict__ src, int ld, int C, int HW, size_t total, float* __restrict__ dst) {
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int pix = (int)(gid % HW);
+  const size_t rc = gid / HW;
+  const int c = (int)(rc % C);
+  const size_t r = rc / C;
+  dst[gid] = to_f(src[(r * HW + pix) * ld + c]);
+}
+
+__global__ void add_bias_kernel(const float* a, const float* b, int n, float* dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = a[i] + (b ? b[i] : 0.f);
+}
+
+struct Act {
+  void* p;
+  int C, H, W;
+};
+
+static int k_elems(const vf_unet* u) { return u->dtype == VF_BF16 ? 2 : 4; }
+
+}  // namespace vf
+
+using namespace vf;
+
+extern "C" __attribute__((visibility("default"))) int vf_unet_create(const vf_unet_config* cfg, int act_dtype, vf_unet** out) {
+  VF_REQUIRE(cfg && out, "vf_unet_create: null args");
+  VF_REQUIRE(act_dtype == VF_F32 || act_dtype == VF_BF16, "vf_unet_create: act_dtype=%d", act_dtype);
+  VF_REQUIRE(cfg->n_mults >= 1 && cfg->n_mults <= VF_MAX_LEVELS && cfg->n_attn_res >= 0 && cfg->n_attn_res <= VF_MAX_LEVELS,
+             "vf_unet_create: bad level counts");
+  VF_REQUIRE(cfg->inner_channel > 0 && cfg->inner_channel % 4 == 0 && cfg->res_blocks >= 1 && cfg->in_channel >= 1,
+             "vf_unet_create: bad channel config");
+  VF_REQUIRE(cfg->norm_groups > 0 && cfg->inner_channel % cfg->norm_groups == 0,
+             "vf_unet_create: inner_channel %d not divisible by norm_groups %d", cfg->inner_channel, cfg->norm_groups);
+  const int outc = cfg->out_channel > 0 ? cfg->out_channel : cfg->in_channel;
+  VF_REQUIRE(outc <= 8, "vf_unet_create: out_channel=%d > 8 unsupported", outc);
+  const int S = cfg->image_size;
+  VF_REQUIRE(S > 0 && (S & (S - 1)) == 0 && (S >> (cfg->n_mults - 1)) >= 1, "vf_unet_create: image_size=%d must be a power of two", S);
+  const int quantum = act_dtype == VF_BF16 ? 64 : 16;
+  for (int i = 0; i < cfg->n_mults; ++i)
+    VF_REQUIRE((cfg->inner_channel * cfg->channel_mults[i]) % quantum == 0,
+               "vf_unet_create: level %d has %d channels; this precision mode needs multiples of %d", i,
+               cfg->inner_channel * cfg->channel_mults[i], quantum);
+  vf_unet* u = new vf_unet();
+  u->cfg = *cfg;
+  u->cfg.out_channel = outc;
+  u->dtype = act_dtype;
+  const int ic = cfg->inner_channel;
+  u->mlp_w0 = add_param(u, "noise_level_mlp.0.weight", {4 * ic, ic});
+  u->mlp_b0 = add_param(u, "noise_level_mlp.0.bias", {4 * ic});
+  u->mlp_w2 = add_param(u, "noise_level_mlp.2.weight", {ic, 4 * ic});
+  u->mlp_b2 = add_param(u, "noise_level_mlp.2.bias", {ic});
+  auto is_attn = [&](int res) {
+    for (int i = 0; i < cfg->n_attn_res; ++i)
+      if (cfg->attn_res[i] == res) return true;
+    return false;
+  };
+  // ---- unet.py:38-64 (downs)
+  int pre = ic, res = S;
+  std::vector<int> feat{pre};
+  {
+    Layer l;
+    l.kind = 0; l.name = "downs.0"; l.c = ic;
+    l.w_idx = add_param(u, "downs.0.weight", {ic, cfg->in_channel, 3, 3});
+    l.b_idx = add_param(u, "downs.0.bias", {ic});
+    u->downs.push_back(l);
+  }
+  for (int i = 0; i < cfg->n_mults; ++i) {
+    const bool last = i == cfg->n_mults - 1;
+    const int cm = ic * cfg->channel_mults[i];
+    for (int r = 0; r < cfg->res_blocks; ++r) {
+      add_resblock(u, u->downs, "downs." + std::to_string(u->downs.size()), pre, 0, cm, is_attn(res));
+      feat.push_back(cm);
+      pre = cm;
+    }
+    if (!last) {
+      add_resample(u, u->downs, "downs." + std::to_string(u->downs.size()), 2, pre);
+      feat.push_back(pre);
+      res /= 2;
+    }
+  }
+  // ---- :66-85 (mid)
+  add_resblock(u, u->mid, "mid.0", pre, 0, pre, true);
+  add_resblock(u, u->mid, "mid.1", pre, 0, pre, false);
+  // ---- :87-108 (ups)
+  for (int i = cfg->n_mults - 1; i >= 0; --i) {
+    const bool last = i < 1;
+    const int cm = ic * cfg->channel_mults[i];
+    for (int r = 0; r < cfg->res_blocks + 1; ++r) {
+      const int skip = feat.back();
+      feat.pop_back();
+      add_resblock(u, u->ups, "ups." + std::to_string(u->ups.size()), pre, skip, cm, is_attn(res));
+      pre = cm;
+    }
+    if (!last) {
+      add_resample(u, u->ups, "ups." + std::to_string(u->ups.size()), 3, pre);
+      res *= 2;
+    }
+  }
+  // ---- :110-112 (final_conv)
+  u->final_c = pre;
+  u->fin_gw = add_param(u, "final_conv.block.0.weight", {pre});
+  u->fin_gb = add_param(u, "final_conv.block.0.bias", {pre});
+  u->fin_w = add_param(u, "final_conv.block.3.weight", {outc, pre, 3, 3});
+  u->fin_b = add_param(u, "final_conv.block.3.bias", {outc});
+
+  // ---- packed-weight layout
+  const size_t es = dtype_size(act_dtype);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { off = align_up(off, 256); size_t o = off; off += bytes; return o; };
+  u->k0 = (int)align_up((size_t)9 * cfg->in_channel, 64);
+  u->conv0_w = take((size_t)ic * u->k0 * es);
+  for (auto& b : u->blocks) {
+    const int cin = b.c0 + b.c1;
+    b.w1 = take((size_t)b.cout * 9 * cin * es);
+    const int k2 = 9 * b.cout + (b.rs_w >= 0 ? cin : 0);
+    b.w2 = take((size_t)b.cout * k2 * es);
+    b.bias2 = take((size_t)b.cout * 4);
+    if (b.attn) {
+      b.wqkv = take((size_t)3 * b.cout * b.cout * es);
+      b.wout = take((size_t)b.cout * b.cout * es);
+    }
+  }
+  for (auto* sec : {&u->downs, &u->mid, &u->ups})
+    for (auto& l : *sec)
+      if (l.kind == 2 || l.kind == 3) l.w = take((size_t)l.c * 9 * l.c * es);
+  u->final_w = take((size_t)16 * 9 * u->final_c * es);
+  u->emb_w_off = take((size_t)u->E * ic * 4);
+  u->emb_b_off = take((size_t)u->E * 4);
+  u->packed_bytes = align_up(off, 256);
+  *out = u;
+  return VF_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) void vf_unet_destroy(vf_unet* u) { delete u; }
+extern "C" __attribute__((visibility("default"))) int vf_unet_num_params(const vf_unet* u) { return u ? (int)u->params.size() : 0; }
+extern "C" __attribute__((visibility("default"))) int vf_unet_emb_channels(const vf_unet* u) { return u ? u->E : 0; }
+extern "C" __attribute__((visibility("default"))) int vf_unet_k0(const vf_unet* u) { return u ? u->k0 : 0; }
+extern "C" __attribute__((visibility("default"))) size_t vf_unet_packed_bytes(const vf_unet* u) { return u ? u->packed_bytes : 0; }
+extern "C" __attribute__((visibility("default"))) int vf_unet_last_launches(const vf_unet* u) { return u ? u->launches : 0; }
+
+extern "C" __attribute__((visibility("default"))) int vf_unet_param_info(const vf_unet* u, int index, char* name_buf, int name_cap, int64_t shape[4], int* ndim) {
+  VF_REQUIRE(u && index >= 0 && index < (int)u->params.size(), "vf_unet_param_info: index %d out of range", index);
+  const ParamInfo& p = u->params[index];
+  if (name_buf && name_cap > 0) snprintf(name_buf, (size_t)name_cap, "%s", p.name.c_str());
+  if (shape) for (int i = 0; i < 4; ++i) shape[i] = p.shape[i];
+  if (ndim) *ndim = p.ndim;
+  return VF_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int vf_unet_pack_weights(vf_unet* u, const float* const* params_host, void* packed, vf_stream stream) {
+  VF_REQUIRE(u && params_host && packed, "vf_unet_pack_weights: null args");
+  cudaStream_t st = as_stream(stream);
+  u->master.assign(params_host, params_host + u->params.size());
+  for (size_t i = 0; i < u->master.size(); ++i) VF_REQUIRE(u->master[i], "vf_unet_pack_weights: parameter %zu (%s) is null", i, u->params[i].name.c_str());
+  uint8_t* pk = reinterpret_cast<uint8_t*>(packed);
+  const int dt = u->dtype;
+  const vf_unet_config& c = u->cfg;
+  VF_CUDA(cudaMemsetAsync(pk, 0, u->packed_bytes, st));
+  int rc;
+#define VF_TRY(call) do { rc = (call); if (rc != VF_OK) return rc; } while (0)
+  VF_TRY(vf_pack_conv_weight(u->master[u->downs[0].w_idx], c.inner_channel, c.in_channel, 3, dt, pk + u->conv0_w, c.inner_channel, u->k0, 0, stream));
+  for (auto& b : u->blocks) {
+    const int cin = b.c0 + b.c1;
+    VF_TRY(vf_pack_conv_weight(u->master[b.c1_w], b.cout, cin, 3, dt, pk + b.w1, b.cout, 9 * cin, 0, stream));
+    const int k2 = 9 * b.cout + (b.rs_w >= 0 ? cin : 0);
+    VF_TRY(vf_pack_conv_weight(u->master[b.c2_w], b.cout, b.cout, 3, dt, pk + b.w2, b.cout, k2, 0, stream));
+    if (b.rs_w >= 0) VF_TRY(vf_pack_conv_weight(u->master[b.rs_w], b.cout, cin, 1, dt, pk + b.w2, b.cout, k2, 9 * b.cout, stream));
+    add_bias_kernel<<<cdiv(b.cout, 128), 128, 0, st>>>(u->master[b.c2_b], b.rs_b >= 0 ? u->master[b.rs_b] : nullptr, b.cout, reinterpret_cast<float*>(pk + b.bias2));
+    if (b.attn) {
+      VF_TRY(vf_pack_conv_weight(u->master[b.qkv_w], 3 * b.cout, b.cout, 1, dt, pk + b.wqkv, 3 * b.cout, b.cout, 0, stream));
+      VF_TRY(vf_pack_conv_weight(u->master[b.ao_w], b.cout, b.cout, 1, dt, pk + b.wout, b.cout, b.cout, 0, stream));
+    }
+    // embedding Linear of this block -> rows [emb_col, emb_col + cout) of the concatenated matrix
+    VF_CUDA(cudaMemcpyAsync(pk + u->emb_w_off + (size_t)b.emb_col * c.inner_channel * 4, u->master[b.nf_w],
+                            (size_t)b.cout * c.inner_channel * 4, cudaMemcpyDeviceToDevice, st));
+    VF_CUDA(cudaMemcpyAsync(pk + u->emb_b_off + (size_t)b.emb_col * 4, u->master[b.nf_b], (size_t)b.cout * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  for (auto* sec : {&u->downs, &u->mid, &u->ups})
+    for (auto& l : *sec)
+      if (l.kind == 2 || l.kind == 3) VF_TRY(vf_pack_conv_weight(u->master[l.w_idx], l.c, l.c, 3, dt, pk + l.w, l.c, 9 * l.c, 0, stream));
+  VF_TRY(vf_pack_conv_weight(u->master[u->fin_w], c.out_channel, u->final_c, 3, dt, pk + u->final_w, 16, 9 * u->final_c, 0, stream));
+#undef VF_TRY
+  VF_LAUNCH_CHECK();
+  u->packed = true;
+  return VF_OK;
+}
+
+namespace vf {
+
+static void conv_call(Exec& ex, const vf_unet* u, vf_conv_args& a) {
+  a.dtype = u->dtype;
+  if (a.out_dtype < 0) a.out_dtype = u->dtype;
+  VF_RUN(ex, 1, vf_conv2d(&a, (vf_stream)ex.st));
+}
+
+static vf_conv_args conv_args_init() {
+  vf_conv_args a{};
+  a.stride = 1;
+  a.out_dtype = -1;
+  return a;
+}
+
+// GroupNorm (+Swish) of cat(x, skip) -> new activation
+static Act gn_block(Exec& ex, const vf_unet* u, int images, const Act& x, const Act* skip, int gw, int gb, bool swish,
+                    float*& stats_cursor) {
+  const int C = x.C + (skip ? skip->C : 0);
+  const int HW = x.H * x.W;
+  float* stats = stats_cursor;
+  stats_cursor += (size_t)images * C * 2;
+  Act y{ex.alloc((size_t)images * HW * C * k_elems(u)), C, x.H, x.W};
+  VF_RUN(ex, 1, vf_gn_stats(x.p, x.C, skip ? skip->p : nullptr, skip ? skip->C : 0, u->dtype, images, HW, stats, (vf_stream)ex.st));
+  VF_RUN(ex, 1, vf_gn_apply(x.p, x.C, skip ? skip->p : nullptr, skip ? skip->C : 0, u->dtype, images, HW, u->cfg.norm_groups, stats,
+                            ex.dry ? nullptr : u->master[gw], ex.dry ? nullptr : u->master[gb], swish ? 1 : 0, y.p, (vf_stream)ex.st));
+  return y;
+}
+
+static Act run_resblock(Exec& ex, vf_unet* u, const uint8_t* pk, int images, const ResBlock& b, const Act& x, const Act* skip,
+                        const float* emb, const int* img_row, float*& stats_cursor) {
+  const int HW = x.H * x.W;
+  const size_t es = k_elems(u);
+  const int cin = b.c0 + b.c1;
+  // block1: GN -> Swish -> conv3x3 (+bias +embedding)                                   unet.py:242-243
+  Act a1 = gn_block(ex, u, images, x, skip, b.g1_w, b.g1_b, true, stats_cursor);
+  Act h1{ex.alloc((size_t)images * HW * b.cout * es), b.cout, x.H, x.W};
+  {
+    vf_conv_args a = conv_args_init();
+    a.images = images; a.H = x.H; a.W = x.W; a.n_seg = 1;
+    a.src[0] = a1.p; a.src_c[0] = cin; a.ksize[0] = 3;
+    a.weight = pk + b.w1; a.cout = b.cout; a.cout_pad = b.cout;
+    a.bias = ex.dry ? nullptr : u->master[b.c1_b];
+    a.emb = emb ? emb + b.emb_col : nullptr; a.img_row = img_row; a.emb_ld = u->E;
+    a.out = h1.p; a.out_ld = b.cout;
+    conv_call(ex, u, a);
+  }
+  // block2: GN -> Swish -> conv3x3, + res_conv(x) or + x                                 unet.py:244-245
+  Act a2 = gn_block(ex, u, images, h1, nullptr, b.g2_w, b.g2_b, true, stats_cursor);
+  Act out{ex.alloc((size_t)images * HW * b.cout * es), b.cout, x.H, x.W};
+  {
+    vf_conv_args a = conv_args_init();
+    a.images = images; a.H = x.H; a.W = x.W;
+    a.src[0] = a2.p; a.src_c[0] = b.cout; a.ksize[0] = 3; a.n_seg = 1;
+    if (b.rs_w >= 0) {
+      a.src[1] = x.p; a.src_c[1] = x.C; a.ksize[1] = 1; a.n_seg = 2;
+      if (skip) { a.src[2] = skip->p; a.src_c[2] = skip->C; a.ksize[2] = 1; a.n_seg = 3; }
+    } else {
+      a.residual = x.p;
+    }
+    a.weight = pk + b.w2; a.cout = b.cout; a.cout_pad = b.cout;
+    a.bias = reinterpret_cast<const float*>(pk + b.bias2);
+    a.out = out.p; a.out_ld = b.cout;
+    conv_call(ex, u, a);
+  }
+  if (!b.attn) return out;
+  // SelfAttention: GN -> qkv 1x1 -> softmax(QK^T/sqrt(C)) V -> out 1x1 (+bias) + input     unet.py:258-277
+  const int C = b.cout;
+  Act n = gn_block(ex, u, images, out, nullptr, b.an_w, b.an_b, false, stats_cursor);
+  void* qkv = ex.alloc((size_t)images * HW * 3 * C * es);
+  void* vt = u->dtype == VF_BF16 ? ex.alloc((size_t)images * HW * C * es) : nullptr;
+  {
+    vf_conv_args a = conv_args_init();
+    a.images = images; a.H = x.H; a.W = x.W; a.n_seg = 1;
+    a.src[0] = n.p; a.src_c[0] = C; a.ksize[0] = 1;
+    a.weight = pk + b.wqkv; a.cout = 3 * C; a.cout_pad = 3 * C;
+    a.out = qkv; a.out_ld = 3 * C;
+    if (u->dtype == VF_BF16) { a.qkv_split = C; a.out_vt = vt; }
+    conv_call(ex, u, a);
+  }
+  Act o{ex.alloc((size_t)images * HW * C * es), C, x.H, x.W};
+  VF_RUN(ex, 1, vf_attention(qkv, vt, u->dtype, images, HW, C, o.p, (vf_stream)ex.st));
+  Act out2{ex.alloc((size_t)images * HW * C * es), C, x.H, x.W};
+  {
+    vf_conv_args a = conv_args_init();
+    a.images = images; a.H = x.H; a.W = x.W; a.n_seg = 1;
+    a.src[0] = o.p; a.src_c[0] = C; a.ksize[0] = 1;
+    a.weight = pk + b.wout; a.cout = C; a.cout_pad = C;
+    a.bias = ex.dry ? nullptr : u->master[b.ao_b];
+    a.residual = out.p;
+    a.out = out2.p; a.out_ld = C;
+    conv_call(ex, u, a);
+  }
+  return out2;
+}
+
+static size_t stats_floats(const vf_unet* u, int images) {
+  size_t n = 0;
+  for (auto& b : u->blocks) n += (size_t)images * 2 * ((b.c0 + b.c1) + b.cout + (b.attn ? b.cout : 0));
+  n += (size_t)images * 2 * u->final_c;
+  return n;
+}
+
+static int walk(vf_unet* u, Exec& ex, const uint8_t* pk, int images, const void* x0, const float* level, const float* angle,
+                int rows, const int* img_row, float* out) {
+  const vf_unet_config& c = u->cfg;
+  const int S = c.image_size;
+  const size_t es = k_elems(u);
+  auto tap = [&](const std::string& name, const Act& a) {
+    if (!ex.dry) u->taps[name] = vf_unet::Tap{(size_t)((uint8_t*)a.p - ex.base), a.C, a.H, a.W, u->dtype, a.C};
+  };
+  // statistics arena, zeroed once per forward
+  const size_t st_bytes = stats_floats(u, images) * 4;
+  float* stats = reinterpret_cast<float*>(ex.alloc(st_bytes));
+  if (!ex.dry && ex.rc == VF_OK && cudaMemsetAsync(stats, 0, st_bytes, ex.st) != cudaSuccess) {
+    set_error("vf_unet_forward: memset failed");
+    ex.rc = VF_ERR_CUDA;
+  }
+  float* stats_cursor = stats;
+  // embedding table [rows, E]
+  float* emb = reinterpret_cast<float*>(ex.alloc((size_t)rows * u->E * 4));
+  VF_RUN(ex, 1, vf_embed(level, angle, rows, c.inner_channel, u->master[u->mlp_w0], u->master[u->mlp_b0], u->master[u->mlp_w2],
+                         u->master[u->mlp_b2], reinterpret_cast<const float*>(pk + u->emb_w_off),
+                         reinterpret_cast<const float*>(pk + u->emb_b_off), u->E, emb, (vf_stream)ex.st));
+  std::vector<Act> feats;
+  Act x{nullptr, c.inner_channel, S, S};
+  // downs[0]: 3x3 conv as a K0 GEMM over the packed im2col rows                            unet.py:42
+  x.p = ex.alloc((size_t)images * S * S * c.inner_channel * es);
+  {
+    vf_conv_args a = conv_args_init();
+    a.images = images; a.H = S; a.W = S; a.n_seg = 1;
+    a.src[0] = x0; a.src_c[0] = u->k0; a.ksize[0] = 1;
+    a.weight = pk + u->conv0_w; a.cout = c.inner_channel; a.cout_pad = c.inner_channel;
+    a.bias = ex.dry ? nullptr : u->master[u->downs[0].b_idx];
+    a.out = x.p; a.out_ld = c.inner_channel;
+    conv_call(ex, u, a);
+  }
+  feats.push_back(x);
+  tap("downs.0", x);
+  for (size_t i = 1; i < u->downs.size(); ++i) {
+    const Layer& l = u->downs[i];
+    if (l.kind == 1) {
+      x = run_resblock(ex, u, pk, images, u->blocks[l.rb], x, nullptr, emb, img_row, stats_cursor);
+    } else {   // Downsample: conv3x3 stride 2                                              unet.py:195-201
+      Act y{ex.alloc((size_t)images * (x.H / 2) * (x.W / 2) * l.c * es), l.c, x.H / 2, x.W / 2};
+      vf_conv_args a = conv_args_init();
+      a.images = images; a.H = y.H; a.W = y.W; a.n_seg = 1; a.stride = 2;
+      a.src[0] = x.p; a.src_c[0] = l.c; a.ksize[0] = 3;
+      a.weight = pk + l.w; a.cout = l.c; a.cout_pad = l.c;
+      a.bias = ex.dry ? nullptr : u->master[l.b_idx];
+      a.out = y.p; a.out_ld = l.c;
+      conv_call(ex, u, a);
+      x = y;
+    }
+    feats.push_back(x);
+    tap(l.name, x);
+  }
+  for (auto& l : u->mid) {
+    x = run_resblock(ex, u, pk, images, u->blocks[l.rb], x, nullptr, emb, img_row, stats_cursor);
+    tap(l.name, x);
+  }
+  for (auto& l : u->ups) {
+    if (l.kind == 1) {
+      Act skip = feats.back();
+      feats.pop_back();
+      x = run_resblock(ex, u, pk, images, u->blocks[l.rb], x, &skip, emb, img_row, stats_cursor);
+    } else {   // Upsample: nearest x2 then conv3x3                                         unet.py:185-192
+      Act up{ex.alloc((size_t)images * 4 * x.H * x.W * l.c * es), l.c, 2 * x.H, 2 * x.W};
+      VF_RUN(ex, 1, vf_upsample2x(x.p, u->dtype, images, x.H, x.W, l.c, up.p, (vf_stream)ex.st));
+      Act y{ex.alloc((size_t)images * up.H * up.W * l.c * es), l.c, up.H, up.W};
+      vf_conv_args a = conv_args_init();
+      a.images = images; a.H = y.H; a.W = y.W; a.n_seg = 1;
+      a.src[0] = up.p; a.src_c[0] = l.c; a.ksize[0] = 3;
+      a.weight = pk + l.w; a.cout = l.c; a.cout_pad = l.c;
+      a.bias = ex.dry ? nullptr : u->master[l.b_idx];
+      a.out = y.p; a.out_ld = l.c;
+      conv_call(ex, u, a);
+      x = y;
+    }
+    tap(l.name, x);
+  }
+  // final_conv: GN -> Swish -> conv3x3 -> fp32 [., 8]                                       unet.py:110-112, :138
+  Act f = gn_block(ex, u, images, x, nullptr, u->fin_gw, u->fin_gb, true, stats_cursor);
+  {
+    vf_conv_args a = conv_args_init();
+    a.images = images; a.H = S; a.W = S; a.n_seg = 1;
+    a.src[0] = f.p; a.src_c[0] = u->final_c; a.ksize[0] = 3;
+    a.weight = pk + u->final_w; a.cout = c.out_channel; a.cout_pad = 16;
+    a.bias = ex.dry ? nullptr : u->master[u->fin_b];
+    a.out = out; a.out_dtype = VF_F32; a.out_ld = 8;
+    conv_call(ex, u, a);
+  }
+  return ex.rc;
+}
+
+}  // namespace vf
+
+extern "C" __attribute__((visibility("default"))) size_t vf_unet_workspace_bytes(const vf_unet* u, int max_images) {
+  if (!u || max_images <= 0) return 0;
+  Exec ex{true, nullptr};
+  ex.st = nullptr;
+  walk(const_cast<vf_unet*>(u), ex, nullptr, max_images, nullptr, nullptr, nullptr, max_images, nullptr, nullptr);
+  return align_up(ex.off, 256) + 256;
+}
+
+extern "C" __attribute__((visibility("default"))) int vf_unet_forward(vf_unet* u, const void* packed, void* workspace, size_t workspace_bytes, int images,
+                               const void* x0, const float* level, const float* angle, int rows, const int* img_row,
+                               float* out, vf_stream stream) {
+  VF_REQUIRE(u && packed && workspace && x0 && level && angle && img_row && out, "vf_unet_forward: null tensor");
+  VF_REQUIRE(images > 0 && rows > 0 && rows <= images, "vf_unet_forward: images=%d rows=%d", images, rows);
+  if (!u->packed) { set_error("vf_unet_forward: weights were not packed (call vf_unet_pack_weights)"); return VF_ERR_STATE; }
+  Exec ex{false, reinterpret_cast<uint8_t*>(workspace)};
+  ex.st = as_stream(stream);
+  ex.cap = workspace_bytes;
+  {
+    Exec dry{true, nullptr};
+    dry.st = nullptr;
+    walk(u, dry, nullptr, images, nullptr, nullptr, nullptr, rows, nullptr, nullptr);
+    VF_REQUIRE(dry.off <= workspace_bytes, "vf_unet_forward: workspace too small (%zu < %zu)", workspace_bytes, dry.off);
+  }
+  u->taps.clear();
+  u->last_images = images;
+  int rc = walk(u, ex, reinterpret_cast<const uint8_t*>(packed), images, x0, level, angle, rows, img_row, out);
+  u->launches = ex.launches;
+  return rc;
+}
+
+extern "C" __attribute__((visibility("default"))) int vf_unet_read_tap(vf_unet* u, const void* workspace, const char* name, float* dst, int64_t* chw, vf_stream stream) {
+  VF_REQUIRE(u && workspace && name && dst, "vf_unet_read_tap: null args");
+  auto it = u->taps.find(name);
+  VF_REQUIRE(it != u->taps.end(), "vf_unet_read_tap: no module '%s' in the last forward", name);
+  const vf_unet::Tap& t = it->second;
+  const size_t total = (size_t)u->last_images * t.C * t.H * t.W;
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(workspace) + t.off;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (t.dtype == VF_BF16)
+    tap_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, t.ld, t.C, t.H * t.W, total, dst);
+  else
+    tap_to_nchw_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)src, t.ld, t.C, t.H * t.W, total, dst);
+  VF_LAUNCH_CHECK();
+  if (chw) { chw[0] = t.C; chw[1] = t.H; chw[2] = t.W; }
+  return VF_OK;
+}

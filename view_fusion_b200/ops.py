@@ -1,0 +1,114 @@
+"""Torch-tensor wrappers over the stage-level C-ABI operators (unit parity tests, ncu captures, bench).
+
+Activations are NHWC matrices `[images*H*W, C]` in torch.float32 or torch.bfloat16.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return _lib.VF_BF16
+    if t.dtype == torch.float32:
+        return _lib.VF_F32
+    raise TypeError(t.dtype)
+
+
+def to_nhwc(x: torch.Tensor, dtype=None) -> torch.Tensor:
+    """(R,C,H,W) -> [R*H*W, C] contiguous."""
+    y = x.permute(0, 2, 3, 1).contiguous().view(-1, x.shape[1])
+    return y if dtype is None else y.to(dtype)
+
+
+def from_nhwc(y: torch.Tensor, R: int, H: int, W: int) -> torch.Tensor:
+    return y.float().view(R, H, W, -1).permute(0, 3, 1, 2).contiguous()
+
+
+def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype, cout_pad=None, k_total=None, k_off=0, dst=None) -> torch.Tensor:
+    lib = _lib.require_device()
+    cout, cin, k, _ = w.shape
+    cout_pad = cout if cout_pad is None else cout_pad
+    k_total = k * k * cin if k_total is None else k_total
+    if dst is None:
+        dst = torch.zeros(cout_pad, k_total, dtype=dtype, device=w.device)
+    _lib.check(lib.vf_pack_conv_weight(w.contiguous().data_ptr(), cout, cin, k, _dt(dst), dst.data_ptr(), cout_pad, k_total, k_off,
+                                       _lib.stream_handle()), "vf_pack_conv_weight")
+    return dst
+
+
+def conv2d(srcs, ksizes, weight, images, H, W, cout, *, stride=1, bias=None, emb=None, img_row=None, residual=None,
+           out_dtype=None, out_ld=None, qkv_split=0, cout_pad=None):
+    """srcs: list of NHWC matrices; weight: packed [cout_pad, K_total].  Returns out (and V^T when qkv_split)."""
+    lib = _lib.require_device()
+    a = _lib.ConvArgs()
+    dt = srcs[0].dtype
+    a.dtype, a.images, a.H, a.W, a.n_seg = _dt(srcs[0]), images, H, W, len(srcs)
+    for i, (s, k) in enumerate(zip(srcs, ksizes)):
+        a.src[i], a.src_c[i], a.ksize[i] = s.data_ptr(), s.shape[1], k
+    a.stride = stride
+    a.weight, a.cout, a.cout_pad = weight.data_ptr(), cout, weight.shape[0] if cout_pad is None else cout_pad
+    a.bias = _lib.ptr(bias)
+    if emb is not None:
+        a.emb, a.img_row, a.emb_ld = emb.data_ptr(), img_row.data_ptr(), emb.shape[1]
+    a.residual = _lib.ptr(residual)
+    out_dtype = dt if out_dtype is None else out_dtype
+    out_ld = cout if out_ld is None else out_ld
+    out = torch.zeros(images * H * W, out_ld, dtype=out_dtype, device=srcs[0].device)
+    a.out, a.out_dtype, a.out_ld = out.data_ptr(), (_lib.VF_BF16 if out_dtype == torch.bfloat16 else _lib.VF_F32), out_ld
+    vt = None
+    if qkv_split and dt == torch.bfloat16:
+        vt = torch.zeros(images, qkv_split, H * W, dtype=dt, device=out.device)
+        a.qkv_split, a.out_vt = qkv_split, vt.data_ptr()
+    _lib.check(lib.vf_conv2d(C.byref(a), _lib.stream_handle()), "vf_conv2d")
+    return (out, vt) if qkv_split else out
+
+
+def gn_stats(src0, src1, images, HW):
+    lib = _lib.require_device()
+    C0, C1 = src0.shape[1], (0 if src1 is None else src1.shape[1])
+    stats = torch.zeros(images, C0 + C1, 2, dtype=torch.float32, device=src0.device)
+    _lib.check(lib.vf_gn_stats(src0.data_ptr(), C0, _lib.ptr(src1), C1, _dt(src0), images, HW, stats.data_ptr(), _lib.stream_handle()),
+               "vf_gn_stats")
+    return stats
+
+
+def gn_apply(src0, src1, images, HW, groups, stats, gamma, beta, swish=True):
+    lib = _lib.require_device()
+    C0, C1 = src0.shape[1], (0 if src1 is None else src1.shape[1])
+    dst = torch.empty(images * HW, C0 + C1, dtype=src0.dtype, device=src0.device)
+    _lib.check(lib.vf_gn_apply(src0.data_ptr(), C0, _lib.ptr(src1), C1, _dt(src0), images, HW, groups, stats.data_ptr(),
+                               gamma.data_ptr(), beta.data_ptr(), int(swish), dst.data_ptr(), _lib.stream_handle()), "vf_gn_apply")
+    return dst
+
+
+def upsample2x(src, images, H, W):
+    lib = _lib.require_device()
+    Cc = src.shape[1]
+    dst = torch.empty(images * 4 * H * W, Cc, dtype=src.dtype, device=src.device)
+    _lib.check(lib.vf_upsample2x(src.data_ptr(), _dt(src), images, H, W, Cc, dst.data_ptr(), _lib.stream_handle()), "vf_upsample2x")
+    return dst
+
+
+def attention(qkv, vt, images, L, Cc):
+    lib = _lib.require_device()
+    out = torch.empty(images * L, Cc, dtype=qkv.dtype, device=qkv.device)
+    _lib.check(lib.vf_attention(qkv.data_ptr(), _lib.ptr(vt), _dt(qkv), images, L, Cc, out.data_ptr(), _lib.stream_handle()), "vf_attention")
+    return out
+
+
+def embed(level, angle, ic, w0, b0, w2, b2, emb_w, emb_b):
+    lib = _lib.require_device()
+    rows, E = level.numel(), emb_w.shape[0]
+    out = torch.empty(rows, E, dtype=torch.float32, device=level.device)
+    _lib.check(lib.vf_embed(level.data_ptr(), angle.data_ptr(), rows, ic, w0.data_ptr(), b0.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                            emb_w.data_ptr(), emb_b.data_ptr(), E, out.data_ptr(), _lib.stream_handle()), "vf_embed")
+    return out
+
+
+def force_simt(on: bool) -> None:
+    _lib.load().vf_debug_force_simt(int(on))

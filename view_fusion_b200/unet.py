@@ -1,0 +1,251 @@
+"""Drop-in `UNet` for the reference's `model/unet.py` (constructor :9-21, forward :114-138).
+
+Same constructor arguments, same `forward(x, angle, time)` contract, same `state_dict()` keys/shapes (SURVEY.md
+Appendix C) and — because the parameter-holding leaf modules are created in the reference's order with torch's
+default initialisers — bit-identical random-init weights under the same `torch.manual_seed`.
+
+The module tree below only HOLDS parameters.  The arithmetic runs in the sm_100a library behind the C ABI
+(`include/viewfusion_b200.h`): `forward` packs the NCHW input, enqueues `vf_unet_forward` on the current CUDA
+stream and converts the NHWC result back.  There is no PyTorch/CPU execution path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+from torch import nn
+
+from . import _lib
+
+
+class Swish(nn.Module):
+    """Placeholder keeping `noise_level_mlp` indices (0, 2) of unet.py:27-32; never executed."""
+
+
+def _holder(**children) -> nn.Module:
+    m = nn.Module()
+    for k, v in children.items():
+        m.add_module(k, v)
+    return m
+
+
+def _block(dim, dim_out, groups):
+    # Sequential(GroupNorm, Swish, Identity, Conv2d) -> parameters at indices 0 and 3 (unet.py:210-215)
+    return _holder(block=nn.Sequential(nn.GroupNorm(groups, dim), Swish(), nn.Identity(), nn.Conv2d(dim, dim_out, 3, padding=1)))
+
+
+def _res_attn_block(dim, dim_out, emb_dim, groups, with_attn):
+    # creation order == unet.py:232-238 then :254-256 so the RNG stream matches the reference's constructor
+    noise_func = _holder(noise_func=nn.Sequential(nn.Linear(emb_dim, dim_out)))
+    block1 = _block(dim, dim_out, groups)
+    block2 = _block(dim_out, dim_out, groups)
+    res_conv = nn.Conv2d(dim, dim_out, 1) if dim != dim_out else nn.Identity()
+    m = _holder(res_block=_holder(noise_func=noise_func, block1=block1, block2=block2, res_conv=res_conv))
+    if with_attn:
+        m.add_module("attn", _holder(norm=nn.GroupNorm(groups, dim_out), qkv=nn.Conv2d(dim_out, dim_out * 3, 1, bias=False),
+                                     out=nn.Conv2d(dim_out, dim_out, 1)))
+    return m
+
+
+class UNet(nn.Module):
+    def __init__(
+        self,
+        in_channel: int = 6,
+        out_channel: Optional[int] = 3,
+        inner_channel: int = 32,
+        norm_groups: int = 32,
+        channel_mults: Sequence[int] = (1, 2, 4, 8, 8),
+        attn_res: Sequence[int] = (8,),
+        res_blocks: int = 3,
+        dropout: float = 0,
+        with_noise_level_emb: bool = True,
+        image_size: int = 128,
+        precision: str = "bf16",
+    ):
+        super().__init__()
+        if dropout != 0:
+            raise NotImplementedError("dropout != 0 is not supported (every reference config uses 0)")
+        if not with_noise_level_emb:
+            raise NotImplementedError("with_noise_level_emb=False is not supported (every reference config uses True)")
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' (tcgen05 tensor cores) or 'fp32' (CUDA cores, reference precision)")
+        self.precision = precision
+        self.config = dict(in_channel=in_channel, out_channel=out_channel if out_channel is not None else in_channel,
+                           inner_channel=inner_channel, norm_groups=norm_groups, channel_mults=tuple(channel_mults),
+                           attn_res=tuple(attn_res), res_blocks=res_blocks, image_size=image_size)
+
+        # ---- parameter tree, mirroring unet.py:24-112 ----
+        self.noise_level_mlp = nn.Sequential(nn.Linear(inner_channel, inner_channel * 4), Swish(),
+                                             nn.Linear(inner_channel * 4, inner_channel))
+        self.noise_level_angle_mlp = nn.Sequential()
+        num_mults = len(channel_mults)
+        pre, feat, res = inner_channel, [inner_channel], image_size
+        downs = [nn.Conv2d(in_channel, inner_channel, kernel_size=3, padding=1)]
+        for ind in range(num_mults):
+            cm = inner_channel * channel_mults[ind]
+            for _ in range(res_blocks):
+                downs.append(_res_attn_block(pre, cm, inner_channel, norm_groups, res in attn_res))
+                feat.append(cm)
+                pre = cm
+            if ind != num_mults - 1:
+                downs.append(_holder(conv=nn.Conv2d(pre, pre, 3, 2, 1)))
+                feat.append(pre)
+                res //= 2
+        self.downs = nn.ModuleList(downs)
+        self.mid = nn.ModuleList([_res_attn_block(pre, pre, inner_channel, norm_groups, True),
+                                  _res_attn_block(pre, pre, inner_channel, norm_groups, False)])
+        ups = []
+        for ind in reversed(range(num_mults)):
+            cm = inner_channel * channel_mults[ind]
+            for _ in range(res_blocks + 1):
+                ups.append(_res_attn_block(pre + feat.pop(), cm, inner_channel, norm_groups, res in attn_res))
+                pre = cm
+            if ind >= 1:
+                ups.append(_holder(conv=nn.Conv2d(pre, pre, 3, padding=1)))
+                res *= 2
+        self.ups = nn.ModuleList(ups)
+        self.final_conv = _block(pre, self.config["out_channel"], norm_groups)
+
+        # ---- native plan (host-side only; created lazily so CPU-side construction needs no GPU) ----
+        self._plan = None
+        self._packed = None
+        self._packed_key = None
+        self._ws = None
+        self._ws_images = 0
+
+    # ------------------------------------------------------------------------------------------
+    def _native(self):
+        if self._plan is None:
+            lib = _lib.require_device()
+            cfg = _lib.UnetConfig()
+            c = self.config
+            cfg.in_channel, cfg.out_channel, cfg.inner_channel = c["in_channel"], c["out_channel"], c["inner_channel"]
+            cfg.norm_groups, cfg.res_blocks, cfg.image_size = c["norm_groups"], c["res_blocks"], c["image_size"]
+            cfg.n_mults = len(c["channel_mults"])
+            for i, m in enumerate(c["channel_mults"]):
+                cfg.channel_mults[i] = m
+            cfg.n_attn_res = len(c["attn_res"])
+            for i, r in enumerate(c["attn_res"]):
+                cfg.attn_res[i] = r
+            h = C.c_void_p()
+            _lib.check(lib.vf_unet_create(C.byref(cfg), _lib.VF_BF16 if self.precision == "bf16" else _lib.VF_F32, C.byref(h)),
+                       "vf_unet_create")
+            self._plan = h
+            # parameter table of the plan must be exactly this module's state_dict
+            names = []
+            buf = C.create_string_buffer(256)
+            shape = (C.c_int64 * 4)()
+            nd = C.c_int()
+            mine = dict(self.named_parameters())
+            for i in range(lib.vf_unet_num_params(h)):
+                _lib.check(lib.vf_unet_param_info(h, i, buf, 256, shape, C.byref(nd)), "vf_unet_param_info")
+                n = buf.value.decode()
+                if n not in mine or tuple(mine[n].shape) != tuple(shape[: nd.value]):
+                    raise RuntimeError(f"plan/module parameter mismatch at {n}")
+                names.append(n)
+            if len(names) != len(mine):
+                raise RuntimeError("plan/module parameter count mismatch")
+            self._param_names = names
+        return self._plan
+
+    def __del__(self):
+        try:
+            if getattr(self, "_plan", None) is not None:
+                _lib.load().vf_unet_destroy(self._plan)
+        except Exception:
+            pass
+
+    @property
+    def act_dtype(self) -> int:
+        return _lib.VF_BF16 if self.precision == "bf16" else _lib.VF_F32
+
+    def packed_weights(self) -> torch.Tensor:
+        """GEMM-ready weight cache; refreshed whenever a master parameter changed (optimizer step, load_state_dict)."""
+        lib = _lib.require_device()
+        h = self._native()
+        params = dict(self.named_parameters())
+        plist = [params[n] for n in self._param_names]
+        key = tuple((p.data_ptr(), p._version) for p in plist)
+        if self._packed is None or key != self._packed_key:
+            for p in plist:
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise RuntimeError("view_fusion_b200.UNet parameters must be contiguous fp32 CUDA tensors (call .cuda())")
+            dev = plist[0].device
+            if self._packed is None or self._packed.device != dev:
+                self._packed = torch.empty(lib.vf_unet_packed_bytes(h), dtype=torch.uint8, device=dev)
+            arr = (C.c_void_p * len(plist))(*[p.data_ptr() for p in plist])
+            _lib.check(lib.vf_unet_pack_weights(h, arr, self._packed.data_ptr(), _lib.stream_handle()), "vf_unet_pack_weights")
+            self._packed_key = key
+        return self._packed
+
+    def workspace(self, images: int) -> torch.Tensor:
+        lib = _lib.require_device()
+        h = self._native()
+        dev = next(self.parameters()).device
+        if self._ws is None or self._ws_images < images or self._ws.device != dev:
+            self._ws = torch.empty(lib.vf_unet_workspace_bytes(h, images), dtype=torch.uint8, device=dev)
+            self._ws_images = images
+        return self._ws
+
+    @property
+    def k0(self) -> int:
+        return _lib.require_device().vf_unet_k0(self._native())
+
+    def run_packed(self, x0: torch.Tensor, images: int, level: torch.Tensor, angle: torch.Tensor, img_row: torch.Tensor,
+                   out: torch.Tensor) -> None:
+        """Enqueue one UNet forward on pre-packed input (the sampler / trainer entry)."""
+        lib = _lib.require_device()
+        h = self._native()
+        packed = self.packed_weights()
+        ws = self.workspace(images)
+        _lib.check(lib.vf_unet_forward(h, packed.data_ptr(), ws.data_ptr(), ws.numel(), images, x0.data_ptr(), level.data_ptr(),
+                                       angle.data_ptr(), level.numel(), img_row.data_ptr(), out.data_ptr(), _lib.stream_handle()),
+                   "vf_unet_forward")
+
+    def last_launches(self) -> int:
+        return _lib.load().vf_unet_last_launches(self._native())
+
+    def read_tap(self, name: str) -> torch.Tensor:
+        """Output activation of module `name` in the last forward, as NCHW fp32 (parity debugging)."""
+        lib = _lib.require_device()
+        h = self._native()
+        chw = (C.c_int64 * 3)()
+        # size query: taps are at most images * Cmax * S * S; allocate generously then trim
+        S = self.config["image_size"]
+        cmax = 2 * self.config["inner_channel"] * max(self.config["channel_mults"])
+        buf = torch.empty(self._last_images * cmax * S * S, dtype=torch.float32, device=self._ws.device)
+        _lib.check(lib.vf_unet_read_tap(h, self._ws.data_ptr(), name.encode(), buf.data_ptr(), chw, _lib.stream_handle()), "vf_unet_read_tap")
+        c, hh, ww = chw[0], chw[1], chw[2]
+        return buf[: self._last_images * c * hh * ww].view(self._last_images, c, hh, ww).clone()
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, angle: torch.Tensor, time: torch.Tensor) -> torch.Tensor:
+        """x (R, Cin, H, W) fp32, angle (R, 1), time (R, 1) [the noise level] -> (R, Cout, H, W) fp32 (unet.py:114-138)."""
+        lib = _lib.require_device()
+        if not x.is_cuda:
+            raise RuntimeError("view_fusion_b200.UNet.forward needs CUDA tensors; there is no CPU fallback")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and x.requires_grad:
+            raise NotImplementedError("gradients w.r.t. the UNet input are not provided")
+        R, Cin, H, W = x.shape
+        S = self.config["image_size"]
+        if (H, W) != (S, S) or Cin != self.config["in_channel"]:
+            raise ValueError(f"expected input (R,{self.config['in_channel']},{S},{S}), got {tuple(x.shape)}")
+        x = x.contiguous().float()
+        k0 = self.k0
+        es = 2 if self.precision == "bf16" else 4
+        x0 = torch.empty(R * H * W * k0 * es, dtype=torch.uint8, device=x.device)
+        st = _lib.stream_handle()
+        _lib.check(lib.vf_pack_nchw(x.data_ptr(), R, Cin, H, W, k0, self.act_dtype, x0.data_ptr(), st), "vf_pack_nchw")
+        level = time.reshape(-1).contiguous().float()
+        ang = angle.reshape(-1).contiguous().float()
+        if level.numel() != R or ang.numel() != R:
+            raise ValueError("angle and time must be (R, 1)")
+        img_row = torch.arange(R, dtype=torch.int32, device=x.device)
+        out8 = torch.empty(R * H * W * 8, dtype=torch.float32, device=x.device)
+        self._last_images = R
+        self.run_packed(x0, R, level, ang, img_row, out8)
+        oc = self.config["out_channel"]
+        out = torch.empty(R, oc, H, W, dtype=torch.float32, device=x.device)
+        _lib.check(lib.vf_nhwc_to_nchw(out8.data_ptr(), 8, R, oc, H, W, out.data_ptr(), st), "vf_nhwc_to_nchw")
+        return out

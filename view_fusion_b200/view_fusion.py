@@ -1,0 +1,259 @@
+"""Drop-in `ViewFusion` for the reference's `model/view_fusion.py`.
+
+Keeps the constructor (:13-20), `set_new_noise_schedule` (:35-68), `forward` (:216-300), `generate` (:179-214),
+`p_sample` (:166-177), `p_mean_variance` (:86-160), `q_sample`, `predict_start_from_noise`, `q_posterior`, the six
+schedule buffers and the `denoise_fn.*` state_dict prefix.  The per-step work — view stacking, the shared UNet over
+all views, softmax-over-views composition and the DDPM posterior update — is enqueued on the current CUDA stream
+through the C ABI (`vf_pack_views` -> `vf_unet_forward` -> `vf_compose_ddpm_step`); the reference's host syncs
+inside the step (`.tolist()`, tensor-valued `repeats`, `any(t > 0)`) are gone: `view_count` is read once per call.
+
+Extra, optional keyword arguments (not in the reference) exist only to inject randomness for parity tests:
+`p_sample(..., noise=)`, `generate(..., noise_steps=)`, `forward(..., t=, u=)`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import _lib
+
+
+def make_beta_schedule(schedule, num_timesteps, linear_start=1e-6, linear_end=1e-2, cosine_s=8e-3):
+    """float64 beta schedules of view_fusion.py:330-362 (host-side numpy; runs once)."""
+    lin = lambda a, b, n: np.linspace(a, b, n, dtype=np.float64)
+    if schedule == "quad":
+        return lin(linear_start ** 0.5, linear_end ** 0.5, num_timesteps) ** 2
+    if schedule == "linear":
+        return lin(linear_start, linear_end, num_timesteps)
+    if schedule in ("warmup10", "warmup50"):
+        betas = linear_end * np.ones(num_timesteps, dtype=np.float64)
+        n = int(num_timesteps * (0.1 if schedule == "warmup10" else 0.5))
+        betas[:n] = lin(linear_start, linear_end, n)
+        return betas
+    if schedule == "const":
+        return linear_end * np.ones(num_timesteps, dtype=np.float64)
+    if schedule == "jsd":
+        return 1.0 / lin(num_timesteps, 1, num_timesteps)
+    if schedule == "cosine":
+        ts = np.arange(num_timesteps + 1, dtype=np.float64) / num_timesteps + cosine_s
+        al = np.cos(ts / (1 + cosine_s) * math.pi / 2) ** 2
+        al = al / al[0]
+        return np.minimum(1 - al[1:] / al[:-1], 0.999)
+    raise NotImplementedError(schedule)
+
+
+class _Plan:
+    """Per-(B, view_count) device state of the sampler / trainer: offsets, staging buffers."""
+
+    def __init__(self, model: "ViewFusion", y_cond: torch.Tensor, view_count: torch.Tensor):
+        dev = y_cond.device
+        vc = view_count.detach().to("cpu", torch.int64)            # the ONE host read of view_count per call
+        self.B = int(vc.numel())
+        self.vc = vc
+        off = torch.zeros(self.B + 1, dtype=torch.int32)
+        off[1:] = torch.cumsum(vc, 0).to(torch.int32)
+        self.images = int(off[-1])
+        self.max_v = int(vc.max())
+        if int(vc.min()) < 1 or self.max_v > y_cond.shape[1]:
+            raise ValueError("view_count must be within [1, y_cond.shape[1]]")
+        self.view_offset = off.to(dev)
+        unet = model.denoise_fn
+        S = unet.config["image_size"]
+        self.H = self.W = S
+        es = 2 if unet.precision == "bf16" else 4
+        self.x0 = torch.empty(self.images * S * S * unet.k0 * es, dtype=torch.uint8, device=dev)
+        self.img_sample = torch.empty(self.images, dtype=torch.int32, device=dev)
+        self.out8 = torch.empty(self.images * S * S * 8, dtype=torch.float32, device=dev)
+        self.t32 = torch.empty(self.B, dtype=torch.int32, device=dev)
+
+
+class ViewFusion(nn.Module):
+    def __init__(self, denoise_fn, beta_schedule, weighting_train=True, weighting_inference=True, **kwargs):
+        super().__init__(**kwargs)
+        self.denoise_fn = denoise_fn
+        self.beta_schedule = beta_schedule
+        self.loss_fn = F.mse_loss
+        self.weighting_train = weighting_train
+        self.weighting_inference = weighting_inference
+        self._noise_seed = None
+        self._noise_offset = 0
+        print("Weighting train and inference:", self.weighting_train, self.weighting_inference)   # view_fusion.py:29-33
+
+    # ---------------------------------------------------------------- schedule (view_fusion.py:35-68)
+    def set_new_noise_schedule(self, device=torch.device("cuda"), phase="train"):
+        betas = make_beta_schedule(**self.beta_schedule[phase])
+        alphas = 1.0 - betas
+        self.num_timesteps = int(betas.shape[0])
+        gammas = np.cumprod(alphas, axis=0)
+        gammas_prev = np.append(1.0, gammas[:-1])
+        var = betas * (1.0 - gammas_prev) / (1.0 - gammas)
+        tt = lambda a: torch.tensor(a, dtype=torch.float32, device=device)
+        self.register_buffer("gammas", tt(gammas))
+        self.register_buffer("sqrt_recip_gammas", tt(np.sqrt(1.0 / gammas)))
+        self.register_buffer("sqrt_recipm1_gammas", tt(np.sqrt(1.0 / gammas - 1)))
+        self.register_buffer("posterior_log_variance_clipped", tt(np.log(np.maximum(var, 1e-20))))
+        self.register_buffer("posterior_mean_coef1", tt(betas * np.sqrt(gammas_prev) / (1.0 - gammas)))
+        self.register_buffer("posterior_mean_coef2", tt((1.0 - gammas_prev) * np.sqrt(alphas) / (1.0 - gammas)))
+
+    def _schedule_struct(self) -> _lib.Schedule:
+        s = _lib.Schedule()
+        for k in ("gammas", "sqrt_recip_gammas", "sqrt_recipm1_gammas", "posterior_log_variance_clipped",
+                  "posterior_mean_coef1", "posterior_mean_coef2"):
+            b = getattr(self, k)
+            if not b.is_cuda:
+                raise RuntimeError("schedule buffers must live on the GPU (set_new_noise_schedule(device='cuda'))")
+            setattr(s, k, b.data_ptr())
+        s.num_timesteps = self.num_timesteps
+        return s
+
+    # ---------------------------------------------------------------- small closed-form helpers (API parity)
+    @staticmethod
+    def _extract(a, t, ndim=4):
+        return a.gather(-1, t).reshape(t.shape[0], *((1,) * (ndim - 1)))
+
+    def predict_start_from_noise(self, y_t, t, noise):                                   # :70-74
+        return self._extract(self.sqrt_recip_gammas, t) * y_t - self._extract(self.sqrt_recipm1_gammas, t) * noise
+
+    def q_posterior(self, y_0_hat, y_t, t):                                              # :76-84
+        mean = self._extract(self.posterior_mean_coef1, t) * y_0_hat + self._extract(self.posterior_mean_coef2, t) * y_t
+        return mean, self._extract(self.posterior_log_variance_clipped, t)
+
+    def q_sample(self, y_0, sample_gammas, noise=None):                                  # :162-164
+        lib = _lib.require_device()
+        noise = torch.randn_like(y_0) if noise is None else noise
+        g = sample_gammas.reshape(-1).contiguous().float()
+        y_0c, nz = y_0.contiguous().float(), noise.contiguous().float()
+        out = torch.empty_like(y_0c)
+        _lib.check(lib.vf_q_sample(y_0c.data_ptr(), nz.data_ptr(), g.data_ptr(), y_0c.shape[0], y_0c[0].numel(),
+                                   out.data_ptr(), _lib.stream_handle()), "vf_q_sample")
+        return out
+
+    # ---------------------------------------------------------------- the fused step
+    def _next_philox(self):
+        if self._noise_seed is None:
+            self._noise_seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        self._noise_offset += 1
+        return self._noise_seed, self._noise_offset
+
+    def _step(self, plan: _Plan, y_t, y_cond, angle, t, y_prev, *, z=None, add_noise=True, clip=True, weighting=True,
+              eps_out=None, weights_out=None, logits_out=None):
+        """view stacking -> UNet over all views -> composition -> DDPM update, all enqueued, no host sync."""
+        lib = _lib.require_device()
+        unet = self.denoise_fn
+        st = _lib.stream_handle()
+        B, n_max, Cc, H, W = y_cond.shape
+        _lib.check(lib.vf_pack_views(y_cond.data_ptr(), y_t.data_ptr(), plan.view_offset.data_ptr(), B, n_max, Cc, H, W,
+                                     plan.images, unet.k0, unet.act_dtype, plan.x0.data_ptr(), plan.img_sample.data_ptr(), st),
+                   "vf_pack_views")
+        level = self.gammas.gather(-1, t)                                                # noise level gamma_t (:98)
+        unet._last_images = plan.images
+        unet.run_packed(plan.x0, plan.images, level, angle.reshape(-1), plan.img_sample, plan.out8)
+        plan.t32.copy_(t)
+        a = _lib.ComposeArgs()
+        a.unet_out, a.view_offset, a.t = plan.out8.data_ptr(), plan.view_offset.data_ptr(), plan.t32.data_ptr()
+        a.y_t, a.y_prev, a.z = y_t.data_ptr(), y_prev.data_ptr(), _lib.ptr(z)
+        if z is None and add_noise:
+            a.seed, a.offset = self._next_philox()
+        a.add_noise, a.clip_denoised, a.weighting = int(add_noise), int(clip), int(weighting)
+        a.B, a.H, a.W = B, H, W
+        a.eps_out, a.weights_out, a.logits_out = _lib.ptr(eps_out), _lib.ptr(weights_out), _lib.ptr(logits_out)
+        a.max_v = plan.max_v
+        sched = self._schedule_struct()
+        _lib.check(lib.vf_compose_ddpm_step(C.byref(a), C.byref(sched), st), "vf_compose_ddpm_step")
+
+    @staticmethod
+    def _prep(y_cond, angle, y_t=None):
+        if not y_cond.is_cuda:
+            raise RuntimeError("view_fusion_b200.ViewFusion needs CUDA tensors; there is no CPU fallback")
+        y_cond = y_cond.contiguous().float()
+        angle = angle.to(y_cond.device).contiguous().float()
+        if angle.numel() != y_cond.shape[0]:
+            raise ValueError("angle must be (B, 1)")
+        if y_t is not None:
+            y_t = y_t.contiguous().float()
+        return y_cond, angle, y_t
+
+    # ---------------------------------------------------------------- p_mean_variance / p_sample (:86-177)
+    @torch.no_grad()
+    def p_mean_variance(self, y_t, y_cond, view_count, angle, t, clip_denoised: bool):
+        y_cond, angle, y_t = self._prep(y_cond, angle, y_t)
+        plan = _Plan(self, y_cond, view_count)
+        t = t.to(y_cond.device).long()
+        mean = torch.empty_like(y_t)
+        H, W = y_t.shape[-2:]
+        w = self.weighting_inference
+        weights = torch.empty(plan.B, plan.max_v, 3, H, W, device=y_t.device) if w else None
+        logits = torch.empty(plan.images, 3, H, W, device=y_t.device) if w else None
+        self._step(plan, y_t, y_cond, angle, t, mean, add_noise=False, clip=clip_denoised, weighting=w,
+                   weights_out=weights, logits_out=logits)
+        return mean, self._extract(self.posterior_log_variance_clipped, t), logits, weights
+
+    @torch.no_grad()
+    def p_sample(self, y_t, y_cond, view_count, angle, t, clip_denoised=True, noise=None, _plan=None, _eps_out=None,
+                 want_weights=True):
+        y_cond, angle, y_t = self._prep(y_cond, angle, y_t)
+        plan = _plan if _plan is not None else _Plan(self, y_cond, view_count)
+        t = t.to(y_cond.device).long()
+        H, W = y_t.shape[-2:]
+        w = self.weighting_inference
+        weights = torch.empty(plan.B, plan.max_v, 3, H, W, device=y_t.device) if (w and want_weights) else None
+        logits = torch.empty(plan.images, 3, H, W, device=y_t.device) if (w and want_weights) else None
+        y_prev = torch.empty_like(y_t)
+        add_noise = bool((t > 0).any())          # the reference's `any(t > 0)` (:176); generate() below avoids this sync
+        if not add_noise:
+            noise = None
+        self._step(plan, y_t, y_cond, angle, t, y_prev, z=None if noise is None else noise.contiguous().float(),
+                   add_noise=add_noise, clip=clip_denoised, weighting=w, eps_out=_eps_out, weights_out=weights,
+                   logits_out=logits)
+        return y_prev, logits, weights
+
+    # ---------------------------------------------------------------- generate (:179-214)
+    @torch.no_grad()
+    def generate(self, y_cond, view_count, angle, y_t=None, sample_num=8, noise_steps=None, steps=None):
+        """T-step reverse loop.  `noise_steps[j]` (optional) is the N(0,1) draw injected at the j-th executed step;
+        `steps` (optional) restricts the loop to a list of time-steps (tests)."""
+        y_cond, angle, y_t = self._prep(y_cond, angle, y_t)
+        b = y_cond.shape[0]
+        assert self.num_timesteps > sample_num, "num_timesteps must greater than sample_num"
+        sample_inter = self.num_timesteps // sample_num
+        dev = y_cond.device
+        if y_t is None:
+            y_t = torch.randn_like(y_cond[:, 0, :3, ...]).contiguous()
+        plan = _Plan(self, y_cond, view_count)
+        H, W = y_t.shape[-2:]
+        w = self.weighting_inference
+        ret_arr, weight_arr, logit_arr = [y_t], [], []
+        order = list(reversed(range(self.num_timesteps))) if steps is None else list(steps)
+        t = torch.empty(b, dtype=torch.long, device=dev)
+        for j, i in enumerate(order):
+            t.fill_(i)
+            snap = i % sample_inter == 0
+            weights = torch.empty(plan.B, plan.max_v, 3, H, W, device=dev) if (w and snap) else None
+            logits = torch.empty(plan.images, 3, H, W, device=dev) if (w and snap) else None
+            y_prev = torch.empty_like(y_t)
+            z = None if noise_steps is None else noise_steps[j].to(dev).contiguous().float()
+            self._step(plan, y_t, y_cond, angle, t, y_prev, z=z if i > 0 else None, add_noise=i > 0, clip=True,
+                       weighting=w, weights_out=weights, logits_out=logits)
+            y_t = y_prev
+            if snap:
+                ret_arr.append(y_t)
+                logit_arr.append(logits)
+                weight_arr.append(weights)
+        ret_arr = torch.stack(ret_arr, dim=1)
+        generated_samples = ret_arr[:, -1, ...]
+        if w and logit_arr:
+            logit_arr = torch.stack(logit_arr, dim=1)
+            weight_arr = torch.stack(weight_arr, dim=1)
+        return y_t, ret_arr, logit_arr, weight_arr, generated_samples
+
+    # ---------------------------------------------------------------- forward (:216-300)
+    def forward(self, y_cond, view_count, angle, y_0=None, noise=None, generate=False, t=None, u=None):
+        if generate:
+            return self.generate(y_cond, view_count, angle)
+        raise NotImplementedError("training forward/backward is not wired yet")
