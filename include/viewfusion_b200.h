@@ -107,6 +107,11 @@ int vf_unet_forward(vf_unet* u, const void* packed, void* workspace, size_t work
 /* Number of kernels enqueued by the last vf_unet_forward on this plan (bench.py's gpu_launches claim). */
 int vf_unet_last_launches(const vf_unet* u);
 
+/* Per-kernel-class device timing of one forward (CUDA events around every launch).  Off by default; used only for
+ * the roofline breakdown in bench.py.  ms[6] / counts[6] = conv, gn_stats, gn_apply, attention, upsample, embed. */
+int vf_unet_set_profiling(vf_unet* u, int on);
+int vf_unet_profile_read(vf_unet* u, float* ms_host, int* counts_host);
+
 /* Debug/parity tap: copies the output activation of module `name` ("downs.3", "mid.0", "ups.17", ...) of the
  * LAST vf_unet_forward on this plan into `dst` as NCHW fp32.  dst must hold images*C*H*W floats. */
 int vf_unet_read_tap(vf_unet* u, const void* workspace, const char* name, float* dst, int64_t* chw, vf_stream stream);

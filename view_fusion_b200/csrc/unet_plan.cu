@@ -65,6 +65,12 @@ struct vf_unet {
   struct Tap { size_t off; int C, H, W; int dtype; int ld; };
   std::map<std::string, Tap> taps;
   int last_images = 0;
+  // optional per-kernel-class timing of one forward (CUDA events around every launch; perturbs overlap, so it is
+  // only enabled for the roofline breakdown, never for the throughput measurement)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> ev_kind;      // kind of the launch between ev[i] and ev[i+1]
+  int ev_used = 0;
 };
 
 namespace vf {
@@ -133,6 +139,7 @@ struct Exec {
   cudaStream_t st;
   int rc = VF_OK;
   int launches = 0;
+  vf_unet* u = nullptr;
   void* alloc(size_t bytes) {
     off = align_up(off, 256);
     void* p = dry ? nullptr : base + off;
@@ -141,12 +148,27 @@ struct Exec {
   }
 };
 
-#define VF_RUN(ex, n, call)               \
-  do {                                    \
-    if (!(ex).dry && (ex).rc == VF_OK) {  \
-      (ex).rc = (call);                   \
-      (ex).launches += (n);               \
-    }                                     \
+enum { K_CONV = 0, K_GN_STATS, K_GN_APPLY, K_ATTN, K_UPSAMPLE, K_EMBED, K_NUM };
+
+static void prof_mark(vf_unet* u, cudaStream_t st, int kind) {
+  if ((size_t)u->ev_used >= u->ev.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    u->ev.push_back(e);
+    u->ev_kind.push_back(-1);
+  }
+  cudaEventRecord(u->ev[u->ev_used], st);
+  u->ev_kind[u->ev_used] = kind;
+  ++u->ev_used;
+}
+
+#define VF_RUN(ex, kind, call)                                       \
+  do {                                                               \
+    if (!(ex).dry && (ex).rc == VF_OK) {                             \
+      if ((ex).u && (ex).u->profiling) prof_mark((ex).u, (ex).st, kind); \
+      (ex).rc = (call);                                              \
+      (ex).launches += 1;                                            \
+    }                                                                \
   } while (0)
 
 template <typename T>
@@ -285,7 +307,11 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_create(const vf_un
   return VF_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) void vf_unet_destroy(vf_unet* u) { delete u; }
+extern "C" __attribute__((visibility("default"))) void vf_unet_destroy(vf_unet* u) {
+  if (!u) return;
+  for (auto e : u->ev) cudaEventDestroy(e);
+  delete u;
+}
 extern "C" __attribute__((visibility("default"))) int vf_unet_num_params(const vf_unet* u) { return u ? (int)u->params.size() : 0; }
 extern "C" __attribute__((visibility("default"))) int vf_unet_emb_channels(const vf_unet* u) { return u ? u->E : 0; }
 extern "C" __attribute__((visibility("default"))) int vf_unet_k0(const vf_unet* u) { return u ? u->k0 : 0; }
@@ -344,7 +370,7 @@ namespace vf {
 static void conv_call(Exec& ex, const vf_unet* u, vf_conv_args& a) {
   a.dtype = u->dtype;
   if (a.out_dtype < 0) a.out_dtype = u->dtype;
-  VF_RUN(ex, 1, vf_conv2d(&a, (vf_stream)ex.st));
+  VF_RUN(ex, K_CONV, vf_conv2d(&a, (vf_stream)ex.st));
 }
 
 static vf_conv_args conv_args_init() {
@@ -362,8 +388,8 @@ static Act gn_block(Exec& ex, const vf_unet* u, int images, const Act& x, const 
   float* stats = stats_cursor;
   stats_cursor += (size_t)images * C * 2;
   Act y{ex.alloc((size_t)images * HW * C * k_elems(u)), C, x.H, x.W};
-  VF_RUN(ex, 1, vf_gn_stats(x.p, x.C, skip ? skip->p : nullptr, skip ? skip->C : 0, u->dtype, images, HW, stats, (vf_stream)ex.st));
-  VF_RUN(ex, 1, vf_gn_apply(x.p, x.C, skip ? skip->p : nullptr, skip ? skip->C : 0, u->dtype, images, HW, u->cfg.norm_groups, stats,
+  VF_RUN(ex, K_GN_STATS, vf_gn_stats(x.p, x.C, skip ? skip->p : nullptr, skip ? skip->C : 0, u->dtype, images, HW, stats, (vf_stream)ex.st));
+  VF_RUN(ex, K_GN_APPLY, vf_gn_apply(x.p, x.C, skip ? skip->p : nullptr, skip ? skip->C : 0, u->dtype, images, HW, u->cfg.norm_groups, stats,
                             ex.dry ? nullptr : u->master[gw], ex.dry ? nullptr : u->master[gb], swish ? 1 : 0, y.p, (vf_stream)ex.st));
   return y;
 }
@@ -420,7 +446,7 @@ static Act run_resblock(Exec& ex, vf_unet* u, const uint8_t* pk, int images, con
     conv_call(ex, u, a);
   }
   Act o{ex.alloc((size_t)images * HW * C * es), C, x.H, x.W};
-  VF_RUN(ex, 1, vf_attention(qkv, vt, u->dtype, images, HW, C, o.p, (vf_stream)ex.st));
+  VF_RUN(ex, K_ATTN, vf_attention(qkv, vt, u->dtype, images, HW, C, o.p, (vf_stream)ex.st));
   Act out2{ex.alloc((size_t)images * HW * C * es), C, x.H, x.W};
   {
     vf_conv_args a = conv_args_init();
@@ -460,7 +486,7 @@ static int walk(vf_unet* u, Exec& ex, const uint8_t* pk, int images, const void*
   float* stats_cursor = stats;
   // embedding table [rows, E]
   float* emb = reinterpret_cast<float*>(ex.alloc((size_t)rows * u->E * 4));
-  VF_RUN(ex, 1, vf_embed(level, angle, rows, c.inner_channel, u->master[u->mlp_w0], u->master[u->mlp_b0], u->master[u->mlp_w2],
+  VF_RUN(ex, K_EMBED, vf_embed(level, angle, rows, c.inner_channel, u->master[u->mlp_w0], u->master[u->mlp_b0], u->master[u->mlp_w2],
                          u->master[u->mlp_b2], reinterpret_cast<const float*>(pk + u->emb_w_off),
                          reinterpret_cast<const float*>(pk + u->emb_b_off), u->E, emb, (vf_stream)ex.st));
   std::vector<Act> feats;
@@ -507,7 +533,7 @@ static int walk(vf_unet* u, Exec& ex, const uint8_t* pk, int images, const void*
       x = run_resblock(ex, u, pk, images, u->blocks[l.rb], x, &skip, emb, img_row, stats_cursor);
     } else {   // Upsample: nearest x2 then conv3x3                                         unet.py:185-192
       Act up{ex.alloc((size_t)images * 4 * x.H * x.W * l.c * es), l.c, 2 * x.H, 2 * x.W};
-      VF_RUN(ex, 1, vf_upsample2x(x.p, u->dtype, images, x.H, x.W, l.c, up.p, (vf_stream)ex.st));
+      VF_RUN(ex, K_UPSAMPLE, vf_upsample2x(x.p, u->dtype, images, x.H, x.W, l.c, up.p, (vf_stream)ex.st));
       Act y{ex.alloc((size_t)images * up.H * up.W * l.c * es), l.c, up.H, up.W};
       vf_conv_args a = conv_args_init();
       a.images = images; a.H = y.H; a.W = y.W; a.n_seg = 1;
@@ -561,9 +587,37 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_forward(vf_unet* u
   }
   u->taps.clear();
   u->last_images = images;
+  ex.u = u;
+  u->ev_used = 0;
   int rc = walk(u, ex, reinterpret_cast<const uint8_t*>(packed), images, x0, level, angle, rows, img_row, out);
+  if (u->profiling) prof_mark(u, ex.st, -1);
   u->launches = ex.launches;
   return rc;
+}
+
+extern "C" __attribute__((visibility("default"))) int vf_unet_set_profiling(vf_unet* u, int on) {
+  VF_REQUIRE(u, "vf_unet_set_profiling: null plan");
+  u->profiling = on != 0;
+  u->ev_used = 0;
+  return VF_OK;
+}
+
+// Synchronises the last recorded event and sums the elapsed ms per kernel class of the last profiled forward:
+// ms[0..5] = conv, gn_stats, gn_apply, attention, upsample, embed; counts[] = launches of each class.
+extern "C" __attribute__((visibility("default"))) int vf_unet_profile_read(vf_unet* u, float* ms_host, int* counts_host) {
+  VF_REQUIRE(u && ms_host && counts_host, "vf_unet_profile_read: null args");
+  for (int k = 0; k < K_NUM; ++k) { ms_host[k] = 0.f; counts_host[k] = 0; }
+  if (u->ev_used < 2) return VF_OK;
+  VF_CUDA(cudaEventSynchronize(u->ev[u->ev_used - 1]));
+  for (int i = 0; i + 1 < u->ev_used; ++i) {
+    const int k = u->ev_kind[i];
+    if (k < 0 || k >= K_NUM) continue;
+    float ms = 0.f;
+    VF_CUDA(cudaEventElapsedTime(&ms, u->ev[i], u->ev[i + 1]));
+    ms_host[k] += ms;
+    counts_host[k] += 1;
+  }
+  return VF_OK;
 }
 
 extern "C" __attribute__((visibility("default"))) int vf_unet_read_tap(vf_unet* u, const void* workspace, const char* name, float* dst, int64_t* chw, vf_stream stream) {

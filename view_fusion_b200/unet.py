@@ -206,6 +206,18 @@ class UNet(nn.Module):
     def last_launches(self) -> int:
         return _lib.load().vf_unet_last_launches(self._native())
 
+    KERNEL_CLASSES = ("conv", "gn_stats", "gn_apply", "attention", "upsample", "embed")
+
+    def set_profiling(self, on: bool) -> None:
+        _lib.check(_lib.load().vf_unet_set_profiling(self._native(), int(on)), "vf_unet_set_profiling")
+
+    def profile(self) -> dict:
+        """{class: (ms, launches)} of the last forward run with profiling on (synchronises)."""
+        ms = (C.c_float * 6)()
+        cnt = (C.c_int * 6)()
+        _lib.check(_lib.load().vf_unet_profile_read(self._native(), ms, cnt), "vf_unet_profile_read")
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
+
     def read_tap(self, name: str) -> torch.Tensor:
         """Output activation of module `name` in the last forward, as NCHW fp32 (parity debugging)."""
         lib = _lib.require_device()
