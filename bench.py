@@ -281,8 +281,10 @@ def main():
                     "peak_source": f"{pk['src']} sustained bf16 (kernel timed inside a long step)"}
             gn_bytes = 9_220_096 * images
             classes = {k: {"ms_per_step": round(v[0], 4), "launches": v[1]} for k, v in acc.items()}
-            classes["gn_apply"]["GBps_algorithmic_4B_per_elem"] = round(gn_bytes * 4 / (acc["gn_apply"][0] * 1e-3) / 1e9, 1)
-            classes["gn_stats"]["GBps_algorithmic_2B_per_elem"] = round(gn_bytes * 2 / (acc["gn_stats"][0] * 1e-3) / 1e9, 1)
+            if acc["gn_apply"][0] > 0:
+                classes["gn_apply"]["GBps_algorithmic_4B_per_elem"] = round(gn_bytes * 4 / (acc["gn_apply"][0] * 1e-3) / 1e9, 1)
+            if acc["gn_stats"][0] > 0:
+                classes["gn_stats"]["GBps_algorithmic_2B_per_elem"] = round(gn_bytes * 2 / (acc["gn_stats"][0] * 1e-3) / 1e9, 1)
             classes["hbm_peak_GBps"] = pk["hbm"]
             classes["step_flop_utilisation"] = round(GFLOP_PER_VIEW * 1e9 * images / (ms_step * 1e-3) / 1e12 / pk["tf_sustained"], 4)
 

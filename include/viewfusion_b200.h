@@ -193,9 +193,12 @@ int vf_embed(const float* level, const float* angle, int rows, int inner_channel
 int vf_gn_stats(const void* src0, int C0, const void* src1, int C1, int dtype, int images, int HW, float* stats,
                 vf_stream stream);
 
-/* GroupNorm(groups, eps=1e-5, affine) + optional Swish (unet.py:207-218,:254) -> dst [., C0+C1]. */
-int vf_gn_apply(const void* src0, int C0, const void* src1, int C1, int dtype, int images, int HW, int groups,
-                const float* stats, const float* gamma, const float* beta, int swish, void* dst, vf_stream stream);
+/* GroupNorm(groups, eps=1e-5, affine) + optional Swish (unet.py:207-218,:254) -> dst [., C0+C1].
+ * statsX: per (image, channel) {sum, sum of squares} of source X, rows of statsX_ld channels ([images, ld, 2]);
+ * they come from vf_gn_stats or from the producing convolution's epilogue (vf_conv_args::stats). */
+int vf_gn_apply(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1,
+                const float* stats1, int stats1_ld, int dtype, int images, int HW, int groups, const float* gamma,
+                const float* beta, int swish, void* dst, vf_stream stream);
 
 /* Nearest-neighbour x2 up-sampling (unet.py:188). */
 int vf_upsample2x(const void* src, int dtype, int images, int H, int W, int C, void* dst, vf_stream stream);
@@ -232,6 +235,11 @@ int vf_conv2d(const vf_conv_args* a, vf_stream stream);
 /* Test hook: route VF_BF16 vf_conv2d / vf_attention through the CUDA-core kernels (same bf16 storage, fp32
  * accumulation) so the tcgen05 kernels can be cross-checked on the device.  Never enabled by the product path. */
 void vf_debug_force_simt(int on);
+
+/* Hardware probe (tests only): out[i][n] = sum_k A[shift_rows + i][k] * B[n][k] through ONE TMA-loaded, 128B-swizzled
+ * smem tile and a tcgen05 descriptor whose start is shifted by `shift_rows` rows. A [rows>=256, 64] bf16, B [64, 64]. */
+int vf_debug_umma_shift(const void* A, int rows, const void* B, int shift_rows, int use_base_offset, float* out,
+                        vf_stream stream);
 
 /* Single-head self-attention core (unet.py:267-274): O = softmax(Q K^T / sqrt(C)) V per image.
  *   qk  : [images*L, 3C] rows hold q in [0,C), k in [C,2C) (v columns unused when vt != NULL)

@@ -292,3 +292,39 @@ def test_upsample_and_pack(lib):
                                  img.data_ptr(), _lib.stream_handle()), "pack")
     assert torch.equal(x0.cpu()[:, :54], cols) and float(x0[:, 54:].abs().sum()) == 0.0
     assert img.cpu().tolist() == sum(([b] * int(v) for b, v in enumerate(bt["view_count"])), [])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv_fused_groupnorm_statistics(lib, dtype):
+    """vf_conv_args::stats == per (image, channel) sum / sum-of-squares of the stored output."""
+    from view_fusion_b200 import ops
+    R, S, segs, cout = 3, 16, [(64, 3)], 128
+    ref, *t = _conv_case(dtype, R, S, segs, cout, 1, True, True)
+    out, stats = _run_conv(dtype, R, S, segs, cout, 1, *t, want_stats=True)
+    o = ops.from_nhwc(out, R, S, S).cpu()                 # stored values (bf16-rounded in bf16 mode)
+    want = torch.stack([o.sum(dim=(2, 3)), (o * o).sum(dim=(2, 3))], dim=-1)
+    assert rel(stats, want) < 1e-5
+    # and GroupNorm driven by the fused statistics == GroupNorm of the stored tensor
+    gamma, beta = torch.rand(cout) + 0.5, torch.randn(cout) * 0.1
+    y = ops.gn_apply(out, None, R, S * S, 32, stats, gamma.cuda(), beta.cuda(), True)
+    refn = O.swish(F.group_norm(o, 32, gamma, beta, eps=1e-5))
+    assert rel(ops.from_nhwc(y, R, S, S), refn) < (4e-3 if dtype == torch.bfloat16 else 2e-6)
+
+
+def test_probe_shifted_umma_descriptor(lib):
+    """Hardware probe: tcgen05 smem descriptor shifted by whole 128-byte rows inside a TMA-written SWIZZLE_128B tile."""
+    from view_fusion_b200 import _lib
+    torch.manual_seed(0)
+    A = bf16r(torch.randn(512, 64))
+    B = bf16r(torch.randn(64, 64))
+    Ad, Bd = A.to(torch.bfloat16).cuda(), B.to(torch.bfloat16).cuda()
+    res = {}
+    for shift in (0, 8, 64, 1, 3, 7, 9, 65, 67):
+        for bo in (0, 1):
+            out = torch.zeros(128, 64, device="cuda")
+            _lib.check(lib.vf_debug_umma_shift(Ad.data_ptr(), 512, Bd.data_ptr(), shift, bo, out.data_ptr(), _lib.stream_handle()), "probe")
+            torch.cuda.synchronize()
+            ref = A[shift:shift + 128] @ B.t()
+            res[(shift, bo)] = rel(out, ref)
+    print("\nUMMA_SHIFT_PROBE", {k: round(v, 5) for k, v in res.items()})
+    assert res[(0, 0)] < 1e-5 and res[(8, 0)] < 1e-5 and res[(64, 0)] < 1e-5     # atom-aligned shifts must work

@@ -22,7 +22,7 @@ SYMBOLS = [
     "vf_unet_last_launches", "vf_unet_read_tap", "vf_unet_set_profiling", "vf_unet_profile_read",
     "vf_pack_views", "vf_pack_nchw", "vf_nhwc_to_nchw", "vf_q_sample",
     "vf_compose_ddpm_step", "vf_compose_mse",
-    "vf_embed", "vf_gn_stats", "vf_gn_apply", "vf_upsample2x", "vf_conv2d", "vf_debug_force_simt", "vf_attention",
+    "vf_embed", "vf_gn_stats", "vf_gn_apply", "vf_upsample2x", "vf_conv2d", "vf_debug_force_simt", "vf_debug_umma_shift", "vf_attention",
     "vf_pack_conv_weight",
 ]
 
@@ -105,10 +105,11 @@ def load() -> C.CDLL:
         "vf_compose_mse": (i, [p, p, p, i, i, i, i, p, p, p, f, p]),
         "vf_embed": (i, [p, p, i, i, p, p, p, p, p, p, i, p, p]),
         "vf_gn_stats": (i, [p, i, p, i, i, i, i, p, p]),
-        "vf_gn_apply": (i, [p, i, p, i, i, i, i, i, p, p, p, i, p, p]),
+        "vf_gn_apply": (i, [p, i, p, i, p, i, p, i, i, i, i, i, p, p, i, p, p]),
         "vf_upsample2x": (i, [p, i, i, i, i, i, p, p]),
         "vf_conv2d": (i, [C.POINTER(ConvArgs), p]),
         "vf_debug_force_simt": (None, [i]),
+        "vf_debug_umma_shift": (i, [p, i, p, i, i, p, p]),
         "vf_attention": (i, [p, p, i, i, i, i, p, p]),
         "vf_pack_conv_weight": (i, [p, i, i, i, i, p, i, i, i, p]),
     }

@@ -28,6 +28,7 @@ struct SimtConvParams {
   int out_ld;
   int qkv_split;
   void* out_vt;
+  float* stats;
 };
 
 __device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
@@ -121,6 +122,11 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtConvParams p) 
         vt[((size_t)img * p.qkv_split + (n - 2 * p.qkv_split)) * HW + (m % HW)] = from_f<TA>(v);
       else
         out[(size_t)m * p.out_ld + n] = from_f<TO>(v);
+      if (p.stats) {
+        const float x = to_f(from_f<TO>(v));
+        atomicAdd(p.stats + ((size_t)img * p.cout + n) * 2, x);
+        atomicAdd(p.stats + ((size_t)img * p.cout + n) * 2 + 1, x * x);
+      }
     }
   }
 }
@@ -136,7 +142,7 @@ int conv2d_simt(const vf_conv_args* a, cudaStream_t st) {
   p.n_seg = a->n_seg; p.stride = a->stride; p.images = a->images; p.H = a->H; p.W = a->W;
   p.weight = a->weight; p.k_total = k_total; p.cout = a->cout; p.cout_pad = a->cout_pad;
   p.bias = a->bias; p.emb = a->emb; p.img_row = a->img_row; p.emb_ld = a->emb_ld; p.residual = a->residual;
-  p.out = a->out; p.out_ld = a->out_ld; p.qkv_split = a->qkv_split; p.out_vt = a->out_vt;
+  p.out = a->out; p.out_ld = a->out_ld; p.qkv_split = a->qkv_split; p.out_vt = a->out_vt; p.stats = a->stats;
   const int M = a->images * a->H * a->W;
   dim3 grid(cdiv(M, SBM), cdiv(a->cout, SBN));
   if (a->dtype == VF_F32) {

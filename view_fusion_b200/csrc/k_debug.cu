@@ -1,0 +1,97 @@
+// Hardware probe (test hook, not on the product path): does a tcgen05 shared-memory descriptor whose start address
+// is shifted by a whole number of 128-byte rows — i.e. not aligned to the 1024-byte swizzle atom — address the
+// rows TMA wrote with SWIZZLE_128B correctly, and does it need the descriptor's base-offset field?
+// The answer decides whether a 3x3 convolution can reuse ONE halo'd activation tile for all nine taps.
+#include <cuda.h>
+
+#include "tc_ptx.cuh"
+#include "vf_common.cuh"
+
+namespace vf {
+
+int encode_bf16_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box);
+
+__global__ void __launch_bounds__(128) umma_shift_probe(const __grid_constant__ CUtensorMap mapA,
+                                                        const __grid_constant__ CUtensorMap mapB, int shift_rows,
+                                                        int use_base_offset, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t bar_ld = base, bar_mma = base + 8, tmem_slot = base + 16;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + 16);
+  const uint32_t sA = base + 1024;               // 256 rows x 128 B
+  const uint32_t sB = sA + 256 * 128;            // 64 rows x 128 B
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(bar_ld, 1);
+    ptx::mbar_init(bar_mma, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) { ptx::tmem_alloc(tmem_slot, 64); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot_ptr;
+  if (threadIdx.x == 0) {
+    ptx::mbar_arrive_expect_tx(bar_ld, 256 * 128 + 64 * 128);
+    ptx::tma_load_2d(sA, &mapA, bar_ld, 0, 0);
+    ptx::tma_load_2d(sB, &mapB, bar_ld, 0, 0);
+    ptx::mbar_wait(bar_ld, 0);
+    ptx::tc_fence_after();
+    const uint32_t a0 = sA + (uint32_t)shift_rows * 128;
+    const uint32_t idesc = ptx::make_idesc_bf16(128, 64, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint64_t ad = ptx::make_smem_desc(a0 + k * 32, 16, 1024);
+      if (use_base_offset) ad |= (uint64_t)((a0 >> 7) & 7) << 49;
+      const uint64_t bd = ptx::make_smem_desc(sB + k * 32, 16, 1024);
+      ptx::umma_f16(tmem_d, ad, bd, idesc, k > 0 ? 1u : 0u);
+    }
+    ptx::umma_commit(bar_mma);
+  }
+  ptx::mbar_wait(bar_mma, 0);
+  ptx::tc_fence_after();
+  const int r = warp * 32 + lane;
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    uint32_t rr[16];
+    ptx::tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, rr);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) out[r * 64 + c0 + j] = __uint_as_float(rr[j]);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_d, 64); }
+}
+
+}  // namespace vf
+
+// A: [rows >= 256, 64] bf16, B: [64, 64] bf16 (row n = output column, K-major), out: [128, 64] fp32
+// out[i][n] = sum_k A[shift_rows + i][k] * B[n][k] if the shifted descriptor works.
+extern "C" __attribute__((visibility("default"))) int vf_debug_umma_shift(const void* A, int rows, const void* B, int shift_rows,
+                                                                          int use_base_offset, float* out, vf_stream stream) {
+  using namespace vf;
+  VF_REQUIRE(A && B && out && rows >= 256 && shift_rows >= 0 && shift_rows <= 128, "vf_debug_umma_shift: bad args");
+  CUtensorMap mA, mB;
+  {
+    const uint64_t dims[2] = {64, (uint64_t)rows};
+    const uint64_t strides[1] = {128};
+    const uint32_t box[2] = {64, 256};
+    int rc = encode_bf16_map(&mA, A, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {64, 64};
+    const uint64_t strides[1] = {128};
+    const uint32_t box[2] = {64, 64};
+    int rc = encode_bf16_map(&mB, B, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  const size_t smem = 1024 + 1024 + 256 * 128 + 64 * 128;
+  VF_CUDA(cudaFuncSetAttribute(umma_shift_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_shift_probe<<<1, 128, smem, as_stream(stream)>>>(mA, mB, shift_rows, use_base_offset, out);
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}

@@ -58,6 +58,7 @@ struct TcParams {
   int qkv_split;
   __nv_bfloat16* out_vt;
   int images;
+  float* stats;   // [images, cout, 2] GroupNorm partial sums of the stored output, or null
 };
 
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0,
@@ -200,11 +201,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       ptx::tmem_ld16(trow + (uint32_t)c0, rr);
       ptx::tmem_ld_wait();
       const int n = n0 + c0;
-      if (valid && (n < p.cout || p.out_f32)) {   // structured: the warp reconverges before the next tcgen05.ld
+      const bool act = valid && (n < p.cout || p.out_f32);   // structured: the warp reconverges before the next tcgen05.ld
       float v[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]) + brow[c0 + j];
-      if (p.residual) {
+      for (int j = 0; j < 16; ++j) v[j] = act ? __uint_as_float(rr[j]) + brow[c0 + j] : 0.f;
+      if (act && p.residual) {
         const __nv_bfloat16* rp = p.residual + (size_t)m * p.cout + n;
         float r0[8], r1[8];
         load_vec(rp, r0);
@@ -212,22 +213,42 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 #pragma unroll
         for (int j = 0; j < 8; ++j) { v[j] += r0[j]; v[8 + j] += r1[j]; }
       }
-      if (p.out_f32) {
-        float* op = reinterpret_cast<float*>(p.out) + (size_t)m * p.out_ld + n;
-        const int cnt = min(16, p.out_ld - n);     // out_ld is the padded channel count of the fp32 output
-        for (int j = 0; j + 4 <= cnt; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else if (p.qkv_split > 0 && n >= 2 * p.qkv_split) {
-        __nv_bfloat16* vp = p.out_vt + ((size_t)img * p.qkv_split + (n - 2 * p.qkv_split)) * p.HW + pix;
+      if (!p.out_f32) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) vp[(size_t)j * p.HW] = __float2bfloat16_rn(v[j]);
-      } else {
-        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.out_ld + n;
-        float lo[8], hi[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
-        store_vec(op, lo);
-        store_vec(op + 8, hi);
+        for (int j = 0; j < 16; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));   // what is stored (and normalised later)
       }
+      if (act) {
+        if (p.out_f32) {
+          float* op = reinterpret_cast<float*>(p.out) + (size_t)m * p.out_ld + n;
+          const int cnt = min(16, p.out_ld - n);     // out_ld is the padded channel count of the fp32 output
+          for (int j = 0; j + 4 <= cnt; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else if (p.qkv_split > 0 && n >= 2 * p.qkv_split) {
+          __nv_bfloat16* vp = p.out_vt + ((size_t)img * p.qkv_split + (n - 2 * p.qkv_split)) * p.HW + pix;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) vp[(size_t)j * p.HW] = __float2bfloat16_rn(v[j]);
+        } else {
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.out_ld + n;
+          float lo[8], hi[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
+          store_vec(op, lo);
+          store_vec(op + 8, hi);
+        }
+      }
+      if (p.stats && n < p.cout) {
+        // GroupNorm partial sums of the stored values, column-reduced over the warp's 32 pixels (16 + 16 shuffles).
+        // HW % 32 == 0 (checked on the host), so a warp never straddles two images; invalid rows contribute zeros.
+        float sq[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+        const float cs = warp_colsum16(v, lane), cq = warp_colsum16(sq, lane);
+        const int wimg = __shfl_sync(0xffffffffu, img, 0);
+        const int wvalid = __shfl_sync(0xffffffffu, (int)valid, 0);
+        if (wvalid && (lane & 1) == 0) {
+          float* sp = p.stats + ((size_t)wimg * p.cout + n + warp_col16(lane)) * 2;
+          atomicAdd(sp, cs);
+          atomicAdd(sp + 1, cq);
+        }
       }
     }
     ptx::tc_fence_before();
@@ -350,6 +371,8 @@ int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
   p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
   p.out = a->out; p.out_f32 = a->out_dtype == VF_F32; p.out_ld = a->out_ld; p.cout = a->cout;
   p.qkv_split = a->qkv_split; p.out_vt = reinterpret_cast<__nv_bfloat16*>(a->out_vt);
+  p.stats = a->stats;
+  VF_REQUIRE(!a->stats || ((H * W) % 32 == 0 && !p.out_f32 && !a->qkv_split), "vf_conv2d(tc): fused statistics need H*W %% 32 == 0 and a plain bf16 output");
   VF_REQUIRE(!p.out_f32 || (a->out_ld % 4 == 0 && a->out_ld <= a->cout_pad && !a->residual), "vf_conv2d(tc): bad fp32 output layout");
   VF_REQUIRE(p.out_f32 || (a->cout % 16 == 0 && a->out_ld % 8 == 0), "vf_conv2d(tc): bf16 output needs cout %% 16 == 0");
   VF_REQUIRE(!a->qkv_split || (a->qkv_split % 16 == 0 && a->out_vt), "vf_conv2d(tc): bad qkv split");

@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const T* __restric
 template <typename T, bool kSwish>
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const T* __restrict__ s0, int C0, const T* __restrict__ s1,
                                                               int C1, int HW, int groups, int pix_per_cta,
-                                                              const float* __restrict__ stats,
+                                                              const float* __restrict__ st0, int ld0,
+                                                              const float* __restrict__ st1, int ld1,
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, T* __restrict__ dst) {
   constexpr int VEC = VecOf<T>::N;
@@ -61,11 +62,16 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const T* __restric
   const int img = blockIdx.y;
   const int gs = C / groups;
   const float inv_n = 1.f / ((float)gs * (float)HW);
-  const float* st = stats + (size_t)img * C * 2;
+  const float* sa = st0 + (size_t)img * ld0 * 2;
+  const float* sb = st1 ? st1 + (size_t)img * ld1 * 2 : nullptr;
   for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
     const int g0 = ch / gs * gs;
     float s = 0.f, q = 0.f;
-    for (int j = 0; j < gs; ++j) { s += __ldg(st + 2 * (g0 + j)); q += __ldg(st + 2 * (g0 + j) + 1); }
+    for (int j = 0; j < gs; ++j) {           // a group may straddle the two sources of a concatenation
+      const int cc = g0 + j;
+      const float* e = cc < C0 ? sa + 2 * cc : sb + 2 * (cc - C0);
+      s += __ldg(e); q += __ldg(e + 1);
+    }
     const float mean = s * inv_n;
     const float var = fmaxf(q * inv_n - mean * mean, 0.f);
     const float rstd = rsqrtf(var + 1e-5f);
@@ -84,7 +90,23 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const T* __restric
 #pragma unroll
   for (int j = 0; j < VEC; ++j) { a[j] = ab[2 * (c + j)]; b[j] = ab[2 * (c + j) + 1]; }
   const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
-  for (int p = p0 + py; p < p1; p += PY) {
+  constexpr int UN = 4;                              // independent 16-byte loads in flight per thread
+  int p = p0 + py;
+  for (; p + (UN - 1) * PY < p1; p += UN * PY) {
+    float v[UN][VEC];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) load_vec(src + (size_t)(p + u * PY) * ld, v[u]);
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        float y = v[u][j] * a[j] + b[j];
+        v[u][j] = kSwish ? silu(y) : y;
+      }
+      store_vec(out + (size_t)(p + u * PY) * C, v[u]);
+    }
+  }
+  for (; p < p1; p += PY) {
     float v[VEC];
     load_vec(src + (size_t)p * ld, v);
 #pragma unroll
@@ -149,12 +171,14 @@ extern "C" __attribute__((visibility("default"))) int vf_gn_stats(const void* sr
   return VF_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int vf_gn_apply(const void* src0, int C0, const void* src1, int C1, int dtype, int images, int HW, int groups,
-                           const float* stats, const float* gamma, const float* beta, int swish, void* dst,
-                           vf_stream stream) {
+extern "C" __attribute__((visibility("default"))) int vf_gn_apply(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1,
+                           const float* stats1, int stats1_ld, int dtype, int images, int HW, int groups,
+                           const float* gamma, const float* beta, int swish, void* dst, vf_stream stream) {
   using namespace vf;
-  VF_REQUIRE(src0 && stats && gamma && beta && dst && images > 0 && HW > 0 && C0 > 0, "vf_gn_apply: bad args");
+  VF_REQUIRE(src0 && stats0 && gamma && beta && dst && images > 0 && HW > 0 && C0 > 0, "vf_gn_apply: bad args");
   if (!src1) C1 = 0;
+  VF_REQUIRE(C1 == 0 || stats1, "vf_gn_apply: second source needs statistics");
+  VF_REQUIRE(stats0_ld >= C0 && (C1 == 0 || stats1_ld >= C1), "vf_gn_apply: bad statistics stride");
   const int vec = dtype == VF_BF16 ? 8 : 4;
   VF_REQUIRE(C0 % vec == 0 && C1 % vec == 0, "vf_gn_apply: channels (%d,%d) not a multiple of %d", C0, C1, vec);
   const int C = C0 + C1;
@@ -165,7 +189,7 @@ extern "C" __attribute__((visibility("default"))) int vf_gn_apply(const void* sr
   const size_t smem = 2 * C * sizeof(float);
   cudaStream_t st = as_stream(stream);
 #define VF_GN_LAUNCH(T, SW) \
-  gn_apply_kernel<T, SW><<<grid, g.threads, smem, st>>>((const T*)src0, C0, (const T*)src1, C1, HW, groups, g.pix_per_cta, stats, gamma, beta, (T*)dst)
+  gn_apply_kernel<T, SW><<<grid, g.threads, smem, st>>>((const T*)src0, C0, (const T*)src1, C1, HW, groups, g.pix_per_cta, stats0, stats0_ld, C1 ? stats1 : nullptr, stats1_ld, gamma, beta, (T*)dst)
   if (dtype == VF_BF16) { if (swish) VF_GN_LAUNCH(__nv_bfloat16, true); else VF_GN_LAUNCH(__nv_bfloat16, false); }
   else { if (swish) VF_GN_LAUNCH(float, true); else VF_GN_LAUNCH(float, false); }
 #undef VF_GN_LAUNCH

@@ -140,6 +140,13 @@ struct Exec {
   int rc = VF_OK;
   int launches = 0;
   vf_unet* u = nullptr;
+  float* stats_base = nullptr;   // GroupNorm statistics arena (zeroed once per forward)
+  size_t stats_used = 0;         // floats
+  float* alloc_stats(size_t n) {
+    float* p = dry ? nullptr : stats_base + stats_used;
+    stats_used += n;
+    return p;
+  }
   void* alloc(size_t bytes) {
     off = align_up(off, 256);
     void* p = dry ? nullptr : base + off;
@@ -190,7 +197,16 @@ __global__ void add_bias_kernel(const float* a, const float* b, int n, float* ds
 struct Act {
   void* p;
   int C, H, W;
+  float* stats;   // [images, C, 2] sum / sum-of-squares written by the producing conv's epilogue, or null
 };
+
+// fused statistics need a warp of 32 consecutive pixels to stay inside one image
+static bool fuse_stats(int H, int W) { return (H * W) % 32 == 0; }
+static Act new_act(Exec& ex, const vf_unet* u, int images, int C, int H, int W, bool want_stats) {
+  Act a{ex.alloc((size_t)images * H * W * C * (u->dtype == VF_BF16 ? 2 : 4)), C, H, W, nullptr};
+  if (want_stats && fuse_stats(H, W)) a.stats = ex.alloc_stats((size_t)images * C * 2);
+  return a;
+}
 
 static int k_elems(const vf_unet* u) { return u->dtype == VF_BF16 ? 2 : 4; }
 
@@ -380,28 +396,33 @@ static vf_conv_args conv_args_init() {
   return a;
 }
 
-// GroupNorm (+Swish) of cat(x, skip) -> new activation
-static Act gn_block(Exec& ex, const vf_unet* u, int images, const Act& x, const Act* skip, int gw, int gb, bool swish,
-                    float*& stats_cursor) {
-  const int C = x.C + (skip ? skip->C : 0);
+// GroupNorm (+Swish) of cat(x, skip) -> new activation.  Statistics come from the producers' epilogues when
+// available, otherwise from a separate vf_gn_stats pass.
+static Act gn_block(Exec& ex, const vf_unet* u, int images, const Act& x, const Act* skip, int gw, int gb, bool swish) {
+  const int C1 = skip ? skip->C : 0;
+  const int C = x.C + C1;
   const int HW = x.H * x.W;
-  float* stats = stats_cursor;
-  stats_cursor += (size_t)images * C * 2;
-  Act y{ex.alloc((size_t)images * HW * C * k_elems(u)), C, x.H, x.W};
-  VF_RUN(ex, K_GN_STATS, vf_gn_stats(x.p, x.C, skip ? skip->p : nullptr, skip ? skip->C : 0, u->dtype, images, HW, stats, (vf_stream)ex.st));
-  VF_RUN(ex, K_GN_APPLY, vf_gn_apply(x.p, x.C, skip ? skip->p : nullptr, skip ? skip->C : 0, u->dtype, images, HW, u->cfg.norm_groups, stats,
-                            ex.dry ? nullptr : u->master[gw], ex.dry ? nullptr : u->master[gb], swish ? 1 : 0, y.p, (vf_stream)ex.st));
+  const float *s0 = x.stats, *s1 = skip ? skip->stats : nullptr;
+  int ld0 = x.C, ld1 = C1;
+  if (!x.stats || (skip && !skip->stats)) {
+    float* st = ex.alloc_stats((size_t)images * C * 2);
+    VF_RUN(ex, K_GN_STATS, vf_gn_stats(x.p, x.C, skip ? skip->p : nullptr, C1, u->dtype, images, HW, st, (vf_stream)ex.st));
+    s0 = st; s1 = st + 2 * x.C; ld0 = ld1 = C;
+  }
+  Act y = new_act(ex, u, images, C, x.H, x.W, false);
+  VF_RUN(ex, K_GN_APPLY, vf_gn_apply(x.p, x.C, s0, ld0, skip ? skip->p : nullptr, C1, s1, ld1, u->dtype, images, HW, u->cfg.norm_groups,
+                                     u->master[gw], u->master[gb], swish ? 1 : 0, y.p, (vf_stream)ex.st));
   return y;
 }
 
 static Act run_resblock(Exec& ex, vf_unet* u, const uint8_t* pk, int images, const ResBlock& b, const Act& x, const Act* skip,
-                        const float* emb, const int* img_row, float*& stats_cursor) {
+                        const float* emb, const int* img_row) {
   const int HW = x.H * x.W;
   const size_t es = k_elems(u);
   const int cin = b.c0 + b.c1;
   // block1: GN -> Swish -> conv3x3 (+bias +embedding)                                   unet.py:242-243
-  Act a1 = gn_block(ex, u, images, x, skip, b.g1_w, b.g1_b, true, stats_cursor);
-  Act h1{ex.alloc((size_t)images * HW * b.cout * es), b.cout, x.H, x.W};
+  Act a1 = gn_block(ex, u, images, x, skip, b.g1_w, b.g1_b, true);
+  Act h1 = new_act(ex, u, images, b.cout, x.H, x.W, true);
   {
     vf_conv_args a = conv_args_init();
     a.images = images; a.H = x.H; a.W = x.W; a.n_seg = 1;
@@ -409,12 +430,12 @@ static Act run_resblock(Exec& ex, vf_unet* u, const uint8_t* pk, int images, con
     a.weight = pk + b.w1; a.cout = b.cout; a.cout_pad = b.cout;
     a.bias = ex.dry ? nullptr : u->master[b.c1_b];
     a.emb = emb ? emb + b.emb_col : nullptr; a.img_row = img_row; a.emb_ld = u->E;
-    a.out = h1.p; a.out_ld = b.cout;
+    a.out = h1.p; a.out_ld = b.cout; a.stats = h1.stats;
     conv_call(ex, u, a);
   }
   // block2: GN -> Swish -> conv3x3, + res_conv(x) or + x                                 unet.py:244-245
-  Act a2 = gn_block(ex, u, images, h1, nullptr, b.g2_w, b.g2_b, true, stats_cursor);
-  Act out{ex.alloc((size_t)images * HW * b.cout * es), b.cout, x.H, x.W};
+  Act a2 = gn_block(ex, u, images, h1, nullptr, b.g2_w, b.g2_b, true);
+  Act out = new_act(ex, u, images, b.cout, x.H, x.W, true);
   {
     vf_conv_args a = conv_args_init();
     a.images = images; a.H = x.H; a.W = x.W;
@@ -427,13 +448,13 @@ static Act run_resblock(Exec& ex, vf_unet* u, const uint8_t* pk, int images, con
     }
     a.weight = pk + b.w2; a.cout = b.cout; a.cout_pad = b.cout;
     a.bias = reinterpret_cast<const float*>(pk + b.bias2);
-    a.out = out.p; a.out_ld = b.cout;
+    a.out = out.p; a.out_ld = b.cout; a.stats = out.stats;
     conv_call(ex, u, a);
   }
   if (!b.attn) return out;
   // SelfAttention: GN -> qkv 1x1 -> softmax(QK^T/sqrt(C)) V -> out 1x1 (+bias) + input     unet.py:258-277
   const int C = b.cout;
-  Act n = gn_block(ex, u, images, out, nullptr, b.an_w, b.an_b, false, stats_cursor);
+  Act n = gn_block(ex, u, images, out, nullptr, b.an_w, b.an_b, false);
   void* qkv = ex.alloc((size_t)images * HW * 3 * C * es);
   void* vt = u->dtype == VF_BF16 ? ex.alloc((size_t)images * HW * C * es) : nullptr;
   {
@@ -445,9 +466,9 @@ static Act run_resblock(Exec& ex, vf_unet* u, const uint8_t* pk, int images, con
     if (u->dtype == VF_BF16) { a.qkv_split = C; a.out_vt = vt; }
     conv_call(ex, u, a);
   }
-  Act o{ex.alloc((size_t)images * HW * C * es), C, x.H, x.W};
+  Act o = new_act(ex, u, images, C, x.H, x.W, false);
   VF_RUN(ex, K_ATTN, vf_attention(qkv, vt, u->dtype, images, HW, C, o.p, (vf_stream)ex.st));
-  Act out2{ex.alloc((size_t)images * HW * C * es), C, x.H, x.W};
+  Act out2 = new_act(ex, u, images, C, x.H, x.W, true);
   {
     vf_conv_args a = conv_args_init();
     a.images = images; a.H = x.H; a.W = x.W; a.n_seg = 1;
@@ -455,17 +476,10 @@ static Act run_resblock(Exec& ex, vf_unet* u, const uint8_t* pk, int images, con
     a.weight = pk + b.wout; a.cout = C; a.cout_pad = C;
     a.bias = ex.dry ? nullptr : u->master[b.ao_b];
     a.residual = out.p;
-    a.out = out2.p; a.out_ld = C;
+    a.out = out2.p; a.out_ld = C; a.stats = out2.stats;
     conv_call(ex, u, a);
   }
   return out2;
-}
-
-static size_t stats_floats(const vf_unet* u, int images) {
-  size_t n = 0;
-  for (auto& b : u->blocks) n += (size_t)images * 2 * ((b.c0 + b.c1) + b.cout + (b.attn ? b.cout : 0));
-  n += (size_t)images * 2 * u->final_c;
-  return n;
 }
 
 static int walk(vf_unet* u, Exec& ex, const uint8_t* pk, int images, const void* x0, const float* level, const float* angle,
@@ -476,30 +490,21 @@ static int walk(vf_unet* u, Exec& ex, const uint8_t* pk, int images, const void*
   auto tap = [&](const std::string& name, const Act& a) {
     if (!ex.dry) u->taps[name] = vf_unet::Tap{(size_t)((uint8_t*)a.p - ex.base), a.C, a.H, a.W, u->dtype, a.C};
   };
-  // statistics arena, zeroed once per forward
-  const size_t st_bytes = stats_floats(u, images) * 4;
-  float* stats = reinterpret_cast<float*>(ex.alloc(st_bytes));
-  if (!ex.dry && ex.rc == VF_OK && cudaMemsetAsync(stats, 0, st_bytes, ex.st) != cudaSuccess) {
-    set_error("vf_unet_forward: memset failed");
-    ex.rc = VF_ERR_CUDA;
-  }
-  float* stats_cursor = stats;
   // embedding table [rows, E]
   float* emb = reinterpret_cast<float*>(ex.alloc((size_t)rows * u->E * 4));
   VF_RUN(ex, K_EMBED, vf_embed(level, angle, rows, c.inner_channel, u->master[u->mlp_w0], u->master[u->mlp_b0], u->master[u->mlp_w2],
                          u->master[u->mlp_b2], reinterpret_cast<const float*>(pk + u->emb_w_off),
                          reinterpret_cast<const float*>(pk + u->emb_b_off), u->E, emb, (vf_stream)ex.st));
   std::vector<Act> feats;
-  Act x{nullptr, c.inner_channel, S, S};
   // downs[0]: 3x3 conv as a K0 GEMM over the packed im2col rows                            unet.py:42
-  x.p = ex.alloc((size_t)images * S * S * c.inner_channel * es);
+  Act x = new_act(ex, u, images, c.inner_channel, S, S, true);
   {
     vf_conv_args a = conv_args_init();
     a.images = images; a.H = S; a.W = S; a.n_seg = 1;
     a.src[0] = x0; a.src_c[0] = u->k0; a.ksize[0] = 1;
     a.weight = pk + u->conv0_w; a.cout = c.inner_channel; a.cout_pad = c.inner_channel;
     a.bias = ex.dry ? nullptr : u->master[u->downs[0].b_idx];
-    a.out = x.p; a.out_ld = c.inner_channel;
+    a.out = x.p; a.out_ld = c.inner_channel; a.stats = x.stats;
     conv_call(ex, u, a);
   }
   feats.push_back(x);
@@ -507,15 +512,15 @@ static int walk(vf_unet* u, Exec& ex, const uint8_t* pk, int images, const void*
   for (size_t i = 1; i < u->downs.size(); ++i) {
     const Layer& l = u->downs[i];
     if (l.kind == 1) {
-      x = run_resblock(ex, u, pk, images, u->blocks[l.rb], x, nullptr, emb, img_row, stats_cursor);
+      x = run_resblock(ex, u, pk, images, u->blocks[l.rb], x, nullptr, emb, img_row);
     } else {   // Downsample: conv3x3 stride 2                                              unet.py:195-201
-      Act y{ex.alloc((size_t)images * (x.H / 2) * (x.W / 2) * l.c * es), l.c, x.H / 2, x.W / 2};
+      Act y = new_act(ex, u, images, l.c, x.H / 2, x.W / 2, true);
       vf_conv_args a = conv_args_init();
       a.images = images; a.H = y.H; a.W = y.W; a.n_seg = 1; a.stride = 2;
       a.src[0] = x.p; a.src_c[0] = l.c; a.ksize[0] = 3;
       a.weight = pk + l.w; a.cout = l.c; a.cout_pad = l.c;
       a.bias = ex.dry ? nullptr : u->master[l.b_idx];
-      a.out = y.p; a.out_ld = l.c;
+      a.out = y.p; a.out_ld = l.c; a.stats = y.stats;
       conv_call(ex, u, a);
       x = y;
     }
@@ -523,31 +528,31 @@ static int walk(vf_unet* u, Exec& ex, const uint8_t* pk, int images, const void*
     tap(l.name, x);
   }
   for (auto& l : u->mid) {
-    x = run_resblock(ex, u, pk, images, u->blocks[l.rb], x, nullptr, emb, img_row, stats_cursor);
+    x = run_resblock(ex, u, pk, images, u->blocks[l.rb], x, nullptr, emb, img_row);
     tap(l.name, x);
   }
   for (auto& l : u->ups) {
     if (l.kind == 1) {
       Act skip = feats.back();
       feats.pop_back();
-      x = run_resblock(ex, u, pk, images, u->blocks[l.rb], x, &skip, emb, img_row, stats_cursor);
+      x = run_resblock(ex, u, pk, images, u->blocks[l.rb], x, &skip, emb, img_row);
     } else {   // Upsample: nearest x2 then conv3x3                                         unet.py:185-192
-      Act up{ex.alloc((size_t)images * 4 * x.H * x.W * l.c * es), l.c, 2 * x.H, 2 * x.W};
+      Act up = new_act(ex, u, images, l.c, 2 * x.H, 2 * x.W, false);
       VF_RUN(ex, K_UPSAMPLE, vf_upsample2x(x.p, u->dtype, images, x.H, x.W, l.c, up.p, (vf_stream)ex.st));
-      Act y{ex.alloc((size_t)images * up.H * up.W * l.c * es), l.c, up.H, up.W};
+      Act y = new_act(ex, u, images, l.c, up.H, up.W, true);
       vf_conv_args a = conv_args_init();
       a.images = images; a.H = y.H; a.W = y.W; a.n_seg = 1;
       a.src[0] = up.p; a.src_c[0] = l.c; a.ksize[0] = 3;
       a.weight = pk + l.w; a.cout = l.c; a.cout_pad = l.c;
       a.bias = ex.dry ? nullptr : u->master[l.b_idx];
-      a.out = y.p; a.out_ld = l.c;
+      a.out = y.p; a.out_ld = l.c; a.stats = y.stats;
       conv_call(ex, u, a);
       x = y;
     }
     tap(l.name, x);
   }
   // final_conv: GN -> Swish -> conv3x3 -> fp32 [., 8]                                       unet.py:110-112, :138
-  Act f = gn_block(ex, u, images, x, nullptr, u->fin_gw, u->fin_gb, true, stats_cursor);
+  Act f = gn_block(ex, u, images, x, nullptr, u->fin_gw, u->fin_gb, true);
   {
     vf_conv_args a = conv_args_init();
     a.images = images; a.H = S; a.W = S; a.n_seg = 1;
@@ -567,7 +572,7 @@ extern "C" __attribute__((visibility("default"))) size_t vf_unet_workspace_bytes
   Exec ex{true, nullptr};
   ex.st = nullptr;
   walk(const_cast<vf_unet*>(u), ex, nullptr, max_images, nullptr, nullptr, nullptr, max_images, nullptr, nullptr);
-  return align_up(ex.off, 256) + 256;
+  return align_up(ex.off, 256) + ex.stats_used * 4 + 256;
 }
 
 extern "C" __attribute__((visibility("default"))) int vf_unet_forward(vf_unet* u, const void* packed, void* workspace, size_t workspace_bytes, int images,
@@ -583,7 +588,10 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_forward(vf_unet* u
     Exec dry{true, nullptr};
     dry.st = nullptr;
     walk(u, dry, nullptr, images, nullptr, nullptr, nullptr, rows, nullptr, nullptr);
-    VF_REQUIRE(dry.off <= workspace_bytes, "vf_unet_forward: workspace too small (%zu < %zu)", workspace_bytes, dry.off);
+    const size_t act = align_up(dry.off, 256), need = act + dry.stats_used * 4;
+    VF_REQUIRE(need <= workspace_bytes, "vf_unet_forward: workspace too small (%zu < %zu)", workspace_bytes, need);
+    ex.stats_base = reinterpret_cast<float*>(ex.base + act);
+    VF_CUDA(cudaMemsetAsync(ex.stats_base, 0, dry.stats_used * 4, ex.st));
   }
   u->taps.clear();
   u->last_images = images;

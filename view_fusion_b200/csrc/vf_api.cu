@@ -62,7 +62,6 @@ extern "C" __attribute__((visibility("default"))) int vf_conv2d(const vf_conv_ar
     VF_REQUIRE(a->ksize[s] == 1 || a->ksize[s] == 3, "vf_conv2d: ksize=%d", a->ksize[s]);
     VF_REQUIRE(s == 0 || a->ksize[s] == 1, "vf_conv2d: only segment 0 may be 3x3");
   }
-  VF_REQUIRE(!a->stats, "vf_conv2d: fused GroupNorm statistics are not implemented yet");
   if (a->dtype == VF_BF16 && !g_force_simt) return conv2d_tc(a, as_stream(stream));
   return conv2d_simt(a, as_stream(stream));
 }

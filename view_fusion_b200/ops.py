@@ -42,7 +42,7 @@ def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype, cout_pad=None, k_total
 
 
 def conv2d(srcs, ksizes, weight, images, H, W, cout, *, stride=1, bias=None, emb=None, img_row=None, residual=None,
-           out_dtype=None, out_ld=None, qkv_split=0, cout_pad=None):
+           out_dtype=None, out_ld=None, qkv_split=0, cout_pad=None, want_stats=False):
     """srcs: list of NHWC matrices; weight: packed [cout_pad, K_total].  Returns out (and V^T when qkv_split)."""
     lib = _lib.require_device()
     a = _lib.ConvArgs()
@@ -64,7 +64,13 @@ def conv2d(srcs, ksizes, weight, images, H, W, cout, *, stride=1, bias=None, emb
     if qkv_split and dt == torch.bfloat16:
         vt = torch.zeros(images, qkv_split, H * W, dtype=dt, device=out.device)
         a.qkv_split, a.out_vt = qkv_split, vt.data_ptr()
+    stats = None
+    if want_stats:
+        stats = torch.zeros(images, cout, 2, dtype=torch.float32, device=out.device)
+        a.stats = stats.data_ptr()
     _lib.check(lib.vf_conv2d(C.byref(a), _lib.stream_handle()), "vf_conv2d")
+    if want_stats:
+        return out, stats
     return (out, vt) if qkv_split else out
 
 
@@ -77,11 +83,16 @@ def gn_stats(src0, src1, images, HW):
     return stats
 
 
-def gn_apply(src0, src1, images, HW, groups, stats, gamma, beta, swish=True):
+def gn_apply(src0, src1, images, HW, groups, stats, gamma, beta, swish=True, stats1=None):
+    """stats: [images, C0+C1, 2] (from gn_stats), or per-source [images, C0, 2] with stats1 [images, C1, 2]."""
     lib = _lib.require_device()
     C0, C1 = src0.shape[1], (0 if src1 is None else src1.shape[1])
     dst = torch.empty(images * HW, C0 + C1, dtype=src0.dtype, device=src0.device)
-    _lib.check(lib.vf_gn_apply(src0.data_ptr(), C0, _lib.ptr(src1), C1, _dt(src0), images, HW, groups, stats.data_ptr(),
+    if stats1 is None:
+        s0, ld0, s1, ld1 = stats.data_ptr(), stats.shape[1], stats.data_ptr() + 8 * C0, stats.shape[1]
+    else:
+        s0, ld0, s1, ld1 = stats.data_ptr(), stats.shape[1], stats1.data_ptr(), stats1.shape[1]
+    _lib.check(lib.vf_gn_apply(src0.data_ptr(), C0, s0, ld0, _lib.ptr(src1), C1, s1 if C1 else 0, ld1, _dt(src0), images, HW, groups,
                                gamma.data_ptr(), beta.data_ptr(), int(swish), dst.data_ptr(), _lib.stream_handle()), "vf_gn_apply")
     return dst
 
