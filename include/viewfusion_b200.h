@@ -18,6 +18,15 @@
  *  - activations inside the library are NHWC ("pixel-major") in fp32 (VF_F32, CUDA-core reference-precision
  *    mode) or bf16 (VF_BF16, tcgen05 tensor-core mode); the reference's NCHW fp32 tensors are converted at
  *    the edges by vf_pack_views / vf_nhwc_to_nchw.
+ *  - two row orders exist for an activation of `images` x H x W pixels with C channels:
+ *      FLAT   : row m = (img*H + y)*W + x,                          images*H*W rows
+ *      PADDED : row p = img*P + (y+1)*(W+1) + (x+1), P = (H+1)*(W+1), images*P rows; rows with y+1 == 0 or
+ *               x+1 == 0 are padding.  One zero row above each image and one zero column left of each row serve
+ *               as the 3x3 halo of BOTH neighbours (the row after the last pixel of a line is the next line's
+ *               padding), so the nine taps of a 3x3 convolution are nine constant row offsets
+ *               (kh-1)*(W+1) + (kw-1) of ONE tensor and a tile of it can be loaded once for all taps.
+ *    Producers of convolution inputs (vf_gn_apply, vf_upsample2x) write exact zeros into the padding rows;
+ *    convolution outputs leave their padding rows unwritten (they are never read as data).
  */
 #ifndef VIEWFUSION_B200_H_
 #define VIEWFUSION_B200_H_
@@ -188,32 +197,44 @@ int vf_embed(const float* level, const float* angle, int rows, int inner_channel
              const float* w2, const float* b2, const float* emb_w, const float* emb_b, int E, float* out,
              vf_stream stream);
 
-/* GroupNorm statistics: per (image, channel) sum and sum of squares over H*W of the channel-concatenation of
- * src0 [.,C0] and src1 [.,C1] (src1 may be NULL).  stats [images, C0+C1, 2] fp32 must be zero on entry. */
-int vf_gn_stats(const void* src0, int C0, const void* src1, int C1, int dtype, int images, int HW, float* stats,
+/* GroupNorm statistics: per (image, channel) sum and sum of squares over the H*W pixels of the channel-concatenation
+ * of src0 [.,C0] and src1 [.,C1] (src1 may be NULL), both PADDED.  stats [images, C0+C1, 2] fp32 must be zero on entry.
+ * (The plan does not use this pass: convolution epilogues emit the same sums, vf_conv_args::stats.) */
+int vf_gn_stats(const void* src0, int C0, const void* src1, int C1, int dtype, int images, int H, int W, float* stats,
                 vf_stream stream);
 
-/* GroupNorm(groups, eps=1e-5, affine) + optional Swish (unet.py:207-218,:254) -> dst [., C0+C1].
+/* GroupNorm(groups, eps=1e-5, affine) + optional Swish (unet.py:207-218,:254): PADDED sources -> PADDED dst [., C0+C1]
+ * with exact zeros in the padding rows.
  * statsX: per (image, channel) {sum, sum of squares} of source X, rows of statsX_ld channels ([images, ld, 2]);
  * they come from vf_gn_stats or from the producing convolution's epilogue (vf_conv_args::stats). */
 int vf_gn_apply(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1,
-                const float* stats1, int stats1_ld, int dtype, int images, int HW, int groups, const float* gamma,
+                const float* stats1, int stats1_ld, int dtype, int images, int H, int W, int groups, const float* gamma,
                 const float* beta, int swish, void* dst, vf_stream stream);
 
-/* Nearest-neighbour x2 up-sampling (unet.py:188). */
+/* Nearest-neighbour x2 up-sampling (unet.py:188): PADDED (H, W) -> PADDED (2H, 2W), zero padding rows. */
 int vf_upsample2x(const void* src, int dtype, int images, int H, int W, int C, void* dst, vf_stream stream);
+
+/* Writes zeros into the padding rows of a PADDED tensor (needed when a convolution OUTPUT is consumed directly by a
+ * 3x3 convolution: Downsample, unet.py:195-201). */
+int vf_zero_padding(void* dst, int dtype, int images, int H, int W, int C, vf_stream stream);
+
+/* Row-order conversions (tests, taps): FLAT <-> PADDED for [., C] matrices in `dtype`. */
+int vf_flat_to_padded(const void* src, int dtype, int images, int H, int W, int C, void* dst, vf_stream stream);
+int vf_padded_to_flat(const void* src, int dtype, int images, int H, int W, int C, void* dst, vf_stream stream);
 
 /* Implicit-GEMM convolution, out[m, n] = sum_seg sum_tap sum_c A_seg[pix(m, tap), c] * Wt[n, koff + tap*C_seg + c]
  * with the fused epilogue  + bias[n] + emb[img_row[img(m)]*emb_ld + n] + residual[m, n].
  * ksize 3 uses padding 1; stride 2 only with ksize 3 (Downsample, unet.py:195-201). */
 typedef struct vf_conv_args {
   int dtype;                 /* VF_F32 -> CUDA-core kernel, VF_BF16 -> tcgen05 kernel */
-  int images, H, W;          /* OUTPUT spatial size */
+  int images, H, W;          /* spatial size of the SOURCES (the output is H/2 x W/2 when stride == 2) */
+  int in_padded;             /* row order of every source: 1 PADDED, 0 FLAT (FLAT only with ksize 1) */
+  int out_padded;            /* row order of out / residual / stats rows */
   int n_seg;                 /* 1..3 K-segments accumulated into the same output tile */
-  const void* src[3];        /* [images*Hin*Win, src_c[i]] */
+  const void* src[3];        /* [rows, src_c[i]] */
   int src_c[3];
-  int ksize[3];              /* 1 or 3 */
-  int stride;                /* 1 or 2 (applies to segment 0 only; others must be ksize 1) */
+  int ksize[3];              /* 1 or 3 (only segment 0 may be 3) */
+  int stride;                /* 1, or 2 = Downsample: computed at source resolution, even pixels kept */
   const void* weight;        /* [Cout_pad, K_total] K-major in `dtype`; K_total = sum ksize^2 * src_c */
   int cout;                  /* logical output channels */
   int cout_pad;              /* rows of `weight` (multiple of 16) */
@@ -221,12 +242,12 @@ typedef struct vf_conv_args {
   const float* emb;          /* [rows, emb_ld] or NULL; column offset already applied */
   const int* img_row;        /* [images] */
   int emb_ld;
-  const void* residual;      /* [images*H*W, cout] in `dtype` or NULL */
-  void* out;                 /* [images*H*W, out_ld] */
+  const void* residual;      /* [out rows, cout] in `dtype` or NULL (same row order as out) */
+  void* out;                 /* [out rows, out_ld] */
   int out_dtype;             /* `dtype`, or VF_F32 for the final layer */
   int out_ld;
   int qkv_split;             /* >0: C of an attention block; columns [2C,3C) are written transposed to out_vt */
-  void* out_vt;              /* [images, C, H*W] (keys contiguous) when qkv_split */
+  void* out_vt;              /* [images, C, H*W] (keys contiguous) when qkv_split (needs out_padded == 0) */
   float* stats;              /* optional [images, cout, 2]: GroupNorm partial sums of the OUTPUT (pre-zeroed) */
 } vf_conv_args;
 
@@ -235,9 +256,15 @@ int vf_conv2d(const vf_conv_args* a, vf_stream stream);
 /* Test hook: route VF_BF16 vf_conv2d / vf_attention through the CUDA-core kernels (same bf16 storage, fp32
  * accumulation) so the tcgen05 kernels can be cross-checked on the device.  Never enabled by the product path. */
 void vf_debug_force_simt(int on);
+/* Test hook: ablation bits for the tcgen05 conv epilogue (timing studies only; results are wrong when set). */
+void vf_debug_flags(int flags);
+/* Test hook: device buffer [148*4] int64 receiving the tcgen05 conv's MMA-thread cycle counters (NULL = off). */
+void vf_debug_counters(long long* dev_buf);
 
 /* Hardware probe (tests only): out[i][n] = sum_k A[shift_rows + i][k] * B[n][k] through ONE TMA-loaded, 128B-swizzled
  * smem tile and a tcgen05 descriptor whose start is shifted by `shift_rows` rows. A [rows>=256, 64] bf16, B [64, 64]. */
+/* Hardware probe: cycles for n_groups x 4 back-to-back tcgen05.mma (M=128, N, K=16) issued by one thread per CTA. */
+int vf_debug_umma_rate(int N, int shift_rows, int n_groups, int commit_every, int grid, long long* cycles_out, vf_stream stream);
 int vf_debug_umma_shift(const void* A, int rows, const void* B, int shift_rows, int use_base_offset, float* out,
                         vf_stream stream);
 

@@ -124,12 +124,15 @@ def test_groupnorm_swish(lib, dtype, C0, C1, HW, groups):
     for swish in (True, False):
         ref = F.group_norm(xc, groups, gamma, beta, eps=1e-5)
         ref = O.swish(ref) if swish else ref
-        s0 = ops.to_nhwc(x0, dtype).cuda()
-        s1 = None if x1 is None else ops.to_nhwc(x1, dtype).cuda()
-        st = ops.gn_stats(s0, s1, R, HW)
-        y = ops.gn_apply(s0, s1, R, HW, groups, st, gamma.cuda(), beta.cuda(), swish)
-        got = ops.from_nhwc(y, R, S, S)
+        # padding rows of the sources hold garbage (conv outputs never write them): they must not be read
+        s0 = ops.to_padded(x0, dtype, fill=float("nan")).cuda()
+        s1 = None if x1 is None else ops.to_padded(x1, dtype, fill=float("nan")).cuda()
+        st = ops.gn_stats(s0, s1, R, S, S)
+        y = ops.gn_apply(s0, s1, R, S, S, groups, st, gamma.cuda(), beta.cuda(), swish)
+        got = ops.from_padded(y, R, S, S)
         assert rel(got, ref) < (4e-3 if dtype == torch.bfloat16 else 2e-6)
+        pad = y.float().view(R, S + 1, S + 1, -1)
+        assert float(pad[:, 0].abs().max()) == 0.0 and float(pad[:, :, 0].abs().max()) == 0.0   # exact zero padding rows
 
 
 def _conv_case(dtype, R, S, segs, cout, stride, use_emb, use_res, seed=0):
@@ -137,7 +140,8 @@ def _conv_case(dtype, R, S, segs, cout, stride, use_emb, use_res, seed=0):
     torch.manual_seed(seed)
     rnd = (lambda *s: bf16r(torch.randn(*s))) if dtype == torch.bfloat16 else (lambda *s: torch.randn(*s))
     Sin = S * stride
-    xs = [rnd(R, c, Sin if i == 0 else S, Sin if i == 0 else S) for i, (c, k) in enumerate(segs)]
+    assert stride == 1 or len(segs) == 1
+    xs = [rnd(R, c, Sin, Sin) for i, (c, k) in enumerate(segs)]
     ws = [rnd(cout, c, k, k) / math.sqrt(c * k * k) for (c, k) in segs]
     if dtype == torch.bfloat16:
         ws = [bf16r(w) for w in ws]
@@ -164,9 +168,14 @@ def _run_conv(dtype, R, S, segs, cout, stride, xs, ws, bias, emb, img_row, res, 
     for (c, k), w in zip(segs, ws):
         ops.pack_conv_weight(w.cuda(), dtype, cout_pad=wp.shape[0], k_total=k_total, k_off=off, dst=wp)
         off += c * k * k
-    out = ops.conv2d([ops.to_nhwc(x, dtype).cuda() for x in xs], [k for _, k in segs], wp, R, S, S, cout, stride=stride,
+    Sin = S * stride
+    srcs = []
+    for i, ((c, k), x) in enumerate(zip(segs, xs)):
+        # 3x3 sources need real zeros in the padding rows; 1x1 sources may hold anything there
+        srcs.append(ops.to_padded(x, dtype, fill=0.0 if k == 3 else 7.0).cuda())
+    out = ops.conv2d(srcs, [k for _, k in segs], wp, R, Sin, Sin, cout, stride=stride,
                      bias=bias.cuda(), emb=None if emb is None else emb.cuda(), img_row=None if img_row is None else img_row.cuda(),
-                     residual=None if res is None else ops.to_nhwc(res, dtype).cuda(), **kw)
+                     residual=None if res is None else ops.to_padded(res, dtype, fill=float("nan")).cuda(), **kw)
     torch.cuda.synchronize()
     return out
 
@@ -180,6 +189,10 @@ CONV_CASES = [
     (1, 32, [(64, 1)], 192, 1, False, False),
     (5, 4, [(320, 3), (320, 1), (320, 1)], 320, 1, True, False),
     (1, 64, [(64, 3)], 64, 1, True, True),
+    (6, 64, [(64, 3)], 64, 1, True, True),          # many work items per CTA, G=4 accumulators, image-straddling warps
+    (40, 16, [(192, 3), (128, 1)], 192, 1, True, False),
+    (150, 8, [(320, 3)], 320, 1, False, True),      # more items than SMs at the smallest resolution
+    (3, 32, [(128, 3)], 128, 2, False, False),
 ]
 
 
@@ -189,7 +202,7 @@ def test_conv_fp32_cuda_core(lib, case):
     R, S, segs, cout, stride, ue, ur = case
     ref, *t = _conv_case(torch.float32, R, S, segs, cout, stride, ue, ur)
     out = _run_conv(torch.float32, R, S, segs, cout, stride, *t)
-    assert rel(ops.from_nhwc(out, R, S, S), ref) < 5e-6
+    assert rel(ops.from_padded(out, R, S, S), ref) < 5e-6
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
@@ -199,21 +212,36 @@ def test_conv_bf16_tcgen05(lib, case):
     R, S, segs, cout, stride, ue, ur = case
     ref, *t = _conv_case(torch.bfloat16, R, S, segs, cout, stride, ue, ur)
     out = _run_conv(torch.bfloat16, R, S, segs, cout, stride, *t)
-    got = ops.from_nhwc(out, R, S, S)
+    got = ops.from_padded(out, R, S, S)
     assert rel(got, ref) < 4e-3, "tensor-core path vs fp32 math on bf16 operands (output rounding only)"
     ops.force_simt(True)
     try:
-        simt = ops.from_nhwc(_run_conv(torch.bfloat16, R, S, segs, cout, stride, *t), R, S, S)
+        simt = ops.from_padded(_run_conv(torch.bfloat16, R, S, segs, cout, stride, *t), R, S, S)
     finally:
         ops.force_simt(False)
     assert rel(got, simt) < 3e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv_flat_source_padded_output(lib, dtype):
+    """1x1 conv over a FLAT source (attention output / packed first layer) into a PADDED output + PADDED residual."""
+    from view_fusion_b200 import ops
+    torch.manual_seed(5)
+    R, S, Cc, cout = 3, 16, 128, 128
+    rnd = (lambda *s: bf16r(torch.randn(*s))) if dtype == torch.bfloat16 else (lambda *s: torch.randn(*s))
+    x, w, res, bias = rnd(R, Cc, S, S), rnd(cout, Cc, 1, 1) / math.sqrt(Cc), rnd(R, cout, S, S), torch.randn(cout)
+    ref = F.conv2d(x, w, bias) + res
+    wp = ops.pack_conv_weight(w.cuda(), dtype)
+    out = ops.conv2d([ops.to_nhwc(x, dtype).cuda()], [1], wp, R, S, S, cout, bias=bias.cuda(),
+                     residual=ops.to_padded(res, dtype, fill=float("nan")).cuda(), in_padded=False, out_padded=True)
+    assert rel(ops.from_padded(out, R, S, S), ref) < (4e-3 if dtype == torch.bfloat16 else 5e-6)
 
 
 def test_conv_bf16_final_layer_fp32_out(lib):
     from view_fusion_b200 import ops
     R, S, segs, cout = 2, 16, [(64, 3)], 6
     ref, *t = _conv_case(torch.bfloat16, R, S, segs, cout, 1, False, False)
-    out = _run_conv(torch.bfloat16, R, S, segs, cout, 1, *t, out_dtype=torch.float32, out_ld=8, cout_pad=16)
+    out = _run_conv(torch.bfloat16, R, S, segs, cout, 1, *t, out_dtype=torch.float32, out_ld=8, cout_pad=16, out_padded=False)
     got = out.view(R, S, S, 8)[..., :6].permute(0, 3, 1, 2).cpu()
     assert rel(got, ref) < 1e-5
 
@@ -222,7 +250,7 @@ def test_conv_bf16_qkv_split_writes_v_transposed(lib):
     from view_fusion_b200 import ops
     R, S, Cc = 3, 8, 128
     ref, *t = _conv_case(torch.bfloat16, R, S, [(Cc, 1)], 3 * Cc, 1, False, False)
-    out, vt = _run_conv(torch.bfloat16, R, S, [(Cc, 1)], 3 * Cc, 1, *t, qkv_split=Cc)
+    out, vt = _run_conv(torch.bfloat16, R, S, [(Cc, 1)], 3 * Cc, 1, *t, qkv_split=Cc, out_padded=False)
     got = ops.from_nhwc(out, R, S, S)
     assert rel(got[:, : 2 * Cc], ref[:, : 2 * Cc]) < 4e-3
     assert rel(vt.float().cpu().view(R, Cc, S, S), ref[:, 2 * Cc:]) < 4e-3
@@ -275,8 +303,11 @@ def test_embed_table(lib):
 def test_upsample_and_pack(lib):
     from view_fusion_b200 import _lib, ops
     x = torch.randn(2, 64, 8, 8)
-    up = ops.upsample2x(ops.to_nhwc(x).cuda(), 2, 8, 8)
-    assert torch.equal(ops.from_nhwc(up, 2, 16, 16).cpu(), F.interpolate(x, scale_factor=2, mode="nearest"))
+    up = ops.upsample2x(ops.to_padded(x, fill=float("nan")).cuda(), 2, 8, 8)
+    assert torch.equal(ops.from_padded(up, 2, 16, 16).cpu(), F.interpolate(x, scale_factor=2, mode="nearest"))
+    assert float(up.view(2, 17, 17, 64)[:, 0].abs().max()) == 0.0 and float(up.view(2, 17, 17, 64)[:, :, 0].abs().max()) == 0.0
+    flat = ops.to_nhwc(x).cuda()
+    assert torch.equal(ops.padded_to_flat(ops.flat_to_padded(flat, 2, 8, 8), 2, 8, 8), flat)
     # pack_views == stack_views + im2col of the first conv
     bt = O.synthetic_batch(3, 4, 16, seed=9, ragged=True, nmax=5)
     y_t = torch.randn(3, 3, 16, 16)
@@ -301,14 +332,14 @@ def test_conv_fused_groupnorm_statistics(lib, dtype):
     R, S, segs, cout = 3, 16, [(64, 3)], 128
     ref, *t = _conv_case(dtype, R, S, segs, cout, 1, True, True)
     out, stats = _run_conv(dtype, R, S, segs, cout, 1, *t, want_stats=True)
-    o = ops.from_nhwc(out, R, S, S).cpu()                 # stored values (bf16-rounded in bf16 mode)
+    o = ops.from_padded(out, R, S, S).cpu()               # stored values (bf16-rounded in bf16 mode)
     want = torch.stack([o.sum(dim=(2, 3)), (o * o).sum(dim=(2, 3))], dim=-1)
     assert rel(stats, want) < 1e-5
     # and GroupNorm driven by the fused statistics == GroupNorm of the stored tensor
     gamma, beta = torch.rand(cout) + 0.5, torch.randn(cout) * 0.1
-    y = ops.gn_apply(out, None, R, S * S, 32, stats, gamma.cuda(), beta.cuda(), True)
+    y = ops.gn_apply(out, None, R, S, S, 32, stats, gamma.cuda(), beta.cuda(), True)
     refn = O.swish(F.group_norm(o, 32, gamma, beta, eps=1e-5))
-    assert rel(ops.from_nhwc(y, R, S, S), refn) < (4e-3 if dtype == torch.bfloat16 else 2e-6)
+    assert rel(ops.from_padded(y, R, S, S), refn) < (4e-3 if dtype == torch.bfloat16 else 2e-6)
 
 
 def test_probe_shifted_umma_descriptor(lib):

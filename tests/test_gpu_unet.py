@@ -32,7 +32,7 @@ def test_unet_bf16_layerwise_vs_oracle():
     worst = {}
     for name, r in taps.items():
         worst[name] = rel(m.denoise_fn.read_tap(name), r)
-    bad = {k: v for k, v in worst.items() if v > 3e-2}
+    bad = {k: v for k, v in worst.items() if not v < 3e-2}       # `not <` also catches NaN
     assert not bad, f"layers off: {bad}"
     assert rel(out, ref) < 3e-2
 

@@ -22,7 +22,7 @@ SYMBOLS = [
     "vf_unet_last_launches", "vf_unet_read_tap", "vf_unet_set_profiling", "vf_unet_profile_read",
     "vf_pack_views", "vf_pack_nchw", "vf_nhwc_to_nchw", "vf_q_sample",
     "vf_compose_ddpm_step", "vf_compose_mse",
-    "vf_embed", "vf_gn_stats", "vf_gn_apply", "vf_upsample2x", "vf_conv2d", "vf_debug_force_simt", "vf_debug_umma_shift", "vf_attention",
+    "vf_embed", "vf_gn_stats", "vf_gn_apply", "vf_upsample2x", "vf_flat_to_padded", "vf_padded_to_flat", "vf_zero_padding", "vf_conv2d", "vf_debug_force_simt", "vf_debug_flags", "vf_debug_counters", "vf_debug_umma_shift", "vf_debug_umma_rate", "vf_attention",
     "vf_pack_conv_weight",
 ]
 
@@ -56,7 +56,8 @@ class ComposeArgs(C.Structure):
 
 class ConvArgs(C.Structure):
     _fields_ = [
-        ("dtype", C.c_int), ("images", C.c_int), ("H", C.c_int), ("W", C.c_int), ("n_seg", C.c_int),
+        ("dtype", C.c_int), ("images", C.c_int), ("H", C.c_int), ("W", C.c_int), ("in_padded", C.c_int),
+        ("out_padded", C.c_int), ("n_seg", C.c_int),
         ("src", C.c_void_p * 3), ("src_c", C.c_int * 3), ("ksize", C.c_int * 3), ("stride", C.c_int),
         ("weight", C.c_void_p), ("cout", C.c_int), ("cout_pad", C.c_int), ("bias", C.c_void_p),
         ("emb", C.c_void_p), ("img_row", C.c_void_p), ("emb_ld", C.c_int), ("residual", C.c_void_p),
@@ -104,11 +105,17 @@ def load() -> C.CDLL:
         "vf_compose_ddpm_step": (i, [C.POINTER(ComposeArgs), C.POINTER(Schedule), p]),
         "vf_compose_mse": (i, [p, p, p, i, i, i, i, p, p, p, f, p]),
         "vf_embed": (i, [p, p, i, i, p, p, p, p, p, p, i, p, p]),
-        "vf_gn_stats": (i, [p, i, p, i, i, i, i, p, p]),
-        "vf_gn_apply": (i, [p, i, p, i, p, i, p, i, i, i, i, i, p, p, i, p, p]),
+        "vf_gn_stats": (i, [p, i, p, i, i, i, i, i, p, p]),
+        "vf_gn_apply": (i, [p, i, p, i, p, i, p, i, i, i, i, i, i, p, p, i, p, p]),
         "vf_upsample2x": (i, [p, i, i, i, i, i, p, p]),
+        "vf_zero_padding": (i, [p, i, i, i, i, i, p]),
+        "vf_flat_to_padded": (i, [p, i, i, i, i, i, p, p]),
+        "vf_padded_to_flat": (i, [p, i, i, i, i, i, p, p]),
         "vf_conv2d": (i, [C.POINTER(ConvArgs), p]),
         "vf_debug_force_simt": (None, [i]),
+        "vf_debug_flags": (None, [i]),
+        "vf_debug_counters": (None, [p]),
+        "vf_debug_umma_rate": (i, [i, i, i, i, i, p, p]),
         "vf_debug_umma_shift": (i, [p, i, p, i, i, p, p]),
         "vf_attention": (i, [p, p, i, i, i, i, p, p]),
         "vf_pack_conv_weight": (i, [p, i, i, i, i, p, i, i, i, p]),

@@ -1,7 +1,7 @@
 // CUDA-core implicit-GEMM convolution: the fp32 "reference-precision" mode of vf_conv2d (1e-4 parity bar, no
 // TF32/bf16 rounding anywhere) and the on-device cross-check for the tcgen05 kernel.  Same contract as the
-// tensor-core path: NHWC activations, K-major weights, up to three K-segments (3x3 main conv + 1x1 res_conv over
-// one or two sources) accumulated into one tile, fused bias + embedding + residual epilogue.
+// tensor-core path: FLAT / PADDED row orders, K-major weights, up to three K-segments (3x3 main conv + 1x1 res_conv
+// over one or two sources) accumulated into one tile, fused bias + embedding + residual epilogue, GroupNorm sums.
 // Reference: nn.Conv2d call sites model/unet.py:42,189,198,214,238,255,256.
 #include "vf_common.cuh"
 
@@ -10,12 +10,11 @@ namespace vf {
 constexpr int SBM = 64, SBN = 64, SBK = 16;
 
 struct SimtConvParams {
+  RowGeom geo;
   const void* src[3];
   int src_c[3];
   int ksize[3];
   int n_seg;
-  int stride;
-  int images, H, W;      // output spatial
   const void* weight;
   int k_total;
   int cout, cout_pad;
@@ -46,16 +45,12 @@ template <typename TA, typename TO>
 __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtConvParams p) {
   __shared__ float As[SBK][SBM + 4];
   __shared__ float Bs[SBK][SBN + 4];
-  const int HW = p.H * p.W;
-  const int M = p.images * HW;
+  const int M = p.geo.rows_total;
   const int m0 = blockIdx.x * SBM, n0 = blockIdx.y * SBN;
   const int tid = threadIdx.x;
   const int tx = tid % 16, ty = tid / 16;          // 16x16 threads, each 4 rows x 4 cols
-  // loader roles
-  const int lrow = tid / 4, lk = (tid % 4) * 4;
+  const int lrow = tid / 4, lk = (tid % 4) * 4;    // loader roles
   const int lm = m0 + lrow;
-  int limg = 0, ly = 0, lx = 0;
-  if (lm < M) { limg = lm / HW; int r = lm % HW; ly = r / p.W; lx = r % p.W; }
   const int ln = n0 + lrow;
   const TA* wt = reinterpret_cast<const TA*>(p.weight);
 
@@ -69,14 +64,13 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtConvParams p) 
   for (int s = 0; s < p.n_seg; ++s) {
     const int C = p.src_c[s];
     const int ks = p.ksize[s];
-    const int st = (s == 0) ? p.stride : 1;
-    const int Hin = p.H * st, Win = p.W * st;
     const TA* src = reinterpret_cast<const TA*>(p.src[s]);
     for (int tap = 0; tap < ks * ks; ++tap) {
-      const int dy = ks == 3 ? tap / 3 - 1 : 0, dx = ks == 3 ? tap % 3 - 1 : 0;
-      const int yy = ly * st + dy, xx = lx * st + dx;
-      const bool inb = lm < M && yy >= 0 && yy < Hin && xx >= 0 && xx < Win;
-      const TA* arow = src + (((size_t)limg * Hin + (inb ? yy : 0)) * Win + (inb ? xx : 0)) * C;
+      // PADDED rows: the 3x3 neighbourhood is a constant row offset; padding rows hold zeros
+      const int off = ks == 3 ? (tap / 3 - 1) * p.geo.W1 + (tap % 3 - 1) : 0;
+      const long row = (long)lm + off;
+      const bool inb = lm < M && row >= 0 && row < M;
+      const TA* arow = src + (inb ? row : 0) * C;
       for (int c0 = 0; c0 < C; c0 += SBK) {
         float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
         if (inb) load4(arow + c0 + lk, a);
@@ -104,12 +98,13 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtConvParams p) 
   TO* out = reinterpret_cast<TO*>(p.out);
   const TA* res = reinterpret_cast<const TA*>(p.residual);
   TA* vt = reinterpret_cast<TA*>(p.out_vt);
+  const int HWo = p.geo.stride2 ? p.geo.HW / 4 : p.geo.HW;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int m = m0 + ty * 4 + i;
-    if (m >= M) continue;
-    const int img = m / HW;
-    const float* erow = p.emb ? p.emb + (size_t)__ldg(p.img_row + img) * p.emb_ld : nullptr;
+    const RowInfo ri = decode_row(p.geo, m);
+    if (!ri.valid) continue;
+    const float* erow = p.emb ? p.emb + (size_t)__ldg(p.img_row + ri.img) * p.emb_ld : nullptr;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
@@ -117,15 +112,15 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtConvParams p) 
       float v = acc[i][j];
       if (p.bias) v += __ldg(p.bias + n);
       if (erow) v += __ldg(erow + n);
-      if (res) v += to_f(res[(size_t)m * p.cout + n]);
+      if (res) v += to_f(res[(size_t)ri.out_row * p.cout + n]);
       if (p.qkv_split > 0 && n >= 2 * p.qkv_split)
-        vt[((size_t)img * p.qkv_split + (n - 2 * p.qkv_split)) * HW + (m % HW)] = from_f<TA>(v);
+        vt[((size_t)ri.img * p.qkv_split + (n - 2 * p.qkv_split)) * HWo + ri.pix] = from_f<TA>(v);
       else
-        out[(size_t)m * p.out_ld + n] = from_f<TO>(v);
+        out[(size_t)ri.out_row * p.out_ld + n] = from_f<TO>(v);
       if (p.stats) {
         const float x = to_f(from_f<TO>(v));
-        atomicAdd(p.stats + ((size_t)img * p.cout + n) * 2, x);
-        atomicAdd(p.stats + ((size_t)img * p.cout + n) * 2 + 1, x * x);
+        atomicAdd(p.stats + ((size_t)ri.img * p.cout + n) * 2, x);
+        atomicAdd(p.stats + ((size_t)ri.img * p.cout + n) * 2 + 1, x * x);
       }
     }
   }
@@ -133,18 +128,19 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtConvParams p) 
 
 int conv2d_simt(const vf_conv_args* a, cudaStream_t st) {
   SimtConvParams p{};
+  p.geo = make_geom(a->images, a->H, a->W, a->in_padded, a->out_padded, a->stride == 2);
   int k_total = 0;
   for (int s = 0; s < a->n_seg; ++s) {
     p.src[s] = a->src[s]; p.src_c[s] = a->src_c[s]; p.ksize[s] = a->ksize[s];
     VF_REQUIRE(a->src_c[s] % SBK == 0, "vf_conv2d(simt): segment channels %d not a multiple of %d", a->src_c[s], SBK);
+    VF_REQUIRE(a->ksize[s] == 1 || a->in_padded, "vf_conv2d(simt): 3x3 needs PADDED sources");
     k_total += a->ksize[s] * a->ksize[s] * a->src_c[s];
   }
-  p.n_seg = a->n_seg; p.stride = a->stride; p.images = a->images; p.H = a->H; p.W = a->W;
+  p.n_seg = a->n_seg;
   p.weight = a->weight; p.k_total = k_total; p.cout = a->cout; p.cout_pad = a->cout_pad;
   p.bias = a->bias; p.emb = a->emb; p.img_row = a->img_row; p.emb_ld = a->emb_ld; p.residual = a->residual;
   p.out = a->out; p.out_ld = a->out_ld; p.qkv_split = a->qkv_split; p.out_vt = a->out_vt; p.stats = a->stats;
-  const int M = a->images * a->H * a->W;
-  dim3 grid(cdiv(M, SBM), cdiv(a->cout, SBN));
+  dim3 grid(cdiv(p.geo.rows_total, SBM), cdiv(a->cout, SBN));
   if (a->dtype == VF_F32) {
     VF_REQUIRE(a->out_dtype == VF_F32, "vf_conv2d(simt): fp32 activations need fp32 output");
     conv_simt_kernel<float, float><<<grid, 256, 0, st>>>(p);

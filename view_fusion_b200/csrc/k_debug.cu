@@ -95,3 +95,88 @@ extern "C" __attribute__((visibility("default"))) int vf_debug_umma_shift(const 
   VF_LAUNCH_CHECK();
   return VF_OK;
 }
+
+// ---- probe 2: sustained tcgen05.mma issue/execute rate from one thread (no loads; smem contents are irrelevant) ------
+namespace vf {
+__global__ void __launch_bounds__(128) umma_rate_probe(int N, int shift_rows, int n_groups, int commit_every, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t bar = base, tmem_slot = base + 16;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + 16);
+  const uint32_t sA = base + 1024, sB = sA + 512 * 128;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { ptx::mbar_init(bar, 1); ptx::fence_barrier_init(); }
+  if (warp == 0) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot_ptr;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = ptx::make_idesc_bf16(128, N, 0, 0);
+    const uint64_t d0 = ptx::make_smem_desc(0, 16, 1024);
+    const uint64_t ad = d0 + (((sA + (uint32_t)shift_rows * 128u) & 0x3FFFF) >> 4), bd = d0 + ((sB & 0x3FFFF) >> 4);
+    uint32_t phase = 0;
+    const long long t0 = clock64();
+    if (commit_every == -100 || commit_every == -101) {
+      // realistic operand pattern: 4 "taps" with distinct weight tiles and row-shifted A, 2 accumulators, k4 per (tap, g);
+      // -101 orders the MMAs k-outer / g-inner so consecutive instructions share the B operand
+      const uint32_t sink_bar = base + 40;
+      ptx::mbar_init(sink_bar, 1);
+      ptx::fence_barrier_init();
+      for (int i = 0; i < n_groups; i += 8) {
+        for (int tap = 0; tap < 4; ++tap) {
+          const uint64_t a_t = ad + (uint64_t)(tap * 67 * 8), b_t = bd + (uint64_t)(tap * N * 8);
+          if (commit_every == -100) {
+            for (int g = 0; g < 2; ++g) ptx::umma_f16_k4(tmem_d + (uint32_t)(g * N), a_t + (uint64_t)(g * 1024), b_t, idesc, 1u);
+          } else {
+            for (int k = 0; k < 4; ++k)
+              for (int g = 0; g < 2; ++g)
+                ptx::umma_f16(tmem_d + (uint32_t)(g * N), a_t + (uint64_t)(g * 1024 + 2 * k), b_t + (uint64_t)(2 * k), idesc, 1u);
+          }
+          ptx::umma_commit(sink_bar);
+        }
+      }
+    } else if (commit_every >= 0) {
+      for (int i = 0; i < n_groups; ++i) {
+        ptx::umma_f16_k4(tmem_d, ad, bd, idesc, 1u);
+        if (commit_every > 0 && (i + 1) % commit_every == 0 && i + 1 < n_groups) { ptx::umma_commit(bar); ptx::mbar_wait(bar, phase); phase ^= 1; }
+      }
+    } else {
+      // mimic the conv main loop: per "tap" = -commit_every groups: wait on an already-complete barrier, fence, MMAs,
+      // commit to a barrier nobody waits on
+      const uint32_t done_bar = base + 32, sink_bar = base + 40;
+      ptx::mbar_init(done_bar, 1); ptx::mbar_init(sink_bar, 1);
+      ptx::fence_barrier_init();
+      ptx::mbar_arrive(done_bar);                       // phase 0 complete
+      const int per = -commit_every;
+      for (int i = 0; i < n_groups; i += per) {
+        ptx::mbar_wait(done_bar, 0);
+        ptx::tc_fence_after();
+        for (int g = 0; g < per; ++g) ptx::umma_f16_k4(tmem_d + (uint32_t)(g * 0), ad + (uint64_t)(g * 1024), bd, idesc, 1u);
+        ptx::umma_commit(sink_bar);
+      }
+    }
+    ptx::umma_commit(bar);
+    ptx::mbar_wait(bar, phase);
+    out[blockIdx.x] = clock64() - t0;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_d, 512); }
+}
+}  // namespace vf
+
+// cycles_out[grid] = SM cycles for n_groups x 4 MMAs (M=128, N, K=16) issued by one thread per CTA; commit_every > 0 waits
+// for completion every that many groups (exposes latency), 0 = fully pipelined.
+extern "C" __attribute__((visibility("default"))) int vf_debug_umma_rate(int N, int shift_rows, int n_groups, int commit_every, int grid,
+                                                                         long long* cycles_out, vf_stream stream) {
+  using namespace vf;
+  VF_REQUIRE(N % 16 == 0 && N >= 16 && N <= 256 && grid > 0 && cycles_out, "vf_debug_umma_rate: bad args");
+  const size_t smem = 1024 + 1024 + 512 * 128 + 4 * 256 * 128;
+  VF_CUDA(cudaFuncSetAttribute(umma_rate_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_rate_probe<<<grid, 128, smem, as_stream(stream)>>>(N, shift_rows, n_groups, commit_every, cycles_out);
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}

@@ -1,21 +1,24 @@
 // tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation in TMEM).
 // Reference call sites: every nn.Conv2d of model/unet.py (:42, :189, :198, :214, :238, :255, :256).
 //
-//   D[m, n] = sum_seg sum_tap sum_c A_seg[pix(m, tap), c] * Wt[n, koff(seg) + tap*C_seg + c]      (fp32, in TMEM)
-//   out     = D + bias[n] + emb[img_row[img(m)], n] + residual[m, n]                              (bf16 or fp32)
+//   D[m, n] = sum_seg sum_tap sum_c A_seg[row(m) + shift(tap), c] * Wt[n, koff(seg) + tap*C_seg + c]   (fp32, in TMEM)
+//   out     = D + bias[n] + emb[img_row[img(m)], n] + residual[m, n]                                  (bf16 or fp32)
 //
-// * M tile = 128 output pixels = one UMMA_M=128 accumulator (TMEM lane == pixel).  A tile is one TMA box
-//   (64 channels x box_w x box_h x box_n) of the NHWC activation: the 3x3 halo and the zero padding come from the
-//   box start coordinate (x0+kw-1, y0+kh-1) and TMA out-of-bounds zero fill, so there is no im2col buffer and no
-//   predication in the loader.  Stride-2 convolutions use a 5-D view (2C, W/2, 2, H/2, N) of the same tensor in
-//   which the row/column parity is a coordinate.
-// * N tile = block_n (<= 256) output channels = one UMMA_N; weights are K-major [Cout][K] rows.
-// * K is walked in 64-channel steps (one 128-byte swizzle row); up to three K segments are accumulated into the
-//   same TMEM tile (3x3 conv over h  +  1x1 res_conv over x and the skip tensor), which fuses the ResnetBlock's
-//   residual projection (unet.py:245) and the decoder's torch.cat (unet.py:134) into the GEMM.
-// * Warp roles: warps 0-3 epilogue (TMEM -> registers -> global), warp 4 TMA producer, warp 5 MMA issuer + TMEM
-//   allocator.  smem ring of `stages` x (A 16 KB + B block_n*128 B); ~100 KB so that two CTAs share an SM and one
-//   CTA's epilogue overlaps the other's main loop.
+// What bounds this kernel on B200 is the L2 -> SM ingest (~42 B/clk/SM measured, B300_MICROARCH.md "LTS cap"), not
+// the tensor pipe: a plain 128 x N tile needs (128+N)*128 B per 64-wide K step, i.e. 2-4x more than an SM can pull
+// in while the MMAs of that step run.  The design therefore maximises operand reuse out of shared memory:
+//   * PADDED row order (include/viewfusion_b200.h): the nine taps of a 3x3 convolution are nine constant ROW
+//     OFFSETS of one matrix.  A K step loads ONE halo'd A slab ((128*G + 2W + 4) rows x 64 channels) and issues the
+//     MMAs of all nine taps from it through smem descriptors whose start address is shifted by whole 128-byte rows
+//     (verified on hardware: the 128B swizzle is a function of the absolute smem address, tests/test_gpu_ops.py::
+//     test_probe_shifted_umma_descriptor).  Activation traffic drops ~9x.
+//   * G accumulators of 128 rows share every weight tile (B traffic / G); TMEM holds 2 sets x G x block_n columns so
+//     the epilogue of work item i overlaps the main loop of item i+1 (persistent CTAs, one per SM).
+//   * (block_n, G) are chosen per layer by a small cost model of ingest bytes vs MMA cycles vs wave quantisation.
+// Up to three K segments accumulate into the same tile (3x3 conv over h + 1x1 res_conv over x and the skip tensor),
+// fusing the ResnetBlock's residual projection (unet.py:245) and the decoder's torch.cat (unet.py:134).
+// Warp roles: warps 0-15 epilogue (TMEM -> registers -> smem -> TMA store, + GroupNorm partial sums), warp 16 TMA
+// producer, warp 17 MMA issuer + TMEM allocator.
 #include <cuda.h>
 
 #include <mutex>
@@ -25,26 +28,27 @@
 
 namespace vf {
 
-constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_THREADS = 192;
-constexpr int TC_MAX_BOXN = 16;
+constexpr int TC_THREADS = 320;     // 8 epilogue warps + TMA producer + MMA issuer
+constexpr int TC_ABOX = 64;        // rows per A TMA box
+constexpr int TC_MAX_STAGES = 16;
 
 struct TcSeg {
-  int ntaps;     // 1 or 9
-  int nchunks;   // C / 64
   int C;
-  int mode;      // 0: stride-1 (4-D map), 2: stride-2 3x3 (5-D map)
+  int nchunks;   // C / 64
+  int ntaps;     // 1 or 9
   int koff;      // first weight column of the segment
+  int halo;      // rows loaded before/after the block: (W+1)+1 for 3x3, 0 for 1x1
 };
 
 struct TcParams {
-  int M, HW, H, W;
-  int box_w, box_h, box_n;
-  int block_n, stages, tmem_cols;
+  RowGeom geo;
+  int G, block_n, n_tiles_n, n_mblocks, n_items;
+  int a_stage_bytes, a_stages, b_stages;
+  int b_resident;                 // the CTA's whole weight tile stays in smem (b_stages == taps * chunks); single N tile
+  int tmem_cols, max_imgs;
   int n_seg;
   TcSeg seg[3];
-  int num_k_iters;
   uint32_t idesc;
   const float* bias;
   const float* emb;
@@ -52,211 +56,358 @@ struct TcParams {
   int emb_ld;
   const __nv_bfloat16* residual;
   void* out;
-  int out_f32;
-  int out_ld;
-  int cout;
+  int out_f32, out_ld, cout;
   int qkv_split;
   __nv_bfloat16* out_vt;
-  int images;
-  float* stats;   // [images, cout, 2] GroupNorm partial sums of the stored output, or null
+  float* stats;
+  long long* dbg_out;   // test hook: per-CTA cycle counters of the MMA thread [grid][4] = total, wait A, wait B, wait acc
+  int dbg;        // test hook (vf_debug_flags): bit0 no stats, bit1 no store, bit2 no unit work, bit3 no bias table
+  int epi_tma;    // staged TMA epilogue enabled (bf16 row-contiguous output, block_n % 64 == 0)
 };
 
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0,
-                                                             const __grid_constant__ CUtensorMap mapA1,
-                                                             const __grid_constant__ CUtensorMap mapA2,
-                                                             const __grid_constant__ CUtensorMap mapB,
-                                                             const TcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0,
+                                                                const __grid_constant__ CUtensorMap mapA1,
+                                                                const __grid_constant__ CUtensorMap mapA2,
+                                                                const __grid_constant__ CUtensorMap mapB,
+                                                                const __grid_constant__ CUtensorMap mapOut,
+                                                                const __grid_constant__ CUtensorMap mapRes,
+                                                                const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* gbase = smem_raw + (base - raw);
-  // header (first 1 KB): barriers, tmem pointer; then bias/emb table; then the ring
-  const uint32_t bar_full = base;                         // stages x 8 B
-  const uint32_t bar_empty = base + 64;                   // stages x 8 B
-  const uint32_t bar_tmem = base + 128;                   // 8 B
-  const uint32_t tmem_slot = base + 136;                  // 4 B
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + 136);
-  float* sm_bias = reinterpret_cast<float*>(gbase + 1024);                 // [box_n][block_n]
-  const uint32_t bias_bytes = ((uint32_t)(p.box_n * p.block_n * 4) + 1023u) & ~1023u;
-  const uint32_t ring = base + 1024 + bias_bytes;
-  const uint32_t a_bytes = TC_BM * TC_BK * 2;
+  // header (1 KB): barriers + tmem pointer; bias/emb table; A ring; B ring
+  const uint32_t bar_afull = base, bar_aempty = base + 32, bar_bfull = base + 64, bar_bempty = base + 192;
+  const uint32_t bar_accfull = base + 320, bar_accempty = base + 336;
+  const uint32_t tmem_slot = base + 352;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + 352);
+  float* sm_bias_all = reinterpret_cast<float*>(gbase + 1024);             // 2 x [max_imgs][block_n] (one per epilogue group)
+  const uint32_t bias_bytes = ((uint32_t)(p.max_imgs * p.block_n * 4) + 1023u) & ~1023u;
+  const uint32_t ringA = base + 1024 + 2 * bias_bytes;
+  const uint32_t ringB = ringA + (uint32_t)p.a_stages * (uint32_t)p.a_stage_bytes;
   const uint32_t b_bytes = (uint32_t)p.block_n * TC_BK * 2;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const int BM = 128 * p.G;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tile_m = blockIdx.x;
-  const int n0 = blockIdx.y * p.block_n;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) {
-      ptx::mbar_init(bar_full + 8 * s, 1);
-      ptx::mbar_init(bar_empty + 8 * s, 1);
-    }
-    ptx::mbar_init(bar_tmem, 1);
+    for (int s = 0; s < p.a_stages; ++s) { ptx::mbar_init(bar_afull + 8 * s, 1); ptx::mbar_init(bar_aempty + 8 * s, 1); }
+    for (int s = 0; s < (p.b_resident ? 1 : p.b_stages); ++s) { ptx::mbar_init(bar_bfull + 8 * s, 1); ptx::mbar_init(bar_bempty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(bar_accfull + 8 * s, 1); ptx::mbar_init(bar_accempty + 8 * s, 256); }
     ptx::fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     ptx::prefetch_tmap(&mapA0);
     ptx::prefetch_tmap(&mapB);
     if (p.n_seg > 1) ptx::prefetch_tmap(&mapA1);
     if (p.n_seg > 2) ptx::prefetch_tmap(&mapA2);
   }
-  if (warp == 5) {
+  if (warp == 9) {
     ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_d = *tmem_slot_ptr;
+  const uint32_t tmem_base = *tmem_slot_ptr;
 
-  // tile origin in (image, row) space; box_w == W always
-  int img0, y0;
-  if (p.box_n == 1) {
-    const int tiles_per_img = p.HW / TC_BM;
-    img0 = tile_m / tiles_per_img;
-    y0 = (tile_m % tiles_per_img) * p.box_h;
-  } else {
-    img0 = tile_m * p.box_n;
-    y0 = 0;
-  }
-
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int it = 0;
-      for (int s = 0; s < p.n_seg; ++s) {
-        const TcSeg sg = p.seg[s];
-        const CUtensorMap* mA = s == 0 ? &mapA0 : (s == 1 ? &mapA1 : &mapA2);
-        for (int tap = 0; tap < sg.ntaps; ++tap) {
-          const int kh = sg.ntaps == 9 ? tap / 3 : 1, kw = sg.ntaps == 9 ? tap % 3 : 1;
-          for (int ch = 0; ch < sg.nchunks; ++ch, ++it) {
-            const int stage = it % p.stages;
-            const uint32_t phase = (uint32_t)(it / p.stages) & 1u;
-            ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-            const uint32_t fb = bar_full + 8 * stage;
-            ptx::mbar_arrive_expect_tx(fb, stage_bytes);
-            const uint32_t sa = ring + stage * stage_bytes;
-            const uint32_t sb = sa + a_bytes;
-            if (sg.mode == 0) {
-              ptx::tma_load_4d(sa, mA, fb, ch * TC_BK, kw - 1, y0 + kh - 1, img0);
-            } else {
-              // input pixel (2y+kh-1, 2x+kw-1): parity = (k != 1), half-index offset = (k == 0 ? -1 : 0)
-              const int wp = kw != 1, hp = kh != 1;
-              ptx::tma_load_5d(sa, mA, fb, wp * sg.C + ch * TC_BK, kw == 0 ? -1 : 0, hp, y0 + (kh == 0 ? -1 : 0), img0);
+      int a_it = 0, b_it = 0;
+      if (p.b_resident) {                        // weights-stationary: every tap's tile is loaded once per CTA
+        ptx::mbar_arrive_expect_tx(bar_bfull, (uint32_t)p.b_stages * b_bytes);
+        int bt = 0;
+        for (int s = 0; s < p.n_seg; ++s)
+          for (int ch = 0; ch < p.seg[s].nchunks; ++ch)
+            for (int tap = 0; tap < p.seg[s].ntaps; ++tap, ++bt)
+              ptx::tma_load_2d(ringB + bt * b_bytes, &mapB, bar_bfull, p.seg[s].koff + tap * p.seg[s].C + ch * TC_BK, 0);
+      }
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int n_tile = item / p.n_mblocks, m_blk = item - n_tile * p.n_mblocks;   // neighbours share the weight tile
+        const int m0 = m_blk * BM, n0 = n_tile * p.block_n;
+        for (int s = 0; s < p.n_seg; ++s) {
+          const TcSeg sg = p.seg[s];
+          const CUtensorMap* mA = s == 0 ? &mapA0 : (s == 1 ? &mapA1 : &mapA2);
+          const int nbox = (BM + 2 * sg.halo + TC_ABOX - 1) / TC_ABOX;
+          for (int ch = 0; ch < sg.nchunks; ++ch, ++a_it) {
+            const int as = a_it % p.a_stages;
+            ptx::mbar_wait(bar_aempty + 8 * as, ((uint32_t)(a_it / p.a_stages) & 1u) ^ 1u);
+            const uint32_t fa = bar_afull + 8 * as;
+            ptx::mbar_arrive_expect_tx(fa, (uint32_t)nbox * TC_ABOX * 128);
+            const uint32_t sa = ringA + (uint32_t)as * (uint32_t)p.a_stage_bytes;
+            for (int b = 0; b < nbox; ++b)
+              ptx::tma_load_2d(sa + b * (TC_ABOX * 128), mA, fa, ch * TC_BK, m0 - sg.halo + b * TC_ABOX);
+            for (int tap = 0; tap < sg.ntaps && !p.b_resident; ++tap, ++b_it) {
+              const int bs = b_it % p.b_stages;
+              ptx::mbar_wait(bar_bempty + 8 * bs, ((uint32_t)(b_it / p.b_stages) & 1u) ^ 1u);
+              const uint32_t fb = bar_bfull + 8 * bs;
+              ptx::mbar_arrive_expect_tx(fb, b_bytes);
+              ptx::tma_load_2d(ringB + bs * b_bytes, &mapB, fb, sg.koff + tap * sg.C + ch * TC_BK, n0);
             }
-            ptx::tma_load_2d(sb, &mapB, fb, sg.koff + tap * sg.C + ch * TC_BK, n0);
           }
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      for (int it = 0; it < p.num_k_iters; ++it) {
-        const int stage = it % p.stages;
-        const uint32_t phase = (uint32_t)(it / p.stages) & 1u;
-        ptx::mbar_wait(bar_full + 8 * stage, phase);
+      int a_it = 0, b_it = 0, it_idx = 0;
+      const uint64_t desc0 = ptx::make_smem_desc(0, 16, 1024);     // K-major SWIZZLE_128B, start address 0
+      const int G = p.G, block_n = p.block_n;
+      const uint32_t idesc = p.idesc;
+      const bool resident = p.b_resident != 0;
+      if (resident) ptx::mbar_wait(bar_bfull, 0);
+      long long t_a = 0, t_b = 0, t_acc = 0;
+      const long long t_start = clock64();
+      const bool prof = p.dbg_out != nullptr;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_idx) {
+        const int set = it_idx & 1;
+        if (resident) b_it = 0;
+        long long t0 = prof ? clock64() : 0;
+        ptx::mbar_wait(bar_accempty + 8 * set, ((uint32_t)(it_idx >> 1) & 1u) ^ 1u);
+        if (prof) t_acc += clock64() - t0;
         ptx::tc_fence_after();
-        const uint32_t sa = ring + stage * stage_bytes;
-        const uint32_t sb = sa + a_bytes;
-#pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          const uint64_t ad = ptx::make_smem_desc(sa + k * 32, 16, 1024);
-          const uint64_t bd = ptx::make_smem_desc(sb + k * 32, 16, 1024);
-          ptx::umma_f16(tmem_d, ad, bd, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+        const uint32_t acc0 = tmem_base + (uint32_t)(set * p.G * p.block_n);
+        bool first = true;
+        for (int s = 0; s < p.n_seg; ++s) {
+          const TcSeg sg = p.seg[s];
+          for (int ch = 0; ch < sg.nchunks; ++ch, ++a_it) {
+            const int as = a_it % p.a_stages;
+            t0 = prof ? clock64() : 0;
+            ptx::mbar_wait(bar_afull + 8 * as, (uint32_t)(a_it / p.a_stages) & 1u);
+            if (prof) t_a += clock64() - t0;
+            const uint32_t sa = ringA + (uint32_t)as * (uint32_t)p.a_stage_bytes;
+            for (int tap = 0; tap < sg.ntaps; ++tap, ++b_it) {
+              const int bs = b_it % p.b_stages;
+              t0 = prof ? clock64() : 0;
+              if (!resident) ptx::mbar_wait(bar_bfull + 8 * bs, (uint32_t)(b_it / p.b_stages) & 1u);
+              if (prof) t_b += clock64() - t0;
+              ptx::tc_fence_after();
+              const uint32_t sb = ringB + bs * b_bytes;
+              // the slab starts `halo` rows before the block: tap (kh, kw) begins at row kh*(W+1) + kw
+              const int shift = sg.ntaps == 9 ? (tap / 3) * p.geo.W1 + (tap % 3) : 0;
+              // descriptors differ only in the 14-bit start-address field: base + (byte offset >> 4)
+              const uint64_t bd = desc0 + (uint64_t)((sb & 0x3FFFF) >> 4);
+              const uint64_t ad0 = desc0 + (uint64_t)(((sa + (uint32_t)shift * 128u) & 0x3FFFF) >> 4);
+              for (int g = 0; g < G; ++g)
+                ptx::umma_f16_k4(acc0 + (uint32_t)(g * block_n), ad0 + (uint64_t)(g * 1024), bd, idesc, first ? 0u : 1u);
+              first = false;
+              if (!resident) ptx::umma_commit(bar_bempty + 8 * bs);
+            }
+            ptx::umma_commit(bar_aempty + 8 * as);
+          }
         }
-        ptx::umma_commit(bar_empty + 8 * stage);   // smem slot is free once these MMAs have read it
+        ptx::umma_commit(bar_accfull + 8 * set);
       }
-      ptx::umma_commit(bar_tmem);                  // accumulator complete
+      if (prof) {
+        long long* o = p.dbg_out + blockIdx.x * 4;
+        o[0] = clock64() - t_start; o[1] = t_a; o[2] = t_b; o[3] = t_acc;
+      }
     }
   } else {
-    // ===================== epilogue (warps 0..3 == TMEM lane quarters 0..3) =====================
-    // bias + embedding table for this tile, built while the main loop runs
-    for (int i = threadIdx.x; i < p.box_n * p.block_n; i += 128) {
-      const int li = i / p.block_n, n = n0 + i % p.block_n;
-      const int img = img0 + li;
-      float v = 0.f;
-      if (n < p.cout) {
-        if (p.bias) v += __ldg(p.bias + n);
-        if (p.emb && img < p.images) v += __ldg(p.emb + (size_t)__ldg(p.img_row + img) * p.emb_ld + n);
+    // ===================== epilogue: 8 warps = 2 x 4 TMEM lane quarters =====================
+    // A unit is (accumulator g, 64-column panel): G * ceil(block_n/64) <= 4 per work item; the two warps of a lane
+    // quarter take alternate units of the same item.
+    // Fast path (bf16 output whose 32 rows per warp are contiguous in memory): the thread adds accumulator + bias
+    // (+ a TMA-fetched residual panel) in a 128B-swizzled staging tile, the tile leaves by TMA store, and the GroupNorm
+    // column sums are read back from the tile: no scattered LSU traffic.
+    // Fallback (fp32 / qkv / stride-2 / non-contiguous rows): row-per-thread global accesses.
+    const int q = warp & 3, sub = warp >> 2;                     // sub in {0, 1}
+    const int et = threadIdx.x;                                  // 0..255
+    const int npanel = (p.block_n + 63) / 64;
+    const int U = p.G * npanel;                                  // <= 4
+    float* sm_bias = sm_bias_all;
+    const uint32_t stg = ringB + (uint32_t)p.b_stages * b_bytes + (uint32_t)warp * 4096u;   // one 4 KB tile per warp
+    uint8_t* stg_g = gbase + (stg - base);
+    const uint32_t rbar = base + 384 + (uint32_t)warp * 8;
+    if (lane == 0) { ptx::mbar_init(rbar, 1); ptx::fence_barrier_init(); }
+    __syncwarp();
+    uint32_t res_phase = 0;
+    const bool has_res = p.residual != nullptr;
+    int k_idx = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++k_idx) {
+      const int set = k_idx & 1;
+      const int n_tile = item / p.n_mblocks, m_blk = item - n_tile * p.n_mblocks;
+      const int m0 = m_blk * BM, n0 = n_tile * p.block_n;
+      const int img_first = m0 / (p.geo.in_padded ? p.geo.P : p.geo.HW);
+      // bias + embedding rows of the images this block touches (built while the main loop runs)
+      if (!(p.dbg & 8)) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // previous item's readers are done
+      for (int i = et; i < p.max_imgs * p.block_n; i += 256) {
+        const int li = i / p.block_n, n = n0 + i - li * p.block_n;
+        const int img = img_first + li;
+        float v = 0.f;
+        if (n < p.cout) {
+          if (p.bias) v += __ldg(p.bias + n);
+          if (p.emb && img < p.geo.images) v += __ldg(p.emb + (size_t)__ldg(p.img_row + img) * p.emb_ld + n);
+        }
+        sm_bias[i] = v;
       }
-      sm_bias[i] = v;
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
 
-    const int r = warp * 32 + lane;                 // row in tile == TMEM lane
-    const int m = tile_m * TC_BM + r;
-    const bool valid = m < p.M;
-    const int img = valid ? m / p.HW : 0;
-    const int pix = valid ? m % p.HW : 0;
-    const float* brow = sm_bias + (p.box_n == 1 ? 0 : (r / p.HW)) * p.block_n;
+      // the first unit's residual is fetched under the main loop
+      RowInfo ri{};
+      long row_base = 0;
+      bool contig = false;
+      auto prep_unit = [&](int u, bool issue) {
+        const int g = u / npanel, c0 = (u - g * npanel) * 64;
+        ri = decode_row(p.geo, m0 + g * 128 + q * 32 + lane);
+        row_base = __shfl_sync(0xffffffffu, ri.out_row, 0);
+        contig = p.epi_tma && __all_sync(0xffffffffu, ri.out_row == row_base + lane);
+        if (issue && contig) {
+          if (lane == 0) {
+            if (has_res) {
+              ptx::tma_store_wait_read<0>();               // the staging tile's previous store has been read out
+              ptx::mbar_arrive_expect_tx(rbar, 4096);
+              ptx::tma_load_2d(stg, &mapRes, rbar, n0 + c0, (int)row_base);
+            }
+          }
+          __syncwarp();
+        }
+      };
+      if (sub < U) prep_unit(sub, true);
 
-    ptx::mbar_wait(bar_tmem, 0);
-    ptx::tc_fence_after();
-    const uint32_t trow = tmem_d + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-      uint32_t rr[16];
-      ptx::tmem_ld16(trow + (uint32_t)c0, rr);
-      ptx::tmem_ld_wait();
-      const int n = n0 + c0;
-      const bool act = valid && (n < p.cout || p.out_f32);   // structured: the warp reconverges before the next tcgen05.ld
-      float v[16];
+      ptx::mbar_wait(bar_accfull + 8 * set, (uint32_t)(k_idx >> 1) & 1u);
+      ptx::tc_fence_after();
+      for (int u = sub; u < U && !(p.dbg & 4); u += 2) {
+        const int g = u / npanel, c0 = (u - g * npanel) * 64;
+        const int width = min(64, p.block_n - c0);
+        if (u != sub) prep_unit(u, true);
+        const bool valid = ri.valid;
+        const int li = ri.img - img_first;
+        const float* brow = sm_bias + (li < p.max_imgs ? li : 0) * p.block_n + c0;
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((set * p.G + g) * p.block_n + c0);
+        const int img_lo = __shfl_sync(0xffffffffu, ri.img, 0), img_hi = __shfl_sync(0xffffffffu, ri.img, 31);
+        if (contig) {
+          // ---------------- fast path: staged through shared memory, TMA in / TMA out ----------------
+          uint8_t* tile = stg_g + lane * 128;                                // this thread's 128-byte row
+          if (has_res) { ptx::mbar_wait(rbar, res_phase); res_phase ^= 1u; }
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = act ? __uint_as_float(rr[j]) + brow[c0 + j] : 0.f;
-      if (act && p.residual) {
-        const __nv_bfloat16* rp = p.residual + (size_t)m * p.cout + n;
-        float r0[8], r1[8];
-        load_vec(rp, r0);
-        load_vec(rp + 8, r1);
+          for (int hh = 0; hh < 2; ++hh) {                                   // two 32-column halves (register budget)
+            uint32_t rr[2][16];
+            ptx::tmem_ld16(trow + 32 * hh, rr[0]);
+            ptx::tmem_ld16(trow + 32 * hh + 16, rr[1]);
+            if (hh == 0 && !has_res) {                                       // the previous store must have read the tile
+              if (lane == 0) ptx::tma_store_wait_read<0>();                  // out; overlaps with the TMEM load latency
+              __syncwarp();
+            }
+            ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { v[j] += r0[j]; v[8 + j] += r1[j]; }
-      }
-      if (!p.out_f32) {
+            for (int jj = 0; jj < 4; ++jj) {                                 // 8 channels = one 16-byte slot
+              const int j = hh * 4 + jj;
+              uint4* slot = reinterpret_cast<uint4*>(tile + ((j ^ (lane & 7)) << 4));
+              const float4 b0 = *reinterpret_cast<const float4*>(brow + j * 8), b1 = *reinterpret_cast<const float4*>(brow + j * 8 + 4);
+              float v[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));   // what is stored (and normalised later)
-      }
-      if (act) {
-        if (p.out_f32) {
-          float* op = reinterpret_cast<float*>(p.out) + (size_t)m * p.out_ld + n;
-          const int cnt = min(16, p.out_ld - n);     // out_ld is the padded channel count of the fp32 output
-          for (int j = 0; j + 4 <= cnt; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else if (p.qkv_split > 0 && n >= 2 * p.qkv_split) {
-          __nv_bfloat16* vp = p.out_vt + ((size_t)img * p.qkv_split + (n - 2 * p.qkv_split)) * p.HW + pix;
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(rr[jj >> 1][(jj & 1) * 8 + e]);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              if (has_res) {
+                const uint4 rv = *slot;
+                const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) vp[(size_t)j * p.HW] = __float2bfloat16_rn(v[j]);
-        } else {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.out_ld + n;
-          float lo[8], hi[8];
+                for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(rb[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+              }
+              uint4 o;
+              __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
-          store_vec(op, lo);
-          store_vec(op + 8, hi);
+              for (int e = 0; e < 4; ++e) ob[e] = valid ? __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]) : __floats2bfloat162_rn(0.f, 0.f);
+              *slot = o;                                                     // padding rows are stored as zeros
+            }
+          }
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && !(p.dbg & 2)) {
+            ptx::tma_store_2d(&mapOut, stg, n0 + c0, (int)row_base);
+            ptx::tma_store_commit();
+          }
+          if (p.stats && !(p.dbg & 1)) {
+            // column sums straight from the staging tile: lane owns channels (2*lane, 2*lane+1); conflict-free reads
+            for (int im = img_lo; im <= img_hi; ++im) {
+              const uint32_t rows = __ballot_sync(0xffffffffu, ri.img == im);
+              float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) {
+                if (!((rows >> r) & 1u)) continue;
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(stg_g + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+                s0 += f.x; q0 += f.x * f.x; s1 += f.y; q1 += f.y * f.y;
+              }
+              if (im < p.geo.images) {
+                float* sp = p.stats + ((size_t)im * p.cout + n0 + c0 + 2 * lane) * 2;
+                atomicAdd(sp, s0); atomicAdd(sp + 1, q0); atomicAdd(sp + 2, s1); atomicAdd(sp + 3, q1);
+              }
+            }
+          }
+        } else if (__any_sync(0xffffffffu, valid)) {
+          // ---------------- fallback: row-per-thread global accesses, 16 columns at a time ----------------
+          for (int cc = 0; cc < width; cc += 16) {
+            uint32_t rr[16];
+            ptx::tmem_ld16(trow + (uint32_t)cc, rr);
+            ptx::tmem_ld_wait();
+            const int n = n0 + c0 + cc;
+            const bool act = valid && (n < p.cout || p.out_f32);  // structured: the warp reconverges before the next tcgen05.ld
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = act ? __uint_as_float(rr[j]) + brow[cc + j] : 0.f;
+            if (act && p.residual) {
+              const __nv_bfloat16* rp = p.residual + (size_t)ri.out_row * p.cout + n;
+              float r0[8], r1[8];
+              load_vec(rp, r0);
+              load_vec(rp + 8, r1);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { v[j] += r0[j]; v[8 + j] += r1[j]; }
+            }
+            if (!p.out_f32) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));   // what is stored (and normalised later)
+            }
+            if (act) {
+              if (p.out_f32) {
+                float* op = reinterpret_cast<float*>(p.out) + (size_t)ri.out_row * p.out_ld + n;
+                const int cnt = min(16, p.out_ld - n);     // out_ld is the padded channel count of the fp32 output
+                for (int j = 0; j + 4 <= cnt; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else if (p.qkv_split > 0 && n >= 2 * p.qkv_split) {
+                __nv_bfloat16* vp = p.out_vt + ((size_t)ri.img * p.qkv_split + (n - 2 * p.qkv_split)) * p.geo.HW + ri.pix;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) vp[(size_t)j * p.geo.HW] = __float2bfloat16_rn(v[j]);
+              } else {
+                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)ri.out_row * p.out_ld + n;
+                float lo[8], hi[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
+                store_vec(op, lo);
+                store_vec(op + 8, hi);
+              }
+            }
+            if (p.stats && n < p.cout) {
+              for (int im = img_lo; im <= img_hi; ++im) {
+                float s1[16], s2[16];
+                const bool own = valid && ri.img == im;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { s1[j] = own ? v[j] : 0.f; s2[j] = s1[j] * s1[j]; }
+                const float cs = warp_colsum16(s1, lane), cq = warp_colsum16(s2, lane);
+                if ((lane & 1) == 0 && im < p.geo.images) {
+                  float* sp = p.stats + ((size_t)im * p.cout + n + warp_col16(lane)) * 2;
+                  atomicAdd(sp, cs);
+                  atomicAdd(sp + 1, cq);
+                }
+              }
+            }
+          }
         }
       }
-      if (p.stats && n < p.cout) {
-        // GroupNorm partial sums of the stored values, column-reduced over the warp's 32 pixels (16 + 16 shuffles).
-        // HW % 32 == 0 (checked on the host), so a warp never straddles two images; invalid rows contribute zeros.
-        float sq[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
-        const float cs = warp_colsum16(v, lane), cq = warp_colsum16(sq, lane);
-        const int wimg = __shfl_sync(0xffffffffu, img, 0);
-        const int wvalid = __shfl_sync(0xffffffffu, (int)valid, 0);
-        if (wvalid && (lane & 1) == 0) {
-          float* sp = p.stats + ((size_t)wimg * p.cout + n + warp_col16(lane)) * 2;
-          atomicAdd(sp, cs);
-          atomicAdd(sp + 1, cq);
-        }
-      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar_accempty + 8 * set);
     }
-    ptx::tc_fence_before();
+    if (lane == 0) ptx::tma_store_wait_all<0>();     // staged stores must land before the CTA exits
   }
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_d, (uint32_t)p.tmem_cols);
+    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -300,62 +451,131 @@ int encode_bf16_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* d
   return VF_OK;
 }
 
-static int pick_block_n(int cout_pad) {
-  for (int t = 1; t <= 16; ++t)
-    if (cout_pad % t == 0 && cout_pad / t <= 256 && (cout_pad / t) % 16 == 0) return cout_pad / t;
-  return 0;
+static int g_tc_dbg = 0;     // test hook: see vf_debug_flags
+static long long* g_tc_dbg_out = nullptr;
+void set_tc_debug(int f) { g_tc_dbg = f; }
+void set_tc_debug_out(long long* p) { g_tc_dbg_out = p; }
+
+// ---- tiling choice -------------------------------------------------------------------------------------
+struct TcTiling {
+  int block_n = 0, G = 0, a_stages = 0, b_stages = 0, a_stage_bytes = 0, max_imgs = 0, b_resident = 0;
+  size_t smem = 0;
+  double cost = 0;
+};
+
+static const double kIngestBytesPerClk = 42.5;   // L2 -> SM, per SM (B300_MICROARCH.md: ~6300 B/clk chip-wide / 148)
+static const size_t kSmemBudget = 227 * 1024;
+
+static bool pick_tiling(const TcParams& p, int cout_pad, int sms, bool epi_tma, TcTiling* best) {
+  bool found = false;
+  const int rows_per_img = p.geo.in_padded ? p.geo.P : p.geo.HW;
+  int halo_max = 0;
+  long chunks = 0, taps = 0;
+  for (int s = 0; s < p.n_seg; ++s) {
+    halo_max = p.seg[s].halo > halo_max ? p.seg[s].halo : halo_max;
+    chunks += p.seg[s].nchunks;
+    taps += (long)p.seg[s].nchunks * p.seg[s].ntaps;
+  }
+  for (int t = 1; t <= 32; ++t) {
+    if (cout_pad % t) continue;
+    const int bn = cout_pad / t;
+    if (bn > 256 || bn % 16) continue;
+    if (epi_tma && bn % 64) continue;
+    const int force_bn = ((g_tc_dbg >> 20) & 0xFF) * 16, force_g = (g_tc_dbg >> 16) & 0xF;     // test hook: tiling sweep
+    if (force_bn && bn != force_bn) continue;
+    for (int G = 1; G <= 4; ++G) {
+      if (force_g && G != force_g) continue;
+      if (2 * G * bn > 512) continue;
+      if (G * ((bn + 63) / 64) > 4) continue;      // one epilogue warp per (accumulator, 64-column panel) and lane quarter
+      const int BM = 128 * G;
+      TcTiling c;
+      c.block_n = bn; c.G = G;
+      c.a_stage_bytes = (int)align_up((size_t)BM + 2 * halo_max, TC_ABOX) * 128;
+      c.max_imgs = (BM + rows_per_img - 1) / rows_per_img + 1;
+      const size_t bias_bytes = align_up((size_t)c.max_imgs * bn * 4, 1024);
+      const size_t fixed = 1024 + 1024 + 2 * bias_bytes + (epi_tma ? 8 * 4096 : 0);   // + staging tiles of the TMA epilogue
+      const size_t bstage = (size_t)bn * 128;
+      // pipeline depth is a hard requirement (both rings run across work items): >= 2 A slabs so the next slab
+      // loads under the current one's MMAs, >= 4 weight tiles so a tap never waits for its own load
+      c.a_stages = 2;
+      if (!(g_tc_dbg & 512) && t == 1 && taps <= 64 && fixed + 2 * (size_t)c.a_stage_bytes + (size_t)taps * bstage <= kSmemBudget) {
+        c.b_resident = 1;                        // weights-stationary: the whole [cout x K] tile lives in smem
+        c.b_stages = (int)taps;
+      } else {
+        const int b_min = taps < 4 ? (int)taps : 4;
+        if (fixed + (size_t)c.a_stages * c.a_stage_bytes + (size_t)b_min * bstage > kSmemBudget) continue;
+        size_t left = kSmemBudget - fixed - (size_t)c.a_stages * c.a_stage_bytes;
+        c.b_stages = (int)(left / bstage);
+        if (c.b_stages > TC_MAX_STAGES) c.b_stages = TC_MAX_STAGES;
+      }
+      // a third A slab when there is room
+      if (fixed + (size_t)3 * c.a_stage_bytes + (size_t)c.b_stages * bstage <= kSmemBudget) c.a_stages = 3;
+      c.smem = fixed + (size_t)c.a_stages * c.a_stage_bytes + (size_t)c.b_stages * bstage;
+      // cost model per work item
+      double bytes = 0, cyc = 0;
+      for (int s = 0; s < p.n_seg; ++s) {
+        const TcSeg& sg = p.seg[s];
+        const double arows = (double)align_up((size_t)BM + 2 * sg.halo, TC_ABOX);
+        bytes += sg.nchunks * (arows * 128.0 + (c.b_resident ? 0.0 : sg.ntaps * bn * 128.0));
+        // measured in situ (vf_debug_counters): the single issuing thread sustains one MMA per ~120 clk for N <= 128 and
+        // ~N/2 + 95 beyond, i.e. wide MMAs are what keeps the tensor pipe busy; + ~250 clk of barrier work per tap
+        const double per_mma = (bn <= 128 ? 120.0 : bn / 2.0 + 95.0) + 250.0 / (4.0 * G);
+        cyc += (double)sg.nchunks * sg.ntaps * 4 * G * per_mma;
+      }
+      // the epilogue of an item is a latency chain of a few microseconds; it overlaps the next item's main loop
+      const double epi = 5000.0 + 1200.0 * ((G * ((bn + 63) / 64) + 1) / 2);
+      double item = cyc > bytes / kIngestBytesPerClk ? cyc : bytes / kIngestBytesPerClk;
+      if (epi > item) item = epi;
+      const long items = (long)((p.geo.rows_total + BM - 1) / BM) * t;
+      const long rounds = (items + sms - 1) / sms;
+      c.cost = rounds * item + 3000.0;
+      if (!found || c.cost < best->cost * 0.999 || (c.cost < best->cost * 1.001 && bn > best->block_n)) { *best = c; found = true; }
+    }
+  }
+  return found;
 }
 
 int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
   VF_REQUIRE(a->dtype == VF_BF16, "vf_conv2d(tc): bf16 activations only");
   const int H = a->H, W = a->W;
-  VF_REQUIRE(W <= TC_BM && (W & (W - 1)) == 0 && (H & (H - 1)) == 0, "vf_conv2d(tc): H=%d W=%d must be powers of two <= 128", H, W);
   TcParams p{};
-  p.H = H; p.W = W; p.HW = H * W; p.images = a->images; p.M = a->images * H * W;
-  p.box_w = W;
-  p.box_h = (TC_BM / W) < H ? (TC_BM / W) : H;
-  p.box_n = TC_BM / (p.box_w * p.box_h);
-  VF_REQUIRE(p.box_n <= TC_MAX_BOXN, "vf_conv2d(tc): feature map %dx%d too small", H, W);
+  p.geo = make_geom(a->images, H, W, a->in_padded, a->out_padded, a->stride == 2);
+  VF_REQUIRE(!p.geo.stride2 || (H % 2 == 0 && W % 2 == 0), "vf_conv2d(tc): stride 2 needs even H, W");
   VF_REQUIRE(a->cout_pad % 16 == 0, "vf_conv2d(tc): cout_pad=%d not a multiple of 16", a->cout_pad);
-  p.block_n = pick_block_n(a->cout_pad);
-  VF_REQUIRE(p.block_n > 0, "vf_conv2d(tc): no N tiling for cout_pad=%d", a->cout_pad);
-  p.tmem_cols = 32;
-  while (p.tmem_cols < p.block_n) p.tmem_cols *= 2;
-  p.idesc = ptx::make_idesc_bf16(TC_BM, p.block_n, 0, 0);
 
-  CUtensorMap maps[3];
   int k_total = 0;
   p.n_seg = a->n_seg;
-  p.num_k_iters = 0;
   for (int s = 0; s < a->n_seg; ++s) {
     const int C = a->src_c[s];
     VF_REQUIRE(C % TC_BK == 0, "vf_conv2d(tc): segment %d channels %d not a multiple of 64", s, C);
-    VF_REQUIRE(a->ksize[s] == 1 || a->ksize[s] == 3, "vf_conv2d(tc): ksize must be 1 or 3");
-    const int stride = s == 0 ? a->stride : 1;
-    VF_REQUIRE(stride == 1 || (stride == 2 && a->ksize[s] == 3), "vf_conv2d(tc): stride 2 needs ksize 3");
+    VF_REQUIRE(a->ksize[s] == 1 || (a->ksize[s] == 3 && a->in_padded), "vf_conv2d(tc): 3x3 needs PADDED sources");
     TcSeg& sg = p.seg[s];
-    sg.ntaps = a->ksize[s] * a->ksize[s];
-    sg.nchunks = C / TC_BK;
-    sg.C = C;
-    sg.mode = stride == 2 ? 2 : 0;
-    sg.koff = k_total;
+    sg.C = C; sg.nchunks = C / TC_BK; sg.ntaps = a->ksize[s] * a->ksize[s]; sg.koff = k_total;
+    sg.halo = a->ksize[s] == 3 ? W + 2 : 0;
     k_total += sg.ntaps * C;
-    p.num_k_iters += sg.ntaps * sg.nchunks;
-    if (stride == 1) {
-      const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)a->images};
-      const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
-      const uint32_t box[4] = {TC_BK, (uint32_t)p.box_w, (uint32_t)p.box_h, (uint32_t)p.box_n};
-      int rc = encode_bf16_map(&maps[s], a->src[s], 4, dims, strides, box);
-      if (rc) return rc;
-    } else {
-      const int Win = 2 * W, Hin = 2 * H;
-      const uint64_t dims[5] = {(uint64_t)2 * C, (uint64_t)W, 2, (uint64_t)H, (uint64_t)a->images};
-      const uint64_t strides[4] = {(uint64_t)2 * C * 2, (uint64_t)Win * C * 2, (uint64_t)2 * Win * C * 2,
-                                   (uint64_t)Hin * Win * C * 2};
-      const uint32_t box[5] = {TC_BK, (uint32_t)p.box_w, 1, (uint32_t)p.box_h, (uint32_t)p.box_n};
-      int rc = encode_bf16_map(&maps[s], a->src[s], 5, dims, strides, box);
-      if (rc) return rc;
-    }
+  }
+  const bool out_f32 = a->out_dtype == VF_F32;
+  p.epi_tma = !out_f32 && !a->qkv_split && !p.geo.stride2 && a->out_padded && a->cout_pad % 64 == 0 && a->cout == a->cout_pad &&
+              (a->in_padded || W % 32 == 0);
+  TcTiling tl;
+  VF_REQUIRE(pick_tiling(p, a->cout_pad, sm_count(), p.epi_tma != 0, &tl), "vf_conv2d(tc): no tiling for cout_pad=%d W=%d", a->cout_pad, W);
+  p.block_n = tl.block_n; p.G = tl.G; p.a_stages = tl.a_stages; p.b_stages = tl.b_stages; p.a_stage_bytes = tl.a_stage_bytes;
+  p.b_resident = tl.b_resident;
+  p.max_imgs = tl.max_imgs;
+  p.n_tiles_n = a->cout_pad / p.block_n;
+  p.n_mblocks = cdiv(p.geo.rows_total, 128 * p.G);
+  p.n_items = p.n_mblocks * p.n_tiles_n;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < 2 * p.G * p.block_n) p.tmem_cols *= 2;
+  p.idesc = ptx::make_idesc_bf16(128, p.block_n, 0, 0);
+
+  CUtensorMap maps[3];
+  for (int s = 0; s < a->n_seg; ++s) {
+    const uint64_t dims[2] = {(uint64_t)a->src_c[s], (uint64_t)p.geo.rows_total};
+    const uint64_t strides[1] = {(uint64_t)a->src_c[s] * 2};
+    const uint32_t box[2] = {TC_BK, TC_ABOX};
+    int rc = encode_bf16_map(&maps[s], a->src[s], 2, dims, strides, box);
+    if (rc) return rc;
   }
   for (int s = a->n_seg; s < 3; ++s) maps[s] = maps[0];
   CUtensorMap mapB;
@@ -372,29 +592,42 @@ int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
   p.out = a->out; p.out_f32 = a->out_dtype == VF_F32; p.out_ld = a->out_ld; p.cout = a->cout;
   p.qkv_split = a->qkv_split; p.out_vt = reinterpret_cast<__nv_bfloat16*>(a->out_vt);
   p.stats = a->stats;
-  VF_REQUIRE(!a->stats || ((H * W) % 32 == 0 && !p.out_f32 && !a->qkv_split), "vf_conv2d(tc): fused statistics need H*W %% 32 == 0 and a plain bf16 output");
+  p.dbg = g_tc_dbg;
+  p.dbg_out = g_tc_dbg_out;
   VF_REQUIRE(!p.out_f32 || (a->out_ld % 4 == 0 && a->out_ld <= a->cout_pad && !a->residual), "vf_conv2d(tc): bad fp32 output layout");
   VF_REQUIRE(p.out_f32 || (a->cout % 16 == 0 && a->out_ld % 8 == 0), "vf_conv2d(tc): bf16 output needs cout %% 16 == 0");
-  VF_REQUIRE(!a->qkv_split || (a->qkv_split % 16 == 0 && a->out_vt), "vf_conv2d(tc): bad qkv split");
+  VF_REQUIRE(!a->qkv_split || (a->qkv_split % 16 == 0 && a->out_vt && !a->out_padded && !p.geo.stride2), "vf_conv2d(tc): bad qkv split");
+  VF_REQUIRE(!a->stats || (!p.out_f32 && !a->qkv_split), "vf_conv2d(tc): fused statistics need a plain bf16 output");
 
-  const uint32_t stage_bytes = TC_BM * TC_BK * 2 + p.block_n * TC_BK * 2;
-  const uint32_t bias_bytes = ((uint32_t)(p.box_n * p.block_n * 4) + 1023u) & ~1023u;
-  const uint32_t fixed = 1024 /*align slack*/ + 1024 /*header*/ + bias_bytes;
-  const uint32_t budget = 110 * 1024;               // two CTAs per SM
-  int stages = (int)((budget - fixed) / stage_bytes);
-  if (stages < 2) stages = 2;
-  if (stages > 8) stages = 8;
-  if (stages > p.num_k_iters) stages = p.num_k_iters < 1 ? 1 : p.num_k_iters;
-  p.stages = stages;
-  const size_t smem = fixed + (size_t)stages * stage_bytes;
+  CUtensorMap mapOut = mapB, mapRes = mapB;
+  if (p.epi_tma) {
+    const uint64_t out_rows = (uint64_t)a->images * (H + 1) * (W + 1);
+    const uint32_t box[2] = {64, 32};
+    {
+      const uint64_t dims[2] = {(uint64_t)a->cout, out_rows};
+      const uint64_t strides[1] = {(uint64_t)a->out_ld * 2};
+      int rc = encode_bf16_map(&mapOut, a->out, 2, dims, strides, box);
+      if (rc) return rc;
+    }
+    if (a->residual) {
+      const uint64_t dims[2] = {(uint64_t)a->cout, out_rows};
+      const uint64_t strides[1] = {(uint64_t)a->cout * 2};
+      int rc = encode_bf16_map(&mapRes, a->residual, 2, dims, strides, box);
+      if (rc) return rc;
+    }
+  }
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
   });
   VF_CUDA(attr_err);
-  dim3 grid(cdiv(p.M, TC_BM), a->cout_pad / p.block_n);
-  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], mapB, p);
+  const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
+  if (g_tc_dbg & 256)
+    fprintf(stderr, "[vf tc] rows %d W %d cout %d segs %d ktot %d | bn %d G %d a_stages %d (%d B) b_stages %d resident %d smem %zu items %d grid %d epi_tma %d\n",
+            p.geo.rows_total, W, a->cout, a->n_seg, k_total, p.block_n, p.G, p.a_stages, p.a_stage_bytes, p.b_stages, p.b_resident, tl.smem,
+            p.n_items, grid, p.epi_tma);
+  conv_tc_kernel<<<grid, TC_THREADS, tl.smem, st>>>(maps[0], maps[1], maps[2], mapB, mapOut, mapRes, p);
   VF_LAUNCH_CHECK();
   return VF_OK;
 }

@@ -1,39 +1,41 @@
 // GroupNorm(32, C, eps=1e-5, affine) + Swish  (reference: model/unet.py:207-218 Block, :254 attention norm).
 //
-// Two HBM-bound passes over NHWC activations with 128-bit accesses:
-//   vf_gn_stats : per (image, channel) sum / sum-of-squares; the convolution epilogues can emit the same
-//                 partials instead (vf_conv_args::stats), in which case this pass is skipped.
-//   vf_gn_apply : turns the channel sums into per-group mean / rstd, folds them with gamma/beta into one
-//                 per-channel FMA held in shared memory, applies x*a+b (+ Swish) and writes the tensor the next
-//                 convolution's TMA reads.  It reads up to two sources so that torch.cat((x, skip), 1)
-//                 (unet.py:134) is never materialised un-normalised.
-// Algorithmic bytes (bf16): stats 2 B/elem, apply 4 B/elem.
+// HBM-bound passes over PADDED NHWC activations with 128-bit accesses:
+//   vf_gn_apply : turns per-(image, channel) sums (emitted by the producing convolution's epilogue) into per-group
+//                 mean / rstd, folds them with gamma/beta into one per-channel FMA held in shared memory, applies
+//                 x*a+b (+ Swish) and writes the PADDED tensor the next convolution's TMA reads (exact zeros in the
+//                 padding rows = the convolution's zero padding).  It reads up to two sources so that
+//                 torch.cat((x, skip), 1) (unet.py:134) is never materialised un-normalised.
+//   vf_gn_stats : stand-alone statistics pass (API completeness / tests; the plan uses the fused sums).
+// Algorithmic bytes (bf16): apply 4 B/elem, stats 2 B/elem.
 #include "vf_common.cuh"
 
 namespace vf {
 
 constexpr int kGnThreads = 256;
 
-// block = (CV channel-vectors) x (PY pixel lanes); every thread keeps sums for its fixed 16-byte channel vector
+// block = (CV channel-vectors) x (PY row lanes); every thread keeps sums for its fixed 16-byte channel vector
 template <typename T>
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const T* __restrict__ s0, int C0, const T* __restrict__ s1,
-                                                              int C1, int HW, int pix_per_cta, float* __restrict__ stats) {
+                                                              int C1, int W1, int P, int rows_per_cta, float* __restrict__ stats) {
   constexpr int VEC = VecOf<T>::N;
   extern __shared__ float acc[];                     // [C][2]
   const int C = C0 + C1, CV = C / VEC;
   const int img = blockIdx.y;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) acc[i] = 0.f;
   __syncthreads();
-  const int PY = blockDim.x / CV;                    // pixel lanes (blockDim = CV*PY exactly)
+  const int PY = blockDim.x / CV;                    // row lanes (blockDim = CV*PY exactly)
   const int cv = threadIdx.x % CV, py = threadIdx.x / CV;
   const int c = cv * VEC;
-  const T* src = c < C0 ? s0 + (size_t)img * HW * C0 + c : s1 + (size_t)img * HW * C1 + (c - C0);
+  const T* src = c < C0 ? s0 + (size_t)img * P * C0 + c : s1 + (size_t)img * P * C1 + (c - C0);
   const int ld = c < C0 ? C0 : C1;
-  const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+  const int p0 = blockIdx.x * rows_per_cta, p1 = min(P, p0 + rows_per_cta);
   float s[VEC], q[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) s[j] = q[j] = 0.f;
   for (int p = p0 + py; p < p1; p += PY) {
+    const int yy = p / W1, xx = p - yy * W1;
+    if (yy == 0 || xx == 0) continue;                // padding row
     float v[VEC];
     load_vec(src + (size_t)p * ld, v);
 #pragma unroll
@@ -51,7 +53,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const T* __restric
 
 template <typename T, bool kSwish>
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const T* __restrict__ s0, int C0, const T* __restrict__ s1,
-                                                              int C1, int HW, int groups, int pix_per_cta,
+                                                              int C1, int HW, int W1, int P, int groups, int rows_per_cta,
                                                               const float* __restrict__ st0, int ld0,
                                                               const float* __restrict__ st1, int ld1,
                                                               const float* __restrict__ gamma,
@@ -83,59 +85,103 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const T* __restric
   const int PY = blockDim.x / CV;
   const int cv = threadIdx.x % CV, py = threadIdx.x / CV;
   const int c = cv * VEC;
-  const T* src = c < C0 ? s0 + (size_t)img * HW * C0 + c : s1 + (size_t)img * HW * C1 + (c - C0);
+  const T* src = c < C0 ? s0 + (size_t)img * P * C0 + c : s1 + (size_t)img * P * C1 + (c - C0);
   const int ld = c < C0 ? C0 : C1;
-  T* out = dst + (size_t)img * HW * C + c;
+  T* out = dst + (size_t)img * P * C + c;
   float a[VEC], b[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) { a[j] = ab[2 * (c + j)]; b[j] = ab[2 * (c + j) + 1]; }
-  const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+  const int p0 = blockIdx.x * rows_per_cta, p1 = min(P, p0 + rows_per_cta);
   constexpr int UN = 4;                              // independent 16-byte loads in flight per thread
-  int p = p0 + py;
-  for (; p + (UN - 1) * PY < p1; p += UN * PY) {
+  for (int pb = p0 + py; pb < p1; pb += UN * PY) {
     float v[UN][VEC];
-#pragma unroll
-    for (int u = 0; u < UN; ++u) load_vec(src + (size_t)(p + u * PY) * ld, v[u]);
+    bool pad[UN], in[UN];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
+      const int p = pb + u * PY;
+      in[u] = p < p1;
+      const int yy = p / W1, xx = p - yy * W1;
+      pad[u] = yy == 0 || xx == 0;
+      if (in[u] && !pad[u]) load_vec(src + (size_t)p * ld, v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      if (!in[u]) continue;
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        float y = v[u][j] * a[j] + b[j];
-        v[u][j] = kSwish ? silu(y) : y;
+        const float y = v[u][j] * a[j] + b[j];
+        v[u][j] = pad[u] ? 0.f : (kSwish ? silu_for<T>(y) : y);
       }
-      store_vec(out + (size_t)(p + u * PY) * C, v[u]);
+      store_vec(out + (size_t)(pb + u * PY) * C, v[u]);
     }
-  }
-  for (; p < p1; p += PY) {
-    float v[VEC];
-    load_vec(src + (size_t)p * ld, v);
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      float y = v[j] * a[j] + b[j];
-      v[j] = kSwish ? silu(y) : y;
-    }
-    store_vec(out + (size_t)p * C, v);
   }
 }
 
+// PADDED (H, W) -> PADDED (2H, 2W); one thread per output (row, 16-byte channel vector)
 template <typename T>
 __global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ src, int H, int W, int C, size_t total,
                                                          T* __restrict__ dst) {
   constexpr int VEC = VecOf<T>::N;
   const int CV = C / VEC;
-  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // over output (img, y, x, cv)
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
   const int cv = (int)(gid % CV);
   size_t r = gid / CV;
-  const int x = (int)(r % (2 * W)); r /= (2 * W);
-  const int y = (int)(r % (2 * H));
-  const size_t img = r / (2 * H);
-  const uint4 v = *reinterpret_cast<const uint4*>(src + ((img * H + (y >> 1)) * W + (x >> 1)) * C + cv * VEC);
+  const int Wo1 = 2 * W + 1, Po = (2 * H + 1) * Wo1;
+  const int rem = (int)(r % Po);
+  const size_t img = r / Po;
+  const int yy = rem / Wo1, xx = rem - yy * Wo1;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (yy > 0 && xx > 0) {
+    const int y = (yy - 1) >> 1, x = (xx - 1) >> 1;
+    v = *reinterpret_cast<const uint4*>(src + ((img * (H + 1) + (y + 1)) * (W + 1) + (x + 1)) * C + cv * VEC);
+  }
   *reinterpret_cast<uint4*>(dst + gid * VEC) = v;
 }
 
+// zeroes the padding rows (top row of every image, left column of every line) of a PADDED tensor
+template <typename T>
+__global__ void __launch_bounds__(256) zero_padding_kernel(T* __restrict__ dst, int H, int W, int C, size_t total) {
+  constexpr int VEC = VecOf<T>::N;
+  const int CV = C / VEC;
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // over (img, padding row index, cv)
+  if (gid >= total) return;
+  const int cv = (int)(gid % CV);
+  size_t r = gid / CV;
+  const int npad = H + W + 1;                                      // (W+1) top-row entries + H left-column entries
+  const int k = (int)(r % npad);
+  const size_t img = r / npad;
+  const int W1 = W + 1;
+  const size_t row = img * (size_t)(H + 1) * W1 + (k <= W ? k : (size_t)(k - W) * W1);
+  *reinterpret_cast<uint4*>(dst + row * C + cv * VEC) = make_uint4(0, 0, 0, 0);
+}
+
+// FLAT <-> PADDED copies (tests / taps); one thread per PADDED (row, 16-byte vector)
+template <typename T, bool kToPadded>
+__global__ void __launch_bounds__(256) repad_kernel(const T* __restrict__ src, int H, int W, int C, size_t total, T* __restrict__ dst) {
+  constexpr int VEC = VecOf<T>::N;
+  const int CV = C / VEC;
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int cv = (int)(gid % CV);
+  size_t r = gid / CV;
+  const int W1 = W + 1, P = (H + 1) * W1;
+  const int rem = (int)(r % P);
+  const size_t img = r / P;
+  const int yy = rem / W1, xx = rem - yy * W1;
+  const bool pad = yy == 0 || xx == 0;
+  const size_t flat = ((img * H + (yy - 1)) * W + (xx - 1)) * C + cv * VEC;
+  if (kToPadded) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (!pad) v = *reinterpret_cast<const uint4*>(src + flat);
+    *reinterpret_cast<uint4*>(dst + gid * VEC) = v;
+  } else if (!pad) {
+    *reinterpret_cast<uint4*>(dst + flat) = *reinterpret_cast<const uint4*>(src + gid * VEC);
+  }
+}
+
 struct GnGeom { int threads, pix_per_cta, splits; };
-static GnGeom gn_geom(int C, int vec, int HW, int images) {
+static GnGeom gn_geom(int C, int vec, int HW, int images) {   // HW = rows per image (P)
   GnGeom g;
   const int CV = C / vec;
   const int PY = kGnThreads / CV > 0 ? kGnThreads / CV : 1;
@@ -151,45 +197,45 @@ static GnGeom gn_geom(int C, int vec, int HW, int images) {
 
 }  // namespace vf
 
-extern "C" __attribute__((visibility("default"))) int vf_gn_stats(const void* src0, int C0, const void* src1, int C1, int dtype, int images, int HW,
+extern "C" __attribute__((visibility("default"))) int vf_gn_stats(const void* src0, int C0, const void* src1, int C1, int dtype, int images, int H, int W,
                            float* stats, vf_stream stream) {
   using namespace vf;
-  VF_REQUIRE(src0 && stats && images > 0 && HW > 0 && C0 > 0, "vf_gn_stats: bad args");
+  VF_REQUIRE(src0 && stats && images > 0 && H > 0 && W > 0 && C0 > 0, "vf_gn_stats: bad args");
   if (!src1) C1 = 0;
   const int vec = dtype == VF_BF16 ? 8 : 4;
   VF_REQUIRE(C0 % vec == 0 && C1 % vec == 0, "vf_gn_stats: channels (%d,%d) not a multiple of %d", C0, C1, vec);
-  const int C = C0 + C1;
+  const int C = C0 + C1, P = (H + 1) * (W + 1);
   VF_REQUIRE(C / vec <= kGnThreads, "vf_gn_stats: C=%d too large", C);
-  GnGeom g = gn_geom(C, vec, HW, images);
+  GnGeom g = gn_geom(C, vec, P, images);
   dim3 grid(g.splits, images);
   const size_t smem = 2 * C * sizeof(float);
   if (dtype == VF_BF16)
-    gn_stats_kernel<__nv_bfloat16><<<grid, g.threads, smem, as_stream(stream)>>>((const __nv_bfloat16*)src0, C0, (const __nv_bfloat16*)src1, C1, HW, g.pix_per_cta, stats);
+    gn_stats_kernel<__nv_bfloat16><<<grid, g.threads, smem, as_stream(stream)>>>((const __nv_bfloat16*)src0, C0, (const __nv_bfloat16*)src1, C1, W + 1, P, g.pix_per_cta, stats);
   else
-    gn_stats_kernel<float><<<grid, g.threads, smem, as_stream(stream)>>>((const float*)src0, C0, (const float*)src1, C1, HW, g.pix_per_cta, stats);
+    gn_stats_kernel<float><<<grid, g.threads, smem, as_stream(stream)>>>((const float*)src0, C0, (const float*)src1, C1, W + 1, P, g.pix_per_cta, stats);
   VF_LAUNCH_CHECK();
   return VF_OK;
 }
 
 extern "C" __attribute__((visibility("default"))) int vf_gn_apply(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1,
-                           const float* stats1, int stats1_ld, int dtype, int images, int HW, int groups,
+                           const float* stats1, int stats1_ld, int dtype, int images, int H, int W, int groups,
                            const float* gamma, const float* beta, int swish, void* dst, vf_stream stream) {
   using namespace vf;
-  VF_REQUIRE(src0 && stats0 && gamma && beta && dst && images > 0 && HW > 0 && C0 > 0, "vf_gn_apply: bad args");
+  VF_REQUIRE(src0 && stats0 && gamma && beta && dst && images > 0 && H > 0 && W > 0 && C0 > 0, "vf_gn_apply: bad args");
   if (!src1) C1 = 0;
   VF_REQUIRE(C1 == 0 || stats1, "vf_gn_apply: second source needs statistics");
   VF_REQUIRE(stats0_ld >= C0 && (C1 == 0 || stats1_ld >= C1), "vf_gn_apply: bad statistics stride");
   const int vec = dtype == VF_BF16 ? 8 : 4;
   VF_REQUIRE(C0 % vec == 0 && C1 % vec == 0, "vf_gn_apply: channels (%d,%d) not a multiple of %d", C0, C1, vec);
-  const int C = C0 + C1;
+  const int C = C0 + C1, P = (H + 1) * (W + 1);
   VF_REQUIRE(groups > 0 && C % groups == 0, "vf_gn_apply: C=%d not divisible by groups=%d", C, groups);
   VF_REQUIRE(C / vec <= kGnThreads, "vf_gn_apply: C=%d too large", C);
-  GnGeom g = gn_geom(C, vec, HW, images);
+  GnGeom g = gn_geom(C, vec, P, images);
   dim3 grid(g.splits, images);
   const size_t smem = 2 * C * sizeof(float);
   cudaStream_t st = as_stream(stream);
 #define VF_GN_LAUNCH(T, SW) \
-  gn_apply_kernel<T, SW><<<grid, g.threads, smem, st>>>((const T*)src0, C0, (const T*)src1, C1, HW, groups, g.pix_per_cta, stats0, stats0_ld, C1 ? stats1 : nullptr, stats1_ld, gamma, beta, (T*)dst)
+  gn_apply_kernel<T, SW><<<grid, g.threads, smem, st>>>((const T*)src0, C0, (const T*)src1, C1, H * W, W + 1, P, groups, g.pix_per_cta, stats0, stats0_ld, C1 ? stats1 : nullptr, stats1_ld, gamma, beta, (T*)dst)
   if (dtype == VF_BF16) { if (swish) VF_GN_LAUNCH(__nv_bfloat16, true); else VF_GN_LAUNCH(__nv_bfloat16, false); }
   else { if (swish) VF_GN_LAUNCH(float, true); else VF_GN_LAUNCH(float, false); }
 #undef VF_GN_LAUNCH
@@ -202,10 +248,48 @@ extern "C" __attribute__((visibility("default"))) int vf_upsample2x(const void* 
   VF_REQUIRE(src && dst && images > 0 && H > 0 && W > 0 && C > 0, "vf_upsample2x: bad args");
   const int vec = dtype == VF_BF16 ? 8 : 4;
   VF_REQUIRE(C % vec == 0, "vf_upsample2x: C=%d not a multiple of %d", C, vec);
-  const size_t total = (size_t)images * 4 * H * W * (C / vec);
+  const size_t total = (size_t)images * (2 * H + 1) * (2 * W + 1) * (C / vec);
   const unsigned grid = (unsigned)((total + 255) / 256);
   if (dtype == VF_BF16) upsample2x_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, H, W, C, total, (__nv_bfloat16*)dst);
   else upsample2x_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)src, H, W, C, total, (float*)dst);
   VF_LAUNCH_CHECK();
   return VF_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int vf_zero_padding(void* dst, int dtype, int images, int H, int W, int C, vf_stream stream) {
+  using namespace vf;
+  VF_REQUIRE(dst && images > 0 && H > 0 && W > 0 && C > 0, "vf_zero_padding: bad args");
+  const int vec = dtype == VF_BF16 ? 8 : 4;
+  VF_REQUIRE(C % vec == 0, "vf_zero_padding: C=%d not a multiple of %d", C, vec);
+  const size_t total = (size_t)images * (H + W + 1) * (C / vec);
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (dtype == VF_BF16) zero_padding_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((__nv_bfloat16*)dst, H, W, C, total);
+  else zero_padding_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((float*)dst, H, W, C, total);
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}
+
+static int repad(const void* src, int dtype, int images, int H, int W, int C, void* dst, vf_stream stream, bool to_padded) {
+  using namespace vf;
+  VF_REQUIRE(src && dst && images > 0 && H > 0 && W > 0 && C > 0, "vf_flat_to_padded/vf_padded_to_flat: bad args");
+  const int vec = dtype == VF_BF16 ? 8 : 4;
+  VF_REQUIRE(C % vec == 0, "repad: C=%d not a multiple of %d", C, vec);
+  const size_t total = (size_t)images * (H + 1) * (W + 1) * (C / vec);
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == VF_BF16) {
+    if (to_padded) repad_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, H, W, C, total, (__nv_bfloat16*)dst);
+    else repad_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, H, W, C, total, (__nv_bfloat16*)dst);
+  } else {
+    if (to_padded) repad_kernel<float, true><<<grid, 256, 0, st>>>((const float*)src, H, W, C, total, (float*)dst);
+    else repad_kernel<float, false><<<grid, 256, 0, st>>>((const float*)src, H, W, C, total, (float*)dst);
+  }
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}
+extern "C" __attribute__((visibility("default"))) int vf_flat_to_padded(const void* src, int dtype, int images, int H, int W, int C, void* dst, vf_stream stream) {
+  return repad(src, dtype, images, H, W, C, dst, stream, true);
+}
+extern "C" __attribute__((visibility("default"))) int vf_padded_to_flat(const void* src, int dtype, int images, int H, int W, int C, void* dst, vf_stream stream) {
+  return repad(src, dtype, images, H, W, C, dst, stream, false);
 }

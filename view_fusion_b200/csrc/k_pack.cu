@@ -107,6 +107,25 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, i
   dst[(size_t)n * k_total + k_off + r] = from_f<T>(v);
 }
 
+// identity block: dst[n][k_off + c] = (c == n), used to ride an identity residual as a 1x1 K-segment of a GEMM
+template <typename T>
+__global__ void pack_identity_kernel(T* __restrict__ dst, int n_rows, int k_total, int k_off) {
+  const size_t total = (size_t)n_rows * n_rows;
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int n = (int)(gid / n_rows), c = (int)(gid % n_rows);
+  dst[(size_t)n * k_total + k_off + c] = from_f<T>(c == n ? 1.f : 0.f);
+}
+
+int pack_identity(void* dst, int dtype, int n_rows, int k_total, int k_off, cudaStream_t st) {
+  const size_t total = (size_t)n_rows * n_rows;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (dtype == VF_BF16) pack_identity_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)dst, n_rows, k_total, k_off);
+  else pack_identity_kernel<float><<<grid, 256, 0, st>>>((float*)dst, n_rows, k_total, k_off);
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}
+
 }  // namespace vf
 
 extern "C" __attribute__((visibility("default"))) int vf_pack_views(const float* y_cond, const float* y_t, const int* view_offset, int B, int n_max,

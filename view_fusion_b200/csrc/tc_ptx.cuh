@@ -85,6 +85,18 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
+// TMA store: shared -> global, bulk-group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- tcgen05 ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -105,6 +117,24 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Four K=16 MMAs of one 64-wide (128-byte, SWIZZLE_128B) K step in a single asm block: the descriptors of step k are
+// the base descriptors + 2*k (32 bytes >> 4) in the start-address field.  Keeps the single issuing thread at a
+// handful of instructions per MMA (it is otherwise the bottleneck for small N).
+__device__ __forceinline__ void umma_f16_k4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t.reg .pred p, pt;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\t"
+      "add.s64 a2, %1, 4;\n\tadd.s64 b2, %2, 4;\n\t"
+      "add.s64 a3, %1, 6;\n\tadd.s64 b3, %2, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, pt;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first)
       : "memory");
 }
 // Arrives on `bar` once every previously issued tcgen05.mma of this thread has completed

@@ -17,6 +17,8 @@
 
 namespace vf {
 
+int pack_identity(void* dst, int dtype, int n_rows, int k_total, int k_off, cudaStream_t st);
+
 struct ParamInfo {
   std::string name;
   int64_t shape[4];
@@ -179,14 +181,16 @@ static void prof_mark(vf_unet* u, cudaStream_t st, int kind) {
   } while (0)
 
 template <typename T>
-__global__ void tap_to_nchw_kernel(const T* __restrict__ src, int ld, int C, int HW, size_t total, float* __restrict__ dst) {
-  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void tap_to_nchw_kernel(const T* __restrict__ src, int ld, int C, int H, int W, size_t total, float* __restrict__ dst) {
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // over (r, c, y, x) of the NCHW output
   if (gid >= total) return;
+  const int HW = H * W;
   const int pix = (int)(gid % HW);
   const size_t rc = gid / HW;
   const int c = (int)(rc % C);
   const size_t r = rc / C;
-  dst[gid] = to_f(src[(r * HW + pix) * ld + c]);
+  const int y = pix / W, x = pix - y * W;
+  dst[gid] = to_f(src[((r * (H + 1) + (y + 1)) * (W + 1) + (x + 1)) * ld + c]);   // PADDED row order
 }
 
 __global__ void add_bias_kernel(const float* a, const float* b, int n, float* dst) {
@@ -200,11 +204,10 @@ struct Act {
   float* stats;   // [images, C, 2] sum / sum-of-squares written by the producing conv's epilogue, or null
 };
 
-// fused statistics need a warp of 32 consecutive pixels to stay inside one image
-static bool fuse_stats(int H, int W) { return (H * W) % 32 == 0; }
 static Act new_act(Exec& ex, const vf_unet* u, int images, int C, int H, int W, bool want_stats) {
-  Act a{ex.alloc((size_t)images * H * W * C * (u->dtype == VF_BF16 ? 2 : 4)), C, H, W, nullptr};
-  if (want_stats && fuse_stats(H, W)) a.stats = ex.alloc_stats((size_t)images * C * 2);
+  // spatial activations live in the PADDED row order: images * (H+1) * (W+1) rows
+  Act a{ex.alloc((size_t)images * (H + 1) * (W + 1) * C * (u->dtype == VF_BF16 ? 2 : 4)), C, H, W, nullptr};
+  if (want_stats) a.stats = ex.alloc_stats((size_t)images * C * 2);
   return a;
 }
 
@@ -304,7 +307,7 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_create(const vf_un
   for (auto& b : u->blocks) {
     const int cin = b.c0 + b.c1;
     b.w1 = take((size_t)b.cout * 9 * cin * es);
-    const int k2 = 9 * b.cout + (b.rs_w >= 0 ? cin : 0);
+    const int k2 = 9 * b.cout + cin;        // conv2 taps + res_conv (or identity) columns: the residual rides in the GEMM
     b.w2 = take((size_t)b.cout * k2 * es);
     b.bias2 = take((size_t)b.cout * 4);
     if (b.attn) {
@@ -358,9 +361,10 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_pack_weights(vf_un
   for (auto& b : u->blocks) {
     const int cin = b.c0 + b.c1;
     VF_TRY(vf_pack_conv_weight(u->master[b.c1_w], b.cout, cin, 3, dt, pk + b.w1, b.cout, 9 * cin, 0, stream));
-    const int k2 = 9 * b.cout + (b.rs_w >= 0 ? cin : 0);
+    const int k2 = 9 * b.cout + cin;
     VF_TRY(vf_pack_conv_weight(u->master[b.c2_w], b.cout, b.cout, 3, dt, pk + b.w2, b.cout, k2, 0, stream));
     if (b.rs_w >= 0) VF_TRY(vf_pack_conv_weight(u->master[b.rs_w], b.cout, cin, 1, dt, pk + b.w2, b.cout, k2, 9 * b.cout, stream));
+    else VF_TRY(pack_identity(pk + b.w2, dt, b.cout, k2, 9 * b.cout, st));    // "h + x" (unet.py:245) as an exact 1x1 segment
     add_bias_kernel<<<cdiv(b.cout, 128), 128, 0, st>>>(u->master[b.c2_b], b.rs_b >= 0 ? u->master[b.rs_b] : nullptr, b.cout, reinterpret_cast<float*>(pk + b.bias2));
     if (b.attn) {
       VF_TRY(vf_pack_conv_weight(u->master[b.qkv_w], 3 * b.cout, b.cout, 1, dt, pk + b.wqkv, 3 * b.cout, b.cout, 0, stream));
@@ -393,6 +397,8 @@ static vf_conv_args conv_args_init() {
   vf_conv_args a{};
   a.stride = 1;
   a.out_dtype = -1;
+  a.in_padded = 1;
+  a.out_padded = 1;
   return a;
 }
 
@@ -401,16 +407,15 @@ static vf_conv_args conv_args_init() {
 static Act gn_block(Exec& ex, const vf_unet* u, int images, const Act& x, const Act* skip, int gw, int gb, bool swish) {
   const int C1 = skip ? skip->C : 0;
   const int C = x.C + C1;
-  const int HW = x.H * x.W;
   const float *s0 = x.stats, *s1 = skip ? skip->stats : nullptr;
   int ld0 = x.C, ld1 = C1;
   if (!x.stats || (skip && !skip->stats)) {
     float* st = ex.alloc_stats((size_t)images * C * 2);
-    VF_RUN(ex, K_GN_STATS, vf_gn_stats(x.p, x.C, skip ? skip->p : nullptr, C1, u->dtype, images, HW, st, (vf_stream)ex.st));
+    VF_RUN(ex, K_GN_STATS, vf_gn_stats(x.p, x.C, skip ? skip->p : nullptr, C1, u->dtype, images, x.H, x.W, st, (vf_stream)ex.st));
     s0 = st; s1 = st + 2 * x.C; ld0 = ld1 = C;
   }
   Act y = new_act(ex, u, images, C, x.H, x.W, false);
-  VF_RUN(ex, K_GN_APPLY, vf_gn_apply(x.p, x.C, s0, ld0, skip ? skip->p : nullptr, C1, s1, ld1, u->dtype, images, HW, u->cfg.norm_groups,
+  VF_RUN(ex, K_GN_APPLY, vf_gn_apply(x.p, x.C, s0, ld0, skip ? skip->p : nullptr, C1, s1, ld1, u->dtype, images, x.H, x.W, u->cfg.norm_groups,
                                      u->master[gw], u->master[gb], swish ? 1 : 0, y.p, (vf_stream)ex.st));
   return y;
 }
@@ -440,12 +445,10 @@ static Act run_resblock(Exec& ex, vf_unet* u, const uint8_t* pk, int images, con
     vf_conv_args a = conv_args_init();
     a.images = images; a.H = x.H; a.W = x.W;
     a.src[0] = a2.p; a.src_c[0] = b.cout; a.ksize[0] = 3; a.n_seg = 1;
-    if (b.rs_w >= 0) {
-      a.src[1] = x.p; a.src_c[1] = x.C; a.ksize[1] = 1; a.n_seg = 2;
-      if (skip) { a.src[2] = skip->p; a.src_c[2] = skip->C; a.ksize[2] = 1; a.n_seg = 3; }
-    } else {
-      a.residual = x.p;
-    }
+    // res_conv(x) — or x itself through identity columns — accumulates in the same TMEM tile: the residual is read
+    // by the TMA-fed main loop instead of by the (latency-bound) epilogue
+    a.src[1] = x.p; a.src_c[1] = x.C; a.ksize[1] = 1; a.n_seg = 2;
+    if (skip) { a.src[2] = skip->p; a.src_c[2] = skip->C; a.ksize[2] = 1; a.n_seg = 3; }
     a.weight = pk + b.w2; a.cout = b.cout; a.cout_pad = b.cout;
     a.bias = reinterpret_cast<const float*>(pk + b.bias2);
     a.out = out.p; a.out_ld = b.cout; a.stats = out.stats;
@@ -462,17 +465,17 @@ static Act run_resblock(Exec& ex, vf_unet* u, const uint8_t* pk, int images, con
     a.images = images; a.H = x.H; a.W = x.W; a.n_seg = 1;
     a.src[0] = n.p; a.src_c[0] = C; a.ksize[0] = 1;
     a.weight = pk + b.wqkv; a.cout = 3 * C; a.cout_pad = 3 * C;
-    a.out = qkv; a.out_ld = 3 * C;
+    a.out = qkv; a.out_ld = 3 * C; a.out_padded = 0;          // attention works on FLAT token rows
     if (u->dtype == VF_BF16) { a.qkv_split = C; a.out_vt = vt; }
     conv_call(ex, u, a);
   }
-  Act o = new_act(ex, u, images, C, x.H, x.W, false);
+  Act o{ex.alloc((size_t)images * HW * C * es), C, x.H, x.W, nullptr};   // FLAT
   VF_RUN(ex, K_ATTN, vf_attention(qkv, vt, u->dtype, images, HW, C, o.p, (vf_stream)ex.st));
   Act out2 = new_act(ex, u, images, C, x.H, x.W, true);
   {
     vf_conv_args a = conv_args_init();
     a.images = images; a.H = x.H; a.W = x.W; a.n_seg = 1;
-    a.src[0] = o.p; a.src_c[0] = C; a.ksize[0] = 1;
+    a.src[0] = o.p; a.src_c[0] = C; a.ksize[0] = 1; a.in_padded = 0;
     a.weight = pk + b.wout; a.cout = C; a.cout_pad = C;
     a.bias = ex.dry ? nullptr : u->master[b.ao_b];
     a.residual = out.p;
@@ -501,7 +504,7 @@ static int walk(vf_unet* u, Exec& ex, const uint8_t* pk, int images, const void*
   {
     vf_conv_args a = conv_args_init();
     a.images = images; a.H = S; a.W = S; a.n_seg = 1;
-    a.src[0] = x0; a.src_c[0] = u->k0; a.ksize[0] = 1;
+    a.src[0] = x0; a.src_c[0] = u->k0; a.ksize[0] = 1; a.in_padded = 0;
     a.weight = pk + u->conv0_w; a.cout = c.inner_channel; a.cout_pad = c.inner_channel;
     a.bias = ex.dry ? nullptr : u->master[u->downs[0].b_idx];
     a.out = x.p; a.out_ld = c.inner_channel; a.stats = x.stats;
@@ -515,8 +518,10 @@ static int walk(vf_unet* u, Exec& ex, const uint8_t* pk, int images, const void*
       x = run_resblock(ex, u, pk, images, u->blocks[l.rb], x, nullptr, emb, img_row);
     } else {   // Downsample: conv3x3 stride 2                                              unet.py:195-201
       Act y = new_act(ex, u, images, l.c, x.H / 2, x.W / 2, true);
+      // x is a raw convolution output: its padding rows were never written, and this 3x3 reads them as the zero halo
+      VF_RUN(ex, K_UPSAMPLE, vf_zero_padding(x.p, u->dtype, images, x.H, x.W, x.C, (vf_stream)ex.st));
       vf_conv_args a = conv_args_init();
-      a.images = images; a.H = y.H; a.W = y.W; a.n_seg = 1; a.stride = 2;
+      a.images = images; a.H = x.H; a.W = x.W; a.n_seg = 1; a.stride = 2;
       a.src[0] = x.p; a.src_c[0] = l.c; a.ksize[0] = 3;
       a.weight = pk + l.w; a.cout = l.c; a.cout_pad = l.c;
       a.bias = ex.dry ? nullptr : u->master[l.b_idx];
@@ -559,7 +564,7 @@ static int walk(vf_unet* u, Exec& ex, const uint8_t* pk, int images, const void*
     a.src[0] = f.p; a.src_c[0] = u->final_c; a.ksize[0] = 3;
     a.weight = pk + u->final_w; a.cout = c.out_channel; a.cout_pad = 16;
     a.bias = ex.dry ? nullptr : u->master[u->fin_b];
-    a.out = out; a.out_dtype = VF_F32; a.out_ld = 8;
+    a.out = out; a.out_dtype = VF_F32; a.out_ld = 8; a.out_padded = 0;
     conv_call(ex, u, a);
   }
   return ex.rc;
@@ -637,9 +642,9 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_read_tap(vf_unet* 
   const uint8_t* src = reinterpret_cast<const uint8_t*>(workspace) + t.off;
   const unsigned grid = (unsigned)((total + 255) / 256);
   if (t.dtype == VF_BF16)
-    tap_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, t.ld, t.C, t.H * t.W, total, dst);
+    tap_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, t.ld, t.C, t.H, t.W, total, dst);
   else
-    tap_to_nchw_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)src, t.ld, t.C, t.H * t.W, total, dst);
+    tap_to_nchw_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)src, t.ld, t.C, t.H, t.W, total, dst);
   VF_LAUNCH_CHECK();
   if (chw) { chw[0] = t.C; chw[1] = t.H; chw[2] = t.W; }
   return VF_OK;

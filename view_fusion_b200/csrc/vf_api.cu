@@ -27,6 +27,8 @@ int conv2d_simt(const vf_conv_args* a, cudaStream_t st);
 int conv2d_tc(const vf_conv_args* a, cudaStream_t st);
 int attention_simt(const void* qk, const void* vt, int dtype, int images, int L, int C, void* out, cudaStream_t st);
 int attention_tc(const void* qk, const void* vt, int images, int L, int C, void* out, cudaStream_t st);
+void set_tc_debug(int f);
+void set_tc_debug_out(long long* p);
 
 }  // namespace vf
 
@@ -49,6 +51,8 @@ extern "C" __attribute__((visibility("default"))) int vf_device_check(void) {
 // force_simt: debugging / cross-check switch (environment VF_FORCE_SIMT=1 is read by the Python tests only)
 static int g_force_simt = 0;
 extern "C" __attribute__((visibility("default"))) void vf_debug_force_simt(int on) { g_force_simt = on; }
+extern "C" __attribute__((visibility("default"))) void vf_debug_flags(int flags) { vf::set_tc_debug(flags); }
+extern "C" __attribute__((visibility("default"))) void vf_debug_counters(long long* dev_buf) { vf::set_tc_debug_out(dev_buf); }
 
 extern "C" __attribute__((visibility("default"))) int vf_conv2d(const vf_conv_args* a, vf_stream stream) {
   using namespace vf;

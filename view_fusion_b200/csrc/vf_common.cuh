@@ -77,6 +77,16 @@ __device__ __forceinline__ void store_vec(__nv_bfloat16* p, const float (&v)[8])
 }
 
 __device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+// x * sigmoid(x) with sigmoid = 0.5 * tanh(0.5 x) + 0.5: one MUFU op per element (tanh.approx, rel. error 2^-11, well
+// below the bf16 rounding of the stored result) instead of ex2 + rcp.  The SiLU pass is otherwise MUFU-bound.
+__device__ __forceinline__ float silu_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return x * fmaf(0.5f, t, 0.5f);
+}
+template <typename T> __device__ __forceinline__ float silu_for(float x);
+template <> __device__ __forceinline__ float silu_for<float>(float x) { return silu(x); }
+template <> __device__ __forceinline__ float silu_for<__nv_bfloat16>(float x) { return silu_fast(x); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -87,6 +97,50 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// ---- FLAT / PADDED row orders (include/viewfusion_b200.h) --------------------------------------------------
+struct RowGeom {
+  int H, W, HW, W1, P, images;
+  int rows_total;                    // GEMM M: images*P (PADDED sources) or images*H*W (FLAT)
+  int in_padded, out_padded, stride2;
+};
+struct RowInfo {
+  int img, pix;      // pix = y*Wo + x at the OUTPUT resolution
+  bool valid;
+  long out_row;
+};
+inline RowGeom make_geom(int images, int H, int W, int in_padded, int out_padded, int stride2) {
+  RowGeom g;
+  g.H = H; g.W = W; g.HW = H * W; g.W1 = W + 1; g.P = (H + 1) * (W + 1); g.images = images;
+  g.in_padded = in_padded; g.out_padded = out_padded; g.stride2 = stride2;
+  g.rows_total = images * (in_padded ? g.P : g.HW);
+  return g;
+}
+__device__ __forceinline__ RowInfo decode_row(const RowGeom& p, int m) {
+  RowInfo r;
+  r.valid = m < p.rows_total;
+  int img = 0, y = 0, x = 0;
+  if (p.in_padded) {
+    img = m / p.P;
+    const int rem = m - img * p.P;
+    const int yy = rem / p.W1, xx = rem - yy * p.W1;
+    r.valid = r.valid && yy >= 1 && xx >= 1;
+    y = yy - 1; x = xx - 1;
+  } else {
+    img = m / p.HW;
+    const int rem = m - img * p.HW;
+    y = rem / p.W; x = rem - y * p.W;
+  }
+  int Wo = p.W, Ho = p.H;
+  if (p.stride2) {
+    r.valid = r.valid && ((y | x) & 1) == 0;
+    y >>= 1; x >>= 1; Wo >>= 1; Ho >>= 1;
+  }
+  r.img = img;
+  r.pix = y * Wo + x;
+  r.out_row = p.out_padded ? (long)img * (Ho + 1) * (Wo + 1) + (long)(y + 1) * (Wo + 1) + (x + 1) : (long)img * Ho * Wo + r.pix;
+  return r;
 }
 
 // Column sums of a 32 x 16 register tile (one row per lane): 16 shuffles instead of 16 x 5.  Every lane returns the

@@ -1,6 +1,7 @@
 """Torch-tensor wrappers over the stage-level C-ABI operators (unit parity tests, ncu captures, bench).
 
-Activations are NHWC matrices `[images*H*W, C]` in torch.float32 or torch.bfloat16.
+Activations are NHWC matrices `[rows, C]` in torch.float32 or torch.bfloat16, in the FLAT (images*H*W rows) or PADDED
+(images*(H+1)*(W+1) rows) row order described in include/viewfusion_b200.h.
 """
 from __future__ import annotations
 
@@ -20,13 +21,40 @@ def _dt(t: torch.Tensor) -> int:
 
 
 def to_nhwc(x: torch.Tensor, dtype=None) -> torch.Tensor:
-    """(R,C,H,W) -> [R*H*W, C] contiguous."""
+    """(R,C,H,W) -> FLAT [R*H*W, C] contiguous."""
     y = x.permute(0, 2, 3, 1).contiguous().view(-1, x.shape[1])
     return y if dtype is None else y.to(dtype)
 
 
 def from_nhwc(y: torch.Tensor, R: int, H: int, W: int) -> torch.Tensor:
     return y.float().view(R, H, W, -1).permute(0, 3, 1, 2).contiguous()
+
+
+def to_padded(x: torch.Tensor, dtype=None, fill: float = 0.0) -> torch.Tensor:
+    """(R,C,H,W) -> PADDED [R*(H+1)*(W+1), C] (host-side reference construction; `fill` goes into the padding rows)."""
+    R, Cc, H, W = x.shape
+    y = torch.full((R, H + 1, W + 1, Cc), fill, dtype=x.dtype, device=x.device)
+    y[:, 1:, 1:, :] = x.permute(0, 2, 3, 1)
+    y = y.view(-1, Cc).contiguous()
+    return y if dtype is None else y.to(dtype)
+
+
+def from_padded(y: torch.Tensor, R: int, H: int, W: int) -> torch.Tensor:
+    return y.float().view(R, H + 1, W + 1, -1)[:, 1:, 1:, :].permute(0, 3, 1, 2).contiguous()
+
+
+def flat_to_padded(src: torch.Tensor, images: int, H: int, W: int) -> torch.Tensor:
+    lib = _lib.require_device()
+    dst = torch.empty(images * (H + 1) * (W + 1), src.shape[1], dtype=src.dtype, device=src.device)
+    _lib.check(lib.vf_flat_to_padded(src.data_ptr(), _dt(src), images, H, W, src.shape[1], dst.data_ptr(), _lib.stream_handle()), "vf_flat_to_padded")
+    return dst
+
+
+def padded_to_flat(src: torch.Tensor, images: int, H: int, W: int) -> torch.Tensor:
+    lib = _lib.require_device()
+    dst = torch.empty(images * H * W, src.shape[1], dtype=src.dtype, device=src.device)
+    _lib.check(lib.vf_padded_to_flat(src.data_ptr(), _dt(src), images, H, W, src.shape[1], dst.data_ptr(), _lib.stream_handle()), "vf_padded_to_flat")
+    return dst
 
 
 def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype, cout_pad=None, k_total=None, k_off=0, dst=None) -> torch.Tensor:
@@ -42,12 +70,16 @@ def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype, cout_pad=None, k_total
 
 
 def conv2d(srcs, ksizes, weight, images, H, W, cout, *, stride=1, bias=None, emb=None, img_row=None, residual=None,
-           out_dtype=None, out_ld=None, qkv_split=0, cout_pad=None, want_stats=False):
-    """srcs: list of NHWC matrices; weight: packed [cout_pad, K_total].  Returns out (and V^T when qkv_split)."""
+           out_dtype=None, out_ld=None, qkv_split=0, cout_pad=None, want_stats=False, in_padded=True, out_padded=True,
+           out=None, stats=None):
+    """srcs: list of [rows, C] matrices at resolution (H, W); weight: packed [cout_pad, K_total].
+    Returns out (+ V^T when qkv_split, + stats when want_stats).  Padding rows of a PADDED output are left as
+    allocated (NaN-filled here so that tests catch any read of them)."""
     lib = _lib.require_device()
     a = _lib.ConvArgs()
     dt = srcs[0].dtype
     a.dtype, a.images, a.H, a.W, a.n_seg = _dt(srcs[0]), images, H, W, len(srcs)
+    a.in_padded, a.out_padded = int(in_padded), int(out_padded)
     for i, (s, k) in enumerate(zip(srcs, ksizes)):
         a.src[i], a.src_c[i], a.ksize[i] = s.data_ptr(), s.shape[1], k
     a.stride = stride
@@ -58,15 +90,18 @@ def conv2d(srcs, ksizes, weight, images, H, W, cout, *, stride=1, bias=None, emb
     a.residual = _lib.ptr(residual)
     out_dtype = dt if out_dtype is None else out_dtype
     out_ld = cout if out_ld is None else out_ld
-    out = torch.zeros(images * H * W, out_ld, dtype=out_dtype, device=srcs[0].device)
+    Ho, Wo = H // stride, W // stride
+    rows = images * ((Ho + 1) * (Wo + 1) if out_padded else Ho * Wo)
+    if out is None:
+        out = torch.full((rows, out_ld), float("nan"), dtype=out_dtype, device=srcs[0].device)
     a.out, a.out_dtype, a.out_ld = out.data_ptr(), (_lib.VF_BF16 if out_dtype == torch.bfloat16 else _lib.VF_F32), out_ld
     vt = None
     if qkv_split and dt == torch.bfloat16:
         vt = torch.zeros(images, qkv_split, H * W, dtype=dt, device=out.device)
         a.qkv_split, a.out_vt = qkv_split, vt.data_ptr()
-    stats = None
     if want_stats:
-        stats = torch.zeros(images, cout, 2, dtype=torch.float32, device=out.device)
+        if stats is None:
+            stats = torch.zeros(images, cout, 2, dtype=torch.float32, device=out.device)
         a.stats = stats.data_ptr()
     _lib.check(lib.vf_conv2d(C.byref(a), _lib.stream_handle()), "vf_conv2d")
     if want_stats:
@@ -74,25 +109,25 @@ def conv2d(srcs, ksizes, weight, images, H, W, cout, *, stride=1, bias=None, emb
     return (out, vt) if qkv_split else out
 
 
-def gn_stats(src0, src1, images, HW):
+def gn_stats(src0, src1, images, H, W):
     lib = _lib.require_device()
     C0, C1 = src0.shape[1], (0 if src1 is None else src1.shape[1])
     stats = torch.zeros(images, C0 + C1, 2, dtype=torch.float32, device=src0.device)
-    _lib.check(lib.vf_gn_stats(src0.data_ptr(), C0, _lib.ptr(src1), C1, _dt(src0), images, HW, stats.data_ptr(), _lib.stream_handle()),
+    _lib.check(lib.vf_gn_stats(src0.data_ptr(), C0, _lib.ptr(src1), C1, _dt(src0), images, H, W, stats.data_ptr(), _lib.stream_handle()),
                "vf_gn_stats")
     return stats
 
 
-def gn_apply(src0, src1, images, HW, groups, stats, gamma, beta, swish=True, stats1=None):
-    """stats: [images, C0+C1, 2] (from gn_stats), or per-source [images, C0, 2] with stats1 [images, C1, 2]."""
+def gn_apply(src0, src1, images, H, W, groups, stats, gamma, beta, swish=True, stats1=None):
+    """PADDED in, PADDED out.  stats: [images, C0+C1, 2] (from gn_stats), or per-source [images, C0, 2] + stats1."""
     lib = _lib.require_device()
     C0, C1 = src0.shape[1], (0 if src1 is None else src1.shape[1])
-    dst = torch.empty(images * HW, C0 + C1, dtype=src0.dtype, device=src0.device)
+    dst = torch.full((images * (H + 1) * (W + 1), C0 + C1), float("nan"), dtype=src0.dtype, device=src0.device)
     if stats1 is None:
         s0, ld0, s1, ld1 = stats.data_ptr(), stats.shape[1], stats.data_ptr() + 8 * C0, stats.shape[1]
     else:
         s0, ld0, s1, ld1 = stats.data_ptr(), stats.shape[1], stats1.data_ptr(), stats1.shape[1]
-    _lib.check(lib.vf_gn_apply(src0.data_ptr(), C0, s0, ld0, _lib.ptr(src1), C1, s1 if C1 else 0, ld1, _dt(src0), images, HW, groups,
+    _lib.check(lib.vf_gn_apply(src0.data_ptr(), C0, s0, ld0, _lib.ptr(src1), C1, s1 if C1 else 0, ld1, _dt(src0), images, H, W, groups,
                                gamma.data_ptr(), beta.data_ptr(), int(swish), dst.data_ptr(), _lib.stream_handle()), "vf_gn_apply")
     return dst
 
@@ -100,7 +135,7 @@ def gn_apply(src0, src1, images, HW, groups, stats, gamma, beta, swish=True, sta
 def upsample2x(src, images, H, W):
     lib = _lib.require_device()
     Cc = src.shape[1]
-    dst = torch.empty(images * 4 * H * W, Cc, dtype=src.dtype, device=src.device)
+    dst = torch.full((images * (2 * H + 1) * (2 * W + 1), Cc), float("nan"), dtype=src.dtype, device=src.device)
     _lib.check(lib.vf_upsample2x(src.data_ptr(), _dt(src), images, H, W, Cc, dst.data_ptr(), _lib.stream_handle()), "vf_upsample2x")
     return dst
 
