@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const T* __restric
 }
 
 template <typename T, bool kSwish>
-__global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const T* __restrict__ s0, int C0, const T* __restrict__ s1,
+__global__ void __launch_bounds__(kGnThreads, 4) gn_apply_kernel(const T* __restrict__ s0, int C0, const T* __restrict__ s1,
                                                               int C1, int HW, int W1, int P, int groups, int rows_per_cta,
                                                               const float* __restrict__ st0, int ld0,
                                                               const float* __restrict__ st1, int ld1,
@@ -92,27 +92,38 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const T* __restric
 #pragma unroll
   for (int j = 0; j < VEC; ++j) { a[j] = ab[2 * (c + j)]; b[j] = ab[2 * (c + j) + 1]; }
   const int p0 = blockIdx.x * rows_per_cta, p1 = min(P, p0 + rows_per_cta);
-  constexpr int UN = 4;                              // independent 16-byte loads in flight per thread
+  constexpr int UN = 4;                              // independent 16-byte loads in flight per thread (kept packed)
+  // (yy, xx) of this thread's row advance incrementally: no integer division in the streaming loop
+  int yy = (p0 + py) / W1, xx = (p0 + py) - yy * W1;
+  const int dy = PY / W1, dx = PY - dy * W1;
   for (int pb = p0 + py; pb < p1; pb += UN * PY) {
-    float v[UN][VEC];
-    bool pad[UN], in[UN];
+    uint4 raw[UN];
+    uint32_t padm = 0, inm = 0;
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       const int p = pb + u * PY;
-      in[u] = p < p1;
-      const int yy = p / W1, xx = p - yy * W1;
-      pad[u] = yy == 0 || xx == 0;
-      if (in[u] && !pad[u]) load_vec(src + (size_t)p * ld, v[u]);
+      const bool in = p < p1, pad = yy == 0 || xx == 0;
+      inm |= (uint32_t)in << u; padm |= (uint32_t)pad << u;
+      if (in && !pad) raw[u] = *reinterpret_cast<const uint4*>(src + (size_t)p * ld);
+      yy += dy; xx += dx;
+      if (xx >= W1) { xx -= W1; ++yy; }
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
-      if (!in[u]) continue;
+      if (!((inm >> u) & 1u)) continue;
+      float v[VEC];
+      if ((padm >> u) & 1u) {
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        const float y = v[u][j] * a[j] + b[j];
-        v[u][j] = pad[u] ? 0.f : (kSwish ? silu_for<T>(y) : y);
+        for (int j = 0; j < VEC; ++j) v[j] = 0.f;
+      } else {
+        load_vec(reinterpret_cast<const T*>(&raw[u]), v);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float y = v[j] * a[j] + b[j];
+          v[j] = kSwish ? silu_for<T>(y) : y;
+        }
       }
-      store_vec(out + (size_t)(pb + u * PY) * C, v[u]);
+      store_vec(out + (size_t)(pb + u * PY) * C, v);
     }
   }
 }
