@@ -265,6 +265,9 @@ void vf_debug_counters(long long* dev_buf);
  * smem tile and a tcgen05 descriptor whose start is shifted by `shift_rows` rows. A [rows>=256, 64] bf16, B [64, 64]. */
 /* Hardware probe: cycles for n_groups x 4 back-to-back tcgen05.mma (M=128, N, K=16) issued by one thread per CTA. */
 int vf_debug_umma_rate(int N, int shift_rows, int n_groups, int commit_every, int grid, long long* cycles_out, vf_stream stream);
+/* Hardware probe: MN-major operands: out[m][n] = sum_{k<64} A[k][m] * B[shift_rows + k][n] (A [.,128], B [.,64] bf16). */
+int vf_debug_umma_mn(const void* A, int rowsA, const void* B, int rowsB, int shift_rows, int lbo_bytes, int sbo_bytes, float* out,
+                     vf_stream stream);
 int vf_debug_umma_shift(const void* A, int rows, const void* B, int shift_rows, int use_base_offset, float* out,
                         vf_stream stream);
 
@@ -277,6 +280,64 @@ int vf_attention(const void* qk, const void* vt, int dtype, int images, int L, i
 /* fp32 OIHW conv weight -> K-major [cout_pad][k_off + tap*cin + c] rows of length k_total in `dtype`. */
 int vf_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, int dtype, void* dst, int cout_pad,
                         int k_total, int k_off, vf_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Training: backward of the LAST vf_unet_forward on this plan (experiment.py:292 loss.backward()).
+ *   packed_t       : transposed weight packs for the data gradients (vf_unet_packed_t_bytes, refreshed by
+ *                    vf_unet_pack_weights_t after every optimizer step)
+ *   grad_workspace : activation gradients + scratch (vf_unet_backward_workspace_bytes, valid after a forward); like the
+ *                    forward workspace it must be zero-filled once per (plan, image count): padding rows are never
+ *                    written and are read as zeros
+ *   grad_out8      : [images*H*W, 8] fp32 gradient of vf_unet_forward's `out` (vf_compose_mse's grad_out)
+ *   param_grads    : host array of vf_unet_num_params() device pointers (fp32, parameter shapes); ACCUMULATED into
+ * ---------------------------------------------------------------------------------------------------- */
+size_t vf_unet_packed_t_bytes(const vf_unet* u);
+int vf_unet_pack_weights_t(vf_unet* u, void* packed_t, vf_stream stream);
+size_t vf_unet_backward_workspace_bytes(vf_unet* u);
+int vf_unet_backward(vf_unet* u, const void* packed_t, void* grad_workspace, size_t grad_workspace_bytes, const float* grad_out8,
+                     float* const* param_grads_host, vf_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Backward operators (training: autograd through model/unet.py, experiment.py:292).  Gradients of activations
+ * use the activation dtype and row order of the tensor they belong to; parameter gradients are fp32.
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* Weight gradient of the convolution described by `fwd` (same struct as the forward call; weight/bias/out unused):
+ *   dwp[n][koff(seg) + tap*C_seg + c] += sum_rows dy[out_row(m)][n] * src_seg[m + shift(tap)][c]
+ * dwp: [cout_pad, K_total] fp32, the forward weight's K-major packed layout (accumulated, zero it first);
+ * dy: gradient of the forward output, [out rows, dy_ld] in fwd->dtype with zero padding rows. */
+int vf_conv2d_wgrad(const vf_conv_args* fwd, const void* dy, int dy_ld, float* dwp, vf_stream stream);
+
+/* dw_oihw[n][c_off + c][tap] += dwp[n][k_off + tap*cin + c]: packed gradient of one K-segment -> its channel slice of an
+ * OIHW parameter gradient with cin_total input channels. */
+int vf_unpack_conv_wgrad(const float* dwp, int cout, int cin, int ksize, int k_total, int k_off, float* dw_oihw, int cin_total,
+                         int c_off, vf_stream stream);
+
+/* Transposed, tap-flipped pack: dst[c][k_off + (taps-1-tap)*n_stride + n] = w[n][c][tap] (zero for c >= cin, n >= cout), so that
+ * the DATA gradient of a convolution is a forward vf_conv2d over dy with this weight (rows = cin_pad, K = taps*n_stride). */
+int vf_pack_conv_weight_t(const float* w_oihw, int cout, int cin, int ksize, int dtype, void* dst, int cin_pad, int k_total, int k_off,
+                          int n_stride, vf_stream stream);
+
+/* GroupNorm(+Swish) backward for dst = vf_gn_apply(src0 | src1): dy [images*P, C0+C1] PADDED.
+ * dxK receives (accK == 0) or accumulates (accK != 0) the gradient of source K; dgamma/dbeta [C0+C1] fp32 are
+ * accumulated; scratch: images*(C0+C1)*2 floats. */
+int vf_gn_backward(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1, const float* stats1,
+                   int stats1_ld, int dtype, int images, int H, int W, int groups, const float* gamma, const float* beta, int swish,
+                   const void* dy, float* scratch, float* dgamma, float* dbeta, void* dx0, int acc0, void* dx1, int acc1,
+                   vf_stream stream);
+
+/* Backward of vf_attention: d_out [images*L, C] -> dqkv [images*L, 3C] (dq | dk | dv). scratch: images*L*2C floats. */
+int vf_attention_backward(const void* qk, const void* vt, const void* d_out, int dtype, int images, int L, int C, float* scratch,
+                          void* dqkv, vf_stream stream);
+
+/* Backward of vf_upsample2x: dx (PADDED H x W) = or += sum of the 2x2 block of dy (PADDED 2H x 2W). */
+int vf_upsample2x_backward(const void* dy, int dtype, int images, int H, int W, int C, void* dx, int accumulate, vf_stream stream);
+/* dst (PADDED 2H x 2W) = dy (PADDED H x W) at even pixels, zero elsewhere: turns the stride-2 Downsample gradients into
+ * stride-1 problems at the source resolution. */
+int vf_zero_insert2x(const void* dy, int dtype, int images, int H, int W, int C, void* dst, vf_stream stream);
+int vf_add_inplace(void* dst, const void* src, int dtype, size_t n_elems, vf_stream stream);
+/* [rows, 8] fp32 (vf_compose_mse's grad_out) -> [rows, ld] activation dtype, zero beyond channel 8. */
+int vf_grad8_to_act(const float* g8, size_t rows, int dtype, int ld, void* dst, vf_stream stream);
 
 #ifdef __cplusplus
 }

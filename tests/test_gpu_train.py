@@ -1,0 +1,61 @@
+"""GPU: training forward/backward through the drop-in ViewFusion module vs the reference goldens
+(loss, per-parameter gradient norms, sampled gradient values; produced by the reference's autograd)."""
+import pytest
+import torch
+
+import vf_oracle as O
+from gpu_util import build_model, load, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(golden_dir, tag, cfg, prec):
+    g = load(golden_dir, f"train_{tag}")
+    m, _ = build_model(cfg, int(g["seed"]), prec)
+    loss = m(y_cond=g["y_cond"].cuda(), view_count=g["view_count"], angle=g["angle"].cuda(), y_0=g["y_0"].cuda(), noise=g["noise"].cuda(),
+             t=g["t"].cuda(), u=g["u"].cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {n: p.grad.detach().cpu() for n, p in m.denoise_fn.named_parameters()}
+    return g, float(loss.detach()), grads
+
+
+@pytest.mark.parametrize("tag,cfg", [("tiny_ragged", O.TINY), ("small_n3", O.SMALL_V100)])
+def test_train_fp32_mode_loss_and_gradients(golden_dir, tag, cfg):
+    g, loss, grads = _run(golden_dir, tag, cfg, "fp32")
+    assert abs(loss - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    names = [str(n) for n in g["grad_names"]]
+    norms = g["grad_norms"].tolist()
+    big = max(norms)
+    bad = {}
+    for n, ref in zip(names, norms):
+        mine = float(grads[n].norm())
+        if ref < 1e-6 * big:
+            if not mine < 1e-5 * big:
+                bad[n] = (mine, ref)
+        elif not abs(mine - ref) < 2e-3 * ref:
+            bad[n] = (mine, ref)
+    assert not bad, f"{len(bad)} gradient norms off, e.g. {list(bad.items())[:6]}"
+    for k in g:
+        if k.startswith("grad:"):
+            full = grads[k[5:]].reshape(-1)
+            stride = max(1, (full.numel() + 8191) // 8192)
+            assert rel(full[::stride], g[k]) < 2e-3, k
+
+
+def test_train_bf16_mode_loss_and_gradient_direction(golden_dir):
+    g, loss, grads = _run(golden_dir, "small_n3", O.SMALL_V100, "bf16")
+    assert abs(loss - float(g["loss"])) < 1e-2 * abs(float(g["loss"]))
+    names = [str(n) for n in g["grad_names"]]
+    norms = dict(zip(names, g["grad_norms"].tolist()))
+    big = max(norms.values())
+    off = {n: (float(grads[n].norm()), r) for n, r in norms.items() if r > 1e-3 * big and not abs(float(grads[n].norm()) - r) < 0.1 * r}
+    assert len(off) <= 4, f"bf16 gradient norms off by > 10 %: {list(off.items())[:8]}"
+    for k in g:
+        if k.startswith("grad:"):
+            full = grads[k[5:]].reshape(-1)
+            stride = max(1, (full.numel() + 8191) // 8192)
+            a, b = full[::stride].double(), g[k].double()
+            if float(b.norm()) > 1e-3 * big:
+                cos = float((a * b).sum() / (a.norm() * b.norm()))
+                assert cos > 0.98, (k, cos)

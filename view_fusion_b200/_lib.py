@@ -22,8 +22,11 @@ SYMBOLS = [
     "vf_unet_last_launches", "vf_unet_read_tap", "vf_unet_set_profiling", "vf_unet_profile_read",
     "vf_pack_views", "vf_pack_nchw", "vf_nhwc_to_nchw", "vf_q_sample",
     "vf_compose_ddpm_step", "vf_compose_mse",
-    "vf_embed", "vf_gn_stats", "vf_gn_apply", "vf_upsample2x", "vf_flat_to_padded", "vf_padded_to_flat", "vf_zero_padding", "vf_conv2d", "vf_debug_force_simt", "vf_debug_flags", "vf_debug_counters", "vf_debug_umma_shift", "vf_debug_umma_rate", "vf_attention",
+    "vf_embed", "vf_gn_stats", "vf_gn_apply", "vf_upsample2x", "vf_flat_to_padded", "vf_padded_to_flat", "vf_zero_padding", "vf_conv2d", "vf_debug_force_simt", "vf_debug_flags", "vf_debug_counters", "vf_debug_umma_shift", "vf_debug_umma_rate", "vf_debug_umma_mn", "vf_attention",
     "vf_pack_conv_weight",
+    "vf_unet_packed_t_bytes", "vf_unet_pack_weights_t", "vf_unet_backward_workspace_bytes", "vf_unet_backward",
+    "vf_conv2d_wgrad", "vf_unpack_conv_wgrad", "vf_pack_conv_weight_t", "vf_gn_backward", "vf_attention_backward",
+    "vf_upsample2x_backward", "vf_zero_insert2x", "vf_add_inplace", "vf_grad8_to_act",
 ]
 
 
@@ -116,9 +119,23 @@ def load() -> C.CDLL:
         "vf_debug_flags": (None, [i]),
         "vf_debug_counters": (None, [p]),
         "vf_debug_umma_rate": (i, [i, i, i, i, i, p, p]),
+        "vf_debug_umma_mn": (i, [p, i, p, i, i, i, i, p, p]),
         "vf_debug_umma_shift": (i, [p, i, p, i, i, p, p]),
         "vf_attention": (i, [p, p, i, i, i, i, p, p]),
         "vf_pack_conv_weight": (i, [p, i, i, i, i, p, i, i, i, p]),
+        "vf_unet_packed_t_bytes": (sz, [p]),
+        "vf_unet_pack_weights_t": (i, [p, p, p]),
+        "vf_unet_backward_workspace_bytes": (sz, [p]),
+        "vf_unet_backward": (i, [p, p, p, sz, p, C.POINTER(p), p]),
+        "vf_conv2d_wgrad": (i, [C.POINTER(ConvArgs), p, i, p, p]),
+        "vf_unpack_conv_wgrad": (i, [p, i, i, i, i, i, p, i, i, p]),
+        "vf_pack_conv_weight_t": (i, [p, i, i, i, i, p, i, i, i, i, p]),
+        "vf_gn_backward": (i, [p, i, p, i, p, i, p, i, i, i, i, i, i, p, p, i, p, p, p, p, p, i, p, i, p]),
+        "vf_attention_backward": (i, [p, p, p, i, i, i, i, p, p, p]),
+        "vf_upsample2x_backward": (i, [p, i, i, i, i, i, p, i, p]),
+        "vf_zero_insert2x": (i, [p, i, i, i, i, i, p, p]),
+        "vf_add_inplace": (i, [p, p, i, sz, p]),
+        "vf_grad8_to_act": (i, [p, sz, i, i, p, p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

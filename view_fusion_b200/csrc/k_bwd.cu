@@ -1,0 +1,589 @@
+// Backward operators of the UNet (reference: autograd through model/unet.py, driven by experiment.py:292).
+//
+//   vf_conv2d_wgrad        dW += dY^T X (per tap / segment) into a packed fp32 buffer, CUDA-core version (all layouts)
+//   vf_pack_conv_weight_t  transposed + tap-flipped weight pack, so that the data gradient is a forward vf_conv2d
+//   vf_unpack_conv_wgrad   packed fp32 weight gradient -> OIHW parameter gradient
+//   vf_gn_backward         GroupNorm (+Swish) backward: two HBM passes (reduce, apply), two-source aware
+//   vf_attention_backward  softmax(QK^T/sqrt(C))V backward (CUDA cores)
+//   vf_upsample2x_backward / vf_zero_insert2x / vf_add_inplace / vf_grad8_to_act   small layout kernels
+#include "vf_common.cuh"
+
+namespace vf {
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight gradient, CUDA cores: block = 64 output channels x 32 K-columns, rows split over blockIdx.z
+// ---------------------------------------------------------------------------------------------------------------
+struct WgradParams {
+  RowGeom geo;
+  const void* src[3];
+  int src_c[3];
+  int ksize[3];
+  int n_seg;
+  const void* dy;
+  int dy_ld;
+  int cout, cout_pad, k_total;
+  float* dwp;
+  int rows_per_split;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(const WgradParams p) {
+  __shared__ float Ys[16][64 + 4];
+  __shared__ float Xs[16][32 + 4];
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 64;
+  // locate the segment / tap / channel of this K tile (a tile never straddles a tap: C % 32 == 0)
+  int seg = 0, koff = 0;
+  while (seg + 1 < p.n_seg && k0 >= koff + p.ksize[seg] * p.ksize[seg] * p.src_c[seg]) { koff += p.ksize[seg] * p.ksize[seg] * p.src_c[seg]; ++seg; }
+  const int C = p.src_c[seg], ks = p.ksize[seg];
+  const int tap = (k0 - koff) / C, c0 = (k0 - koff) - tap * C;
+  const int shift = ks == 3 ? (tap / 3 - 1) * p.geo.W1 + (tap % 3 - 1) : 0;
+  const T* X = reinterpret_cast<const T*>(p.src[seg]);
+  const T* dY = reinterpret_cast<const T*>(p.dy);
+  const int M = p.geo.rows_total;
+  const int r0 = blockIdx.z * p.rows_per_split, r1 = min(M, r0 + p.rows_per_split);
+  const int tid = threadIdx.x;
+  const int tn = tid % 16, tk = tid / 16;          // thread computes n = tn*4..+3, k = tk*2..+1
+  float acc[4][2] = {};
+  for (int rb = r0; rb < r1; rb += 16) {
+    // stage 16 rows of dY (64 n) and of the shifted X (32 c)
+    for (int i = tid; i < 16 * 64; i += 256) {
+      const int rr = i / 64, n = i % 64;
+      const int m = rb + rr;
+      float v = 0.f;
+      if (m < r1 && n0 + n < p.cout) {
+        const RowInfo ri = decode_row(p.geo, m);
+        if (ri.valid) v = to_f(dY[(size_t)ri.out_row * p.dy_ld + n0 + n]);
+      }
+      Ys[rr][n] = v;
+    }
+    for (int i = tid; i < 16 * 32; i += 256) {
+      const int rr = i / 32, c = i % 32;
+      const long m = (long)rb + rr + shift;
+      float v = 0.f;
+      if (rb + rr < r1 && m >= 0 && m < M) v = to_f(X[(size_t)m * C + c0 + c]);
+      Xs[rr][c] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+      float y[4], x[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) y[i] = Ys[rr][tn * 4 + i];
+      x[0] = Xs[rr][tk * 2]; x[1] = Xs[rr][tk * 2 + 1];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc[i][0] += y[i] * x[0]; acc[i][1] += y[i] * x[1]; }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + tn * 4 + i;
+    if (n >= p.cout) continue;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) atomicAdd(p.dwp + (size_t)n * p.k_total + k0 + tk * 2 + j, acc[i][j]);
+  }
+}
+
+template <typename T>
+__global__ void pack_conv_weight_t_kernel(const float* __restrict__ w, int cout, int cin, int kk, T* __restrict__ dst, int cin_pad,
+                                          int k_total, int k_off, int n_stride) {
+  // dst[c][k_off + tap' * n_stride + n] = w[n][c][tap], tap' = kk-1-tap (the data gradient correlates with flipped taps)
+  const size_t total = (size_t)cin_pad * kk * n_stride;
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int c = (int)(gid / ((size_t)kk * n_stride));
+  const int r = (int)(gid % ((size_t)kk * n_stride));
+  const int tapf = r / n_stride, n = r % n_stride;
+  const int tap = kk - 1 - tapf;
+  const float v = (c < cin && n < cout) ? __ldg(w + ((size_t)n * cin + c) * kk + tap) : 0.f;
+  dst[(size_t)c * k_total + k_off + r] = from_f<T>(v);
+}
+
+__global__ void unpack_conv_wgrad_kernel(const float* __restrict__ dwp, int cout, int cin, int kk, int k_total, int k_off,
+                                         float* __restrict__ dw, int cin_total, int c_off) {
+  const size_t total = (size_t)cout * cin * kk;
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // over the segment's [cout][cin][kk] slice
+  if (gid >= total) return;
+  const int tap = (int)(gid % kk);
+  const int c = (int)((gid / kk) % cin);
+  const int n = (int)(gid / ((size_t)kk * cin));
+  dw[((size_t)n * cin_total + c_off + c) * kk + tap] += dwp[(size_t)n * k_total + k_off + tap * cin + c];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// GroupNorm (+Swish) backward
+//   z = xh*gamma + beta, xh = (x-mu)*rstd, y = swish(z);  dz = dy * swish'(z)
+//   pass 1: per (image, channel)  A = sum dz, B = sum dz*xh         (+ dgamma += B, dbeta += A)
+//   pass 2: dx = rstd * (gamma*dz - S1/n - xh*S2/n),  S1 = sum_group gamma*A, S2 = sum_group gamma*B
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kGbThreads = 256;
+
+struct GnBwdParams {
+  const void* s0; int C0; const float* st0; int ld0;
+  const void* s1; int C1; const float* st1; int ld1;
+  int HW, W1, P, groups, rows_per_cta, swish;
+  const float* gamma; const float* beta;
+  const void* dy;
+  float* red;            // [images][C][2]
+  float* dgamma; float* dbeta;
+  void* dx0; int acc0; void* dx1; int acc1;
+};
+
+__device__ __forceinline__ float dswish(float z) {
+  const float s = 1.f / (1.f + __expf(-z));
+  return s * (1.f + z * (1.f - s));
+}
+
+// shared prologue: per channel mu / rstd of its group -> smem mr[C][2]
+__device__ __forceinline__ void gn_group_stats(const GnBwdParams& p, int img, float* mr) {
+  const int C = p.C0 + p.C1, gs = C / p.groups;
+  const float inv_n = 1.f / ((float)gs * (float)p.HW);
+  const float* sa = p.st0 + (size_t)img * p.ld0 * 2;
+  const float* sb = p.st1 ? p.st1 + (size_t)img * p.ld1 * 2 : nullptr;
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    const int g0 = ch / gs * gs;
+    float s = 0.f, q = 0.f;
+    for (int j = 0; j < gs; ++j) {
+      const int cc = g0 + j;
+      const float* e = cc < p.C0 ? sa + 2 * cc : sb + 2 * (cc - p.C0);
+      s += __ldg(e); q += __ldg(e + 1);
+    }
+    const float mean = s * inv_n;
+    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+    mr[2 * ch] = mean;
+    mr[2 * ch + 1] = rsqrtf(var + 1e-5f);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kGbThreads) gn_bwd_reduce_kernel(const GnBwdParams p) {
+  constexpr int VEC = VecOf<T>::N;
+  extern __shared__ float sm[];
+  const int C = p.C0 + p.C1, CV = C / VEC;
+  float* mr = sm;              // [C][2]
+  float* acc = sm + 2 * C;     // [C][2]
+  const int img = blockIdx.y;
+  gn_group_stats(p, img, mr);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  const int PY = blockDim.x / CV;
+  const int cv = threadIdx.x % CV, py = threadIdx.x / CV;
+  const int c = cv * VEC;
+  const T* src = c < p.C0 ? (const T*)p.s0 + (size_t)img * p.P * p.C0 + c : (const T*)p.s1 + (size_t)img * p.P * p.C1 + (c - p.C0);
+  const int ld = c < p.C0 ? p.C0 : p.C1;
+  const T* dy = (const T*)p.dy + (size_t)img * p.P * C + c;
+  float mu[VEC], rs[VEC], ga[VEC], be[VEC], sA[VEC], sB[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) { mu[j] = mr[2 * (c + j)]; rs[j] = mr[2 * (c + j) + 1]; ga[j] = __ldg(p.gamma + c + j); be[j] = __ldg(p.beta + c + j); sA[j] = sB[j] = 0.f; }
+  const int p0 = blockIdx.x * p.rows_per_cta, p1 = min(p.P, p0 + p.rows_per_cta);
+  for (int r = p0 + py; r < p1; r += PY) {
+    const int yy = r / p.W1, xx = r - yy * p.W1;
+    if (yy == 0 || xx == 0) continue;
+    float x[VEC], g[VEC];
+    load_vec(src + (size_t)r * ld, x);
+    load_vec(dy + (size_t)r * C, g);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float xh = (x[j] - mu[j]) * rs[j];
+      const float dz = p.swish ? g[j] * dswish(xh * ga[j] + be[j]) : g[j];
+      sA[j] += dz; sB[j] += dz * xh;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) { atomicAdd(&acc[2 * (c + j)], sA[j]); atomicAdd(&acc[2 * (c + j) + 1], sB[j]); }
+  __syncthreads();
+  float* red = p.red + (size_t)img * C * 2;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(red + 2 * i, acc[2 * i]);
+    atomicAdd(red + 2 * i + 1, acc[2 * i + 1]);
+    atomicAdd(p.dbeta + i, acc[2 * i]);
+    atomicAdd(p.dgamma + i, acc[2 * i + 1]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kGbThreads) gn_bwd_apply_kernel(const GnBwdParams p) {
+  constexpr int VEC = VecOf<T>::N;
+  extern __shared__ float sm[];
+  const int C = p.C0 + p.C1, CV = C / VEC;
+  float* mr = sm;              // [C][2] mean, rstd
+  float* tt = sm + 2 * C;      // [C][2] t1 = rstd*S1/n, t2 = rstd*S2/n
+  const int img = blockIdx.y;
+  gn_group_stats(p, img, mr);
+  __syncthreads();
+  {
+    const int gs = C / p.groups;
+    const float inv_n = 1.f / ((float)gs * (float)p.HW);
+    const float* red = p.red + (size_t)img * C * 2;
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+      const int g0 = ch / gs * gs;
+      float S1 = 0.f, S2 = 0.f;
+      for (int j = 0; j < gs; ++j) { const float gm = __ldg(p.gamma + g0 + j); S1 += gm * __ldg(red + 2 * (g0 + j)); S2 += gm * __ldg(red + 2 * (g0 + j) + 1); }
+      tt[2 * ch] = mr[2 * ch + 1] * S1 * inv_n;
+      tt[2 * ch + 1] = mr[2 * ch + 1] * S2 * inv_n;
+    }
+  }
+  __syncthreads();
+  const int PY = blockDim.x / CV;
+  const int cv = threadIdx.x % CV, py = threadIdx.x / CV;
+  const int c = cv * VEC;
+  const bool first = c < p.C0;
+  const T* src = first ? (const T*)p.s0 + (size_t)img * p.P * p.C0 + c : (const T*)p.s1 + (size_t)img * p.P * p.C1 + (c - p.C0);
+  const int ld = first ? p.C0 : p.C1;
+  T* dx = first ? (T*)p.dx0 + (size_t)img * p.P * p.C0 + c : (T*)p.dx1 + (size_t)img * p.P * p.C1 + (c - p.C0);
+  const bool accum = first ? p.acc0 : p.acc1;
+  const T* dy = (const T*)p.dy + (size_t)img * p.P * C + c;
+  float mu[VEC], rs[VEC], ga[VEC], be[VEC], t1[VEC], t2[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    mu[j] = mr[2 * (c + j)]; rs[j] = mr[2 * (c + j) + 1]; ga[j] = __ldg(p.gamma + c + j); be[j] = __ldg(p.beta + c + j);
+    t1[j] = tt[2 * (c + j)]; t2[j] = tt[2 * (c + j) + 1];
+  }
+  const int p0 = blockIdx.x * p.rows_per_cta, p1 = min(p.P, p0 + p.rows_per_cta);
+  for (int r = p0 + py; r < p1; r += PY) {
+    const int yy = r / p.W1, xx = r - yy * p.W1;
+    float o[VEC];
+    if (yy == 0 || xx == 0) {
+      if (accum) continue;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o[j] = 0.f;          // gradients of padding rows are exact zeros
+    } else {
+      float x[VEC], g[VEC];
+      load_vec(src + (size_t)r * ld, x);
+      load_vec(dy + (size_t)r * C, g);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const float xh = (x[j] - mu[j]) * rs[j];
+        const float dz = p.swish ? g[j] * dswish(xh * ga[j] + be[j]) : g[j];
+        o[j] = rs[j] * ga[j] * dz - t1[j] - xh * t2[j];
+      }
+      if (accum) {
+        float old[VEC];
+        load_vec(dx + (size_t)r * ld, old);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) o[j] += old[j];
+      }
+    }
+    store_vec(dx + (size_t)r * ld, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// attention backward (CUDA cores): per (image, 8 queries)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int BQ = 8;
+template <typename T>
+__global__ void __launch_bounds__(256) attn_bwd_simt_kernel(const T* __restrict__ qk, int ld, const T* __restrict__ vt, const T* __restrict__ dO,
+                                                            int L, int C, T* __restrict__ dq_out, int dq_ld, float* __restrict__ dkv) {
+  extern __shared__ float sm[];
+  float* q = sm;                 // [BQ][C]
+  float* go = q + BQ * C;        // [BQ][C]  dO rows
+  float* pr = go + BQ * C;       // [BQ][L]  P then dS
+  float* dp = pr + BQ * L;       // [BQ][L]
+  const int img = blockIdx.y, q0 = blockIdx.x * BQ;
+  const T* base = qk + (size_t)img * L * ld;
+  for (int i = threadIdx.x; i < BQ * C; i += blockDim.x) {
+    const int qi = i / C, c = i % C;
+    const bool in = q0 + qi < L;
+    q[i] = in ? to_f(base[(size_t)(q0 + qi) * ld + c]) : 0.f;
+    go[i] = in ? to_f(dO[((size_t)img * L + q0 + qi) * C + c]) : 0.f;
+  }
+  __syncthreads();
+  const float scale = rsqrtf((float)C);
+  for (int i = threadIdx.x; i < BQ * L; i += blockDim.x) {
+    const int qi = i / L, kj = i % L;
+    const T* kr = base + (size_t)kj * ld + C;
+    float s = 0.f, d = 0.f;
+    for (int c = 0; c < C; ++c) {
+      s += q[qi * C + c] * to_f(kr[c]);
+      const float v = vt ? to_f(vt[((size_t)img * C + c) * L + kj]) : to_f(base[(size_t)kj * ld + 2 * C + c]);
+      d += go[qi * C + c] * v;
+    }
+    pr[i] = s * scale;
+    dp[i] = d;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int qi = warp; qi < BQ; qi += blockDim.x >> 5) {
+    float* row = pr + qi * L;
+    float* drow = dp + qi * L;
+    float m = -INFINITY;
+    for (int j = lane; j < L; j += 32) m = fmaxf(m, row[j]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int j = lane; j < L; j += 32) { const float e = expf(row[j] - m); row[j] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    float delta = 0.f;
+    for (int j = lane; j < L; j += 32) { row[j] *= inv; delta += row[j] * drow[j]; }
+    delta = warp_sum(delta);
+    // dV[j][c] += P[qi][j] * dO[qi][c] is accumulated below; here dS = P * (dP - delta)
+    for (int j = lane; j < L; j += 32) { const float pj = row[j]; drow[j] = pj * (drow[j] - delta); }
+  }
+  __syncthreads();
+  // dQ[qi][c] = scale * sum_j dS[qi][j] K[j][c]
+  for (int i = threadIdx.x; i < BQ * C; i += blockDim.x) {
+    const int qi = i / C, c = i % C;
+    if (q0 + qi >= L) continue;
+    float acc = 0.f;
+    for (int j = 0; j < L; ++j) acc += dp[qi * L + j] * to_f(base[(size_t)j * ld + C + c]);
+    dq_out[((size_t)img * L + q0 + qi) * dq_ld + c] = from_f<T>(acc * scale);
+  }
+  // dK[j][c] += scale * sum_qi dS[qi][j] Q[qi][c];  dV[j][c] += sum_qi P[qi][j] dO[qi][c]   (fp32 atomics)
+  float* dk = dkv + (size_t)img * L * 2 * C;
+  for (int i = threadIdx.x; i < L * C; i += blockDim.x) {
+    const int j = i / C, c = i % C;
+    float ak = 0.f, av = 0.f;
+#pragma unroll
+    for (int qi = 0; qi < BQ; ++qi) { ak += dp[qi * L + j] * q[qi * C + c]; av += pr[qi * L + j] * go[qi * C + c]; }
+    atomicAdd(dk + (size_t)j * 2 * C + c, ak * scale);
+    atomicAdd(dk + (size_t)j * 2 * C + C + c, av);
+  }
+}
+
+template <typename T>
+__global__ void dkv_to_act_kernel(const float* __restrict__ dkv, int C, size_t rows, T* __restrict__ dqkv) {
+  const size_t total = rows * 2 * C;
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const size_t r = gid / (2 * C);
+  const int c = (int)(gid % (2 * C));
+  dqkv[r * 3 * C + C + c] = from_f<T>(dkv[gid]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// small layout kernels (PADDED tensors, 16-byte vectors)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T* __restrict__ dy, int H, int W, int C, size_t total, T* __restrict__ dx, int accumulate) {
+  constexpr int VEC = VecOf<T>::N;
+  const int CV = C / VEC;
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       // over PADDED low-res (row, vec)
+  if (gid >= total) return;
+  const int cv = (int)(gid % CV);
+  size_t r = gid / CV;
+  const int W1 = W + 1, P = (H + 1) * W1;
+  const int rem = (int)(r % P);
+  const size_t img = r / P;
+  const int yy = rem / W1, xx = rem - yy * W1;
+  float o[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) o[j] = 0.f;
+  if (yy > 0 && xx > 0) {
+    const int Wo1 = 2 * W + 1;
+    const T* b = dy + (img * (size_t)(2 * H + 1) * Wo1) * C + cv * VEC;
+#pragma unroll
+    for (int dyy = 0; dyy < 2; ++dyy)
+#pragma unroll
+      for (int dxx = 0; dxx < 2; ++dxx) {
+        float v[VEC];
+        load_vec(b + ((size_t)(2 * (yy - 1) + dyy + 1) * Wo1 + (2 * (xx - 1) + dxx + 1)) * C, v);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) o[j] += v[j];
+      }
+    if (accumulate) {
+      float old[VEC];
+      load_vec(dx + gid * VEC, old);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o[j] += old[j];
+    }
+  } else if (accumulate) {
+    return;
+  }
+  store_vec(dx + gid * VEC, o);
+}
+
+// dst (PADDED 2H x 2W) = dy (PADDED H x W) at even pixels, zero elsewhere
+template <typename T>
+__global__ void __launch_bounds__(256) zero_insert2x_kernel(const T* __restrict__ dy, int H, int W, int C, size_t total, T* __restrict__ dst) {
+  constexpr int VEC = VecOf<T>::N;
+  const int CV = C / VEC;
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       // over PADDED full-res (row, vec)
+  if (gid >= total) return;
+  const int cv = (int)(gid % CV);
+  size_t r = gid / CV;
+  const int Wo1 = 2 * W + 1, Po = (2 * H + 1) * Wo1;
+  const int rem = (int)(r % Po);
+  const size_t img = r / Po;
+  const int yy = rem / Wo1, xx = rem - yy * Wo1;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (yy > 0 && xx > 0 && ((yy - 1) & 1) == 0 && ((xx - 1) & 1) == 0)
+    v = *reinterpret_cast<const uint4*>(dy + ((img * (H + 1) + ((yy - 1) / 2 + 1)) * (size_t)(W + 1) + ((xx - 1) / 2 + 1)) * C + cv * VEC);
+  *reinterpret_cast<uint4*>(dst + gid * VEC) = v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) add_inplace_kernel(T* __restrict__ dst, const T* __restrict__ src, size_t nvec) {
+  constexpr int VEC = VecOf<T>::N;
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= nvec) return;
+  float a[VEC], b[VEC];
+  load_vec(dst + gid * VEC, a);
+  load_vec(src + gid * VEC, b);
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) a[j] += b[j];
+  store_vec(dst + gid * VEC, a);
+}
+
+template <typename T>
+__global__ void grad8_to_act_kernel(const float* __restrict__ g8, size_t rows, int ld, T* __restrict__ dst) {
+  const size_t total = rows * ld;
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const size_t r = gid / ld;
+  const int c = (int)(gid % ld);
+  dst[gid] = from_f<T>(c < 8 ? g8[r * 8 + c] : 0.f);
+}
+
+}  // namespace vf
+
+using namespace vf;
+#define VF_API extern "C" __attribute__((visibility("default")))
+
+VF_API int vf_conv2d_wgrad(const vf_conv_args* a, const void* dy, int dy_ld, float* dwp, vf_stream stream) {
+  VF_REQUIRE(a && dy && dwp, "vf_conv2d_wgrad: null args");
+  WgradParams p{};
+  p.geo = make_geom(a->images, a->H, a->W, a->in_padded, a->out_padded, a->stride == 2);
+  int k_total = 0;
+  for (int s = 0; s < a->n_seg; ++s) {
+    p.src[s] = a->src[s]; p.src_c[s] = a->src_c[s]; p.ksize[s] = a->ksize[s];
+    VF_REQUIRE(a->src_c[s] % 32 == 0, "vf_conv2d_wgrad: segment channels %d not a multiple of 32", a->src_c[s]);
+    k_total += a->ksize[s] * a->ksize[s] * a->src_c[s];
+  }
+  p.n_seg = a->n_seg; p.dy = dy; p.dy_ld = dy_ld; p.cout = a->cout; p.cout_pad = a->cout_pad; p.k_total = k_total; p.dwp = dwp;
+  const int M = p.geo.rows_total;
+  int splits = cdiv(M, 4096);
+  if (splits > 512) splits = 512;
+  p.rows_per_split = (int)align_up((size_t)cdiv(M, splits), 16);
+  splits = cdiv(M, p.rows_per_split);
+  dim3 grid(k_total / 32, cdiv(a->cout, 64), splits);
+  if (a->dtype == VF_BF16) conv_wgrad_simt_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(p);
+  else conv_wgrad_simt_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(p);
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}
+
+VF_API int vf_pack_conv_weight_t(const float* w_oihw, int cout, int cin, int ksize, int dtype, void* dst, int cin_pad, int k_total,
+                                 int k_off, int n_stride, vf_stream stream) {
+  VF_REQUIRE(w_oihw && dst && cout > 0 && cin > 0 && (ksize == 1 || ksize == 3) && n_stride >= cout && cin_pad >= cin, "vf_pack_conv_weight_t: bad args");
+  VF_REQUIRE(k_off + ksize * ksize * n_stride <= k_total, "vf_pack_conv_weight_t: row overflow");
+  const size_t total = (size_t)cin_pad * ksize * ksize * n_stride;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (dtype == VF_BF16) pack_conv_weight_t_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(w_oihw, cout, cin, ksize * ksize, (__nv_bfloat16*)dst, cin_pad, k_total, k_off, n_stride);
+  else pack_conv_weight_t_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(w_oihw, cout, cin, ksize * ksize, (float*)dst, cin_pad, k_total, k_off, n_stride);
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}
+
+VF_API int vf_unpack_conv_wgrad(const float* dwp, int cout, int cin, int ksize, int k_total, int k_off, float* dw_oihw, int cin_total,
+                                int c_off, vf_stream stream) {
+  VF_REQUIRE(dwp && dw_oihw && cout > 0 && cin > 0 && c_off >= 0 && c_off + cin <= cin_total, "vf_unpack_conv_wgrad: bad args");
+  const size_t total = (size_t)cout * cin * ksize * ksize;
+  unpack_conv_wgrad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(dwp, cout, cin, ksize * ksize, k_total, k_off, dw_oihw, cin_total, c_off);
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}
+
+VF_API int vf_gn_backward(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1, const float* stats1,
+                          int stats1_ld, int dtype, int images, int H, int W, int groups, const float* gamma, const float* beta, int swish,
+                          const void* dy, float* scratch, float* dgamma, float* dbeta, void* dx0, int acc0, void* dx1, int acc1,
+                          vf_stream stream) {
+  VF_REQUIRE(src0 && stats0 && gamma && beta && dy && scratch && dgamma && dbeta && dx0, "vf_gn_backward: null args");
+  if (!src1) C1 = 0;
+  VF_REQUIRE(C1 == 0 || (stats1 && dx1), "vf_gn_backward: second source needs stats and dx");
+  const int vec = dtype == VF_BF16 ? 8 : 4;
+  const int C = C0 + C1;
+  VF_REQUIRE(C0 % vec == 0 && C1 % vec == 0 && C % groups == 0 && C / vec <= kGbThreads, "vf_gn_backward: bad channel counts (%d, %d)", C0, C1);
+  GnBwdParams p{};
+  p.s0 = src0; p.C0 = C0; p.st0 = stats0; p.ld0 = stats0_ld; p.s1 = src1; p.C1 = C1; p.st1 = C1 ? stats1 : nullptr; p.ld1 = stats1_ld;
+  p.HW = H * W; p.W1 = W + 1; p.P = (H + 1) * (W + 1); p.groups = groups; p.swish = swish;
+  p.gamma = gamma; p.beta = beta; p.dy = dy; p.red = scratch; p.dgamma = dgamma; p.dbeta = dbeta;
+  p.dx0 = dx0; p.acc0 = acc0; p.dx1 = dx1; p.acc1 = acc1;
+  const int CV = C / vec, PY = kGbThreads / CV > 0 ? kGbThreads / CV : 1;
+  const int threads = CV * PY;
+  int want = cdiv(148 * 8, images);
+  int max_splits = p.P / (PY * 4) > 0 ? p.P / (PY * 4) : 1;
+  int splits = want < 1 ? 1 : (want > max_splits ? max_splits : want);
+  p.rows_per_cta = cdiv(p.P, splits);
+  splits = cdiv(p.P, p.rows_per_cta);
+  cudaStream_t st = as_stream(stream);
+  VF_CUDA(cudaMemsetAsync(scratch, 0, (size_t)images * C * 2 * sizeof(float), st));
+  dim3 grid(splits, images);
+  const size_t smem = 4 * C * sizeof(float);
+  if (dtype == VF_BF16) {
+    gn_bwd_reduce_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>(p);
+    gn_bwd_apply_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>(p);
+  } else {
+    gn_bwd_reduce_kernel<float><<<grid, threads, smem, st>>>(p);
+    gn_bwd_apply_kernel<float><<<grid, threads, smem, st>>>(p);
+  }
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}
+
+VF_API int vf_attention_backward(const void* qk, const void* vt, const void* d_out, int dtype, int images, int L, int C, float* scratch,
+                                 void* dqkv, vf_stream stream) {
+  VF_REQUIRE(qk && d_out && scratch && dqkv && images > 0 && L > 0 && C > 0, "vf_attention_backward: bad args");
+  const size_t smem = (size_t)BQ * (2 * C + 2 * L) * sizeof(float);
+  VF_REQUIRE(smem <= 48 * 1024, "vf_attention_backward: L=%d C=%d too large", L, C);
+  cudaStream_t st = as_stream(stream);
+  VF_CUDA(cudaMemsetAsync(scratch, 0, (size_t)images * L * 2 * C * sizeof(float), st));
+  dim3 grid(cdiv(L, BQ), images);
+  const size_t rows = (size_t)images * L;
+  const unsigned g2 = (unsigned)((rows * 2 * C + 255) / 256);
+  if (dtype == VF_BF16) {
+    attn_bwd_simt_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16*)qk, 3 * C, (const __nv_bfloat16*)vt, (const __nv_bfloat16*)d_out, L, C, (__nv_bfloat16*)dqkv, 3 * C, scratch);
+    dkv_to_act_kernel<__nv_bfloat16><<<g2, 256, 0, st>>>(scratch, C, rows, (__nv_bfloat16*)dqkv);
+  } else {
+    attn_bwd_simt_kernel<float><<<grid, 256, smem, st>>>((const float*)qk, 3 * C, (const float*)vt, (const float*)d_out, L, C, (float*)dqkv, 3 * C, scratch);
+    dkv_to_act_kernel<float><<<g2, 256, 0, st>>>(scratch, C, rows, (float*)dqkv);
+  }
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}
+
+VF_API int vf_upsample2x_backward(const void* dy, int dtype, int images, int H, int W, int C, void* dx, int accumulate, vf_stream stream) {
+  VF_REQUIRE(dy && dx && images > 0 && H > 0 && W > 0 && C > 0, "vf_upsample2x_backward: bad args");
+  const int vec = dtype == VF_BF16 ? 8 : 4;
+  VF_REQUIRE(C % vec == 0, "vf_upsample2x_backward: C=%d", C);
+  const size_t total = (size_t)images * (H + 1) * (W + 1) * (C / vec);
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (dtype == VF_BF16) upsample2x_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)dy, H, W, C, total, (__nv_bfloat16*)dx, accumulate);
+  else upsample2x_bwd_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)dy, H, W, C, total, (float*)dx, accumulate);
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}
+
+VF_API int vf_zero_insert2x(const void* dy, int dtype, int images, int H, int W, int C, void* dst, vf_stream stream) {
+  VF_REQUIRE(dy && dst && images > 0 && H > 0 && W > 0 && C > 0, "vf_zero_insert2x: bad args");
+  const int vec = dtype == VF_BF16 ? 8 : 4;
+  VF_REQUIRE(C % vec == 0, "vf_zero_insert2x: C=%d", C);
+  const size_t total = (size_t)images * (2 * H + 1) * (2 * W + 1) * (C / vec);
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (dtype == VF_BF16) zero_insert2x_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)dy, H, W, C, total, (__nv_bfloat16*)dst);
+  else zero_insert2x_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)dy, H, W, C, total, (float*)dst);
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}
+
+VF_API int vf_add_inplace(void* dst, const void* src, int dtype, size_t n_elems, vf_stream stream) {
+  VF_REQUIRE(dst && src, "vf_add_inplace: null args");
+  const size_t vec = dtype == VF_BF16 ? 8 : 4;
+  VF_REQUIRE(n_elems % vec == 0, "vf_add_inplace: n_elems not a multiple of %zu", vec);
+  const size_t nvec = n_elems / vec;
+  const unsigned grid = (unsigned)((nvec + 255) / 256);
+  if (dtype == VF_BF16) add_inplace_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((__nv_bfloat16*)dst, (const __nv_bfloat16*)src, nvec);
+  else add_inplace_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((float*)dst, (const float*)src, nvec);
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}
+
+VF_API int vf_grad8_to_act(const float* g8, size_t rows, int dtype, int ld, void* dst, vf_stream stream) {
+  VF_REQUIRE(g8 && dst && ld >= 8, "vf_grad8_to_act: bad args");
+  const size_t total = rows * ld;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (dtype == VF_BF16) grad8_to_act_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(g8, rows, ld, (__nv_bfloat16*)dst);
+  else grad8_to_act_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(g8, rows, ld, (float*)dst);
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}

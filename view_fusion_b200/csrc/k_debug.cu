@@ -180,3 +180,83 @@ extern "C" __attribute__((visibility("default"))) int vf_debug_umma_rate(int N, 
   VF_LAUNCH_CHECK();
   return VF_OK;
 }
+
+// ---- probe 3: MN-major operands (the weight-gradient GEMM reduces over pixel ROWS, so both operands have the reduction
+// dimension K as the slow axis: A[k][m], B[k][n] as TMA loads them from NHWC matrices) ------------------------------------
+namespace vf {
+__global__ void __launch_bounds__(128) umma_mn_probe(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                                                     int shift_rows, int lbo_bytes, int sbo_bytes, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t bar_ld = base, bar_mma = base + 8, tmem_slot = base + 16;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + 16);
+  const uint32_t sA = base + 1024;               // 2 boxes of [64 k-rows x 64 m] = 2 x 8 KB  (M = 128)
+  const uint32_t sB = sA + 2 * 8192;             // [128 k-rows x 64 n] (rows 0..127 loaded so that shifted reads stay inside)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { ptx::mbar_init(bar_ld, 1); ptx::mbar_init(bar_mma, 1); ptx::fence_barrier_init(); }
+  if (warp == 0) { ptx::tmem_alloc(tmem_slot, 64); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot_ptr;
+  if (threadIdx.x == 0) {
+    ptx::mbar_arrive_expect_tx(bar_ld, 2 * 8192 + 2 * 8192);
+    ptx::tma_load_2d(sA, &mapA, bar_ld, 0, 0);          // m 0..63,  k-rows 0..63
+    ptx::tma_load_2d(sA + 8192, &mapA, bar_ld, 64, 0);  // m 64..127
+    ptx::tma_load_2d(sB, &mapB, bar_ld, 0, 0);          // n 0..63, k-rows 0..63
+    ptx::tma_load_2d(sB + 8192, &mapB, bar_ld, 0, 64);  // k-rows 64..127
+    ptx::mbar_wait(bar_ld, 0);
+    ptx::tc_fence_after();
+    const uint32_t idesc = ptx::make_idesc_bf16(128, 64, 1, 1);     // both operands MN-major
+    for (int k = 0; k < 4; ++k) {                                    // K = 64 rows = 4 x 16
+      const uint64_t ad = ptx::make_smem_desc(sA + k * 2048, (uint32_t)lbo_bytes, (uint32_t)sbo_bytes);
+      const uint64_t bd = ptx::make_smem_desc(sB + (uint32_t)shift_rows * 128 + k * 2048, (uint32_t)lbo_bytes, (uint32_t)sbo_bytes);
+      ptx::umma_f16(tmem_d, ad, bd, idesc, k > 0 ? 1u : 0u);
+    }
+    ptx::umma_commit(bar_mma);
+  }
+  ptx::mbar_wait(bar_mma, 0);
+  ptx::tc_fence_after();
+  const int r = warp * 32 + lane;
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    uint32_t rr[16];
+    ptx::tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, rr);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) out[r * 64 + c0 + j] = __uint_as_float(rr[j]);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_d, 64); }
+}
+}  // namespace vf
+
+// A: [rows >= 64, 128] bf16 (row = k, col = m), B: [rows >= 128, 64] bf16 (row = k, col = n); out [128, 64] fp32:
+// out[m][n] = sum_{k<64} A[k][m] * B[shift_rows + k][n]
+extern "C" __attribute__((visibility("default"))) int vf_debug_umma_mn(const void* A, int rowsA, const void* B, int rowsB, int shift_rows,
+                                                                       int lbo_bytes, int sbo_bytes, float* out, vf_stream stream) {
+  using namespace vf;
+  VF_REQUIRE(A && B && out && rowsA >= 64 && rowsB >= 128 && shift_rows >= 0 && shift_rows <= 64, "vf_debug_umma_mn: bad args");
+  CUtensorMap mA, mB;
+  {
+    const uint64_t dims[2] = {128, (uint64_t)rowsA};
+    const uint64_t strides[1] = {256};
+    const uint32_t box[2] = {64, 64};
+    int rc = encode_bf16_map(&mA, A, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {64, (uint64_t)rowsB};
+    const uint64_t strides[1] = {128};
+    const uint32_t box[2] = {64, 64};
+    int rc = encode_bf16_map(&mB, B, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  const size_t smem = 1024 + 1024 + 2 * 8192 + 2 * 8192;
+  VF_CUDA(cudaFuncSetAttribute(umma_mn_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_mn_probe<<<1, 128, smem, as_stream(stream)>>>(mA, mB, shift_rows, lbo_bytes, sbo_bytes, out);
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}

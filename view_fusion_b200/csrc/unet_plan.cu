@@ -35,6 +35,8 @@ struct ResBlock {
   int an_w = -1, an_b = -1, qkv_w = -1, ao_w = -1, ao_b = -1;
   // packed offsets (bytes from the start of the packed buffer)
   size_t w1 = 0, w2 = 0, wqkv = 0, wout = 0, bias2 = 0;
+  // transposed (data-gradient) packs in packed_t
+  size_t wt1 = 0, wt2 = 0, wtr0 = 0, wtr1 = 0, wtqkv = 0, wtout = 0;
   int emb_col = 0;
 };
 
@@ -44,7 +46,7 @@ struct Layer {
   std::string name;
   int c = 0;
   int w_idx = -1, b_idx = -1;
-  size_t w = 0;
+  size_t w = 0, wt = 0;
 };
 
 }  // namespace vf
@@ -56,7 +58,8 @@ struct vf_unet {
   std::vector<vf::ResBlock> blocks;
   std::vector<vf::Layer> downs, mid, ups;
   int final_c = 0, fin_gw = -1, fin_gb = -1, fin_w = -1, fin_b = -1;
-  size_t final_w = 0;
+  size_t final_w = 0, final_wt = 0;
+  int final_npad = 16;
   int mlp_w0, mlp_b0, mlp_w2, mlp_b2;
   int E = 0;
   int k0 = 0;
@@ -69,6 +72,28 @@ struct vf_unet {
   int last_images = 0;
   // optional per-kernel-class timing of one forward (CUDA events around every launch; perturbs overlap, so it is
   // only enabled for the roofline breakdown, never for the throughput measurement)
+  // training tape: what the last forward did, in order (replayed in reverse by vf_unet_backward)
+  struct TapeOp {
+    int kind;                          // 0 conv, 1 gn, 2 attention, 3 upsample
+    vf_conv_args conv;
+    int w_idx[3], c_off[3], cin_total[3];   // OIHW parameter of each K segment (-1: identity / none), channel offset in it
+    int b_idx[2];                      // bias parameters summed into this conv's bias (-1: none)
+    int emb_col, nf_w, nf_b;           // embedding columns added in the epilogue (-1: none)
+    size_t wt_off[3];                  // transposed weight pack per segment in packed_t (SIZE_MAX: no data gradient)
+    const void* gsrc0; const void* gsrc1; int gC0, gC1; const float* gst0; const float* gst1; int gld0, gld1; int gw, gb, swish;
+    void* gdst; int gH, gW;
+    const void* qkv; const void* vt; void* o; int aC, aL;
+    const void* usrc; void* udst; int uH, uW, uC;
+  };
+  std::vector<TapeOp> tape;
+  std::map<const void*, size_t> act_bytes;
+  const float* last_emb = nullptr;     // [rows, E] of the last forward
+  const float* emb_w_dev = nullptr;    // concatenated embedding matrix inside the packed buffer of the last forward
+  const float* last_level = nullptr; const float* last_angle = nullptr; const int* last_img_row = nullptr;
+  int last_rows = 0;
+  const void* last_x0 = nullptr; float* last_out = nullptr;
+  size_t packed_t_bytes = 0;
+  bool packed_t = false;
   bool profiling = false;
   std::vector<cudaEvent_t> ev;
   std::vector<int> ev_kind;      // kind of the launch between ev[i] and ev[i+1]
@@ -153,6 +178,7 @@ struct Exec {
     off = align_up(off, 256);
     void* p = dry ? nullptr : base + off;
     off += bytes;
+    if (!dry && u) u->act_bytes[p] = bytes;
     return p;
   }
 };
@@ -322,6 +348,27 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_create(const vf_un
   u->emb_w_off = take((size_t)u->E * ic * 4);
   u->emb_b_off = take((size_t)u->E * 4);
   u->packed_bytes = align_up(off, 256);
+  // transposed packs (data gradients): rows = source channels, K = taps * (gradient channels)
+  off = 0;
+  for (auto& b : u->blocks) {
+    const int cin = b.c0 + b.c1;
+    b.wt1 = take((size_t)cin * 9 * b.cout * es);
+    b.wt2 = take((size_t)b.cout * 9 * b.cout * es);
+    if (b.rs_w >= 0) {
+      b.wtr0 = take((size_t)b.c0 * b.cout * es);
+      if (b.c1) b.wtr1 = take((size_t)b.c1 * b.cout * es);
+    }
+    if (b.attn) {
+      b.wtqkv = take((size_t)b.cout * 3 * b.cout * es);
+      b.wtout = take((size_t)b.cout * b.cout * es);
+    }
+  }
+  for (auto* sec : {&u->downs, &u->mid, &u->ups})
+    for (auto& l : *sec)
+      if (l.kind == 2 || l.kind == 3) l.wt = take((size_t)l.c * 9 * l.c * es);
+  u->final_npad = act_dtype == VF_BF16 ? 64 : 16;
+  u->final_wt = take((size_t)u->final_c * 9 * u->final_npad * es);
+  u->packed_t_bytes = align_up(off, 256);
   *out = u;
   return VF_OK;
 }
@@ -387,10 +434,25 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_pack_weights(vf_un
 
 namespace vf {
 
-static void conv_call(Exec& ex, const vf_unet* u, vf_conv_args& a) {
+struct ConvMeta {
+  int w_idx[3] = {-1, -1, -1}, c_off[3] = {0, 0, 0}, cin_total[3] = {0, 0, 0};
+  int b_idx[2] = {-1, -1};
+  int emb_col = -1, nf_w = -1, nf_b = -1;
+  size_t wt_off[3] = {SIZE_MAX, SIZE_MAX, SIZE_MAX};
+};
+
+static void conv_call(Exec& ex, vf_unet* u, vf_conv_args& a, const ConvMeta& m) {
   a.dtype = u->dtype;
   if (a.out_dtype < 0) a.out_dtype = u->dtype;
   VF_RUN(ex, K_CONV, vf_conv2d(&a, (vf_stream)ex.st));
+  if (!ex.dry) {
+    vf_unet::TapeOp t{};
+    t.kind = 0; t.conv = a;
+    for (int i = 0; i < 3; ++i) { t.w_idx[i] = m.w_idx[i]; t.c_off[i] = m.c_off[i]; t.cin_total[i] = m.cin_total[i]; t.wt_off[i] = m.wt_off[i]; }
+    t.b_idx[0] = m.b_idx[0]; t.b_idx[1] = m.b_idx[1];
+    t.emb_col = m.emb_col; t.nf_w = m.nf_w; t.nf_b = m.nf_b;
+    u->tape.push_back(t);
+  }
 }
 
 static vf_conv_args conv_args_init() {
@@ -404,7 +466,7 @@ static vf_conv_args conv_args_init() {
 
 // GroupNorm (+Swish) of cat(x, skip) -> new activation.  Statistics come from the producers' epilogues when
 // available, otherwise from a separate vf_gn_stats pass.
-static Act gn_block(Exec& ex, const vf_unet* u, int images, const Act& x, const Act* skip, int gw, int gb, bool swish) {
+static Act gn_block(Exec& ex, vf_unet* u, int images, const Act& x, const Act* skip, int gw, int gb, bool swish) {
   const int C1 = skip ? skip->C : 0;
   const int C = x.C + C1;
   const float *s0 = x.stats, *s1 = skip ? skip->stats : nullptr;
@@ -417,6 +479,14 @@ static Act gn_block(Exec& ex, const vf_unet* u, int images, const Act& x, const 
   Act y = new_act(ex, u, images, C, x.H, x.W, false);
   VF_RUN(ex, K_GN_APPLY, vf_gn_apply(x.p, x.C, s0, ld0, skip ? skip->p : nullptr, C1, s1, ld1, u->dtype, images, x.H, x.W, u->cfg.norm_groups,
                                      u->master[gw], u->master[gb], swish ? 1 : 0, y.p, (vf_stream)ex.st));
+  if (!ex.dry) {
+    vf_unet::TapeOp t{};
+    t.kind = 1;
+    t.gsrc0 = x.p; t.gC0 = x.C; t.gst0 = s0; t.gld0 = ld0;
+    t.gsrc1 = skip ? skip->p : nullptr; t.gC1 = C1; t.gst1 = s1; t.gld1 = ld1;
+    t.gw = gw; t.gb = gb; t.swish = swish ? 1 : 0; t.gdst = y.p; t.gH = x.H; t.gW = x.W;
+    u->tape.push_back(t);
+  }
   return y;
 }
 
@@ -436,7 +506,10 @@ static Act run_resblock(Exec& ex, vf_unet* u, const uint8_t* pk, int images, con
     a.bias = ex.dry ? nullptr : u->master[b.c1_b];
     a.emb = emb ? emb + b.emb_col : nullptr; a.img_row = img_row; a.emb_ld = u->E;
     a.out = h1.p; a.out_ld = b.cout; a.stats = h1.stats;
-    conv_call(ex, u, a);
+    ConvMeta m;
+    m.w_idx[0] = b.c1_w; m.cin_total[0] = cin; m.b_idx[0] = b.c1_b; m.wt_off[0] = b.wt1;
+    m.emb_col = b.emb_col; m.nf_w = b.nf_w; m.nf_b = b.nf_b;
+    conv_call(ex, u, a, m);
   }
   // block2: GN -> Swish -> conv3x3, + res_conv(x) or + x                                 unet.py:244-245
   Act a2 = gn_block(ex, u, images, h1, nullptr, b.g2_w, b.g2_b, true);
@@ -452,7 +525,12 @@ static Act run_resblock(Exec& ex, vf_unet* u, const uint8_t* pk, int images, con
     a.weight = pk + b.w2; a.cout = b.cout; a.cout_pad = b.cout;
     a.bias = reinterpret_cast<const float*>(pk + b.bias2);
     a.out = out.p; a.out_ld = b.cout; a.stats = out.stats;
-    conv_call(ex, u, a);
+    ConvMeta m;
+    m.w_idx[0] = b.c2_w; m.cin_total[0] = b.cout; m.b_idx[0] = b.c2_b; m.b_idx[1] = b.rs_b; m.wt_off[0] = b.wt2;
+    // segments 1 (x) and 2 (skip): res_conv weight slices, or the identity (w_idx -1: gradient is a plain add)
+    m.w_idx[1] = b.rs_w; m.c_off[1] = 0; m.cin_total[1] = cin; m.wt_off[1] = b.rs_w >= 0 ? b.wtr0 : SIZE_MAX;
+    if (skip) { m.w_idx[2] = b.rs_w; m.c_off[2] = b.c0; m.cin_total[2] = cin; m.wt_off[2] = b.wtr1; }
+    conv_call(ex, u, a, m);
   }
   if (!b.attn) return out;
   // SelfAttention: GN -> qkv 1x1 -> softmax(QK^T/sqrt(C)) V -> out 1x1 (+bias) + input     unet.py:258-277
@@ -467,10 +545,17 @@ static Act run_resblock(Exec& ex, vf_unet* u, const uint8_t* pk, int images, con
     a.weight = pk + b.wqkv; a.cout = 3 * C; a.cout_pad = 3 * C;
     a.out = qkv; a.out_ld = 3 * C; a.out_padded = 0;          // attention works on FLAT token rows
     if (u->dtype == VF_BF16) { a.qkv_split = C; a.out_vt = vt; }
-    conv_call(ex, u, a);
+    ConvMeta m;
+    m.w_idx[0] = b.qkv_w; m.cin_total[0] = C; m.wt_off[0] = b.wtqkv;
+    conv_call(ex, u, a, m);
   }
   Act o{ex.alloc((size_t)images * HW * C * es), C, x.H, x.W, nullptr};   // FLAT
   VF_RUN(ex, K_ATTN, vf_attention(qkv, vt, u->dtype, images, HW, C, o.p, (vf_stream)ex.st));
+  if (!ex.dry) {
+    vf_unet::TapeOp t{};
+    t.kind = 2; t.qkv = qkv; t.vt = vt; t.o = o.p; t.aC = C; t.aL = HW;
+    u->tape.push_back(t);
+  }
   Act out2 = new_act(ex, u, images, C, x.H, x.W, true);
   {
     vf_conv_args a = conv_args_init();
@@ -480,7 +565,9 @@ static Act run_resblock(Exec& ex, vf_unet* u, const uint8_t* pk, int images, con
     a.bias = ex.dry ? nullptr : u->master[b.ao_b];
     a.residual = out.p;
     a.out = out2.p; a.out_ld = C; a.stats = out2.stats;
-    conv_call(ex, u, a);
+    ConvMeta m;
+    m.w_idx[0] = b.ao_w; m.cin_total[0] = C; m.b_idx[0] = b.ao_b; m.wt_off[0] = b.wtout;
+    conv_call(ex, u, a, m);
   }
   return out2;
 }
@@ -495,6 +582,7 @@ static int walk(vf_unet* u, Exec& ex, const uint8_t* pk, int images, const void*
   };
   // embedding table [rows, E]
   float* emb = reinterpret_cast<float*>(ex.alloc((size_t)rows * u->E * 4));
+  if (!ex.dry) { u->last_emb = emb; u->emb_w_dev = reinterpret_cast<const float*>(pk + u->emb_w_off); }
   VF_RUN(ex, K_EMBED, vf_embed(level, angle, rows, c.inner_channel, u->master[u->mlp_w0], u->master[u->mlp_b0], u->master[u->mlp_w2],
                          u->master[u->mlp_b2], reinterpret_cast<const float*>(pk + u->emb_w_off),
                          reinterpret_cast<const float*>(pk + u->emb_b_off), u->E, emb, (vf_stream)ex.st));
@@ -508,7 +596,9 @@ static int walk(vf_unet* u, Exec& ex, const uint8_t* pk, int images, const void*
     a.weight = pk + u->conv0_w; a.cout = c.inner_channel; a.cout_pad = c.inner_channel;
     a.bias = ex.dry ? nullptr : u->master[u->downs[0].b_idx];
     a.out = x.p; a.out_ld = c.inner_channel; a.stats = x.stats;
-    conv_call(ex, u, a);
+    ConvMeta m;                       // first layer: weight gradient only (no gradient w.r.t. the images)
+    m.w_idx[0] = u->downs[0].w_idx; m.cin_total[0] = c.in_channel; m.b_idx[0] = u->downs[0].b_idx;
+    conv_call(ex, u, a, m);
   }
   feats.push_back(x);
   tap("downs.0", x);
@@ -526,7 +616,9 @@ static int walk(vf_unet* u, Exec& ex, const uint8_t* pk, int images, const void*
       a.weight = pk + l.w; a.cout = l.c; a.cout_pad = l.c;
       a.bias = ex.dry ? nullptr : u->master[l.b_idx];
       a.out = y.p; a.out_ld = l.c; a.stats = y.stats;
-      conv_call(ex, u, a);
+      ConvMeta m;
+      m.w_idx[0] = l.w_idx; m.cin_total[0] = l.c; m.b_idx[0] = l.b_idx; m.wt_off[0] = l.wt;
+      conv_call(ex, u, a, m);
       x = y;
     }
     feats.push_back(x);
@@ -544,6 +636,11 @@ static int walk(vf_unet* u, Exec& ex, const uint8_t* pk, int images, const void*
     } else {   // Upsample: nearest x2 then conv3x3                                         unet.py:185-192
       Act up = new_act(ex, u, images, l.c, 2 * x.H, 2 * x.W, false);
       VF_RUN(ex, K_UPSAMPLE, vf_upsample2x(x.p, u->dtype, images, x.H, x.W, l.c, up.p, (vf_stream)ex.st));
+      if (!ex.dry) {
+        vf_unet::TapeOp t{};
+        t.kind = 3; t.usrc = x.p; t.udst = up.p; t.uH = x.H; t.uW = x.W; t.uC = l.c;
+        u->tape.push_back(t);
+      }
       Act y = new_act(ex, u, images, l.c, up.H, up.W, true);
       vf_conv_args a = conv_args_init();
       a.images = images; a.H = y.H; a.W = y.W; a.n_seg = 1;
@@ -551,7 +648,9 @@ static int walk(vf_unet* u, Exec& ex, const uint8_t* pk, int images, const void*
       a.weight = pk + l.w; a.cout = l.c; a.cout_pad = l.c;
       a.bias = ex.dry ? nullptr : u->master[l.b_idx];
       a.out = y.p; a.out_ld = l.c; a.stats = y.stats;
-      conv_call(ex, u, a);
+      ConvMeta m;
+      m.w_idx[0] = l.w_idx; m.cin_total[0] = l.c; m.b_idx[0] = l.b_idx; m.wt_off[0] = l.wt;
+      conv_call(ex, u, a, m);
       x = y;
     }
     tap(l.name, x);
@@ -565,7 +664,9 @@ static int walk(vf_unet* u, Exec& ex, const uint8_t* pk, int images, const void*
     a.weight = pk + u->final_w; a.cout = c.out_channel; a.cout_pad = 16;
     a.bias = ex.dry ? nullptr : u->master[u->fin_b];
     a.out = out; a.out_dtype = VF_F32; a.out_ld = 8; a.out_padded = 0;
-    conv_call(ex, u, a);
+    ConvMeta m;
+    m.w_idx[0] = u->fin_w; m.cin_total[0] = u->final_c; m.b_idx[0] = u->fin_b; m.wt_off[0] = u->final_wt;
+    conv_call(ex, u, a, m);
   }
   return ex.rc;
 }
@@ -599,7 +700,10 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_forward(vf_unet* u
     VF_CUDA(cudaMemsetAsync(ex.stats_base, 0, dry.stats_used * 4, ex.st));
   }
   u->taps.clear();
+  u->tape.clear();
+  u->act_bytes.clear();
   u->last_images = images;
+  u->last_level = level; u->last_angle = angle; u->last_img_row = img_row; u->last_rows = rows; u->last_x0 = x0; u->last_out = out;
   ex.u = u;
   u->ev_used = 0;
   int rc = walk(u, ex, reinterpret_cast<const uint8_t*>(packed), images, x0, level, angle, rows, img_row, out);
@@ -648,4 +752,423 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_read_tap(vf_unet* 
   VF_LAUNCH_CHECK();
   if (chw) { chw[0] = t.C; chw[1] = t.H; chw[2] = t.W; }
   return VF_OK;
+}
+
+// =====================================================================================================================
+// Training: backward of the last vf_unet_forward (reference: loss.backward(), experiment.py:292)
+// =====================================================================================================================
+namespace vf {
+
+// per-image column sums of a [rows, ld] matrix (padding rows hold zeros): cs[img][n] = sum_rows dY[row][n]
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ dy, int ld, int cout, int rows_per_img, int rows_per_cta, float* __restrict__ cs) {
+  const int img = blockIdx.y;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows_per_img, r0 + rows_per_cta);
+  const T* base = dy + (size_t)img * rows_per_img * ld;
+  for (int n = threadIdx.x; n < cout; n += blockDim.x) {
+    float s = 0.f;
+    for (int r = r0; r < r1; ++r) s += to_f(base[(size_t)r * ld + n]);
+    atomicAdd(cs + (size_t)img * cout + n, s);
+  }
+}
+
+// db0 / db1 += sum_img cs;  demb[img_row[img]][col + n] += cs[img][n]
+__global__ void bias_emb_grad_kernel(const float* __restrict__ cs, int images, int cout, float* db0, float* db1, float* demb,
+                                     const int* __restrict__ img_row, int emb_ld, int col) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= cout) return;
+  float tot = 0.f;
+  for (int i = 0; i < images; ++i) {
+    const float v = cs[(size_t)i * cout + n];
+    tot += v;
+    if (demb) atomicAdd(demb + (size_t)__ldg(img_row + i) * emb_ld + col + n, v);
+  }
+  if (db0) db0[n] += tot;
+  if (db1) db1[n] += tot;
+}
+
+// [M, 8] fp32 FLAT gradient of the UNet output -> [rows_p, ld] activation dtype, PADDED, zero padding rows / channels
+template <typename T>
+__global__ void grad8_to_padded_kernel(const float* __restrict__ g8, int H, int W, int ld, size_t total, T* __restrict__ dst) {
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // over (padded row, channel)
+  if (gid >= total) return;
+  const int c = (int)(gid % ld);
+  const size_t r = gid / ld;
+  const int W1 = W + 1, P = (H + 1) * W1;
+  const int rem = (int)(r % P);
+  const size_t img = r / P;
+  const int yy = rem / W1, xx = rem - yy * W1;
+  float v = 0.f;
+  if (yy > 0 && xx > 0 && c < 8) v = g8[((img * H + (yy - 1)) * W + (xx - 1)) * 8 + c];
+  dst[gid] = from_f<T>(v);
+}
+
+__global__ void axpy_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
+// Backward of vf_embed for one embedding row per CTA: recomputes pe / hidden / t, then
+//   dEw[e][i] += demb[e]*t[i]; dEb[e] += demb[e]; dt = Ew^T demb; dW2 += dt h^T; db2 += dt; dh = W2^T dt;
+//   da = dh * swish'(a); dW0 += da pe^T; db0 += da
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict__ level, const float* __restrict__ angle, int ic,
+                                                        const float* __restrict__ w0, const float* __restrict__ b0,
+                                                        const float* __restrict__ w2, const float* __restrict__ b2,
+                                                        const float* __restrict__ ew, int E, const float* __restrict__ demb,
+                                                        float* dw0, float* db0, float* dw2, float* db2, float* dew, float* deb) {
+  extern __shared__ float sm[];
+  float* pe = sm;              // [ic]
+  float* av = pe + ic;         // [4ic] pre-activation
+  float* hid = av + 4 * ic;    // [4ic]
+  float* tv = hid + 4 * ic;    // [ic]
+  float* dt = tv + ic;         // [ic]
+  float* dh = dt + ic;         // [4ic]
+  const int row = blockIdx.x;
+  const int half = ic / 2, cnt = ic / 4;
+  for (int i = threadIdx.x; i < ic; i += blockDim.x) {
+    const float x = i < half ? __ldg(level + row) : __ldg(angle + row);
+    const int j = i % half, k = j % cnt;
+    const float f = expf(-9.210340371976184f * ((float)k / (float)cnt));
+    pe[i] = j < cnt ? sinf(x * f) : cosf(x * f);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < 4 * ic; o += blockDim.x) {
+    float acc = __ldg(b0 + o);
+    for (int i = 0; i < ic; ++i) acc += __ldg(w0 + (size_t)o * ic + i) * pe[i];
+    av[o] = acc;
+    hid[o] = acc / (1.f + expf(-acc));
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < ic; o += blockDim.x) {
+    float acc = __ldg(b2 + o);
+    for (int i = 0; i < 4 * ic; ++i) acc += __ldg(w2 + (size_t)o * 4 * ic + i) * hid[i];
+    tv[o] = acc;
+    dt[o] = 0.f;
+  }
+  __syncthreads();
+  const float* g = demb + (size_t)row * E;
+  // embedding Linears
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const float ge = __ldg(g + e);
+    atomicAdd(deb + e, ge);
+    for (int i = 0; i < ic; ++i) atomicAdd(dew + (size_t)e * ic + i, ge * tv[i]);
+  }
+  for (int i = threadIdx.x; i < ic; i += blockDim.x) {
+    float acc = 0.f;
+    for (int e = 0; e < E; ++e) acc += __ldg(g + e) * __ldg(ew + (size_t)e * ic + i);
+    dt[i] = acc;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < ic; o += blockDim.x) {
+    atomicAdd(db2 + o, dt[o]);
+    for (int i = 0; i < 4 * ic; ++i) atomicAdd(dw2 + (size_t)o * 4 * ic + i, dt[o] * hid[i]);
+  }
+  for (int i = threadIdx.x; i < 4 * ic; i += blockDim.x) {
+    float acc = 0.f;
+    for (int o = 0; o < ic; ++o) acc += dt[o] * __ldg(w2 + (size_t)o * 4 * ic + i);
+    const float a = av[i], s = 1.f / (1.f + expf(-a));
+    dh[i] = acc * s * (1.f + a * (1.f - s));
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < 4 * ic; o += blockDim.x) {
+    atomicAdd(db0 + o, dh[o]);
+    for (int i = 0; i < ic; ++i) atomicAdd(dw0 + (size_t)o * ic + i, dh[o] * pe[i]);
+  }
+}
+
+struct BwdCtx {
+  vf_unet* u;
+  cudaStream_t st;
+  uint8_t* gbase;
+  size_t goff = 0, gcap = 0;
+  bool dry = false;
+  int rc = VF_OK;
+  std::map<const void*, std::pair<void*, bool>> grads;     // forward tensor -> (gradient buffer, written?)
+  void* galloc(size_t bytes) {
+    goff = align_up(goff, 256);
+    void* p = dry ? nullptr : gbase + goff;
+    goff += bytes;
+    return p;
+  }
+  std::pair<void*, bool>& grad_of(const void* fwd) {
+    auto it = grads.find(fwd);
+    if (it != grads.end()) return it->second;
+    size_t bytes = 0;
+    auto ab = u->act_bytes.find(fwd);
+    if (ab != u->act_bytes.end()) bytes = ab->second;
+    auto& e = grads[fwd];
+    e.first = galloc(bytes);
+    e.second = false;
+    return e;
+  }
+};
+
+#define VF_B(call)                                  \
+  do {                                              \
+    if (!cx.dry && cx.rc == VF_OK) cx.rc = (call);  \
+  } while (0)
+
+static void conv_backward(BwdCtx& cx, const vf_unet::TapeOp& t, const uint8_t* pkt, const void* dY, int dy_ld, float* dwp, float* cs,
+                          float* const* pg, float* demb) {
+  vf_unet* u = cx.u;
+  const vf_conv_args& f = t.conv;
+  const int dt = u->dtype;
+  const size_t es = dtype_size(dt);
+  vf_conv_args a = f;                              // geometry for the gradient problems
+  const void* dYs = dY;
+  int H = f.H, W = f.W;
+  const int images = f.images;
+  if (f.stride == 2) {
+    // Downsample: scatter dY (H/2 x W/2) onto the even pixels of a zeroed H x W grid -> stride-1 problems at source resolution
+    void* z = cx.galloc((size_t)images * (H + 1) * (W + 1) * dy_ld * es);
+    VF_B(vf_zero_insert2x(dY, dt, images, H / 2, W / 2, dy_ld, z, (vf_stream)cx.st));
+    dYs = z;
+    a.stride = 1;
+  }
+  const int out_rows_per_img = a.out_padded ? (H + 1) * (W + 1) : H * W;
+  // ---- bias / embedding gradients: per-image column sums of dY
+  if (t.b_idx[0] >= 0 || t.emb_col >= 0) {
+    if (!cx.dry && cx.rc == VF_OK) {
+      cudaMemsetAsync(cs, 0, (size_t)images * f.cout * 4, cx.st);
+      const int per = 256;
+      dim3 grid(cdiv(out_rows_per_img, per), images);
+      if (dt == VF_BF16) colsum_kernel<__nv_bfloat16><<<grid, 256, 0, cx.st>>>((const __nv_bfloat16*)dYs, dy_ld, f.cout, out_rows_per_img, per, cs);
+      else colsum_kernel<float><<<grid, 256, 0, cx.st>>>((const float*)dYs, dy_ld, f.cout, out_rows_per_img, per, cs);
+      bias_emb_grad_kernel<<<cdiv(f.cout, 128), 128, 0, cx.st>>>(cs, images, f.cout, t.b_idx[0] >= 0 ? pg[t.b_idx[0]] : nullptr,
+                                                                 t.b_idx[1] >= 0 ? pg[t.b_idx[1]] : nullptr, t.emb_col >= 0 ? demb : nullptr,
+                                                                 u->last_img_row, u->E, t.emb_col >= 0 ? t.emb_col : 0);
+      if (t.nf_b >= 0) {}   // the per-block embedding Linear gradients are produced by embed_bwd_kernel from demb
+    }
+  }
+  // ---- weight gradient into the packed scratch, then scatter to the OIHW parameter gradients
+  int k_total = 0;
+  for (int s = 0; s < f.n_seg; ++s) k_total += f.ksize[s] * f.ksize[s] * f.src_c[s];
+  if (!cx.dry && cx.rc == VF_OK) cudaMemsetAsync(dwp, 0, (size_t)f.cout_pad * k_total * 4, cx.st);
+  VF_B(vf_conv2d_wgrad(&a, dYs, dy_ld, dwp, (vf_stream)cx.st));
+  int koff = 0;
+  for (int s = 0; s < f.n_seg; ++s) {
+    const int kk = f.ksize[s] * f.ksize[s];
+    if (t.w_idx[s] >= 0) {
+      if (s == 0 && f.src[0] == u->last_x0) {
+        // first layer: the K0 columns are (tap, channel) of the im2col'd input with cin_total real channels
+        VF_B(vf_unpack_conv_wgrad(dwp, f.cout, t.cin_total[0], 3, k_total, 0, pg[t.w_idx[0]], t.cin_total[0], 0, (vf_stream)cx.st));
+      } else {
+        VF_B(vf_unpack_conv_wgrad(dwp, f.cout, f.src_c[s], f.ksize[s], k_total, koff, pg[t.w_idx[s]], t.cin_total[s], t.c_off[s],
+                                  (vf_stream)cx.st));
+      }
+    }
+    koff += kk * f.src_c[s];
+  }
+  // ---- data gradients
+  koff = 0;
+  for (int s = 0; s < f.n_seg; ++s) {
+    const bool first_layer = s == 0 && f.src[0] == u->last_x0;
+    if (!first_layer) {
+      auto& g = cx.grad_of(f.src[s]);
+      const size_t n_elems = (size_t)images * (a.in_padded ? (H + 1) * (W + 1) : H * W) * f.src_c[s];
+      if (t.w_idx[s] < 0) {
+        // identity segment: grad(x) (+)= dY
+        if (g.second) VF_B(vf_add_inplace(g.first, dYs, dt, n_elems, (vf_stream)cx.st));
+        else if (!cx.dry && cx.rc == VF_OK && cudaMemcpyAsync(g.first, dYs, n_elems * es, cudaMemcpyDeviceToDevice, cx.st) != cudaSuccess) cx.rc = VF_ERR_CUDA;
+      } else {
+        vf_conv_args d{};
+        d.dtype = dt; d.images = images; d.H = H; d.W = W;
+        d.in_padded = a.out_padded; d.out_padded = a.in_padded;
+        d.n_seg = 1; d.src[0] = dYs; d.src_c[0] = dy_ld; d.ksize[0] = f.ksize[s]; d.stride = 1;
+        d.weight = pkt + t.wt_off[s]; d.cout = f.src_c[s]; d.cout_pad = f.src_c[s];
+        d.residual = g.second ? g.first : nullptr;
+        d.out = g.first; d.out_dtype = dt; d.out_ld = f.src_c[s];
+        VF_B(vf_conv2d(&d, (vf_stream)cx.st));
+      }
+      g.second = true;
+    }
+    koff += f.ksize[s] * f.ksize[s] * f.src_c[s];
+  }
+  // ---- epilogue residual (attention: out + input): gradient flows through unchanged
+  if (f.residual) {
+    auto& g = cx.grad_of(f.residual);
+    const size_t n_elems = (size_t)images * out_rows_per_img * f.cout;
+    if (g.second) VF_B(vf_add_inplace(g.first, dYs, dt, n_elems, (vf_stream)cx.st));
+    else if (!cx.dry && cx.rc == VF_OK && cudaMemcpyAsync(g.first, dYs, n_elems * es, cudaMemcpyDeviceToDevice, cx.st) != cudaSuccess) cx.rc = VF_ERR_CUDA;
+    g.second = true;
+  }
+}
+
+}  // namespace vf
+
+namespace vf {
+
+static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float* const* pg) {
+  vf_unet* u = cx.u;
+  const int dt = u->dtype;
+  const size_t es = dtype_size(dt);
+  const int images = u->last_images, S = u->cfg.image_size;
+  const vf_unet_config& c = u->cfg;
+  // scratch: packed weight gradient (largest conv), per-image column sums, embedding-table gradient
+  size_t dwp_floats = 0, cs_floats = 0;
+  for (auto& t : u->tape)
+    if (t.kind == 0) {
+      size_t k = 0;
+      for (int s = 0; s < t.conv.n_seg; ++s) k += (size_t)t.conv.ksize[s] * t.conv.ksize[s] * t.conv.src_c[s];
+      dwp_floats = std::max(dwp_floats, (size_t)t.conv.cout_pad * k);
+      cs_floats = std::max(cs_floats, (size_t)images * t.conv.cout);
+    }
+  float* dwp = (float*)cx.galloc(dwp_floats * 4);
+  float* cs = (float*)cx.galloc(cs_floats * 4);
+  float* demb = (float*)cx.galloc((size_t)u->last_rows * u->E * 4);
+  float* dew = (float*)cx.galloc((size_t)u->E * c.inner_channel * 4);
+  float* deb = (float*)cx.galloc((size_t)u->E * 4);
+  size_t gn_floats = 0, att_floats = 0;
+  for (auto& t : u->tape) {
+    if (t.kind == 1) gn_floats = std::max(gn_floats, (size_t)images * (t.gC0 + t.gC1) * 2);
+    if (t.kind == 2) att_floats = std::max(att_floats, (size_t)images * t.aL * 2 * t.aC);
+  }
+  float* gn_scratch = (float*)cx.galloc(gn_floats * 4);
+  float* att_scratch = (float*)cx.galloc(att_floats * 4);
+  if (!cx.dry) {
+    cudaMemsetAsync(demb, 0, (size_t)u->last_rows * u->E * 4, cx.st);
+    cudaMemsetAsync(dew, 0, (size_t)u->E * c.inner_channel * 4, cx.st);
+    cudaMemsetAsync(deb, 0, (size_t)u->E * 4, cx.st);
+  }
+  // gradient of the UNet output -> PADDED activation-dtype matrix with final_npad channels
+  const int np = u->final_npad;
+  void* g_out = cx.galloc((size_t)images * (S + 1) * (S + 1) * np * es);
+  if (!cx.dry) {
+    const size_t total = (size_t)images * (S + 1) * (S + 1) * np;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (dt == VF_BF16) grad8_to_padded_kernel<__nv_bfloat16><<<grid, 256, 0, cx.st>>>(g8, S, S, np, total, (__nv_bfloat16*)g_out);
+    else grad8_to_padded_kernel<float><<<grid, 256, 0, cx.st>>>(g8, S, S, np, total, (float*)g_out);
+  }
+  for (int i = (int)u->tape.size() - 1; i >= 0 && cx.rc == VF_OK; --i) {
+    const vf_unet::TapeOp& t = u->tape[i];
+    if (t.kind == 0) {
+      if (t.conv.out == (void*)u->last_out) {
+        vf_unet::TapeOp tf = t;               // final conv: its gradient arrives PADDED with np channels
+        tf.conv.out_padded = 1;
+        tf.conv.cout = np; tf.conv.cout_pad = np;
+        // only the real output channels have parameters: unpack / bias use the true cout below
+        vf_unet::TapeOp tt = tf;
+        tt.conv.cout = c.out_channel; tt.conv.cout_pad = np;
+        conv_backward(cx, tt, pkt, g_out, np, dwp, cs, pg, demb);
+      } else {
+        auto& g = cx.grad_of(t.conv.out);
+        const int ld = t.conv.qkv_split ? 3 * t.conv.qkv_split : t.conv.out_ld;
+        conv_backward(cx, t, pkt, g.first, ld, dwp, cs, pg, demb);
+      }
+    } else if (t.kind == 1) {
+      auto& gy = cx.grad_of(t.gdst);
+      auto& g0 = cx.grad_of(t.gsrc0);
+      std::pair<void*, bool>* g1 = t.gsrc1 ? &cx.grad_of(t.gsrc1) : nullptr;
+      VF_B(vf_gn_backward(t.gsrc0, t.gC0, t.gst0, t.gld0, t.gsrc1, t.gC1, t.gst1, t.gld1, dt, images, t.gH, t.gW, c.norm_groups,
+                          u->master[t.gw], u->master[t.gb], t.swish, gy.first, gn_scratch, pg[t.gw], pg[t.gb], g0.first, g0.second ? 1 : 0,
+                          g1 ? g1->first : nullptr, g1 && g1->second ? 1 : 0, (vf_stream)cx.st));
+      g0.second = true;
+      if (g1) g1->second = true;
+    } else if (t.kind == 2) {
+      auto& go = cx.grad_of(t.o);
+      auto& gq = cx.grad_of(t.qkv);
+      VF_B(vf_attention_backward(t.qkv, t.vt, go.first, dt, images, t.aL, t.aC, att_scratch, gq.first, (vf_stream)cx.st));
+      gq.second = true;
+    } else if (t.kind == 3) {
+      auto& gd = cx.grad_of(t.udst);
+      auto& gs = cx.grad_of(t.usrc);
+      VF_B(vf_upsample2x_backward(gd.first, dt, images, t.uH, t.uW, t.uC, gs.first, gs.second ? 1 : 0, (vf_stream)cx.st));
+      gs.second = true;
+    }
+  }
+  // embedding path: demb [rows, E] -> noise_level_mlp and the per-block Linear(ic -> Cout) parameters
+  if (!cx.dry && cx.rc == VF_OK) {
+    const int ic = c.inner_channel;
+    const uint8_t* pk = nullptr; (void)pk;
+    embed_bwd_kernel<<<u->last_rows, 256, (size_t)(15 * ic) * sizeof(float), cx.st>>>(
+        u->last_level, u->last_angle, ic, u->master[u->mlp_w0], u->master[u->mlp_b0], u->master[u->mlp_w2], u->master[u->mlp_b2],
+        u->emb_w_dev, u->E, demb, pg[u->mlp_w0], pg[u->mlp_b0], pg[u->mlp_w2], pg[u->mlp_b2], dew, deb);
+    for (auto& b : u->blocks) {
+      const size_t nw = (size_t)b.cout * ic;
+      axpy_f32_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, cx.st>>>(pg[b.nf_w], dew + (size_t)b.emb_col * ic, nw);
+      axpy_f32_kernel<<<(unsigned)((b.cout + 255) / 256), 256, 0, cx.st>>>(pg[b.nf_b], deb + b.emb_col, (size_t)b.cout);
+    }
+    if (cudaGetLastError() != cudaSuccess) { set_error("vf_unet_backward: embedding backward launch failed"); cx.rc = VF_ERR_CUDA; }
+  }
+  return cx.rc;
+}
+
+}  // namespace vf
+
+namespace vf {
+template <typename T>
+__global__ void pack_t_slice_kernel(const float* __restrict__ w, int cout, int cin, int c_off, int c_cnt, T* __restrict__ dst) {
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (size_t)c_cnt * cout) return;
+  const int c = (int)(gid / cout), n = (int)(gid % cout);
+  dst[gid] = from_f<T>(__ldg(w + (size_t)n * cin + c_off + c));
+}
+static int pack_t_slice(const float* w, int cout, int cin, int c_off, int c_cnt, int dtype, void* dst, cudaStream_t st) {
+  const size_t total = (size_t)c_cnt * cout;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (dtype == VF_BF16) pack_t_slice_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(w, cout, cin, c_off, c_cnt, (__nv_bfloat16*)dst);
+  else pack_t_slice_kernel<float><<<grid, 256, 0, st>>>(w, cout, cin, c_off, c_cnt, (float*)dst);
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}
+}  // namespace vf
+
+extern "C" __attribute__((visibility("default"))) size_t vf_unet_packed_t_bytes(const vf_unet* u) { return u ? u->packed_t_bytes : 0; }
+
+extern "C" __attribute__((visibility("default"))) int vf_unet_pack_weights_t(vf_unet* u, void* packed_t, vf_stream stream) {
+  VF_REQUIRE(u && packed_t, "vf_unet_pack_weights_t: null args");
+  if (!u->packed) { set_error("vf_unet_pack_weights_t: call vf_unet_pack_weights first"); return VF_ERR_STATE; }
+  uint8_t* pk = reinterpret_cast<uint8_t*>(packed_t);
+  const int dt = u->dtype;
+  VF_CUDA(cudaMemsetAsync(pk, 0, u->packed_t_bytes, as_stream(stream)));
+  int rc;
+#define VF_TRY(call) do { rc = (call); if (rc != VF_OK) return rc; } while (0)
+  for (auto& b : u->blocks) {
+    const int cin = b.c0 + b.c1;
+    VF_TRY(vf_pack_conv_weight_t(u->master[b.c1_w], b.cout, cin, 3, dt, pk + b.wt1, cin, 9 * b.cout, 0, b.cout, stream));
+    VF_TRY(vf_pack_conv_weight_t(u->master[b.c2_w], b.cout, b.cout, 3, dt, pk + b.wt2, b.cout, 9 * b.cout, 0, b.cout, stream));
+    if (b.rs_w >= 0) {
+      // res_conv [cout][cin][1][1]: the x slice (channels 0..c0) and the skip slice (c0..cin) get their own transposed packs
+      VF_TRY(pack_t_slice(u->master[b.rs_w], b.cout, cin, 0, b.c0, dt, pk + b.wtr0, as_stream(stream)));
+      if (b.c1) VF_TRY(pack_t_slice(u->master[b.rs_w], b.cout, cin, b.c0, b.c1, dt, pk + b.wtr1, as_stream(stream)));
+    }
+    if (b.attn) {
+      VF_TRY(vf_pack_conv_weight_t(u->master[b.qkv_w], 3 * b.cout, b.cout, 1, dt, pk + b.wtqkv, b.cout, 3 * b.cout, 0, 3 * b.cout, stream));
+      VF_TRY(vf_pack_conv_weight_t(u->master[b.ao_w], b.cout, b.cout, 1, dt, pk + b.wtout, b.cout, b.cout, 0, b.cout, stream));
+    }
+  }
+  for (auto* sec : {&u->downs, &u->mid, &u->ups})
+    for (auto& l : *sec)
+      if (l.kind == 2 || l.kind == 3) VF_TRY(vf_pack_conv_weight_t(u->master[l.w_idx], l.c, l.c, 3, dt, pk + l.wt, l.c, 9 * l.c, 0, l.c, stream));
+  VF_TRY(vf_pack_conv_weight_t(u->master[u->fin_w], u->cfg.out_channel, u->final_c, 3, dt, pk + u->final_wt, u->final_c, 9 * u->final_npad, 0,
+                               u->final_npad, stream));
+#undef VF_TRY
+  u->packed_t = true;
+  return VF_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) size_t vf_unet_backward_workspace_bytes(vf_unet* u) {
+  if (!u || u->tape.empty()) return 0;
+  BwdCtx cx{u, nullptr, nullptr};
+  cx.dry = true;
+  backward_walk(cx, nullptr, nullptr, nullptr);
+  return align_up(cx.goff, 256) + 256;
+}
+
+extern "C" __attribute__((visibility("default"))) int vf_unet_backward(vf_unet* u, const void* packed_t, void* grad_workspace, size_t grad_workspace_bytes,
+                                                                     const float* grad_out8, float* const* param_grads_host, vf_stream stream) {
+  VF_REQUIRE(u && packed_t && grad_workspace && grad_out8 && param_grads_host, "vf_unet_backward: null args");
+  if (u->tape.empty() || !u->packed_t) { set_error("vf_unet_backward: needs a forward and vf_unet_pack_weights_t first"); return VF_ERR_STATE; }
+  for (size_t i = 0; i < u->params.size(); ++i) VF_REQUIRE(param_grads_host[i], "vf_unet_backward: gradient %zu (%s) is null", i, u->params[i].name.c_str());
+  {
+    BwdCtx dry{u, nullptr, nullptr};
+    dry.dry = true;
+    backward_walk(dry, nullptr, nullptr, nullptr);
+    VF_REQUIRE(dry.goff <= grad_workspace_bytes, "vf_unet_backward: workspace too small (%zu < %zu)", grad_workspace_bytes, dry.goff);
+  }
+  BwdCtx cx{u, as_stream(stream), reinterpret_cast<uint8_t*>(grad_workspace)};
+  cx.gcap = grad_workspace_bytes;
+  int rc = backward_walk(cx, reinterpret_cast<const uint8_t*>(packed_t), grad_out8, param_grads_host);
+  if (rc == VF_OK) VF_LAUNCH_CHECK();
+  return rc;
 }

@@ -111,8 +111,13 @@ class UNet(nn.Module):
         self._plan = None
         self._packed = None
         self._packed_key = None
+        self._packed_t = None
+        self._packed_t_key = None
         self._ws = None
         self._ws_images = 0
+        self._gws = None
+        self._gws_images = -1
+        self._flat_grad = None
 
     # ------------------------------------------------------------------------------------------
     def _native(self):
@@ -183,10 +188,61 @@ class UNet(nn.Module):
         lib = _lib.require_device()
         h = self._native()
         dev = next(self.parameters()).device
-        if self._ws is None or self._ws_images < images or self._ws.device != dev:
-            self._ws = torch.empty(lib.vf_unet_workspace_bytes(h, images), dtype=torch.uint8, device=dev)
+        # zero-filled, and re-zeroed when the image count (hence the layout) changes: padding rows of convolution
+        # outputs are never written and must read as zeros (3x3 halos, weight-gradient reductions)
+        if self._ws is None or self._ws_images != images or self._ws.device != dev:
+            nbytes = lib.vf_unet_workspace_bytes(h, images)
+            if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
+                self._ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+            else:
+                self._ws.zero_()
             self._ws_images = images
         return self._ws
+
+    # ---------------------------------------------------------------- training support
+    def _params_in_order(self):
+        self._native()
+        params = dict(self.named_parameters())
+        return [params[n] for n in self._param_names]
+
+    def packed_weights_t(self) -> torch.Tensor:
+        """Transposed packs for the data gradients; refreshed together with the forward packs."""
+        lib = _lib.require_device()
+        h = self._native()
+        self.packed_weights()
+        if self._packed_t is None or self._packed_t_key != self._packed_key:
+            dev = self._packed.device
+            if self._packed_t is None or self._packed_t.device != dev:
+                self._packed_t = torch.empty(lib.vf_unet_packed_t_bytes(h), dtype=torch.uint8, device=dev)
+            _lib.check(lib.vf_unet_pack_weights_t(h, self._packed_t.data_ptr(), _lib.stream_handle()), "vf_unet_pack_weights_t")
+            self._packed_t_key = self._packed_key
+        return self._packed_t
+
+    def run_backward(self, grad_out8: torch.Tensor):
+        """Backward of the last run_packed: returns per-parameter fp32 gradients (views of one flat buffer)."""
+        lib = _lib.require_device()
+        h = self._native()
+        plist = self._params_in_order()
+        pt = self.packed_weights_t()
+        dev = plist[0].device
+        nbytes = lib.vf_unet_backward_workspace_bytes(h)
+        if self._gws is None or self._gws.numel() < nbytes or self._gws_images != self._last_images or self._gws.device != dev:
+            if self._gws is None or self._gws.numel() < nbytes or self._gws.device != dev:
+                self._gws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+            else:
+                self._gws.zero_()
+            self._gws_images = self._last_images
+        total = sum(p.numel() for p in plist)
+        flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        grads, off = [], 0
+        for p in plist:
+            grads.append(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        arr = (C.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
+        _lib.check(lib.vf_unet_backward(h, pt.data_ptr(), self._gws.data_ptr(), self._gws.numel(), grad_out8.data_ptr(), arr,
+                                        _lib.stream_handle()), "vf_unet_backward")
+        self._flat_grad = flat
+        return plist, grads
 
     @property
     def k0(self) -> int:

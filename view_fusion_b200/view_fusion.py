@@ -254,6 +254,64 @@ class ViewFusion(nn.Module):
 
     # ---------------------------------------------------------------- forward (:216-300)
     def forward(self, y_cond, view_count, angle, y_0=None, noise=None, generate=False, t=None, u=None):
+        """generate=True -> generate().  Otherwise the training branch (view_fusion.py:229-300): scalar MSE loss whose
+        backward() fills the gradients of every UNet parameter through the hand-written CUDA backward.
+        `t` (B,) and `u` (B,1) optionally inject the reference's randint / rand draws (parity tests)."""
         if generate:
             return self.generate(y_cond, view_count, angle)
-        raise NotImplementedError("training forward/backward is not wired yet")
+        y_cond, angle, y_0 = self._prep(y_cond, angle, y_0)
+        dev = y_0.device
+        b = y_0.shape[0]
+        # the reference's draw order: randint (:231) -> rand (:234) -> randn_like (:239)
+        if t is None:
+            t = torch.randint(1, self.num_timesteps, (b,), device=dev)
+        t = t.to(dev).long()
+        if u is None:
+            u = torch.rand((b, 1), device=dev)
+        u = u.to(dev).float()
+        g1 = self.gammas.gather(-1, t - 1).view(b, 1)
+        g2 = self.gammas.gather(-1, t).view(b, 1)
+        sample_gammas = ((g2 - g1) * u + g1).view(b).contiguous()
+        if noise is None:
+            noise = torch.randn_like(y_0)
+        noise = noise.to(dev).contiguous().float()
+        params = self.denoise_fn._params_in_order()
+        return _TrainStep.apply(self, y_0, y_cond, view_count, angle, noise, sample_gammas, *params)
+
+
+class _TrainStep(torch.autograd.Function):
+    """loss = mse(noise, eps_hat(UNet over all views)); backward = hand-written CUDA backward of the whole step."""
+
+    @staticmethod
+    def forward(ctx, model, y_0, y_cond, view_count, angle, noise, sample_gammas, *params):
+        lib = _lib.require_device()
+        unet = model.denoise_fn
+        st = _lib.stream_handle()
+        B, n_max, Cc, H, W = y_cond.shape
+        y_noisy = model.q_sample(y_0, sample_gammas, noise)                              # :240-242
+        plan = _Plan(model, y_cond, view_count)
+        _lib.check(lib.vf_pack_views(y_cond.data_ptr(), y_noisy.data_ptr(), plan.view_offset.data_ptr(), B, n_max, Cc, H, W,
+                                     plan.images, unet.k0, unet.act_dtype, plan.x0.data_ptr(), plan.img_sample.data_ptr(), st),
+                   "vf_pack_views")
+        unet._last_images = plan.images
+        ang = angle.reshape(-1).contiguous()
+        unet.run_packed(plan.x0, plan.images, sample_gammas, ang, plan.img_sample, plan.out8)
+        loss = torch.zeros(1, dtype=torch.float32, device=y_0.device)
+        grad8 = torch.empty_like(plan.out8)
+        weighting = int(model.weighting_train)
+        _lib.check(lib.vf_compose_mse(plan.out8.data_ptr(), plan.view_offset.data_ptr(), noise.data_ptr(), B, H, W, weighting,
+                                      loss.data_ptr(), 0, grad8.data_ptr(), 1.0, st), "vf_compose_mse")
+        ctx.model = model
+        ctx.grad8 = grad8
+        ctx.keep = (plan, ang, sample_gammas, y_noisy)          # device buffers the recorded tape points into
+        ctx.n_params = len(params)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        unet = ctx.model.denoise_fn
+        g8 = ctx.grad8
+        if not (grad_loss.numel() == 1 and float(grad_loss) == 1.0):
+            g8 = g8 * grad_loss
+        _, grads = unet.run_backward(g8)
+        return (None,) * 7 + tuple(grads)
