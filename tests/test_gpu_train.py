@@ -59,3 +59,45 @@ def test_train_bf16_mode_loss_and_gradient_direction(golden_dir):
             if float(b.norm()) > 1e-3 * big:
                 cos = float((a * b).sum() / (a.norm() * b.norm()))
                 assert cos > 0.98, (k, cos)
+
+
+@pytest.mark.parametrize("case", [(3, 16, [(64, 3)], 64), (2, 32, [(128, 3)], 128), (3, 16, [(128, 3), (64, 1), (192, 1)], 192),
+                                  (5, 8, [(320, 3)], 320), (2, 64, [(64, 3), (64, 1)], 64)])
+def test_wgrad_tcgen05_vs_cuda_cores(case):
+    """tcgen05 MN-major weight-gradient GEMM vs the CUDA-core kernel and vs fp64 math on the same bf16 operands."""
+    import ctypes as C
+    from view_fusion_b200 import _lib, ops
+    lib = _lib.require_device()
+    R, S, segs, cout = case
+    torch.manual_seed(1)
+    bf = lambda t: t.to(torch.bfloat16)
+    xs = [bf(torch.randn(R, c, S, S)) for c, _ in segs]
+    dy = bf(torch.randn(R, cout, S, S))
+    srcs = [ops.to_padded(x.float(), torch.bfloat16).cuda() for x in xs]       # zero padding rows
+    dyp = ops.to_padded(dy.float(), torch.bfloat16).cuda()
+    k_total = sum(c * k * k for c, k in segs)
+    a = _lib.ConvArgs()
+    a.dtype, a.images, a.H, a.W, a.in_padded, a.out_padded, a.n_seg, a.stride = _lib.VF_BF16, R, S, S, 1, 1, len(segs), 1
+    for i, ((c, k), s) in enumerate(zip(segs, srcs)):
+        a.src[i], a.src_c[i], a.ksize[i] = s.data_ptr(), c, k
+    a.cout, a.cout_pad = cout, cout
+    outs = []
+    for simt in (False, True):
+        ops.force_simt(simt)
+        try:
+            dwp = torch.zeros(cout, k_total, device="cuda")
+            _lib.check(lib.vf_conv2d_wgrad(C.byref(a), dyp.data_ptr(), cout, dwp.data_ptr(), _lib.stream_handle()), "wgrad")
+            torch.cuda.synchronize()
+            outs.append(dwp.cpu())
+        finally:
+            ops.force_simt(False)
+    # reference: dW[n][tap][c] = sum_pixels dy[n] * x[c] shifted
+    ref = torch.zeros(cout, k_total, dtype=torch.float64)
+    off = 0
+    for (c, k), x in zip(segs, xs):
+        xd = torch.nn.functional.unfold(x.double(), k, padding=k // 2).view(R, c, k * k, S * S)          # (R, c, taps, L)
+        g = torch.einsum("rnl,rctl->ntc", dy.double().view(R, cout, S * S), xd).reshape(cout, k * k * c)
+        ref[:, off:off + k * k * c] = g
+        off += k * k * c
+    assert rel(outs[1], ref.float()) < 1e-4, "CUDA-core weight gradient"
+    assert rel(outs[0], ref.float()) < 1e-4, "tcgen05 weight gradient"

@@ -440,8 +440,15 @@ __global__ void grad8_to_act_kernel(const float* __restrict__ g8, size_t rows, i
 using namespace vf;
 #define VF_API extern "C" __attribute__((visibility("default")))
 
+namespace vf {
+bool wgrad_tc_supported(const vf_conv_args* a, int dy_ld);
+int conv2d_wgrad_tc(const vf_conv_args* a, const void* dy, int dy_ld, float* dwp, cudaStream_t st);
+extern int g_force_simt_flag;
+}  // namespace vf
+
 VF_API int vf_conv2d_wgrad(const vf_conv_args* a, const void* dy, int dy_ld, float* dwp, vf_stream stream) {
   VF_REQUIRE(a && dy && dwp, "vf_conv2d_wgrad: null args");
+  if (!g_force_simt_flag && wgrad_tc_supported(a, dy_ld)) return conv2d_wgrad_tc(a, dy, dy_ld, dwp, as_stream(stream));
   WgradParams p{};
   p.geo = make_geom(a->images, a->H, a->W, a->in_padded, a->out_padded, a->stride == 2);
   int k_total = 0;

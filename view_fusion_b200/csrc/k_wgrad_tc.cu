@@ -1,0 +1,245 @@
+// tcgen05 weight-gradient GEMM (reference: the dW half of conv autograd, experiment.py:292).
+//
+//   dWp[n][koff + tap*C + c] += sum_rows  X[row + shift(tap)][c] * dY[row][n]
+//
+// The reduction runs over pixel ROWS, so both operands are "MN-major" for the tensor core exactly as TMA loads them
+// from the NHWC matrices (row = K, 64 channels = one 128-byte swizzle atom): no transposes anywhere.
+//   A (M = 128) = two taps of the same 64-channel slab: atom 0 / atom 1 are the slab shifted by the taps' row offsets,
+//                 i.e. the descriptor's leading-dimension offset is the difference of the two tap shifts
+//   B (N = block_n <= 256) = dY tile, atoms of 64 output channels, one TMA box each
+//   D = fp32 in TMEM, one accumulator per tap pair; after the CTA's row range it is added to the packed gradient
+//       with coalesced fp32 reductions (lane == channel c, column == output channel n)
+// Work item (blockIdx.y) = (segment, 64-channel chunk, group of tap pairs, N tile); blockIdx.x splits the rows.
+// Both hardware facts used here were probed first (k_debug.cu): MN-major SWIZZLE_128B descriptors with LBO = atom
+// stride / SBO = 1024, and start addresses shifted by whole rows.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "tc_ptx.cuh"
+#include "vf_common.cuh"
+
+namespace vf {
+
+int encode_bf16_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box);
+
+constexpr int WG_R = 128;          // rows per K chunk
+constexpr int WG_THREADS = 192;    // warps 0-3 epilogue, 4 TMA, 5 MMA
+constexpr int WG_MAX_ACC = 8;
+
+struct WgSeg {
+  int C, nchunks, ntaps, koff, halo;
+  int npairs;        // accumulators needed per chunk: ceil(ntaps / 2)
+  int ngroups;       // ceil(npairs / acc_max)
+};
+
+struct WgParams {
+  int rows_total, W1;
+  int n_seg;
+  WgSeg seg[3];
+  int block_n, n_tiles_n, acc_max, stages;
+  int x_rows;              // slab rows per stage (multiple of 64)
+  int stage_bytes, x_bytes;
+  int k_total, cout;
+  int rows_per_split;
+  int tmem_cols;
+  float* dwp;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0,
+                                                                      const __grid_constant__ CUtensorMap mapX1,
+                                                                      const __grid_constant__ CUtensorMap mapX2,
+                                                                      const __grid_constant__ CUtensorMap mapDY, const WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t bar_full = base, bar_empty = base + 64, bar_done = base + 128, tmem_slot = base + 136;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + 136);
+  const uint32_t ring = base + 1024;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // decode the work item
+  int job = blockIdx.y, seg = 0;
+  for (; seg < p.n_seg; ++seg) {
+    const int per = p.seg[seg].nchunks * p.seg[seg].ngroups * p.n_tiles_n;
+    if (job < per) break;
+    job -= per;
+  }
+  const WgSeg sg = p.seg[seg];
+  const int n_tile = job % p.n_tiles_n;
+  const int grp = (job / p.n_tiles_n) % sg.ngroups;
+  const int chunk = job / (p.n_tiles_n * sg.ngroups);
+  const int pair0 = grp * p.acc_max;
+  const int npair = min(p.acc_max, sg.npairs - pair0);
+  const int n0 = n_tile * p.block_n;
+  const int r_begin = blockIdx.x * p.rows_per_split;
+  const int r_end = min(p.rows_total, r_begin + p.rows_per_split);
+  const int nk = r_begin < r_end ? (r_end - r_begin + WG_R - 1) / WG_R : 0;
+  const int nbox_x = (WG_R + 2 * sg.halo + 63) / 64;
+  const int natom_n = p.block_n / 64;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(bar_full + 8 * s, 1); ptx::mbar_init(bar_empty + 8 * s, 1); }
+    ptx::mbar_init(bar_done, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 5) { ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 4) {
+    if (lane == 0 && nk > 0) {
+      const CUtensorMap* mX = seg == 0 ? &mapX0 : (seg == 1 ? &mapX1 : &mapX2);
+      for (int it = 0; it < nk; ++it) {
+        const int st = it % p.stages;
+        ptx::mbar_wait(bar_empty + 8 * st, ((uint32_t)(it / p.stages) & 1u) ^ 1u);
+        const uint32_t fb = bar_full + 8 * st;
+        ptx::mbar_arrive_expect_tx(fb, (uint32_t)nbox_x * 64 * 128 + (uint32_t)natom_n * WG_R * 128);
+        const uint32_t sx = ring + (uint32_t)st * (uint32_t)p.stage_bytes;
+        const uint32_t sy = sx + (uint32_t)p.x_bytes;
+        const int row0 = r_begin + it * WG_R;
+        for (int b = 0; b < nbox_x; ++b) ptx::tma_load_2d(sx + b * 8192, mX, fb, chunk * 64, row0 - sg.halo + b * 64);
+        for (int a = 0; a < natom_n; ++a) ptx::tma_load_2d(sy + a * (WG_R * 128), &mapDY, fb, n0 + a * 64, row0);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0 && nk > 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(128, p.block_n, 1, 1);       // A and B MN-major
+      for (int it = 0; it < nk; ++it) {
+        const int st = it % p.stages;
+        ptx::mbar_wait(bar_full + 8 * st, (uint32_t)(it / p.stages) & 1u);
+        ptx::tc_fence_after();
+        const uint32_t sx = ring + (uint32_t)st * (uint32_t)p.stage_bytes;
+        const uint32_t sy = sx + (uint32_t)p.x_bytes;
+        // splits are multiples of WG_R rows; rows past the end of the tensors are zero-filled by TMA
+        const int ksteps = WG_R / 16;
+        for (int a = 0; a < npair; ++a) {
+          const int t0 = 2 * (pair0 + a), t1 = min(t0 + 1, sg.ntaps - 1);
+          const int sh0 = sg.ntaps == 9 ? (t0 / 3) * p.W1 + (t0 % 3) : 0;       // slab starts `halo` rows before the chunk
+          const int sh1 = sg.ntaps == 9 ? (t1 / 3) * p.W1 + (t1 % 3) : 0;
+          const uint32_t lbo = t1 > t0 ? (uint32_t)(sh1 - sh0) * 128u : 128u;   // single tap: atom 1 is a harmless neighbour
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t ad = ptx::make_smem_desc(sx + (uint32_t)(sh0 + 16 * k) * 128u, lbo, 1024);
+            const uint64_t bd = ptx::make_smem_desc(sy + (uint32_t)(16 * k) * 128u, WG_R * 128, 1024);
+            ptx::umma_f16(tmem_base + (uint32_t)(a * p.block_n), ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        ptx::umma_commit(bar_empty + 8 * st);
+      }
+      ptx::umma_commit(bar_done);
+    }
+  } else if (nk > 0) {
+    // epilogue: lane quarter q holds accumulator rows 32q..32q+31 = (atom, channel)
+    ptx::mbar_wait(bar_done, 0);
+    ptx::tc_fence_after();
+    const int m = warp * 32 + lane;
+    const int atom = m >> 6, c = m & 63;
+    for (int a = 0; a < npair; ++a) {
+      const int tap = 2 * (pair0 + a) + atom;
+      const bool live = tap < sg.ntaps;
+      float* dst = p.dwp + (size_t)sg.koff + (size_t)tap * sg.C + chunk * 64 + c;
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        uint32_t rr[16];
+        ptx::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * p.block_n + c0), rr);
+        ptx::tmem_ld_wait();
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = n0 + c0 + j;
+            if (n < p.cout) atomicAdd(dst + (size_t)n * p.k_total, __uint_as_float(rr[j]));
+          }
+        }
+      }
+    }
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+}
+
+// Supported: bf16, PADDED -> PADDED, stride 1, every segment a multiple of 64 channels, cout a multiple of 64.
+bool wgrad_tc_supported(const vf_conv_args* a, int dy_ld) {
+  if (a->dtype != VF_BF16 || !a->in_padded || !a->out_padded || a->stride != 1) return false;
+  if (a->cout % 64 || dy_ld % 64) return false;
+  for (int s = 0; s < a->n_seg; ++s)
+    if (a->src_c[s] % 64) return false;
+  return true;
+}
+
+int conv2d_wgrad_tc(const vf_conv_args* a, const void* dy, int dy_ld, float* dwp, cudaStream_t st) {
+  WgParams p{};
+  const int H = a->H, W = a->W;
+  p.rows_total = a->images * (H + 1) * (W + 1);
+  p.W1 = W + 1;
+  p.cout = a->cout;
+  p.dwp = dwp;
+  // N tile: the largest multiple of 64 <= 256 dividing cout
+  p.block_n = 64;
+  for (int bn = 256; bn >= 64; bn -= 64)
+    if (a->cout % bn == 0) { p.block_n = bn; break; }
+  p.n_tiles_n = a->cout / p.block_n;
+  p.acc_max = 512 / p.block_n;
+  if (p.acc_max > WG_MAX_ACC) p.acc_max = WG_MAX_ACC;
+  p.n_seg = a->n_seg;
+  int k_total = 0, halo_max = 0, jobs = 0, max_pairs = 0;
+  for (int s = 0; s < a->n_seg; ++s) {
+    WgSeg& sg = p.seg[s];
+    sg.C = a->src_c[s]; sg.nchunks = sg.C / 64; sg.ntaps = a->ksize[s] * a->ksize[s]; sg.koff = k_total;
+    sg.halo = a->ksize[s] == 3 ? W + 2 : 0;
+    sg.npairs = (sg.ntaps + 1) / 2;
+    sg.ngroups = (sg.npairs + p.acc_max - 1) / p.acc_max;
+    k_total += sg.ntaps * sg.C;
+    halo_max = sg.halo > halo_max ? sg.halo : halo_max;
+    jobs += sg.nchunks * sg.ngroups * p.n_tiles_n;
+    const int mp = sg.npairs < p.acc_max ? sg.npairs : p.acc_max;
+    max_pairs = mp > max_pairs ? mp : max_pairs;
+  }
+  p.k_total = k_total;
+  p.x_rows = (int)align_up((size_t)WG_R + 2 * halo_max, 64);
+  p.x_bytes = p.x_rows * 128;
+  p.stage_bytes = p.x_bytes + p.block_n / 64 * WG_R * 128;
+  p.stages = (int)((227 * 1024 - 2048) / p.stage_bytes);
+  if (p.stages > 4) p.stages = 4;
+  VF_REQUIRE(p.stages >= 2, "vf_conv2d_wgrad(tc): stage of %d B does not fit twice", p.stage_bytes);
+  p.tmem_cols = 32;
+  while (p.tmem_cols < max_pairs * p.block_n) p.tmem_cols *= 2;
+  // row splits: enough CTAs for ~2 waves, each at least 8 chunks deep
+  int splits = cdiv(2 * sm_count(), jobs);
+  const int max_splits = cdiv(p.rows_total, 8 * WG_R);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.rows_per_split = (int)align_up((size_t)cdiv(p.rows_total, splits), WG_R);
+  splits = cdiv(p.rows_total, p.rows_per_split);
+
+  CUtensorMap maps[3], mapDY;
+  for (int s = 0; s < a->n_seg; ++s) {
+    const uint64_t dims[2] = {(uint64_t)a->src_c[s], (uint64_t)p.rows_total};
+    const uint64_t strides[1] = {(uint64_t)a->src_c[s] * 2};
+    const uint32_t box[2] = {64, 64};
+    int rc = encode_bf16_map(&maps[s], a->src[s], 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  for (int s = a->n_seg; s < 3; ++s) maps[s] = maps[0];
+  {
+    const uint64_t dims[2] = {(uint64_t)dy_ld, (uint64_t)p.rows_total};
+    const uint64_t strides[1] = {(uint64_t)dy_ld * 2};
+    const uint32_t box[2] = {64, WG_R};
+    int rc = encode_bf16_map(&mapDY, dy, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  VF_CUDA(attr_err);
+  const size_t smem = 2048 + (size_t)p.stages * p.stage_bytes;
+  dim3 grid(splits, jobs);
+  conv_wgrad_tc_kernel<<<grid, WG_THREADS, smem, st>>>(maps[0], maps[1], maps[2], mapDY, p);
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}
+
+}  // namespace vf

@@ -50,7 +50,8 @@ extern "C" __attribute__((visibility("default"))) int vf_device_check(void) {
 
 // force_simt: debugging / cross-check switch (environment VF_FORCE_SIMT=1 is read by the Python tests only)
 static int g_force_simt = 0;
-extern "C" __attribute__((visibility("default"))) void vf_debug_force_simt(int on) { g_force_simt = on; }
+namespace vf { int g_force_simt_flag = 0; }
+extern "C" __attribute__((visibility("default"))) void vf_debug_force_simt(int on) { g_force_simt = on; vf::g_force_simt_flag = on; }
 extern "C" __attribute__((visibility("default"))) void vf_debug_flags(int flags) { vf::set_tc_debug(flags); }
 extern "C" __attribute__((visibility("default"))) void vf_debug_counters(long long* dev_buf) { vf::set_tc_debug_out(dev_buf); }
 
