@@ -274,8 +274,10 @@ int vf_debug_umma_shift(const void* A, int rows, const void* B, int shift_rows, 
 /* Single-head self-attention core (unet.py:267-274): O = softmax(Q K^T / sqrt(C)) V per image.
  *   qk  : [images*L, 3C] rows hold q in [0,C), k in [C,2C) (v columns unused when vt != NULL)
  *   vt  : [images, C, L] V transposed (bf16 tensor-core path) or NULL (fp32 path reads v from qk)
- *   out : [images*L, C] */
-int vf_attention(const void* qk, const void* vt, int dtype, int images, int L, int C, void* out, vf_stream stream);
+ *   out : [images*L, C]
+ *   lse : optional [images*L] fp32, written by the tensor-core path for vf_attention_backward: log2 of the softmax
+ *         denominator in the scaled domain, P = exp2(s * log2(e)/sqrt(C) - lse).  NULL when not training. */
+int vf_attention(const void* qk, const void* vt, int dtype, int images, int L, int C, void* out, float* lse, vf_stream stream);
 
 /* fp32 OIHW conv weight -> K-major [cout_pad][k_off + tap*cin + c] rows of length k_total in `dtype`. */
 int vf_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, int dtype, void* dst, int cout_pad,
@@ -326,9 +328,12 @@ int vf_gn_backward(const void* src0, int C0, const float* stats0, int stats0_ld,
                    const void* dy, float* scratch, float* dgamma, float* dbeta, void* dx0, int acc0, void* dx1, int acc1,
                    vf_stream stream);
 
-/* Backward of vf_attention: d_out [images*L, C] -> dqkv [images*L, 3C] (dq | dk | dv). scratch: images*L*2C floats. */
-int vf_attention_backward(const void* qk, const void* vt, const void* d_out, int dtype, int images, int L, int C, float* scratch,
-                          void* dqkv, vf_stream stream);
+/* Backward of vf_attention: d_out [images*L, C] -> dqkv [images*L, 3C] (dq | dk | dv).
+ *   out, lse : the forward results (tensor-core path: bf16, L in {128, 256}, C in {128, 192}; otherwise unused / NULL
+ *              and the CUDA-core kernel recomputes the softmax)
+ *   scratch  : images*L*2C*max(1, L/128) floats */
+int vf_attention_backward(const void* qk, const void* vt, const void* out, const float* lse, const void* d_out, int dtype, int images,
+                          int L, int C, float* scratch, void* dqkv, vf_stream stream);
 
 /* Backward of vf_upsample2x: dx (PADDED H x W) = or += sum of the 2x2 block of dy (PADDED 2H x 2W). */
 int vf_upsample2x_backward(const void* dy, int dtype, int images, int H, int W, int C, void* dx, int accumulate, vf_stream stream);

@@ -101,3 +101,62 @@ def test_wgrad_tcgen05_vs_cuda_cores(case):
         off += k * k * c
     assert rel(outs[1], ref.float()) < 1e-4, "CUDA-core weight gradient"
     assert rel(outs[0], ref.float()) < 1e-4, "tcgen05 weight gradient"
+
+
+@pytest.mark.parametrize("R,L,Cc", [(3, 256, 192), (2, 128, 128), (5, 256, 128), (2, 64, 128)])
+def test_attention_backward_bf16(R, L, Cc):
+    """Attention backward (tcgen05 where the shape fits, CUDA cores otherwise) vs autograd on the same bf16 operands."""
+    import math
+    from gpu_util import bf16r
+    from view_fusion_b200 import ops
+    torch.manual_seed(5)
+    qkv = bf16r(torch.randn(R, L, 3 * Cc) * 1.2).double().requires_grad_(True)
+    d_out = bf16r(torch.randn(R, L, Cc))
+    q, k, v = qkv[..., :Cc], qkv[..., Cc:2 * Cc], qkv[..., 2 * Cc:]
+    o = torch.softmax(q @ k.transpose(1, 2) / math.sqrt(Cc), dim=-1) @ v
+    o.backward(d_out.double())
+    ref = qkv.grad.reshape(R * L, 3 * Cc).float()
+    qd = qkv.detach().reshape(R * L, 3 * Cc).to(torch.bfloat16).cuda()
+    vt = v.detach().transpose(1, 2).contiguous().to(torch.bfloat16).cuda()
+    lse = torch.zeros(R * L, device="cuda")
+    out = ops.attention(qd, vt, R, L, Cc, lse=lse)
+    dod = d_out.reshape(R * L, Cc).to(torch.bfloat16).cuda()
+    got = ops.attention_backward(qd, vt, out, lse, dod, R, L, Cc)
+    ops.force_simt(True)
+    try:
+        simt = ops.attention_backward(qd, vt, None, None, dod, R, L, Cc)
+    finally:
+        ops.force_simt(False)
+    torch.cuda.synchronize()
+    for name, sl in (("dq", slice(0, Cc)), ("dk", slice(Cc, 2 * Cc)), ("dv", slice(2 * Cc, 3 * Cc))):
+        assert rel(simt[:, sl], ref[:, sl]) < 1e-2, ("cuda cores", name)
+        assert rel(got[:, sl], ref[:, sl]) < 1.5e-2, ("tcgen05", name)
+
+
+@pytest.mark.parametrize("case", [(3, 16, 192, 576, 576, False), (2, 64, 64, 64, 64, False), (2, 32, 128, 6, 64, True)])
+def test_wgrad_tcgen05_1x1_flat_rows_and_padded_columns(case):
+    """1x1 weight gradient on FLAT rows (qkv / out-projection / first layer) and with dY columns beyond cout (final conv)."""
+    import ctypes as C
+    from view_fusion_b200 import _lib, ops
+    lib = _lib.require_device()
+    R, S, cin, cout, ld, padded = case
+    torch.manual_seed(2)
+    x = torch.randn(R, cin, S, S).to(torch.bfloat16)
+    dy = torch.zeros(R, ld, S, S)
+    dy[:, :cout] = torch.randn(R, cout, S, S)
+    dy = dy.to(torch.bfloat16)
+    if padded:
+        xs, dys = ops.to_padded(x.float(), torch.bfloat16).cuda(), ops.to_padded(dy.float(), torch.bfloat16).cuda()
+    else:
+        xs = x.permute(0, 2, 3, 1).reshape(-1, cin).contiguous().cuda()
+        dys = dy.permute(0, 2, 3, 1).reshape(-1, ld).contiguous().cuda()
+    a = _lib.ConvArgs()
+    a.dtype, a.images, a.H, a.W, a.in_padded, a.out_padded, a.n_seg, a.stride = _lib.VF_BF16, R, S, S, int(padded), int(padded), 1, 1
+    a.src[0], a.src_c[0], a.ksize[0] = xs.data_ptr(), cin, 1
+    a.cout, a.cout_pad = cout, ld
+    dwp = torch.zeros(ld, cin, device="cuda")
+    _lib.check(lib.vf_conv2d_wgrad(C.byref(a), dys.data_ptr(), ld, dwp.data_ptr(), _lib.stream_handle()), "wgrad")
+    torch.cuda.synchronize()
+    ref = torch.einsum("rnl,rcl->nc", dy.double().view(R, ld, S * S), x.double().view(R, cin, S * S)).float()
+    assert rel(dwp.cpu()[:cout], ref[:cout]) < 1e-4
+    assert float(dwp[cout:].abs().max()) == 0.0 if cout < ld else True

@@ -121,7 +121,7 @@ def load() -> C.CDLL:
         "vf_debug_umma_rate": (i, [i, i, i, i, i, p, p]),
         "vf_debug_umma_mn": (i, [p, i, p, i, i, i, i, p, p]),
         "vf_debug_umma_shift": (i, [p, i, p, i, i, p, p]),
-        "vf_attention": (i, [p, p, i, i, i, i, p, p]),
+        "vf_attention": (i, [p, p, i, i, i, i, p, p, p]),
         "vf_pack_conv_weight": (i, [p, i, i, i, i, p, i, i, i, p]),
         "vf_unet_packed_t_bytes": (sz, [p]),
         "vf_unet_pack_weights_t": (i, [p, p, p]),
@@ -131,7 +131,7 @@ def load() -> C.CDLL:
         "vf_unpack_conv_wgrad": (i, [p, i, i, i, i, i, p, i, i, p]),
         "vf_pack_conv_weight_t": (i, [p, i, i, i, i, p, i, i, i, i, p]),
         "vf_gn_backward": (i, [p, i, p, i, p, i, p, i, i, i, i, i, i, p, p, i, p, p, p, p, p, i, p, i, p]),
-        "vf_attention_backward": (i, [p, p, p, i, i, i, i, p, p, p]),
+        "vf_attention_backward": (i, [p, p, p, p, p, i, i, i, i, p, p, p]),
         "vf_upsample2x_backward": (i, [p, i, i, i, i, i, p, i, p]),
         "vf_zero_insert2x": (i, [p, i, i, i, i, i, p, p]),
         "vf_add_inplace": (i, [p, p, i, sz, p]),

@@ -34,6 +34,7 @@ struct AttnTcParams {
   int tmem_cols;
   float scale_log2;   // log2(e) / sqrt(C)
   __nv_bfloat16* out;
+  float* lse;          // optional [images*L]: log2 of the softmax denominator in the scaled-log2 domain (training)
 };
 
 constexpr int ATT_THREADS = 160;
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
     ptx::fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
     ptx::mbar_arrive(bar_p);
     const float inv = 1.f / sum;
+    if (p.lse && valid) p.lse[m] = mx * p.scale_log2 + log2f(sum);   // P = exp2(s * scale_log2 - lse)
     ptx::mbar_wait(bar_o, 0);
     ptx::tc_fence_after();
     for (int c0 = 0; c0 < p.C; c0 += 16) {
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
   }
 }
 
-int attention_tc(const void* qk, const void* vt, int images, int L, int C, void* out, cudaStream_t st) {
+int attention_tc(const void* qk, const void* vt, int images, int L, int C, void* out, float* lse, cudaStream_t st) {
   VF_REQUIRE(vt, "vf_attention(tc): needs the transposed V tensor");
   VF_REQUIRE(C % 64 == 0, "vf_attention(tc): C=%d not a multiple of 64", C);
   VF_REQUIRE(L == 64 || (L >= 128 && L <= 256 && L % 128 == 0), "vf_attention(tc): L=%d unsupported (64, 128, 256)", L);
@@ -216,6 +218,7 @@ int attention_tc(const void* qk, const void* vt, int images, int L, int C, void*
   p.idesc_o = ptx::make_idesc_bf16(128, p.n_half, 0, 0);
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)C);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.lse = lse;
   const uint32_t q_bytes = (uint32_t)p.kchunks * 128 * 128, pp_bytes = (uint32_t)p.pchunks * 128 * 128;
   const uint32_t k_bytes = (uint32_t)p.kchunks * p.nkeys * 128, v_bytes = (uint32_t)p.pchunks * C * 128;
   p.off_k = q_bytes > pp_bytes ? q_bytes : pp_bytes;

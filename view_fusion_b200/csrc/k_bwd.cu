@@ -528,9 +528,17 @@ VF_API int vf_gn_backward(const void* src0, int C0, const float* stats0, int sta
   return VF_OK;
 }
 
-VF_API int vf_attention_backward(const void* qk, const void* vt, const void* d_out, int dtype, int images, int L, int C, float* scratch,
-                                 void* dqkv, vf_stream stream) {
+namespace vf {
+bool attention_bwd_tc_supported(int L, int C);
+int attention_bwd_tc(const void* qkv, const void* vt, const void* out, const float* lse, const void* d_out, int images, int L, int C,
+                     float* scratch, void* dqkv, cudaStream_t st);
+}  // namespace vf
+
+VF_API int vf_attention_backward(const void* qk, const void* vt, const void* out, const float* lse, const void* d_out, int dtype, int images,
+                                 int L, int C, float* scratch, void* dqkv, vf_stream stream) {
   VF_REQUIRE(qk && d_out && scratch && dqkv && images > 0 && L > 0 && C > 0, "vf_attention_backward: bad args");
+  if (dtype == VF_BF16 && !g_force_simt_flag && vt && out && lse && attention_bwd_tc_supported(L, C))
+    return attention_bwd_tc(qk, vt, out, lse, d_out, images, L, C, scratch, dqkv, as_stream(stream));
   const size_t smem = (size_t)BQ * (2 * C + 2 * L) * sizeof(float);
   VF_REQUIRE(smem <= 48 * 1024, "vf_attention_backward: L=%d C=%d too large", L, C);
   cudaStream_t st = as_stream(stream);

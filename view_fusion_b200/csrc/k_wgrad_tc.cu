@@ -161,27 +161,31 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
   if (warp == 5) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
 }
 
-// Supported: bf16, PADDED -> PADDED, stride 1, every segment a multiple of 64 channels, cout a multiple of 64.
+// Supported: bf16, stride 1, X and dY in the same row order (3x3 taps need PADDED), every segment a multiple of 64
+// channels, dY leading dimension a multiple of 64 (columns >= cout are skipped by the epilogue).
 bool wgrad_tc_supported(const vf_conv_args* a, int dy_ld) {
-  if (a->dtype != VF_BF16 || !a->in_padded || !a->out_padded || a->stride != 1) return false;
-  if (a->cout % 64 || dy_ld % 64) return false;
-  for (int s = 0; s < a->n_seg; ++s)
+  if (a->dtype != VF_BF16 || a->stride != 1 || (a->in_padded != 0) != (a->out_padded != 0)) return false;
+  if (dy_ld % 64) return false;
+  for (int s = 0; s < a->n_seg; ++s) {
     if (a->src_c[s] % 64) return false;
+    if (a->ksize[s] == 3 && !a->in_padded) return false;
+  }
   return true;
 }
 
 int conv2d_wgrad_tc(const vf_conv_args* a, const void* dy, int dy_ld, float* dwp, cudaStream_t st) {
   WgParams p{};
   const int H = a->H, W = a->W;
-  p.rows_total = a->images * (H + 1) * (W + 1);
+  p.rows_total = a->in_padded ? a->images * (H + 1) * (W + 1) : a->images * H * W;
   p.W1 = W + 1;
   p.cout = a->cout;
   p.dwp = dwp;
-  // N tile: the largest multiple of 64 <= 256 dividing cout
+  // N tile: the largest multiple of 64 <= 256 dividing the (64-padded) output channels
+  const int n_cols = (int)align_up((size_t)a->cout, 64);
   p.block_n = 64;
   for (int bn = 256; bn >= 64; bn -= 64)
-    if (a->cout % bn == 0) { p.block_n = bn; break; }
-  p.n_tiles_n = a->cout / p.block_n;
+    if (n_cols % bn == 0) { p.block_n = bn; break; }
+  p.n_tiles_n = n_cols / p.block_n;
   p.acc_max = 512 / p.block_n;
   if (p.acc_max > WG_MAX_ACC) p.acc_max = WG_MAX_ACC;
   p.n_seg = a->n_seg;

@@ -82,7 +82,7 @@ struct vf_unet {
     size_t wt_off[3];                  // transposed weight pack per segment in packed_t (SIZE_MAX: no data gradient)
     const void* gsrc0; const void* gsrc1; int gC0, gC1; const float* gst0; const float* gst1; int gld0, gld1; int gw, gb, swish;
     void* gdst; int gH, gW;
-    const void* qkv; const void* vt; void* o; int aC, aL;
+    const void* qkv; const void* vt; void* o; float* lse; int aC, aL;
     const void* usrc; void* udst; int uH, uW, uC;
   };
   std::vector<TapeOp> tape;
@@ -550,10 +550,11 @@ static Act run_resblock(Exec& ex, vf_unet* u, const uint8_t* pk, int images, con
     conv_call(ex, u, a, m);
   }
   Act o{ex.alloc((size_t)images * HW * C * es), C, x.H, x.W, nullptr};   // FLAT
-  VF_RUN(ex, K_ATTN, vf_attention(qkv, vt, u->dtype, images, HW, C, o.p, (vf_stream)ex.st));
+  float* lse = reinterpret_cast<float*>(ex.alloc((size_t)images * HW * 4));
+  VF_RUN(ex, K_ATTN, vf_attention(qkv, vt, u->dtype, images, HW, C, o.p, lse, (vf_stream)ex.st));
   if (!ex.dry) {
     vf_unet::TapeOp t{};
-    t.kind = 2; t.qkv = qkv; t.vt = vt; t.o = o.p; t.aC = C; t.aL = HW;
+    t.kind = 2; t.qkv = qkv; t.vt = vt; t.o = o.p; t.lse = lse; t.aC = C; t.aL = HW;
     u->tape.push_back(t);
   }
   Act out2 = new_act(ex, u, images, C, x.H, x.W, true);
@@ -944,7 +945,27 @@ static void conv_backward(BwdCtx& cx, const vf_unet::TapeOp& t, const uint8_t* p
   int k_total = 0;
   for (int s = 0; s < f.n_seg; ++s) k_total += f.ksize[s] * f.ksize[s] * f.src_c[s];
   if (!cx.dry && cx.rc == VF_OK) cudaMemsetAsync(dwp, 0, (size_t)f.cout_pad * k_total * 4, cx.st);
-  VF_B(vf_conv2d_wgrad(&a, dYs, dy_ld, dwp, (vf_stream)cx.st));
+  {
+    vf_conv_args aw = a;
+    const void* dYw = dYs;
+    bool all_1x1 = true;
+    for (int s = 0; s < f.n_seg; ++s) all_1x1 = all_1x1 && f.ksize[s] == 1;
+    if (dt == VF_BF16 && all_1x1 && (a.in_padded != 0) != (a.out_padded != 0)) {
+      // 1x1 convolution between the two row orders (qkv, attention out-projection, first layer): bring dY into the
+      // row order of X so the tensor-core weight-gradient GEMM sees one row index on both operands
+      if (a.in_padded) {
+        void* z = cx.galloc((size_t)images * (H + 1) * (W + 1) * dy_ld * es);
+        VF_B(vf_flat_to_padded(dYs, dt, images, H, W, dy_ld, z, (vf_stream)cx.st));
+        dYw = z;
+      } else {
+        void* z = cx.galloc((size_t)images * H * W * dy_ld * es);
+        VF_B(vf_padded_to_flat(dYs, dt, images, H, W, dy_ld, z, (vf_stream)cx.st));
+        dYw = z;
+      }
+      aw.out_padded = a.in_padded;
+    }
+    VF_B(vf_conv2d_wgrad(&aw, dYw, dy_ld, dwp, (vf_stream)cx.st));
+  }
   int koff = 0;
   for (int s = 0; s < f.n_seg; ++s) {
     const int kk = f.ksize[s] * f.ksize[s];
@@ -1021,7 +1042,7 @@ static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float*
   size_t gn_floats = 0, att_floats = 0;
   for (auto& t : u->tape) {
     if (t.kind == 1) gn_floats = std::max(gn_floats, (size_t)images * (t.gC0 + t.gC1) * 2);
-    if (t.kind == 2) att_floats = std::max(att_floats, (size_t)images * t.aL * 2 * t.aC);
+    if (t.kind == 2) att_floats = std::max(att_floats, (size_t)images * t.aL * 2 * t.aC * std::max(1, t.aL / 128));
   }
   float* gn_scratch = (float*)cx.galloc(gn_floats * 4);
   float* att_scratch = (float*)cx.galloc(att_floats * 4);
@@ -1067,7 +1088,7 @@ static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float*
     } else if (t.kind == 2) {
       auto& go = cx.grad_of(t.o);
       auto& gq = cx.grad_of(t.qkv);
-      VF_B(vf_attention_backward(t.qkv, t.vt, go.first, dt, images, t.aL, t.aC, att_scratch, gq.first, (vf_stream)cx.st));
+      VF_B(vf_attention_backward(t.qkv, t.vt, t.o, t.lse, go.first, dt, images, t.aL, t.aC, att_scratch, gq.first, (vf_stream)cx.st));
       gq.second = true;
     } else if (t.kind == 3) {
       auto& gd = cx.grad_of(t.udst);

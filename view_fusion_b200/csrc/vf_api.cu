@@ -26,7 +26,7 @@ int sm_count() {
 int conv2d_simt(const vf_conv_args* a, cudaStream_t st);
 int conv2d_tc(const vf_conv_args* a, cudaStream_t st);
 int attention_simt(const void* qk, const void* vt, int dtype, int images, int L, int C, void* out, cudaStream_t st);
-int attention_tc(const void* qk, const void* vt, int images, int L, int C, void* out, cudaStream_t st);
+int attention_tc(const void* qk, const void* vt, int images, int L, int C, void* out, float* lse, cudaStream_t st);
 void set_tc_debug(int f);
 void set_tc_debug_out(long long* p);
 
@@ -71,9 +71,9 @@ extern "C" __attribute__((visibility("default"))) int vf_conv2d(const vf_conv_ar
   return conv2d_simt(a, as_stream(stream));
 }
 
-extern "C" __attribute__((visibility("default"))) int vf_attention(const void* qk, const void* vt, int dtype, int images, int L, int C, void* out, vf_stream stream) {
+extern "C" __attribute__((visibility("default"))) int vf_attention(const void* qk, const void* vt, int dtype, int images, int L, int C, void* out, float* lse, vf_stream stream) {
   using namespace vf;
   VF_REQUIRE(qk && out && images > 0 && L > 0 && C > 0, "vf_attention: bad args");
-  if (dtype == VF_BF16 && !g_force_simt) return attention_tc(qk, vt, images, L, C, out, as_stream(stream));
+  if (dtype == VF_BF16 && !g_force_simt) return attention_tc(qk, vt, images, L, C, out, lse, as_stream(stream));
   return attention_simt(qk, vt, dtype, images, L, C, out, as_stream(stream));
 }

@@ -140,11 +140,22 @@ def upsample2x(src, images, H, W):
     return dst
 
 
-def attention(qkv, vt, images, L, Cc):
+def attention(qkv, vt, images, L, Cc, lse=None):
     lib = _lib.require_device()
     out = torch.empty(images * L, Cc, dtype=qkv.dtype, device=qkv.device)
-    _lib.check(lib.vf_attention(qkv.data_ptr(), _lib.ptr(vt), _dt(qkv), images, L, Cc, out.data_ptr(), _lib.stream_handle()), "vf_attention")
+    _lib.check(lib.vf_attention(qkv.data_ptr(), _lib.ptr(vt), _dt(qkv), images, L, Cc, out.data_ptr(), _lib.ptr(lse), _lib.stream_handle()),
+               "vf_attention")
     return out
+
+
+def attention_backward(qkv, vt, out, lse, d_out, images, L, Cc):
+    """dqkv [images*L, 3C] of softmax(QK^T/sqrt(C))V given d_out (tensor cores when out/lse are given and the shape fits)."""
+    lib = _lib.require_device()
+    scratch = torch.empty(images * L * 2 * Cc * max(1, L // 128), dtype=torch.float32, device=qkv.device)
+    dqkv = torch.empty(images * L, 3 * Cc, dtype=qkv.dtype, device=qkv.device)
+    _lib.check(lib.vf_attention_backward(qkv.data_ptr(), _lib.ptr(vt), _lib.ptr(out), _lib.ptr(lse), d_out.data_ptr(), _dt(qkv), images, L, Cc,
+                                         scratch.data_ptr(), dqkv.data_ptr(), _lib.stream_handle()), "vf_attention_backward")
+    return dqkv
 
 
 def embed(level, angle, ic, w0, b0, w2, b2, emb_w, emb_b):
