@@ -132,6 +132,33 @@ def cpu_psample_rate(B, N, steps, warmup, threads):
     return B / (T_STEPS * sec), sec
 
 
+def cpu_train_rate(B, N, steps, warmup, threads):
+    """Reference-equivalent CPU training step (oracle forward + torch autograd backward + Adam), samples/s."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import vf_oracle as O
+    torch.set_num_threads(threads)
+    sd = O.init_state_dict(O.SMALL_V100, 0, prefix="denoise_fn.")
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt = torch.optim.Adam(list(params.values()), lr=1e-4)
+    sched = O.make_schedule(**O.BETA_TRAIN)
+    y_cond, noise, angle, vc = synthetic(B, N)
+    g = torch.Generator().manual_seed(5)
+    y0 = torch.rand(B, 3, 64, 64, generator=g)
+    times = []
+    for j in range(warmup + steps):
+        t = torch.randint(1, T_STEPS, (B,), generator=g)
+        u = torch.rand(B, 1, generator=g)
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss, _ = O.train_loss(params, O.SMALL_V100, sched, y0, y_cond, vc, angle, t, u, noise)
+        loss.backward()
+        opt.step()
+        if j >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = statistics.median(times)
+    return B / sec, sec
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -163,6 +190,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--ref-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-batch", type=int, default=28, help="training samples per GPU (weak scaling)")
+    ap.add_argument("--train-steps", type=int, default=10)
+    ap.add_argument("--no-train", action="store_true", help="skip the training-throughput leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -288,6 +318,73 @@ def main():
             classes["hbm_peak_GBps"] = pk["hbm"]
             classes["step_flop_utilisation"] = round(GFLOP_PER_VIEW * 1e9 * images / (ms_step * 1e-3) / 1e12 / pk["tf_sustained"], 4)
 
+    # ---- training leg: zero_grad -> forward -> backward (+ gradient all-reduce) -> Adam ------------------------
+    train = None
+    if not args.no_train:
+        from view_fusion_b200.distributed import data_parallel
+        del plan, bufs
+        torch.cuda.empty_cache()
+        Bt = args.train_batch
+        yc_h, eps_h, an_h, vct = synthetic(Bt, N, seed=4321 + rank)
+        y0_h = torch.rand(Bt, 3, 64, 64, generator=torch.Generator().manual_seed(99 + rank))
+        pin = lambda x: x.contiguous().pin_memory()
+        yc_p, y0_p, an_p = pin(yc_h), pin(y0_h), pin(an_h)
+        yc_d, y0_d, an_d = yc_h.to(dev), y0_h.to(dev), an_h.to(dev)
+        if world > 1:
+            data_parallel(model)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+
+        def train_step(host: bool):
+            if host:
+                yc, y0, an = yc_p.to(dev, non_blocking=True), y0_p.to(dev, non_blocking=True), an_p.to(dev, non_blocking=True)
+            else:
+                yc, y0, an = yc_d, y0_d, an_d
+            opt.zero_grad(set_to_none=True)
+            loss = model(y_cond=yc, view_count=vct, angle=an, y_0=y0)
+            loss.backward()
+            opt.step()
+            return float(loss.detach()) if host else loss.detach()
+
+        for _ in range(3):
+            train_step(False)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.train_steps):
+            last_loss = train_step(False)
+        e1.record()
+        barrier()
+        tr_ms = e0.elapsed_time(e1) / args.train_steps
+        train_step(True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.train_steps):
+            last = train_step(True)
+        barrier()
+        tr_e2e = (time.perf_counter() - t0) / args.train_steps
+        if world > 1:
+            tm = torch.tensor([tr_ms, tr_e2e], device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            tr_ms, tr_e2e = float(tm[0]), float(tm[1])
+        pk = peaks()
+        tr_flops = 3 * GFLOP_PER_VIEW * 1e9 * Bt * N
+        train = {
+            "metric": "train_samples_per_sec", "value": world * Bt / (tr_ms * 1e-3), "unit": "samples/s", "ms_per_step": tr_ms,
+            "steps": args.train_steps, "scaling": "weak", "B_per_gpu": Bt, "N": N,
+            "step": "zero_grad -> ViewFusion.forward (loss) -> backward (hand-written CUDA) -> "
+                    + ("flat-gradient NCCL all-reduce (mean, 4 chunks) -> " if world > 1 else "") + "torch Adam",
+            "e2e": {"value": world * Bt / tr_e2e, "unit": "samples/s", "ms_per_step": tr_e2e * 1e3,
+                    "h2d_bytes_per_step": (yc_p.numel() + y0_p.numel() + an_p.numel()) * 4, "d2h_bytes_per_step": 4},
+            "flop_utilisation": round(tr_flops / (tr_ms * 1e-3) / 1e12 / pk["tf_sustained"], 4),
+            "loss": float(last),
+        }
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sps, sec = cpu_train_rate(2, N, steps=2, warmup=1, threads=threads)
+            train["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
+                                     "sample": f"oracle train step (fwd + torch autograd bwd + Adam), B=2 N={N}: 1 warm-up + 2 timed, "
+                                               f"median {sec:.2f} s/step"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -313,6 +410,7 @@ def main():
             "roofline": roof,
             "kernel_classes": classes,
             "cpu_baseline": cpu,
+            "train": train,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

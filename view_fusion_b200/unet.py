@@ -242,6 +242,10 @@ class UNet(nn.Module):
         _lib.check(lib.vf_unet_backward(h, pt.data_ptr(), self._gws.data_ptr(), self._gws.numel(), grad_out8.data_ptr(), arr,
                                         _lib.stream_handle()), "vf_unet_backward")
         self._flat_grad = flat
+        sync = getattr(self, "_grad_sync", None)
+        if sync is not None:
+            from .distributed import allreduce_mean_
+            allreduce_mean_(flat, sync[0], sync[1])      # the one collective of the path (training gradient mean)
         return plist, grads
 
     @property

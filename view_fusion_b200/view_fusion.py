@@ -310,8 +310,6 @@ class _TrainStep(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss):
         unet = ctx.model.denoise_fn
-        g8 = ctx.grad8
-        if not (grad_loss.numel() == 1 and float(grad_loss) == 1.0):
-            g8 = g8 * grad_loss
+        g8 = ctx.grad8 * grad_loss            # device-side scale: no host read of the incoming gradient
         _, grads = unet.run_backward(g8)
         return (None,) * 7 + tuple(grads)
