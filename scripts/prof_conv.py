@@ -14,6 +14,10 @@ cfgs = {
     "c128": dict(S=32, segs=[(128, 3)], cout=128, flat=False),
     "c192": dict(S=16, segs=[(192, 3)], cout=192, flat=False),
     "c320": dict(S=8, segs=[(320, 3)], cout=320, flat=False),
+    "u8a": dict(S=8, segs=[(640, 3)], cout=320, flat=False),
+    "u8b": dict(S=8, segs=[(320, 3), (640, 1)], cout=320, flat=False),
+    "u16a": dict(S=16, segs=[(512, 3)], cout=192, flat=False),
+    "u32a": dict(S=32, segs=[(320, 3)], cout=128, flat=False),
     "u64": dict(S=64, segs=[(64, 3), (64, 1), (64, 1)], cout=64, flat=False),
 }
 c = cfgs[case]
@@ -29,7 +33,7 @@ stats = torch.zeros(R, cout, 2, device="cuda")
 flops = 2 * R * S * S * cout * k_total
 variants = [("full", 0, True, True)]
 if len(sys.argv) > 2 and sys.argv[2] == "ablate":
-    variants += [("no-res-no-stats", 0, False, False), ("dbg:no-store", 2, True, True), ("dbg:no-unit-work", 4, True, True), ("dbg:no-unit-no-table", 12, True, True)]
+    variants += [("no-res (typical)", 0, False, True), ("no-res dbg:no-table", 8, False, True), ("no-res-no-stats", 0, False, False), ("dbg:no-store", 2, True, True), ("dbg:no-unit-work", 4, True, True), ("dbg:no-unit-no-table", 12, True, True)]
 if len(sys.argv) > 2 and sys.argv[2] == "sweep":
     variants = []
     for bn in sorted({b for b in (64, 96, 128, 160, 192, 256, 320) if cout % b == 0 and b <= 256}):

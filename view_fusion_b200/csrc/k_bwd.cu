@@ -129,43 +129,67 @@ struct GnBwdParams {
   void* dx0; int acc0; void* dx1; int acc1;
 };
 
-__device__ __forceinline__ float dswish(float z) {
+// d/dz [z * sigmoid(z)]; the bf16 path takes sigmoid from one tanh.approx like the forward kernel
+template <typename T> __device__ __forceinline__ float dswish_for(float z);
+template <> __device__ __forceinline__ float dswish_for<float>(float z) {
   const float s = 1.f / (1.f + __expf(-z));
   return s * (1.f + z * (1.f - s));
 }
+template <> __device__ __forceinline__ float dswish_for<__nv_bfloat16>(float z) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+  const float s = 0.5f * t + 0.5f;
+  return s * (1.f + z * (1.f - s));
+}
 
-// shared prologue: per channel mu / rstd of its group -> smem mr[C][2]
-__device__ __forceinline__ void gn_group_stats(const GnBwdParams& p, int img, float* mr) {
+// shared prologue: per channel mu / rstd of its group -> smem mr[C][2].  The raw (sum, sumsq) pairs of the image are
+// staged into smem with one coalesced load first, so the per-group loops run out of shared memory (one global round
+// trip instead of one per group member).  `raw` is scratch of 2C floats; ends with a __syncthreads().
+__device__ __forceinline__ void gn_group_stats(const GnBwdParams& p, int img, float* mr, float* raw) {
   const int C = p.C0 + p.C1, gs = C / p.groups;
   const float inv_n = 1.f / ((float)gs * (float)p.HW);
   const float* sa = p.st0 + (size_t)img * p.ld0 * 2;
   const float* sb = p.st1 ? p.st1 + (size_t)img * p.ld1 * 2 : nullptr;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) raw[i] = i < 2 * p.C0 ? __ldg(sa + i) : __ldg(sb + (i - 2 * p.C0));
+  __syncthreads();
   for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
     const int g0 = ch / gs * gs;
     float s = 0.f, q = 0.f;
-    for (int j = 0; j < gs; ++j) {
-      const int cc = g0 + j;
-      const float* e = cc < p.C0 ? sa + 2 * cc : sb + 2 * (cc - p.C0);
-      s += __ldg(e); q += __ldg(e + 1);
-    }
+    for (int j = 0; j < gs; ++j) { s += raw[2 * (g0 + j)]; q += raw[2 * (g0 + j) + 1]; }
     const float mean = s * inv_n;
     const float var = fmaxf(q * inv_n - mean * mean, 0.f);
     mr[2 * ch] = mean;
     mr[2 * ch + 1] = rsqrtf(var + 1e-5f);
   }
+  __syncthreads();
 }
 
+constexpr int kGbUnroll = 4;     // rows in flight per thread: independent 16-byte loads issued before any use
+
+// (yy, xx) of a thread's PADDED row advance incrementally by a constant stride: no division in the streaming loops
+struct RowWalk {
+  int yy, xx, dy, dx, W1;
+  __device__ __forceinline__ RowWalk(int row, int stride, int w1) : W1(w1) {
+    yy = row / w1; xx = row - yy * w1;
+    dy = stride / w1; dx = stride - dy * w1;
+  }
+  __device__ __forceinline__ bool pad() const { return yy == 0 || xx == 0; }
+  __device__ __forceinline__ void step() {
+    yy += dy; xx += dx;
+    if (xx >= W1) { xx -= W1; ++yy; }
+  }
+};
+
 template <typename T>
-__global__ void __launch_bounds__(kGbThreads) gn_bwd_reduce_kernel(const GnBwdParams p) {
+__global__ void __launch_bounds__(kGbThreads, 2) gn_bwd_reduce_kernel(const GnBwdParams p) {
   constexpr int VEC = VecOf<T>::N;
+  constexpr int UN = kGbUnroll;
   extern __shared__ float sm[];
   const int C = p.C0 + p.C1, CV = C / VEC;
   float* mr = sm;              // [C][2]
-  float* acc = sm + 2 * C;     // [C][2]
+  float* part = sm + 2 * C;    // [PY][C][2] per-row-lane partial sums (also the staging scratch of the prologue)
   const int img = blockIdx.y;
-  gn_group_stats(p, img, mr);
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) acc[i] = 0.f;
-  __syncthreads();
+  gn_group_stats(p, img, mr, part);
   const int PY = blockDim.x / CV;
   const int cv = threadIdx.x % CV, py = threadIdx.x / CV;
   const int c = cv * VEC;
@@ -176,49 +200,73 @@ __global__ void __launch_bounds__(kGbThreads) gn_bwd_reduce_kernel(const GnBwdPa
 #pragma unroll
   for (int j = 0; j < VEC; ++j) { mu[j] = mr[2 * (c + j)]; rs[j] = mr[2 * (c + j) + 1]; ga[j] = __ldg(p.gamma + c + j); be[j] = __ldg(p.beta + c + j); sA[j] = sB[j] = 0.f; }
   const int p0 = blockIdx.x * p.rows_per_cta, p1 = min(p.P, p0 + p.rows_per_cta);
-  for (int r = p0 + py; r < p1; r += PY) {
-    const int yy = r / p.W1, xx = r - yy * p.W1;
-    if (yy == 0 || xx == 0) continue;
-    float x[VEC], g[VEC];
-    load_vec(src + (size_t)r * ld, x);
-    load_vec(dy + (size_t)r * C, g);
+  RowWalk rw(p0 + py, PY, p.W1);
+  for (int rb = p0 + py; rb < p1; rb += UN * PY) {
+    uint4 xr[UN], gr[UN];
+    uint32_t live = 0;
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      const float xh = (x[j] - mu[j]) * rs[j];
-      const float dz = p.swish ? g[j] * dswish(xh * ga[j] + be[j]) : g[j];
-      sA[j] += dz; sB[j] += dz * xh;
+    for (int u = 0; u < UN; ++u) {
+      const int r = rb + u * PY;
+      const bool ok = r < p1 && !rw.pad();
+      live |= (uint32_t)ok << u;
+      if (ok) {
+        xr[u] = *reinterpret_cast<const uint4*>(src + (size_t)r * ld);
+        gr[u] = *reinterpret_cast<const uint4*>(dy + (size_t)r * C);
+      }
+      rw.step();
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      if (!((live >> u) & 1u)) continue;
+      float x[VEC], g[VEC];
+      load_vec(reinterpret_cast<const T*>(&xr[u]), x);
+      load_vec(reinterpret_cast<const T*>(&gr[u]), g);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const float xh = (x[j] - mu[j]) * rs[j];
+        const float dz = p.swish ? g[j] * dswish_for<T>(xh * ga[j] + be[j]) : g[j];
+        sA[j] += dz; sB[j] += dz * xh;
+      }
     }
   }
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) { atomicAdd(&acc[2 * (c + j)], sA[j]); atomicAdd(&acc[2 * (c + j) + 1], sB[j]); }
+  for (int j = 0; j < VEC; ++j) { part[(py * C + c + j) * 2] = sA[j]; part[(py * C + c + j) * 2 + 1] = sB[j]; }
   __syncthreads();
+  // per-image sums; gn_bwd_apply folds them into dgamma / dbeta (one CTA per image)
   float* red = p.red + (size_t)img * C * 2;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    atomicAdd(red + 2 * i, acc[2 * i]);
-    atomicAdd(red + 2 * i + 1, acc[2 * i + 1]);
-    atomicAdd(p.dbeta + i, acc[2 * i]);
-    atomicAdd(p.dgamma + i, acc[2 * i + 1]);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float t = 0.f;
+    for (int q = 0; q < PY; ++q) t += part[q * 2 * C + i];
+    atomicAdd(red + i, t);
   }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kGbThreads) gn_bwd_apply_kernel(const GnBwdParams p) {
+__global__ void __launch_bounds__(kGbThreads, 2) gn_bwd_apply_kernel(const GnBwdParams p) {
   constexpr int VEC = VecOf<T>::N;
+  constexpr int UN = kGbUnroll;
   extern __shared__ float sm[];
   const int C = p.C0 + p.C1, CV = C / VEC;
   float* mr = sm;              // [C][2] mean, rstd
   float* tt = sm + 2 * C;      // [C][2] t1 = rstd*S1/n, t2 = rstd*S2/n
+  float* raw = sm + 4 * C;     // [C][2] staging: forward statistics, then gamma-weighted reduce sums
   const int img = blockIdx.y;
-  gn_group_stats(p, img, mr);
-  __syncthreads();
+  gn_group_stats(p, img, mr, raw);
   {
     const int gs = C / p.groups;
     const float inv_n = 1.f / ((float)gs * (float)p.HW);
     const float* red = p.red + (size_t)img * C * 2;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+      const float r = __ldg(red + i);
+      raw[i] = r * __ldg(p.gamma + (i >> 1));
+      // parameter gradients: dbeta = sum_img red[.][0], dgamma = sum_img red[.][1] (one CTA per image adds them)
+      if (blockIdx.x == 0) atomicAdd(((i & 1) ? p.dgamma : p.dbeta) + (i >> 1), r);
+    }
+    __syncthreads();
     for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
       const int g0 = ch / gs * gs;
       float S1 = 0.f, S2 = 0.f;
-      for (int j = 0; j < gs; ++j) { const float gm = __ldg(p.gamma + g0 + j); S1 += gm * __ldg(red + 2 * (g0 + j)); S2 += gm * __ldg(red + 2 * (g0 + j) + 1); }
+      for (int j = 0; j < gs; ++j) { S1 += raw[2 * (g0 + j)]; S2 += raw[2 * (g0 + j) + 1]; }
       tt[2 * ch] = mr[2 * ch + 1] * S1 * inv_n;
       tt[2 * ch + 1] = mr[2 * ch + 1] * S2 * inv_n;
     }
@@ -240,31 +288,50 @@ __global__ void __launch_bounds__(kGbThreads) gn_bwd_apply_kernel(const GnBwdPar
     t1[j] = tt[2 * (c + j)]; t2[j] = tt[2 * (c + j) + 1];
   }
   const int p0 = blockIdx.x * p.rows_per_cta, p1 = min(p.P, p0 + p.rows_per_cta);
-  for (int r = p0 + py; r < p1; r += PY) {
-    const int yy = r / p.W1, xx = r - yy * p.W1;
-    float o[VEC];
-    if (yy == 0 || xx == 0) {
-      if (accum) continue;
+  RowWalk rw(p0 + py, PY, p.W1);
+  for (int rb = p0 + py; rb < p1; rb += UN * PY) {
+    uint4 xr[UN], gr[UN], orr[UN];
+    uint32_t live = 0, padm = 0;
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) o[j] = 0.f;          // gradients of padding rows are exact zeros
-    } else {
-      float x[VEC], g[VEC];
-      load_vec(src + (size_t)r * ld, x);
-      load_vec(dy + (size_t)r * C, g);
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        const float xh = (x[j] - mu[j]) * rs[j];
-        const float dz = p.swish ? g[j] * dswish(xh * ga[j] + be[j]) : g[j];
-        o[j] = rs[j] * ga[j] * dz - t1[j] - xh * t2[j];
+    for (int u = 0; u < UN; ++u) {
+      const int r = rb + u * PY;
+      const bool in = r < p1, pad = rw.pad();
+      live |= (uint32_t)in << u; padm |= (uint32_t)pad << u;
+      if (in && !pad) {
+        xr[u] = *reinterpret_cast<const uint4*>(src + (size_t)r * ld);
+        gr[u] = *reinterpret_cast<const uint4*>(dy + (size_t)r * C);
+        if (accum) orr[u] = *reinterpret_cast<const uint4*>(dx + (size_t)r * ld);
       }
-      if (accum) {
-        float old[VEC];
-        load_vec(dx + (size_t)r * ld, old);
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) o[j] += old[j];
-      }
+      rw.step();
     }
-    store_vec(dx + (size_t)r * ld, o);
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      if (!((live >> u) & 1u)) continue;
+      const int r = rb + u * PY;
+      float o[VEC];
+      if ((padm >> u) & 1u) {
+        if (accum) continue;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) o[j] = 0.f;          // gradients of padding rows are exact zeros
+      } else {
+        float x[VEC], g[VEC];
+        load_vec(reinterpret_cast<const T*>(&xr[u]), x);
+        load_vec(reinterpret_cast<const T*>(&gr[u]), g);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float xh = (x[j] - mu[j]) * rs[j];
+          const float dz = p.swish ? g[j] * dswish_for<T>(xh * ga[j] + be[j]) : g[j];
+          o[j] = rs[j] * ga[j] * dz - t1[j] - xh * t2[j];
+        }
+        if (accum) {
+          float old[VEC];
+          load_vec(reinterpret_cast<const T*>(&orr[u]), old);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) o[j] += old[j];
+        }
+      }
+      store_vec(dx + (size_t)r * ld, o);
+    }
   }
 }
 
@@ -516,13 +583,14 @@ VF_API int vf_gn_backward(const void* src0, int C0, const float* stats0, int sta
   cudaStream_t st = as_stream(stream);
   VF_CUDA(cudaMemsetAsync(scratch, 0, (size_t)images * C * 2 * sizeof(float), st));
   dim3 grid(splits, images);
-  const size_t smem = 4 * C * sizeof(float);
+  const size_t smem_r = (size_t)(2 * C + 2 * C * PY) * sizeof(float), smem_a = (size_t)6 * C * sizeof(float);
+  VF_REQUIRE(smem_r <= 48 * 1024, "vf_gn_backward: C=%d needs %zu B of shared memory", C, smem_r);
   if (dtype == VF_BF16) {
-    gn_bwd_reduce_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>(p);
-    gn_bwd_apply_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>(p);
+    gn_bwd_reduce_kernel<__nv_bfloat16><<<grid, threads, smem_r, st>>>(p);
+    gn_bwd_apply_kernel<__nv_bfloat16><<<grid, threads, smem_a, st>>>(p);
   } else {
-    gn_bwd_reduce_kernel<float><<<grid, threads, smem, st>>>(p);
-    gn_bwd_apply_kernel<float><<<grid, threads, smem, st>>>(p);
+    gn_bwd_reduce_kernel<float><<<grid, threads, smem_r, st>>>(p);
+    gn_bwd_apply_kernel<float><<<grid, threads, smem_a, st>>>(p);
   }
   VF_LAUNCH_CHECK();
   return VF_OK;

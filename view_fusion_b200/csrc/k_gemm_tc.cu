@@ -65,6 +65,90 @@ struct TcParams {
   int epi_tma;    // staged TMA epilogue enabled (bf16 row-contiguous output, block_n % 64 == 0)
 };
 
+struct MmaCtx {
+  uint32_t bar_afull, bar_aempty, bar_bfull, bar_bempty, bar_accfull, bar_accempty, ringA, ringB, b_bytes, tmem_base;
+};
+
+// The single MMA-issuing thread.  tcgen05.mma is asynchronous, but the tensor pipe only stays busy if the scalar work
+// between two instructions is shorter than one MMA (57-64 cycles for N <= 128, scripts/probe_rate.py): ring indices,
+// phases and descriptors therefore advance incrementally (no division / modulo), the nine tap offsets sit in
+// registers, taps and row tiles are unrolled, and the cycle counters exist only in the PROF instantiation.
+template <int G, bool RESIDENT, bool PROF>
+__device__ __forceinline__ void mma_issue_loop(const TcParams& p, const MmaCtx& c) {
+  const uint64_t desc0 = ptx::make_smem_desc(0, 16, 1024);     // K-major SWIZZLE_128B, start address 0
+  const uint32_t block_n = (uint32_t)p.block_n, idesc = p.idesc;
+  const uint32_t b_step = c.b_bytes >> 4;                       // descriptors hold (byte address >> 4)
+  const uint64_t bd_base = desc0 + (uint64_t)(c.ringB >> 4);
+  const uint32_t a_step = (uint32_t)p.a_stage_bytes >> 4;
+  const uint64_t ad_ring = desc0 + (uint64_t)(c.ringA >> 4);
+  const int a_stages = p.a_stages, b_stages = p.b_stages;
+  uint32_t sh[9];                                               // tap (kh, kw) starts kh*(W+1) + kw rows into the slab
+#pragma unroll
+  for (int t = 0; t < 9; ++t) sh[t] = (uint32_t)((t / 3) * p.geo.W1 + (t % 3)) * 8u;
+  int as = 0, bs = 0;
+  uint32_t a_par = 0, b_par = 0, set = 0, acc_par = 1;
+  uint64_t bd = bd_base, ad_stage = ad_ring;
+  long long t_a = 0, t_b = 0, t_acc = 0, t0 = 0;
+  const long long t_start = PROF ? clock64() : 0;
+  if (RESIDENT) ptx::mbar_wait(c.bar_bfull, 0);
+
+  auto tap_mma = [&](uint32_t acc0, uint64_t ad, uint32_t accum) {
+    if (!RESIDENT) {
+      if (PROF) t0 = clock64();
+      ptx::mbar_wait(c.bar_bfull + 8 * bs, b_par);
+      if (PROF) t_b += clock64() - t0;
+      ptx::tc_fence_after();
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) ptx::umma_f16_k4(acc0 + (uint32_t)g * block_n, ad + (uint64_t)(g * 1024), bd, idesc, accum);
+    if (!RESIDENT) {
+      ptx::umma_commit(c.bar_bempty + 8 * bs);
+      if (++bs == b_stages) { bs = 0; b_par ^= 1u; bd = bd_base; } else bd += b_step;
+    } else {
+      bd += b_step;
+    }
+  };
+
+  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    if (RESIDENT) bd = bd_base;
+    if (PROF) t0 = clock64();
+    ptx::mbar_wait(c.bar_accempty + 8 * set, acc_par);
+    if (PROF) t_acc += clock64() - t0;
+    ptx::tc_fence_after();
+    const uint32_t acc0 = c.tmem_base + set * (uint32_t)G * block_n;
+    uint32_t accum = 0;
+    for (int s = 0; s < p.n_seg; ++s) {
+      const int nchunks = p.seg[s].nchunks;
+      const bool nine = p.seg[s].ntaps == 9;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        if (PROF) t0 = clock64();
+        ptx::mbar_wait(c.bar_afull + 8 * as, a_par);
+        if (PROF) t_a += clock64() - t0;
+        ptx::tc_fence_after();
+        if (nine) {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            tap_mma(acc0, ad_stage + sh[tap], accum);
+            accum = 1;
+          }
+        } else {
+          tap_mma(acc0, ad_stage, accum);
+          accum = 1;
+        }
+        ptx::umma_commit(c.bar_aempty + 8 * as);
+        if (++as == a_stages) { as = 0; a_par ^= 1u; ad_stage = ad_ring; } else ad_stage += a_step;
+      }
+    }
+    ptx::umma_commit(c.bar_accfull + 8 * set);
+    set ^= 1u;
+    if (set == 0) acc_par ^= 1u;
+  }
+  if (PROF) {
+    long long* o = p.dbg_out + blockIdx.x * 4;
+    o[0] = clock64() - t_start; o[1] = t_a; o[2] = t_b; o[3] = t_acc;
+  }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0,
                                                                 const __grid_constant__ CUtensorMap mapA1,
                                                                 const __grid_constant__ CUtensorMap mapA2,
@@ -153,58 +237,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   } else if (warp == 9) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      int a_it = 0, b_it = 0, it_idx = 0;
-      const uint64_t desc0 = ptx::make_smem_desc(0, 16, 1024);     // K-major SWIZZLE_128B, start address 0
-      const int G = p.G, block_n = p.block_n;
-      const uint32_t idesc = p.idesc;
-      const bool resident = p.b_resident != 0;
-      if (resident) ptx::mbar_wait(bar_bfull, 0);
-      long long t_a = 0, t_b = 0, t_acc = 0;
-      const long long t_start = clock64();
+      MmaCtx mc{bar_afull, bar_aempty, bar_bfull, bar_bempty, bar_accfull, bar_accempty, ringA, ringB, b_bytes, tmem_base};
       const bool prof = p.dbg_out != nullptr;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_idx) {
-        const int set = it_idx & 1;
-        if (resident) b_it = 0;
-        long long t0 = prof ? clock64() : 0;
-        ptx::mbar_wait(bar_accempty + 8 * set, ((uint32_t)(it_idx >> 1) & 1u) ^ 1u);
-        if (prof) t_acc += clock64() - t0;
-        ptx::tc_fence_after();
-        const uint32_t acc0 = tmem_base + (uint32_t)(set * p.G * p.block_n);
-        bool first = true;
-        for (int s = 0; s < p.n_seg; ++s) {
-          const TcSeg sg = p.seg[s];
-          for (int ch = 0; ch < sg.nchunks; ++ch, ++a_it) {
-            const int as = a_it % p.a_stages;
-            t0 = prof ? clock64() : 0;
-            ptx::mbar_wait(bar_afull + 8 * as, (uint32_t)(a_it / p.a_stages) & 1u);
-            if (prof) t_a += clock64() - t0;
-            const uint32_t sa = ringA + (uint32_t)as * (uint32_t)p.a_stage_bytes;
-            for (int tap = 0; tap < sg.ntaps; ++tap, ++b_it) {
-              const int bs = b_it % p.b_stages;
-              t0 = prof ? clock64() : 0;
-              if (!resident) ptx::mbar_wait(bar_bfull + 8 * bs, (uint32_t)(b_it / p.b_stages) & 1u);
-              if (prof) t_b += clock64() - t0;
-              ptx::tc_fence_after();
-              const uint32_t sb = ringB + bs * b_bytes;
-              // the slab starts `halo` rows before the block: tap (kh, kw) begins at row kh*(W+1) + kw
-              const int shift = sg.ntaps == 9 ? (tap / 3) * p.geo.W1 + (tap % 3) : 0;
-              // descriptors differ only in the 14-bit start-address field: base + (byte offset >> 4)
-              const uint64_t bd = desc0 + (uint64_t)((sb & 0x3FFFF) >> 4);
-              const uint64_t ad0 = desc0 + (uint64_t)(((sa + (uint32_t)shift * 128u) & 0x3FFFF) >> 4);
-              for (int g = 0; g < G; ++g)
-                ptx::umma_f16_k4(acc0 + (uint32_t)(g * block_n), ad0 + (uint64_t)(g * 1024), bd, idesc, first ? 0u : 1u);
-              first = false;
-              if (!resident) ptx::umma_commit(bar_bempty + 8 * bs);
-            }
-            ptx::umma_commit(bar_aempty + 8 * as);
-          }
-        }
-        ptx::umma_commit(bar_accfull + 8 * set);
+      // one instantiation per (row-tile count, weights resident?, cycle counters?): the loop body is a few scalar
+      // instructions per tap so the tensor pipe, not this thread, sets the pace
+#define VF_MMA_CASE(GG)                                                                       \
+  case GG:                                                                                    \
+    if (p.b_resident) { if (prof) mma_issue_loop<GG, true, true>(p, mc); else mma_issue_loop<GG, true, false>(p, mc); }    \
+    else { if (prof) mma_issue_loop<GG, false, true>(p, mc); else mma_issue_loop<GG, false, false>(p, mc); }               \
+    break;
+      switch (p.G) {
+        VF_MMA_CASE(1)
+        VF_MMA_CASE(2)
+        VF_MMA_CASE(3)
+        default:
+        VF_MMA_CASE(4)
       }
-      if (prof) {
-        long long* o = p.dbg_out + blockIdx.x * 4;
-        o[0] = clock64() - t_start; o[1] = t_a; o[2] = t_b; o[3] = t_acc;
-      }
+#undef VF_MMA_CASE
     }
   } else {
     // ===================== epilogue: 8 warps = 2 x 4 TMEM lane quarters =====================
@@ -324,20 +373,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             ptx::tma_store_commit();
           }
           if (p.stats && !(p.dbg & 1)) {
-            // column sums straight from the staging tile: lane owns channels (2*lane, 2*lane+1); conflict-free reads
-            for (int im = img_lo; im <= img_hi; ++im) {
-              const uint32_t rows = __ballot_sync(0xffffffffu, ri.img == im);
+            // column sums straight from the staging tile: lane owns channels (2*lane, 2*lane+1); conflict-free reads.
+            // Padding rows were stored as zeros, so a tile inside one image is summed without any per-row test.
+            const uint8_t* col = stg_g + (lane & 3) * 4;
+            const uint32_t sw = (uint32_t)(lane >> 2);
+            if (img_lo == img_hi) {
               float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll 8
+#pragma unroll
               for (int r = 0; r < 32; ++r) {
-                if (!((rows >> r) & 1u)) continue;
-                const uint32_t w = *reinterpret_cast<const uint32_t*>(stg_g + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
-                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
-                s0 += f.x; q0 += f.x * f.x; s1 += f.y; q1 += f.y * f.y;
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(col + r * 128 + ((sw ^ (uint32_t)(r & 7)) << 4));
+                const float a = __uint_as_float(w << 16), b = __uint_as_float(w & 0xFFFF0000u);
+                s0 += a; q0 = fmaf(a, a, q0); s1 += b; q1 = fmaf(b, b, q1);
               }
-              if (im < p.geo.images) {
-                float* sp = p.stats + ((size_t)im * p.cout + n0 + c0 + 2 * lane) * 2;
+              if (img_lo < p.geo.images) {
+                float* sp = p.stats + ((size_t)img_lo * p.cout + n0 + c0 + 2 * lane) * 2;
                 atomicAdd(sp, s0); atomicAdd(sp + 1, q0); atomicAdd(sp + 2, s1); atomicAdd(sp + 3, q1);
+              }
+            } else {
+              for (int im = img_lo; im <= img_hi; ++im) {
+                const uint32_t rows = __ballot_sync(0xffffffffu, ri.img == im);
+                float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                  if (!((rows >> r) & 1u)) continue;
+                  const uint32_t w = *reinterpret_cast<const uint32_t*>(col + r * 128 + ((sw ^ (uint32_t)(r & 7)) << 4));
+                  const float a = __uint_as_float(w << 16), b = __uint_as_float(w & 0xFFFF0000u);
+                  s0 += a; q0 = fmaf(a, a, q0); s1 += b; q1 = fmaf(b, b, q1);
+                }
+                if (im < p.geo.images) {
+                  float* sp = p.stats + ((size_t)im * p.cout + n0 + c0 + 2 * lane) * 2;
+                  atomicAdd(sp, s0); atomicAdd(sp + 1, q0); atomicAdd(sp + 2, s1); atomicAdd(sp + 3, q1);
+                }
               }
             }
           }

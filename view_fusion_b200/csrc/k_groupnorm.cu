@@ -59,21 +59,21 @@ __global__ void __launch_bounds__(kGnThreads, 4) gn_apply_kernel(const T* __rest
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, T* __restrict__ dst) {
   constexpr int VEC = VecOf<T>::N;
-  extern __shared__ float ab[];                      // [C][2]: y = x*a + b
+  extern __shared__ float ab[];                      // [C][2]: y = x*a + b, then [C][2] staging of the raw statistics
   const int C = C0 + C1, CV = C / VEC;
+  float* raw = ab + 2 * C;
   const int img = blockIdx.y;
   const int gs = C / groups;
   const float inv_n = 1.f / ((float)gs * (float)HW);
   const float* sa = st0 + (size_t)img * ld0 * 2;
   const float* sb = st1 ? st1 + (size_t)img * ld1 * 2 : nullptr;
+  // one coalesced load of the image's (sum, sumsq) pairs; the per-group loops then run out of shared memory
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) raw[i] = i < 2 * C0 ? __ldg(sa + i) : __ldg(sb + (i - 2 * C0));
+  __syncthreads();
   for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
     const int g0 = ch / gs * gs;
     float s = 0.f, q = 0.f;
-    for (int j = 0; j < gs; ++j) {           // a group may straddle the two sources of a concatenation
-      const int cc = g0 + j;
-      const float* e = cc < C0 ? sa + 2 * cc : sb + 2 * (cc - C0);
-      s += __ldg(e); q += __ldg(e + 1);
-    }
+    for (int j = 0; j < gs; ++j) { s += raw[2 * (g0 + j)]; q += raw[2 * (g0 + j) + 1]; }   // a group may straddle the two sources
     const float mean = s * inv_n;
     const float var = fmaxf(q * inv_n - mean * mean, 0.f);
     const float rstd = rsqrtf(var + 1e-5f);
@@ -243,7 +243,7 @@ extern "C" __attribute__((visibility("default"))) int vf_gn_apply(const void* sr
   VF_REQUIRE(C / vec <= kGnThreads, "vf_gn_apply: C=%d too large", C);
   GnGeom g = gn_geom(C, vec, P, images);
   dim3 grid(g.splits, images);
-  const size_t smem = 2 * C * sizeof(float);
+  const size_t smem = 4 * C * sizeof(float);
   cudaStream_t st = as_stream(stream);
 #define VF_GN_LAUNCH(T, SW) \
   gn_apply_kernel<T, SW><<<grid, g.threads, smem, st>>>((const T*)src0, C0, (const T*)src1, C1, H * W, W + 1, P, groups, g.pix_per_cta, stats0, stats0_ld, C1 ? stats1 : nullptr, stats1_ld, gamma, beta, (T*)dst)

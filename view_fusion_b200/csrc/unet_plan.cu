@@ -760,32 +760,52 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_read_tap(vf_unet* 
 // =====================================================================================================================
 namespace vf {
 
-// per-image column sums of a [rows, ld] matrix (padding rows hold zeros): cs[img][n] = sum_rows dY[row][n]
+// Bias / embedding gradients of one convolution: per-image column sums of dY [rows, ld] (padding rows hold zeros),
+//   db0 / db1 [n] += sum_rows dY[row][n];   demb[img_row[img]][col + n] += sum_rows(img) dY[row][n]
+// thread = (16-byte column vector, row lane); four independent loads in flight; block-level reduction in smem,
+// then one atomic per (CTA, column) and destination.
 template <typename T>
-__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ dy, int ld, int cout, int rows_per_img, int rows_per_cta, float* __restrict__ cs) {
+__global__ void __launch_bounds__(256) colsum_bias_kernel(const T* __restrict__ dy, int ld, int cout, int rows_per_img, int rows_per_cta,
+                                                          float* db0, float* db1, float* demb, const int* __restrict__ img_row, int emb_ld,
+                                                          int col) {
+  constexpr int VEC = VecOf<T>::N;
+  constexpr int UN = 4;
+  extern __shared__ float red[];                 // [PY][CV * VEC] per-row-lane partial sums
+  const int CV = (cout + VEC - 1) / VEC, PY = blockDim.x / CV;
   const int img = blockIdx.y;
   const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows_per_img, r0 + rows_per_cta);
-  const T* base = dy + (size_t)img * rows_per_img * ld;
+  const int cv = threadIdx.x % CV, py = threadIdx.x / CV;
+  {
+    const T* base = dy + (size_t)img * rows_per_img * ld + cv * VEC;
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+    for (int rb = r0 + py; rb < r1; rb += UN * PY) {
+      uint4 raw[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u)
+        if (rb + u * PY < r1) raw[u] = *reinterpret_cast<const uint4*>(base + (size_t)(rb + u * PY) * ld);
+#pragma unroll
+      for (int u = 0; u < UN; ++u)
+        if (rb + u * PY < r1) {
+          float v[VEC];
+          load_vec(reinterpret_cast<const T*>(&raw[u]), v);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) acc[j] += v[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) red[(py * CV + cv) * VEC + j] = acc[j];
+  }
+  __syncthreads();
+  const int row = demb ? __ldg(img_row + img) : 0;
   for (int n = threadIdx.x; n < cout; n += blockDim.x) {
-    float s = 0.f;
-    for (int r = r0; r < r1; ++r) s += to_f(base[(size_t)r * ld + n]);
-    atomicAdd(cs + (size_t)img * cout + n, s);
+    float v = 0.f;
+    for (int q = 0; q < PY; ++q) v += red[q * CV * VEC + n];
+    if (db0) atomicAdd(db0 + n, v);
+    if (db1) atomicAdd(db1 + n, v);
+    if (demb) atomicAdd(demb + (size_t)row * emb_ld + col + n, v);
   }
-}
-
-// db0 / db1 += sum_img cs;  demb[img_row[img]][col + n] += cs[img][n]
-__global__ void bias_emb_grad_kernel(const float* __restrict__ cs, int images, int cout, float* db0, float* db1, float* demb,
-                                     const int* __restrict__ img_row, int emb_ld, int col) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= cout) return;
-  float tot = 0.f;
-  for (int i = 0; i < images; ++i) {
-    const float v = cs[(size_t)i * cout + n];
-    tot += v;
-    if (demb) atomicAdd(demb + (size_t)__ldg(img_row + i) * emb_ld + col + n, v);
-  }
-  if (db0) db0[n] += tot;
-  if (db1) db1[n] += tot;
 }
 
 // [M, 8] fp32 FLAT gradient of the UNet output -> [rows_p, ld] activation dtype, PADDED, zero padding rows / channels
@@ -809,28 +829,32 @@ __global__ void axpy_f32_kernel(float* __restrict__ dst, const float* __restrict
   if (i < n) dst[i] += src[i];
 }
 
-// Backward of vf_embed for one embedding row per CTA: recomputes pe / hidden / t, then
-//   dEw[e][i] += demb[e]*t[i]; dEb[e] += demb[e]; dt = Ew^T demb; dW2 += dt h^T; db2 += dt; dh = W2^T dt;
-//   da = dh * swish'(a); dW0 += da pe^T; db0 += da
-__global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict__ level, const float* __restrict__ angle, int ic,
-                                                        const float* __restrict__ w0, const float* __restrict__ b0,
-                                                        const float* __restrict__ w2, const float* __restrict__ b2,
-                                                        const float* __restrict__ ew, int E, const float* __restrict__ demb,
-                                                        float* dw0, float* db0, float* dw2, float* db2, float* dew, float* deb) {
+// Backward of vf_embed in two launches (no atomics):
+//   embed_bwd_rows_kernel    one CTA per embedding row: recompute pe / a / h / t, then dt = Ew^T demb, da = (W2^T dt) * swish'(a);
+//                            writes the per-row vectors [pe(ic) | h(4ic) | t(ic) | dt(ic) | da(4ic)] to scratch
+//   embed_bwd_params_kernel  one thread per parameter-gradient element: sums the rank-1 contributions over the rows
+//                            dEw[e][i] = sum demb[e] t[i]; dEb[e] = sum demb[e]; dW2[o][i] = sum dt[o] h[i]; db2 = sum dt;
+//                            dW0[o][i] = sum da[o] pe[i]; db0 = sum da
+__global__ void __launch_bounds__(256) embed_bwd_rows_kernel(const float* __restrict__ level, const float* __restrict__ angle, int ic,
+                                                             const float* __restrict__ w0, const float* __restrict__ b0,
+                                                             const float* __restrict__ w2, const float* __restrict__ b2,
+                                                             const float* __restrict__ ew, int E, const float* __restrict__ demb,
+                                                             float* __restrict__ rowbuf) {
   extern __shared__ float sm[];
   float* pe = sm;              // [ic]
   float* av = pe + ic;         // [4ic] pre-activation
   float* hid = av + 4 * ic;    // [4ic]
-  float* tv = hid + 4 * ic;    // [ic]
-  float* dt = tv + ic;         // [ic]
-  float* dh = dt + ic;         // [4ic]
+  float* dt = hid + 4 * ic;    // [ic]
+  float* part = dt + ic;       // [4][ic] partial dt
   const int row = blockIdx.x;
   const int half = ic / 2, cnt = ic / 4;
+  float* out = rowbuf + (size_t)row * 11 * ic;
   for (int i = threadIdx.x; i < ic; i += blockDim.x) {
     const float x = i < half ? __ldg(level + row) : __ldg(angle + row);
     const int j = i % half, k = j % cnt;
     const float f = expf(-9.210340371976184f * ((float)k / (float)cnt));
     pe[i] = j < cnt ? sinf(x * f) : cosf(x * f);
+    out[i] = pe[i];
   }
   __syncthreads();
   for (int o = threadIdx.x; o < 4 * ic; o += blockDim.x) {
@@ -838,43 +862,87 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict_
     for (int i = 0; i < ic; ++i) acc += __ldg(w0 + (size_t)o * ic + i) * pe[i];
     av[o] = acc;
     hid[o] = acc / (1.f + expf(-acc));
+    out[ic + o] = hid[o];
   }
   __syncthreads();
   for (int o = threadIdx.x; o < ic; o += blockDim.x) {
     float acc = __ldg(b2 + o);
     for (int i = 0; i < 4 * ic; ++i) acc += __ldg(w2 + (size_t)o * 4 * ic + i) * hid[i];
-    tv[o] = acc;
-    dt[o] = 0.f;
+    out[5 * ic + o] = acc;
   }
-  __syncthreads();
+  // dt[i] = sum_e demb[e] * Ew[e][i]: the E range is split over blockDim/ic thread groups (coalesced over i)
   const float* g = demb + (size_t)row * E;
-  // embedding Linears
-  for (int e = threadIdx.x; e < E; e += blockDim.x) {
-    const float ge = __ldg(g + e);
-    atomicAdd(deb + e, ge);
-    for (int i = 0; i < ic; ++i) atomicAdd(dew + (size_t)e * ic + i, ge * tv[i]);
-  }
-  for (int i = threadIdx.x; i < ic; i += blockDim.x) {
-    float acc = 0.f;
-    for (int e = 0; e < E; ++e) acc += __ldg(g + e) * __ldg(ew + (size_t)e * ic + i);
-    dt[i] = acc;
+  {
+    const int ngrp = blockDim.x / ic > 0 ? (int)(blockDim.x / ic) : 1;
+    const int grp = threadIdx.x / ic, i = threadIdx.x % ic;
+    if (grp < ngrp && grp < 4) {
+      const int gcount = ngrp < 4 ? ngrp : 4;
+      float acc = 0.f;
+      for (int e = grp; e < E; e += gcount) acc += __ldg(g + e) * __ldg(ew + (size_t)e * ic + i);
+      part[grp * ic + i] = acc;
+    }
+    __syncthreads();
+    const int gcount = ngrp < 4 ? ngrp : 4;
+    for (int k = threadIdx.x; k < ic; k += blockDim.x) {
+      float acc = 0.f;
+      for (int q = 0; q < gcount; ++q) acc += part[q * ic + k];
+      dt[k] = acc;
+      out[6 * ic + k] = acc;
+    }
   }
   __syncthreads();
-  for (int o = threadIdx.x; o < ic; o += blockDim.x) {
-    atomicAdd(db2 + o, dt[o]);
-    for (int i = 0; i < 4 * ic; ++i) atomicAdd(dw2 + (size_t)o * 4 * ic + i, dt[o] * hid[i]);
-  }
   for (int i = threadIdx.x; i < 4 * ic; i += blockDim.x) {
     float acc = 0.f;
     for (int o = 0; o < ic; ++o) acc += dt[o] * __ldg(w2 + (size_t)o * 4 * ic + i);
-    const float a = av[i], s = 1.f / (1.f + expf(-a));
-    dh[i] = acc * s * (1.f + a * (1.f - s));
+    const float a = av[i], sg = 1.f / (1.f + expf(-a));
+    out[7 * ic + i] = acc * sg * (1.f + a * (1.f - sg));
   }
-  __syncthreads();
-  for (int o = threadIdx.x; o < 4 * ic; o += blockDim.x) {
-    atomicAdd(db0 + o, dh[o]);
-    for (int i = 0; i < ic; ++i) atomicAdd(dw0 + (size_t)o * ic + i, dh[o] * pe[i]);
+}
+
+__global__ void __launch_bounds__(256) embed_bwd_params_kernel(const float* __restrict__ rowbuf, const float* __restrict__ demb, int rows,
+                                                               int ic, int E, float* __restrict__ dew, float* __restrict__ deb,
+                                                               float* dw0, float* db0, float* dw2, float* db2) {
+  const size_t n_ew = (size_t)E * ic, n_w2 = (size_t)ic * 4 * ic, n_w0 = (size_t)4 * ic * ic;
+  const size_t total = n_ew + E + n_w2 + ic + n_w0 + 4 * ic;
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int R = 11 * ic;
+  float acc = 0.f;
+  if (gid < n_ew) {
+    const int e = (int)(gid / ic), i = (int)(gid % ic);
+    for (int r = 0; r < rows; ++r) acc += __ldg(demb + (size_t)r * E + e) * __ldg(rowbuf + (size_t)r * R + 5 * ic + i);
+    dew[gid] = acc;
+    return;
   }
+  gid -= n_ew;
+  if (gid < (size_t)E) {
+    for (int r = 0; r < rows; ++r) acc += __ldg(demb + (size_t)r * E + gid);
+    deb[gid] = acc;
+    return;
+  }
+  gid -= E;
+  if (gid < n_w2) {
+    const int o = (int)(gid / (4 * ic)), i = (int)(gid % (4 * ic));
+    for (int r = 0; r < rows; ++r) acc += __ldg(rowbuf + (size_t)r * R + 6 * ic + o) * __ldg(rowbuf + (size_t)r * R + ic + i);
+    dw2[gid] += acc;
+    return;
+  }
+  gid -= n_w2;
+  if (gid < (size_t)ic) {
+    for (int r = 0; r < rows; ++r) acc += __ldg(rowbuf + (size_t)r * R + 6 * ic + gid);
+    db2[gid] += acc;
+    return;
+  }
+  gid -= ic;
+  if (gid < n_w0) {
+    const int o = (int)(gid / ic), i = (int)(gid % ic);
+    for (int r = 0; r < rows; ++r) acc += __ldg(rowbuf + (size_t)r * R + 7 * ic + o) * __ldg(rowbuf + (size_t)r * R + i);
+    dw0[gid] += acc;
+    return;
+  }
+  gid -= n_w0;
+  for (int r = 0; r < rows; ++r) acc += __ldg(rowbuf + (size_t)r * R + 7 * ic + gid);
+  db0[gid] += acc;
 }
 
 struct BwdCtx {
@@ -930,15 +998,23 @@ static void conv_backward(BwdCtx& cx, const vf_unet::TapeOp& t, const uint8_t* p
   // ---- bias / embedding gradients: per-image column sums of dY
   if (t.b_idx[0] >= 0 || t.emb_col >= 0) {
     if (!cx.dry && cx.rc == VF_OK) {
-      cudaMemsetAsync(cs, 0, (size_t)images * f.cout * 4, cx.st);
-      const int per = 256;
+      const int vec = dt == VF_BF16 ? 8 : 4;
+      const int cv = (f.cout + vec - 1) / vec;
+      const int py = 256 / cv;
+      int per = py * 4 * 8;                                   // >= 8 unrolled iterations per thread
+      if (per < 512) per = 512;
       dim3 grid(cdiv(out_rows_per_img, per), images);
-      if (dt == VF_BF16) colsum_kernel<__nv_bfloat16><<<grid, 256, 0, cx.st>>>((const __nv_bfloat16*)dYs, dy_ld, f.cout, out_rows_per_img, per, cs);
-      else colsum_kernel<float><<<grid, 256, 0, cx.st>>>((const float*)dYs, dy_ld, f.cout, out_rows_per_img, per, cs);
-      bias_emb_grad_kernel<<<cdiv(f.cout, 128), 128, 0, cx.st>>>(cs, images, f.cout, t.b_idx[0] >= 0 ? pg[t.b_idx[0]] : nullptr,
-                                                                 t.b_idx[1] >= 0 ? pg[t.b_idx[1]] : nullptr, t.emb_col >= 0 ? demb : nullptr,
-                                                                 u->last_img_row, u->E, t.emb_col >= 0 ? t.emb_col : 0);
-      if (t.nf_b >= 0) {}   // the per-block embedding Linear gradients are produced by embed_bwd_kernel from demb
+      const size_t smem = (size_t)py * cv * vec * sizeof(float);
+      float* db0 = t.b_idx[0] >= 0 ? pg[t.b_idx[0]] : nullptr;
+      float* db1 = t.b_idx[1] >= 0 ? pg[t.b_idx[1]] : nullptr;
+      float* de = t.emb_col >= 0 ? demb : nullptr;
+      const int col = t.emb_col >= 0 ? t.emb_col : 0;
+      if (dt == VF_BF16)
+        colsum_bias_kernel<__nv_bfloat16><<<grid, cv * py, smem, cx.st>>>((const __nv_bfloat16*)dYs, dy_ld, f.cout, out_rows_per_img, per, db0, db1, de,
+                                                                          u->last_img_row, u->E, col);
+      else
+        colsum_bias_kernel<float><<<grid, cv * py, smem, cx.st>>>((const float*)dYs, dy_ld, f.cout, out_rows_per_img, per, db0, db1, de,
+                                                                  u->last_img_row, u->E, col);
     }
   }
   // ---- weight gradient into the packed scratch, then scatter to the OIHW parameter gradients
@@ -1039,6 +1115,7 @@ static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float*
   float* demb = (float*)cx.galloc((size_t)u->last_rows * u->E * 4);
   float* dew = (float*)cx.galloc((size_t)u->E * c.inner_channel * 4);
   float* deb = (float*)cx.galloc((size_t)u->E * 4);
+  float* emb_rows = (float*)cx.galloc((size_t)u->last_rows * 11 * c.inner_channel * 4);
   size_t gn_floats = 0, att_floats = 0;
   for (auto& t : u->tape) {
     if (t.kind == 1) gn_floats = std::max(gn_floats, (size_t)images * (t.gC0 + t.gC1) * 2);
@@ -1101,9 +1178,13 @@ static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float*
   if (!cx.dry && cx.rc == VF_OK) {
     const int ic = c.inner_channel;
     const uint8_t* pk = nullptr; (void)pk;
-    embed_bwd_kernel<<<u->last_rows, 256, (size_t)(15 * ic) * sizeof(float), cx.st>>>(
+    const int rows = u->last_rows;
+    embed_bwd_rows_kernel<<<rows, 256, (size_t)(14 * ic) * sizeof(float), cx.st>>>(
         u->last_level, u->last_angle, ic, u->master[u->mlp_w0], u->master[u->mlp_b0], u->master[u->mlp_w2], u->master[u->mlp_b2],
-        u->emb_w_dev, u->E, demb, pg[u->mlp_w0], pg[u->mlp_b0], pg[u->mlp_w2], pg[u->mlp_b2], dew, deb);
+        u->emb_w_dev, u->E, demb, emb_rows);
+    const size_t total = (size_t)u->E * ic + u->E + (size_t)8 * ic * ic + 5 * ic;
+    embed_bwd_params_kernel<<<(unsigned)((total + 255) / 256), 256, 0, cx.st>>>(emb_rows, demb, rows, ic, u->E, dew, deb, pg[u->mlp_w0],
+                                                                               pg[u->mlp_b0], pg[u->mlp_w2], pg[u->mlp_b2]);
     for (auto& b : u->blocks) {
       const size_t nw = (size_t)b.cout * ic;
       axpy_f32_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, cx.st>>>(pg[b.nf_w], dew + (size_t)b.emb_col * ic, nw);
