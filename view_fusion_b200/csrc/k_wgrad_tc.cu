@@ -94,9 +94,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
   if (warp == 4) {
     if (lane == 0 && nk > 0) {
       const CUtensorMap* mX = seg == 0 ? &mapX0 : (seg == 1 ? &mapX1 : &mapX2);
+      int st = 0;
+      uint32_t par = 1;
       for (int it = 0; it < nk; ++it) {
-        const int st = it % p.stages;
-        ptx::mbar_wait(bar_empty + 8 * st, ((uint32_t)(it / p.stages) & 1u) ^ 1u);
+        ptx::mbar_wait(bar_empty + 8 * st, par);
         const uint32_t fb = bar_full + 8 * st;
         ptx::mbar_arrive_expect_tx(fb, (uint32_t)nbox_x * 64 * 128 + (uint32_t)natom_n * WG_R * 128);
         const uint32_t sx = ring + (uint32_t)st * (uint32_t)p.stage_bytes;
@@ -104,31 +105,46 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
         const int row0 = r_begin + it * WG_R;
         for (int b = 0; b < nbox_x; ++b) ptx::tma_load_2d(sx + b * 8192, mX, fb, chunk * 64, row0 - sg.halo + b * 64);
         for (int a = 0; a < natom_n; ++a) ptx::tma_load_2d(sy + a * (WG_R * 128), &mapDY, fb, n0 + a * 64, row0);
+        if (++st == p.stages) { st = 0; par ^= 1u; }
       }
     }
   } else if (warp == 5) {
     if (lane == 0 && nk > 0) {
+      // Everything that does not depend on the pipeline stage is computed once: the per-pair A descriptors (tap shift
+      // in the start address, shift difference as the leading-dimension offset) and the dY descriptor.  Per chunk the
+      // thread then only adds the stage offset and the k-step (16 rows = 2048 bytes) to the start-address fields, so the
+      // tensor pipe is not left waiting for scalar code between MMAs.
       const uint32_t idesc = ptx::make_idesc_bf16(128, p.block_n, 1, 1);       // A and B MN-major
+      uint64_t adp[WG_MAX_ACC];
+#pragma unroll
+      for (int a = 0; a < WG_MAX_ACC; ++a) {
+        const int t0 = min(2 * (pair0 + a), sg.ntaps - 1), t1 = min(t0 + 1, sg.ntaps - 1);
+        const int sh0 = sg.ntaps == 9 ? (t0 / 3) * p.W1 + (t0 % 3) : 0;         // slab starts `halo` rows before the chunk
+        const int sh1 = sg.ntaps == 9 ? (t1 / 3) * p.W1 + (t1 % 3) : 0;
+        const uint32_t lbo = t1 > t0 ? (uint32_t)(sh1 - sh0) * 128u : 128u;     // single tap: atom 1 is a harmless neighbour
+        adp[a] = ptx::make_smem_desc(ring + (uint32_t)sh0 * 128u, lbo, 1024);
+      }
+      const uint64_t bd0 = ptx::make_smem_desc(ring + (uint32_t)p.x_bytes, WG_R * 128, 1024);
+      const uint32_t st_step = (uint32_t)p.stage_bytes >> 4;
+      const uint32_t block_n = (uint32_t)p.block_n;
+      int st = 0;
+      uint32_t par = 0, st_off = 0, acc = 0;
+      // splits are multiples of WG_R rows; rows past the end of the tensors are zero-filled by TMA
       for (int it = 0; it < nk; ++it) {
-        const int st = it % p.stages;
-        ptx::mbar_wait(bar_full + 8 * st, (uint32_t)(it / p.stages) & 1u);
+        ptx::mbar_wait(bar_full + 8 * st, par);
         ptx::tc_fence_after();
-        const uint32_t sx = ring + (uint32_t)st * (uint32_t)p.stage_bytes;
-        const uint32_t sy = sx + (uint32_t)p.x_bytes;
-        // splits are multiples of WG_R rows; rows past the end of the tensors are zero-filled by TMA
-        const int ksteps = WG_R / 16;
-        for (int a = 0; a < npair; ++a) {
-          const int t0 = 2 * (pair0 + a), t1 = min(t0 + 1, sg.ntaps - 1);
-          const int sh0 = sg.ntaps == 9 ? (t0 / 3) * p.W1 + (t0 % 3) : 0;       // slab starts `halo` rows before the chunk
-          const int sh1 = sg.ntaps == 9 ? (t1 / 3) * p.W1 + (t1 % 3) : 0;
-          const uint32_t lbo = t1 > t0 ? (uint32_t)(sh1 - sh0) * 128u : 128u;   // single tap: atom 1 is a harmless neighbour
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t ad = ptx::make_smem_desc(sx + (uint32_t)(sh0 + 16 * k) * 128u, lbo, 1024);
-            const uint64_t bd = ptx::make_smem_desc(sy + (uint32_t)(16 * k) * 128u, WG_R * 128, 1024);
-            ptx::umma_f16(tmem_base + (uint32_t)(a * p.block_n), ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int a = 0; a < WG_MAX_ACC; ++a) {
+          if (a < npair) {
+            const uint64_t ad = adp[a] + st_off, bd = bd0 + st_off;
+#pragma unroll
+            for (int k = 0; k < WG_R / 16; ++k)
+              ptx::umma_f16(tmem_base + (uint32_t)a * block_n, ad + (uint64_t)(k * 128), bd + (uint64_t)(k * 128), idesc, k > 0 ? 1u : acc);
           }
         }
         ptx::umma_commit(bar_empty + 8 * st);
+        acc = 1;
+        if (++st == p.stages) { st = 0; par ^= 1u; st_off = 0; } else st_off += st_step;
       }
       ptx::umma_commit(bar_done);
     }
