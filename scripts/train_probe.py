@@ -32,6 +32,8 @@ for _ in range(3):
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / 3
 print(f"B={B}: {dt*1e3:.1f} ms/step, {B/dt:.1f} samples/s, loss {float(l):.4f}")
+if len(sys.argv) > 2 and sys.argv[2] == "noprof":
+    sys.exit(0)
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     step(); torch.cuda.synchronize()

@@ -16,41 +16,51 @@ __global__ void img_sample_kernel(const int* __restrict__ voff, int B, int image
   img_sample[i] = b;
 }
 
-// one thread per (image, pixel, 16-byte chunk of the K0 row)
+// One thread per (image, pixel), consecutive threads = consecutive x: every (tap, channel) load is coalesced along the
+// image row (the 9x re-reads of a pixel hit L1), the K0 values of the pixel are staged in a conflict-free smem column
+// and leave as one contiguous K0*sizeof(T) row.
+constexpr int kPackThreads = 128;
 template <typename T>
-__global__ void __launch_bounds__(256) pack_views_kernel(const float* __restrict__ y_cond, const float* __restrict__ y_t,
-                                                         const int* __restrict__ voff, const int* __restrict__ img_sample,
-                                                         int n_max, int Cc, int H, int W, int images, int K0,
-                                                         T* __restrict__ x0) {
+__global__ void __launch_bounds__(kPackThreads) pack_views_kernel(const float* __restrict__ y_cond, const float* __restrict__ y_t,
+                                                                  const int* __restrict__ voff, const int* __restrict__ img_sample,
+                                                                  int n_max, int Cc, int H, int W, int images, int K0,
+                                                                  T* __restrict__ x0) {
   constexpr int VEC = VecOf<T>::N;
-  const int chunks = K0 / VEC;
-  const size_t total = (size_t)images * H * W * chunks;
-  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= total) return;
-  const int ch = (int)(gid % chunks);
-  const size_t ip = gid / chunks;
-  const int pix = (int)(ip % (H * W));
-  const int img = (int)(ip / (H * W));
-  const int y = pix / W, x = pix % W;
+  extern __shared__ float stage[];                 // [K0][kPackThreads]
+  const size_t total = (size_t)images * H * W;
+  const size_t gid = (size_t)blockIdx.x * kPackThreads + threadIdx.x;
+  const bool live = gid < total;
+  const size_t ip = live ? gid : total - 1;
+  const int pix = (int)(ip % (size_t)(H * W));
+  const int img = (int)(ip / (size_t)(H * W));
+  const int y = pix / W, x = pix - y * W;
   const int b = __ldg(img_sample + img);
   const int view = img - __ldg(voff + b);
   const int Cin = Cc + 3;
   const float* cond = y_cond + ((size_t)b * n_max + view) * Cc * H * W;
   const float* tgt = y_t + (size_t)b * 3 * H * W;
-  float v[VEC];
+  float* col = stage + threadIdx.x;
+  int k = 0;
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    const int k = ch * VEC + j;
-    float val = 0.f;
-    if (k < 9 * Cin) {
-      const int tap = k / Cin, c = k % Cin;
-      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
-        val = c < Cc ? __ldg(cond + ((size_t)c * H + yy) * W + xx) : __ldg(tgt + ((size_t)(c - Cc) * H + yy) * W + xx);
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+    const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+    const size_t off = (size_t)yy * W + xx;
+    for (int c = 0; c < Cin; ++c, ++k) {
+      float val = 0.f;
+      if (in) val = c < Cc ? __ldg(cond + (size_t)c * H * W + off) : __ldg(tgt + (size_t)(c - Cc) * H * W + off);
+      col[k * kPackThreads] = val;
     }
-    v[j] = val;
   }
-  store_vec(x0 + gid * VEC, v);
+  for (; k < K0; ++k) col[k * kPackThreads] = 0.f;
+  if (!live) return;                               // (own column only: no barrier needed)
+  T* out = x0 + gid * (size_t)K0;
+  for (int k0 = 0; k0 < K0; k0 += VEC) {
+    float v[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) v[j] = col[(k0 + j) * kPackThreads];
+    store_vec(out + k0, v);
+  }
 }
 
 template <typename T>
@@ -139,13 +149,14 @@ extern "C" __attribute__((visibility("default"))) int vf_pack_views(const float*
   cudaStream_t st = as_stream(stream);
   img_sample_kernel<<<cdiv(images, 128), 128, 0, st>>>(view_offset, B, images, img_sample);
   VF_LAUNCH_CHECK();
-  const size_t vec = x0_dtype == VF_BF16 ? 8 : 4;
-  const size_t total = (size_t)images * H * W * (k0 / vec);
-  const unsigned grid = (unsigned)((total + 255) / 256);
+  const size_t total = (size_t)images * H * W;
+  const unsigned grid = (unsigned)((total + kPackThreads - 1) / kPackThreads);
+  const size_t smem = (size_t)k0 * kPackThreads * sizeof(float);
+  VF_REQUIRE(smem <= 48 * 1024, "vf_pack_views: k0=%d too large", k0);
   if (x0_dtype == VF_BF16)
-    pack_views_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(y_cond, y_t, view_offset, img_sample, n_max, cond_channels, H, W, images, k0, (__nv_bfloat16*)x0);
+    pack_views_kernel<__nv_bfloat16><<<grid, kPackThreads, smem, st>>>(y_cond, y_t, view_offset, img_sample, n_max, cond_channels, H, W, images, k0, (__nv_bfloat16*)x0);
   else
-    pack_views_kernel<float><<<grid, 256, 0, st>>>(y_cond, y_t, view_offset, img_sample, n_max, cond_channels, H, W, images, k0, (float*)x0);
+    pack_views_kernel<float><<<grid, kPackThreads, smem, st>>>(y_cond, y_t, view_offset, img_sample, n_max, cond_channels, H, W, images, k0, (float*)x0);
   VF_LAUNCH_CHECK();
   return VF_OK;
 }

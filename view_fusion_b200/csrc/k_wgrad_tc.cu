@@ -9,7 +9,7 @@
 //   B (N = block_n <= 256) = dY tile, atoms of 64 output channels, one TMA box each
 //   D = fp32 in TMEM, one accumulator per tap pair; after the CTA's row range it is added to the packed gradient
 //       with coalesced fp32 reductions (lane == channel c, column == output channel n)
-// Work item (blockIdx.y) = (segment, 64-channel chunk, group of tap pairs, N tile); blockIdx.x splits the rows.
+// Work item (blockIdx.x) = (segment, 64-channel chunk, group of tap pairs, N tile); blockIdx.y splits the rows.
 // Both hardware facts used here were probed first (k_debug.cu): MN-major SWIZZLE_128B descriptors with LBO = atom
 // stride / SBO = 1024, and start addresses shifted by whole rows.
 #include <cuda.h>
@@ -61,7 +61,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // decode the work item
-  int job = blockIdx.y, seg = 0;
+  // jobs are the fast grid axis: the CTAs that stream the same row range (other taps / channel chunks / N tiles) are
+  // scheduled together, so their re-reads of X and dY hit L2 instead of HBM
+  int job = blockIdx.x, seg = 0;
   for (; seg < p.n_seg; ++seg) {
     const int per = p.seg[seg].nchunks * p.seg[seg].ngroups * p.n_tiles_n;
     if (job < per) break;
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
   const int pair0 = grp * p.acc_max;
   const int npair = min(p.acc_max, sg.npairs - pair0);
   const int n0 = n_tile * p.block_n;
-  const int r_begin = blockIdx.x * p.rows_per_split;
+  const int r_begin = blockIdx.y * p.rows_per_split;
   const int r_end = min(p.rows_total, r_begin + p.rows_per_split);
   const int nk = r_begin < r_end ? (r_end - r_begin + WG_R - 1) / WG_R : 0;
   const int nbox_x = (WG_R + 2 * sg.halo + 63) / 64;
@@ -256,7 +258,7 @@ int conv2d_wgrad_tc(const vf_conv_args* a, const void* dy, int dy_ld, float* dwp
   std::call_once(once, [] { attr_err = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
   VF_CUDA(attr_err);
   const size_t smem = 2048 + (size_t)p.stages * p.stage_bytes;
-  dim3 grid(splits, jobs);
+  dim3 grid(jobs, splits);
   conv_wgrad_tc_kernel<<<grid, WG_THREADS, smem, st>>>(maps[0], maps[1], maps[2], mapDY, p);
   VF_LAUNCH_CHECK();
   return VF_OK;
