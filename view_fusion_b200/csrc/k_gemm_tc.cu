@@ -520,6 +520,7 @@ int encode_bf16_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* d
 static int g_tc_dbg = 0;     // test hook: see vf_debug_flags
 static long long* g_tc_dbg_out = nullptr;
 void set_tc_debug(int f) { g_tc_dbg = f; }
+int tc_debug_flags() { return g_tc_dbg; }
 void set_tc_debug_out(long long* p) { g_tc_dbg_out = p; }
 
 // ---- tiling choice -------------------------------------------------------------------------------------
