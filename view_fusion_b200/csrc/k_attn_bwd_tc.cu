@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_tc_kernel(const __grid
   const uint32_t tm_s = tm, tm_dp = tm + 128, tm_dq = tm + 256, tm_kv = tm;
 
   if (warp == 4) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(bar_q, 2u * p.tile_bytes);
       for (int c = 0; c < p.kchunks; ++c) {
         ptx::tma_load_2d(regQ + c * CH, &mapQKV, bar_q, c * 64, row0);

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
   const uint32_t v_chunk = (uint32_t)p.C * 128;             // C rows (channels) x 64 keys
 
   if (warp == 4) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       // ---- phase A: Q, K -> smem; S = Q K^T
       ptx::mbar_arrive_expect_tx(bar_qk, (uint32_t)p.kchunks * (q_chunk + k_chunk));
       for (int c = 0; c < p.kchunks; ++c) {

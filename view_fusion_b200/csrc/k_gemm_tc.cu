@@ -198,8 +198,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
   if (warp == 8) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int a_it = 0, b_it = 0;
+    if (ptx::elect_one()) {
+      int as = 0, bs = 0;
+      uint32_t a_par = 1, b_par = 1;                 // "empty" barriers: the first pass over each ring does not wait
       if (p.b_resident) {                        // weights-stationary: every tap's tile is loaded once per CTA
         ptx::mbar_arrive_expect_tx(bar_bfull, (uint32_t)p.b_stages * b_bytes);
         int bt = 0;
@@ -208,6 +209,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int tap = 0; tap < p.seg[s].ntaps; ++tap, ++bt)
               ptx::tma_load_2d(ringB + bt * b_bytes, &mapB, bar_bfull, p.seg[s].koff + tap * p.seg[s].C + ch * TC_BK, 0);
       }
+      const int a_stages = p.a_stages, b_stages = p.b_stages;
+      const bool stream_b = !p.b_resident;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int n_tile = item / p.n_mblocks, m_blk = item - n_tile * p.n_mblocks;   // neighbours share the weight tile
         const int m0 = m_blk * BM, n0 = n_tile * p.block_n;
@@ -215,20 +218,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           const TcSeg sg = p.seg[s];
           const CUtensorMap* mA = s == 0 ? &mapA0 : (s == 1 ? &mapA1 : &mapA2);
           const int nbox = (BM + 2 * sg.halo + TC_ABOX - 1) / TC_ABOX;
-          for (int ch = 0; ch < sg.nchunks; ++ch, ++a_it) {
-            const int as = a_it % p.a_stages;
-            ptx::mbar_wait(bar_aempty + 8 * as, ((uint32_t)(a_it / p.a_stages) & 1u) ^ 1u);
+          for (int ch = 0; ch < sg.nchunks; ++ch) {
+            ptx::mbar_wait(bar_aempty + 8 * as, a_par);
             const uint32_t fa = bar_afull + 8 * as;
             ptx::mbar_arrive_expect_tx(fa, (uint32_t)nbox * TC_ABOX * 128);
             const uint32_t sa = ringA + (uint32_t)as * (uint32_t)p.a_stage_bytes;
             for (int b = 0; b < nbox; ++b)
               ptx::tma_load_2d(sa + b * (TC_ABOX * 128), mA, fa, ch * TC_BK, m0 - sg.halo + b * TC_ABOX);
-            for (int tap = 0; tap < sg.ntaps && !p.b_resident; ++tap, ++b_it) {
-              const int bs = b_it % p.b_stages;
-              ptx::mbar_wait(bar_bempty + 8 * bs, ((uint32_t)(b_it / p.b_stages) & 1u) ^ 1u);
-              const uint32_t fb = bar_bfull + 8 * bs;
-              ptx::mbar_arrive_expect_tx(fb, b_bytes);
-              ptx::tma_load_2d(ringB + bs * b_bytes, &mapB, fb, sg.koff + tap * sg.C + ch * TC_BK, n0);
+            if (++as == a_stages) { as = 0; a_par ^= 1u; }
+            if (stream_b) {
+              int kcol = sg.koff + ch * TC_BK;
+              for (int tap = 0; tap < sg.ntaps; ++tap, kcol += sg.C) {
+                ptx::mbar_wait(bar_bempty + 8 * bs, b_par);
+                const uint32_t fb = bar_bfull + 8 * bs;
+                ptx::mbar_arrive_expect_tx(fb, b_bytes);
+                ptx::tma_load_2d(ringB + bs * b_bytes, &mapB, fb, kcol, n0);
+                if (++bs == b_stages) { bs = 0; b_par ^= 1u; }
+              }
             }
           }
         }
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
   } else if (warp == 9) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       MmaCtx mc{bar_afull, bar_aempty, bar_bfull, bar_bempty, bar_accfull, bar_accempty, ringA, ringB, b_bytes, tmem_base};
       const bool prof = p.dbg_out != nullptr;
       // one instantiation per (row-tile count, weights resident?, cycle counters?): the loop body is a few scalar
@@ -584,18 +590,23 @@ static bool pick_tiling(const TcParams& p, int cout_pad, int sms, bool epi_tma, 
         const TcSeg& sg = p.seg[s];
         const double arows = (double)align_up((size_t)BM + 2 * sg.halo, TC_ABOX);
         bytes += sg.nchunks * (arows * 128.0 + (c.b_resident ? 0.0 : sg.ntaps * bn * 128.0));
-        // measured in situ (vf_debug_counters): the single issuing thread sustains one MMA per ~120 clk for N <= 128 and
-        // ~N/2 + 95 beyond, i.e. wide MMAs are what keeps the tensor pipe busy; + ~250 clk of barrier work per tap
-        const double per_mma = (bn <= 128 ? 120.0 : bn / 2.0 + 95.0) + 250.0 / (4.0 * G);
+        // measured (scripts/probe_rate.py, prof_conv.py): with two or more accumulators in rotation an MMA completes every
+        // max(N/2, ~58) clk (the floor is the smem operand fetch); a single accumulator chains at ~91 clk; plus ~120 clk
+        // of barrier / descriptor work per tap
+        double base = bn <= 64 ? 60.0 : (bn <= 128 ? 66.0 : bn / 2.0 + 4.0);
+        if (G == 1 && base < 91.0) base = 91.0;
+        const double per_mma = base + 120.0 / (4.0 * G);
         cyc += (double)sg.nchunks * sg.ntaps * 4 * G * per_mma;
       }
-      // the epilogue of an item is a latency chain of a few microseconds; it overlaps the next item's main loop
-      const double epi = 5000.0 + 1200.0 * ((G * ((bn + 63) / 64) + 1) / 2);
+      // the epilogue of an item overlaps the next item's main loop; the two warps of a TMEM lane quarter take alternate
+      // (row tile, 64-column panel) units, ~2600 clk each with the GroupNorm sums
+      const double epi = 1500.0 + 2600.0 * ((G * ((bn + 63) / 64) + 1) / 2);
       double item = cyc > bytes / kIngestBytesPerClk ? cyc : bytes / kIngestBytesPerClk;
       if (epi > item) item = epi;
       const long items = (long)((p.geo.rows_total + BM - 1) / BM) * t;
       const long rounds = (items + sms - 1) / sms;
-      c.cost = rounds * item + 3000.0;
+      // larger row groups shrink the weight ring and lengthen the drain of the last item: measured ~8 % per extra tile
+      c.cost = rounds * item * (G > 2 ? 1.0 + 0.08 * (G - 2) : 1.0) + 3000.0;
       if (!found || c.cost < best->cost * 0.999 || (c.cost < best->cost * 1.001 && bn > best->block_n)) { *best = c; found = true; }
     }
   }

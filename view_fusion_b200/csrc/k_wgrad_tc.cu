@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
       }
     }
   } else if (warp == 5) {
-    if (lane == 0 && nk > 0) {
+    if (nk > 0 && ptx::elect_one()) {
       // Everything that does not depend on the pipeline stage is computed once: the per-pair A descriptors (tap shift
       // in the start address, shift difference as the leading-dimension offset) and the dY descriptor.  Per chunk the
       // thread then only adds the stage offset and the k-step (16 rows = 2048 bytes) to the start-address fields, so the
