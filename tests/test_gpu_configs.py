@@ -1,0 +1,89 @@
+"""GPU parity on the remaining BASELINE.json configurations (the oracle runs live on the CPU at small batch):
+  * extrapolation: N = 12 and N = 24 conditioning views (beyond the training N = 6), ragged view counts,
+  * autoregressive generation: one primed view, every generated view appended to y_cond (experiment.py:535-544),
+  * the no-weighting ablation (out_channel 3, mean over views; view_fusion.py:139-150).
+Reference semantics: model/view_fusion.py:86-214."""
+import math
+
+import pytest
+import torch
+
+import vf_oracle as O
+from gpu_util import build_model, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(B, nmax, vc, size, seed):
+    g = torch.Generator().manual_seed(seed)
+    y_cond = torch.rand(B, nmax, 3, size, size, generator=g)
+    y_t = torch.randn(B, 3, size, size, generator=g)
+    angle = (2 * math.pi / 24) * torch.randint(0, 24, (B, 1), generator=g).float()
+    z = torch.randn(B, 3, size, size, generator=g)
+    return y_cond, y_t, angle, torch.tensor(vc, dtype=torch.long), z
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+@pytest.mark.parametrize("nmax,vc", [(12, [12, 12]), (24, [24, 7])])
+def test_extrapolation_views_p_sample(prec, tol, nmax, vc):
+    cfg = O.SMALL_V100
+    m, sd = build_model(cfg, 3, prec)
+    sched = O.make_schedule(**O.BETA_TRAIN)
+    y_cond, y_t, angle, view_count, z = _inputs(len(vc), nmax, vc, 64, 11)
+    t = torch.tensor([1500, 3][: len(vc)], dtype=torch.long)
+    with torch.no_grad():
+        y_ref, eps_ref, logits_ref, w_ref = O.p_sample(sd, cfg, sched, y_t, y_cond, view_count, angle, t, z)
+    eps = torch.empty(len(vc), 3, 64, 64, device="cuda")
+    y_prev, logits, weights = m.p_sample(y_t.cuda(), y_cond.cuda(), view_count, angle.cuda(), t.cuda(), noise=z.cuda(), _eps_out=eps)
+    assert rel(eps, eps_ref) < tol, rel(eps, eps_ref)
+    assert rel(y_prev, y_ref) < tol
+    assert weights.shape == w_ref.shape == (len(vc), max(vc), 3, 64, 64) and logits.shape == logits_ref.shape
+    # padded view slots carry exactly zero weight, the live ones sum to one
+    for b, v in enumerate(vc):
+        assert float(weights[b, v:].abs().max()) == 0.0 if v < max(vc) else True
+        assert torch.allclose(weights[b, :v].sum(0).cpu(), torch.ones(3, 64, 64), atol=1e-5)
+    if prec == "fp32":
+        assert torch.equal(weights.cpu().argmax(1), w_ref.argmax(1))
+        assert rel(weights, w_ref) < 1e-4
+
+
+def test_autoregressive_orbit_fp32():
+    """B = 1, count = 1..4: generate a view with `count` conditioning views, append it, continue (short reverse loops)."""
+    cfg = O.TINY
+    m, sd = build_model(cfg, 5, "fp32")
+    sched = O.make_schedule(**O.BETA_TRAIN)
+    S = cfg["image_size"]
+    g = torch.Generator().manual_seed(21)
+    prime = torch.rand(1, 1, 3, S, S, generator=g)
+    steps = [1999, 1000, 250, 1, 0]
+    ref_cond, got_cond = prime.clone(), prime.clone().cuda()
+    for count in range(1, 5):
+        angle = torch.full((1, 1), 2 * math.pi * count / 24)
+        y_T = torch.randn(1, 3, S, S, generator=g)
+        zs = [torch.randn(1, 3, S, S, generator=g) for _ in steps]
+        vc = torch.tensor([count], dtype=torch.long)
+        with torch.no_grad():
+            y_ref, *_ = O.generate(sd, cfg, sched, ref_cond, vc, angle, y_T, zs, steps=steps)
+        y, ret, la, wa, last = m.generate(got_cond, vc, angle.cuda(), y_t=y_T.cuda(), noise_steps=zs, steps=steps)
+        assert rel(y, y_ref) < 2e-4, (count, rel(y, y_ref))
+        assert wa.shape[2] == count and la.shape[0] == count
+        ref_cond = torch.cat([ref_cond, y_ref.clamp(0, 1)[:, None]], dim=1)
+        got_cond = torch.cat([got_cond, y.clamp(0, 1)[:, None]], dim=1)
+    assert got_cond.shape == (1, 5, 3, S, S)
+    assert float(O.psnr(got_cond[:, -1].cpu(), ref_cond[:, -1]).min()) > 60.0
+
+
+def test_no_weighting_ablation_mean_over_views():
+    """weighting flags off + out_channel 3: eps_hat is the plain mean over a sample's views."""
+    cfg = dict(O.TINY, out_channel=3)
+    m, sd = build_model(cfg, 2, "fp32", weighting=False)
+    sched = O.make_schedule(**O.BETA_TRAIN)
+    vc = [3, 1, 2]
+    y_cond, y_t, angle, view_count, z = _inputs(3, 3, vc, cfg["image_size"], 4)
+    t = torch.tensor([1999, 40, 0], dtype=torch.long)
+    with torch.no_grad():
+        y_ref, eps_ref, _, _ = O.p_sample(sd, cfg, sched, y_t, y_cond, view_count, angle, t, z, weighting=False)
+    eps = torch.empty(3, 3, cfg["image_size"], cfg["image_size"], device="cuda")
+    y_prev, logits, weights = m.p_sample(y_t.cuda(), y_cond.cuda(), view_count, angle.cuda(), t.cuda(), noise=z.cuda(), _eps_out=eps)
+    assert rel(eps, eps_ref) < 1e-4 and rel(y_prev, y_ref) < 1e-4
+    assert logits is None and weights is None
