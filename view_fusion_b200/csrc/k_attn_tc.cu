@@ -42,6 +42,7 @@ constexpr int ATT_THREADS = 160;
 __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_constant__ CUtensorMap mapQK,
                                                                  const __grid_constant__ CUtensorMap mapVT,
                                                                  const AttnTcParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
   ptx::tc_fence_after();
   const uint32_t tmem_s = *tmem_slot_ptr;
   const uint32_t tmem_o = tmem_s + (uint32_t)p.nkeys;
+  pdl_wait();
 
   const uint32_t q_chunk = 128 * 128;                       // 128 rows x 128 B
   const uint32_t k_chunk = (uint32_t)p.nkeys * 128;
@@ -245,7 +247,7 @@ int attention_tc(const void* qk, const void* vt, int images, int L, int C, void*
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] { attr_err = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
   VF_CUDA(attr_err);
-  attn_tc_kernel<<<cdiv(p.M, 128), ATT_THREADS, smem, st>>>(mapQK, mapVT, p);
+  VF_CUDA(launch_pdl(attn_tc_kernel, dim3(cdiv(p.M, 128)), dim3(ATT_THREADS), smem, st, mapQK, mapVT, p));
   VF_LAUNCH_CHECK();
   return VF_OK;
 }

@@ -81,6 +81,8 @@ __device__ __forceinline__ void compose_pixel(const float* __restrict__ out, int
 
 template <bool kWeighting>
 __global__ void __launch_bounds__(256) compose_ddpm_kernel(const ComposeParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const vf_compose_args& a = p.a;
   const int HW = a.H * a.W;
   const int b = blockIdx.y;
@@ -208,8 +210,8 @@ extern "C" __attribute__((visibility("default"))) int vf_compose_ddpm_step(const
   ComposeParams p{*a, *s};
   const int HW = a->H * a->W;
   dim3 grid(cdiv(HW, 256), a->B);
-  if (a->weighting) compose_ddpm_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(p);
-  else compose_ddpm_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(p);
+  if (a->weighting) VF_CUDA(launch_pdl(compose_ddpm_kernel<true>, grid, dim3(256), 0, as_stream(stream), p));
+  else VF_CUDA(launch_pdl(compose_ddpm_kernel<false>, grid, dim3(256), 0, as_stream(stream), p));
   VF_LAUNCH_CHECK();
   return VF_OK;
 }

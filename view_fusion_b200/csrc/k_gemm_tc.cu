@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap mapOut,
                                                                 const __grid_constant__ CUtensorMap mapRes,
                                                                 const TcParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-byte alignment
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();                                            // set-up above overlapped the previous kernel's tail
 
   if (warp == 8) {
     // ===================== TMA producer =====================
@@ -705,7 +707,7 @@ int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
     fprintf(stderr, "[vf tc] rows %d W %d cout %d segs %d ktot %d | bn %d G %d a_stages %d (%d B) b_stages %d resident %d smem %zu items %d grid %d epi_tma %d\n",
             p.geo.rows_total, W, a->cout, a->n_seg, k_total, p.block_n, p.G, p.a_stages, p.a_stage_bytes, p.b_stages, p.b_resident, tl.smem,
             p.n_items, grid, p.epi_tma);
-  conv_tc_kernel<<<grid, TC_THREADS, tl.smem, st>>>(maps[0], maps[1], maps[2], mapB, mapOut, mapRes, p);
+  VF_CUDA(launch_pdl(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), tl.smem, st, maps[0], maps[1], maps[2], mapB, mapOut, mapRes, p));
   VF_LAUNCH_CHECK();
   return VF_OK;
 }

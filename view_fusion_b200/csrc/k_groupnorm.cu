@@ -59,6 +59,8 @@ __global__ void __launch_bounds__(kGnThreads, 4) gn_apply_kernel(const T* __rest
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, T* __restrict__ dst) {
   constexpr int VEC = VecOf<T>::N;
+  pdl_launch_dependents();
+  pdl_wait();                                        // the statistics and the sources come from the previous kernels
   extern __shared__ float ab[];                      // [C][2]: y = x*a + b, then [C][2] staging of the raw statistics
   const int C = C0 + C1, CV = C / VEC;
   float* raw = ab + 2 * C;
@@ -132,6 +134,8 @@ __global__ void __launch_bounds__(kGnThreads, 4) gn_apply_kernel(const T* __rest
 template <typename T>
 __global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ src, int H, int W, int C, size_t total,
                                                          T* __restrict__ dst) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int VEC = VecOf<T>::N;
   const int CV = C / VEC;
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -153,6 +157,8 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ s
 // zeroes the padding rows (top row of every image, left column of every line) of a PADDED tensor
 template <typename T>
 __global__ void __launch_bounds__(256) zero_padding_kernel(T* __restrict__ dst, int H, int W, int C, size_t total) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int VEC = VecOf<T>::N;
   const int CV = C / VEC;
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // over (img, padding row index, cv)
@@ -246,7 +252,7 @@ extern "C" __attribute__((visibility("default"))) int vf_gn_apply(const void* sr
   const size_t smem = 4 * C * sizeof(float);
   cudaStream_t st = as_stream(stream);
 #define VF_GN_LAUNCH(T, SW) \
-  gn_apply_kernel<T, SW><<<grid, g.threads, smem, st>>>((const T*)src0, C0, (const T*)src1, C1, H * W, W + 1, P, groups, g.pix_per_cta, stats0, stats0_ld, C1 ? stats1 : nullptr, stats1_ld, gamma, beta, (T*)dst)
+  VF_CUDA(launch_pdl(gn_apply_kernel<T, SW>, grid, dim3(g.threads), smem, st, (const T*)src0, C0, (const T*)src1, C1, H * W, W + 1, P, groups, g.pix_per_cta, stats0, stats0_ld, C1 ? stats1 : nullptr, stats1_ld, gamma, beta, (T*)dst))
   if (dtype == VF_BF16) { if (swish) VF_GN_LAUNCH(__nv_bfloat16, true); else VF_GN_LAUNCH(__nv_bfloat16, false); }
   else { if (swish) VF_GN_LAUNCH(float, true); else VF_GN_LAUNCH(float, false); }
 #undef VF_GN_LAUNCH
@@ -261,8 +267,8 @@ extern "C" __attribute__((visibility("default"))) int vf_upsample2x(const void* 
   VF_REQUIRE(C % vec == 0, "vf_upsample2x: C=%d not a multiple of %d", C, vec);
   const size_t total = (size_t)images * (2 * H + 1) * (2 * W + 1) * (C / vec);
   const unsigned grid = (unsigned)((total + 255) / 256);
-  if (dtype == VF_BF16) upsample2x_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, H, W, C, total, (__nv_bfloat16*)dst);
-  else upsample2x_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)src, H, W, C, total, (float*)dst);
+  if (dtype == VF_BF16) VF_CUDA(launch_pdl(upsample2x_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, as_stream(stream), (const __nv_bfloat16*)src, H, W, C, total, (__nv_bfloat16*)dst));
+  else VF_CUDA(launch_pdl(upsample2x_kernel<float>, dim3(grid), dim3(256), 0, as_stream(stream), (const float*)src, H, W, C, total, (float*)dst));
   VF_LAUNCH_CHECK();
   return VF_OK;
 }
@@ -274,8 +280,8 @@ extern "C" __attribute__((visibility("default"))) int vf_zero_padding(void* dst,
   VF_REQUIRE(C % vec == 0, "vf_zero_padding: C=%d not a multiple of %d", C, vec);
   const size_t total = (size_t)images * (H + W + 1) * (C / vec);
   const unsigned grid = (unsigned)((total + 255) / 256);
-  if (dtype == VF_BF16) zero_padding_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((__nv_bfloat16*)dst, H, W, C, total);
-  else zero_padding_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((float*)dst, H, W, C, total);
+  if (dtype == VF_BF16) VF_CUDA(launch_pdl(zero_padding_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, as_stream(stream), (__nv_bfloat16*)dst, H, W, C, total));
+  else VF_CUDA(launch_pdl(zero_padding_kernel<float>, dim3(grid), dim3(256), 0, as_stream(stream), (float*)dst, H, W, C, total));
   VF_LAUNCH_CHECK();
   return VF_OK;
 }

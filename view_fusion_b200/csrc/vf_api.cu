@@ -49,6 +49,12 @@ extern "C" __attribute__((visibility("default"))) int vf_device_check(void) {
 }
 
 // force_simt: debugging / cross-check switch (environment VF_FORCE_SIMT=1 is read by the Python tests only)
+namespace vf {
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("VF_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+}  // namespace vf
 static int g_force_simt = 0;
 namespace vf { int g_force_simt_flag = 0; }
 extern "C" __attribute__((visibility("default"))) void vf_debug_force_simt(int on) { g_force_simt = on; vf::g_force_simt_flag = on; }

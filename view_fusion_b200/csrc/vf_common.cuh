@@ -34,6 +34,29 @@ void set_error(const char* fmt, ...);
 
 #define VF_LAUNCH_CHECK() VF_CUDA(cudaGetLastError())
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
+// Consecutive kernels of a step are launched with programmatic stream serialization: a kernel calls
+// pdl_launch_dependents() first thing (the next kernel may then be scheduled onto SMs as they drain) and pdl_wait()
+// before its first access to global memory (returns once every earlier kernel has completed and flushed).  Launch
+// latency, barrier / TMEM set-up and the tail of the previous grid overlap; both calls are no-ops in a plain launch.
+// EVERY thread that touches global memory must have passed pdl_wait(): the predecessor may itself still be waiting.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();      // VF_PDL=0 in the environment turns the launch attribute off (vf_api.cu)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline cudaStream_t as_stream(vf_stream s) { return reinterpret_cast<cudaStream_t>(s); }
 inline size_t dtype_size(int dt) { return dt == VF_BF16 ? 2 : 4; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
