@@ -101,6 +101,8 @@ __global__ void pack_conv_weight_t_kernel(const float* __restrict__ w, int cout,
 
 __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ dwp, int cout, int cin, int kk, int k_total, int k_off,
                                          float* __restrict__ dw, int cin_total, int c_off) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t total = (size_t)cout * cin * kk;
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // over the segment's [cout][cin][kk] slice
   if (gid >= total) return;
@@ -182,6 +184,8 @@ struct RowWalk {
 
 template <typename T>
 __global__ void __launch_bounds__(kGbThreads, 2) gn_bwd_reduce_kernel(const GnBwdParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int VEC = VecOf<T>::N;
   constexpr int UN = kGbUnroll;    // (three rows in flight at 3 CTAs per SM measured 20 % slower)
   extern __shared__ float sm[];
@@ -248,6 +252,8 @@ __global__ void __launch_bounds__(kGbThreads, 2) gn_bwd_reduce_kernel(const GnBw
 
 template <typename T>
 __global__ void __launch_bounds__(kGbThreads, 3) gn_bwd_apply_kernel(const GnBwdParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int VEC = VecOf<T>::N;
   constexpr int UN = 2;            // up to three 16-byte loads per row: two rows in flight keep the kernel at 3 CTAs per SM
   extern __shared__ float sm[];
@@ -559,15 +565,16 @@ VF_API int vf_unpack_conv_wgrad(const float* dwp, int cout, int cin, int ksize, 
                                 int c_off, vf_stream stream) {
   VF_REQUIRE(dwp && dw_oihw && cout > 0 && cin > 0 && c_off >= 0 && c_off + cin <= cin_total, "vf_unpack_conv_wgrad: bad args");
   const size_t total = (size_t)cout * cin * ksize * ksize;
-  unpack_conv_wgrad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(dwp, cout, cin, ksize * ksize, k_total, k_off, dw_oihw, cin_total, c_off);
+  VF_CUDA(launch_pdl(unpack_conv_wgrad_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, as_stream(stream), dwp, cout, cin, ksize * ksize, k_total, k_off, dw_oihw, cin_total, c_off));
   VF_LAUNCH_CHECK();
   return VF_OK;
 }
 
-VF_API int vf_gn_backward(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1, const float* stats1,
-                          int stats1_ld, int dtype, int images, int H, int W, int groups, const float* gamma, const float* beta, int swish,
-                          const void* dy, float* scratch, float* dgamma, float* dbeta, void* dx0, int acc0, void* dx1, int acc1,
-                          vf_stream stream) {
+namespace vf {
+int gn_backward_impl(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1, const float* stats1,
+                     int stats1_ld, int dtype, int images, int H, int W, int groups, const float* gamma, const float* beta, int swish,
+                     const void* dy, float* scratch, bool scratch_zeroed, float* dgamma, float* dbeta, void* dx0, int acc0, void* dx1,
+                     int acc1, cudaStream_t st) {
   VF_REQUIRE(src0 && stats0 && gamma && beta && dy && scratch && dgamma && dbeta && dx0, "vf_gn_backward: null args");
   if (!src1) C1 = 0;
   VF_REQUIRE(C1 == 0 || (stats1 && dx1), "vf_gn_backward: second source needs stats and dx");
@@ -583,23 +590,31 @@ VF_API int vf_gn_backward(const void* src0, int C0, const float* stats0, int sta
   const int threads = CV * PY;
   int want = cdiv(148 * 8, images);
   int max_splits = p.P / (PY * 4) > 0 ? p.P / (PY * 4) : 1;
-  int splits = want < 1 ? 1 : (want > max_splits ? max_splits : want);
+  int splits = wave_splits(images, want, max_splits, 148 * 3);
   p.rows_per_cta = cdiv(p.P, splits);
   splits = cdiv(p.P, p.rows_per_cta);
-  cudaStream_t st = as_stream(stream);
-  VF_CUDA(cudaMemsetAsync(scratch, 0, (size_t)images * C * 2 * sizeof(float), st));
+  if (!scratch_zeroed) VF_CUDA(cudaMemsetAsync(scratch, 0, (size_t)images * C * 2 * sizeof(float), st));
   dim3 grid(splits, images);
   const size_t smem_r = (size_t)(2 * C + 2 * C * PY) * sizeof(float), smem_a = (size_t)6 * C * sizeof(float);
   VF_REQUIRE(smem_r <= 48 * 1024, "vf_gn_backward: C=%d needs %zu B of shared memory", C, smem_r);
   if (dtype == VF_BF16) {
-    gn_bwd_reduce_kernel<__nv_bfloat16><<<grid, threads, smem_r, st>>>(p);
-    gn_bwd_apply_kernel<__nv_bfloat16><<<grid, threads, smem_a, st>>>(p);
+    VF_CUDA(launch_pdl(gn_bwd_reduce_kernel<__nv_bfloat16>, grid, dim3(threads), smem_r, st, p));
+    VF_CUDA(launch_pdl(gn_bwd_apply_kernel<__nv_bfloat16>, grid, dim3(threads), smem_a, st, p));
   } else {
-    gn_bwd_reduce_kernel<float><<<grid, threads, smem_r, st>>>(p);
-    gn_bwd_apply_kernel<float><<<grid, threads, smem_a, st>>>(p);
+    VF_CUDA(launch_pdl(gn_bwd_reduce_kernel<float>, grid, dim3(threads), smem_r, st, p));
+    VF_CUDA(launch_pdl(gn_bwd_apply_kernel<float>, grid, dim3(threads), smem_a, st, p));
   }
   VF_LAUNCH_CHECK();
   return VF_OK;
+}
+}  // namespace vf
+
+VF_API int vf_gn_backward(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1, const float* stats1,
+                          int stats1_ld, int dtype, int images, int H, int W, int groups, const float* gamma, const float* beta, int swish,
+                          const void* dy, float* scratch, float* dgamma, float* dbeta, void* dx0, int acc0, void* dx1, int acc1,
+                          vf_stream stream) {
+  return vf::gn_backward_impl(src0, C0, stats0, stats0_ld, src1, C1, stats1, stats1_ld, dtype, images, H, W, groups, gamma, beta, swish, dy,
+                              scratch, false, dgamma, dbeta, dx0, acc0, dx1, acc1, as_stream(stream));
 }
 
 namespace vf {

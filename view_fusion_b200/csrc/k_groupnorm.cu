@@ -206,7 +206,7 @@ static GnGeom gn_geom(int C, int vec, int HW, int images) {   // HW = rows per i
   // enough CTAs for ~4 waves of 148 SMs x 4 resident CTAs, but at least 4 pixels per pixel-lane
   int want = cdiv(148 * 16, images > 0 ? images : 1);
   int max_splits = HW / (PY * 4) > 0 ? HW / (PY * 4) : 1;
-  g.splits = want < 1 ? 1 : (want > max_splits ? max_splits : want);
+  g.splits = wave_splits(images > 0 ? images : 1, want, max_splits, 148 * 4);
   g.pix_per_cta = cdiv(HW, g.splits);
   g.splits = cdiv(HW, g.pix_per_cta);
   return g;

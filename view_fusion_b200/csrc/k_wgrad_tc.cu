@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
                                                                       const __grid_constant__ CUtensorMap mapX1,
                                                                       const __grid_constant__ CUtensorMap mapX2,
                                                                       const __grid_constant__ CUtensorMap mapDY, const WgParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();
 
   if (warp == 4) {
     if (lane == 0 && nk > 0) {
@@ -291,7 +293,7 @@ int conv2d_wgrad_tc(const vf_conv_args* a, const void* dy, int dy_ld, float* dwp
   VF_CUDA(attr_err);
   const size_t smem = 2048 + (size_t)p.stages * p.stage_bytes;
   dim3 grid(splits, jobs);
-  conv_wgrad_tc_kernel<<<grid, WG_THREADS, smem, st>>>(maps[0], maps[1], maps[2], mapDY, p);
+  VF_CUDA(launch_pdl(conv_wgrad_tc_kernel, grid, dim3(WG_THREADS), smem, st, maps[0], maps[1], maps[2], mapDY, p));
   VF_LAUNCH_CHECK();
   return VF_OK;
 }

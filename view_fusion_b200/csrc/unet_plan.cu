@@ -717,6 +717,7 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_set_profiling(vf_u
   VF_REQUIRE(u, "vf_unet_set_profiling: null plan");
   u->profiling = on != 0;
   u->ev_used = 0;
+  vf::pdl_set_suspended(on != 0);      // per-launch event times are only meaningful when the launches do not overlap
   return VF_OK;
 }
 
@@ -768,6 +769,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) colsum_bias_kernel(const T* __restrict__ dy, int ld, int cout, int rows_per_img, int rows_per_cta,
                                                           float* db0, float* db1, float* demb, const int* __restrict__ img_row, int emb_ld,
                                                           int col) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int VEC = VecOf<T>::N;
   constexpr int UN = 4;
   extern __shared__ float red[];                 // [PY][CV * VEC] per-row-lane partial sums
@@ -945,6 +948,11 @@ __global__ void __launch_bounds__(256) embed_bwd_params_kernel(const float* __re
   db0[gid] += acc;
 }
 
+int gn_backward_impl(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1, const float* stats1,
+                     int stats1_ld, int dtype, int images, int H, int W, int groups, const float* gamma, const float* beta, int swish,
+                     const void* dy, float* scratch, bool scratch_zeroed, float* dgamma, float* dbeta, void* dx0, int acc0, void* dx1,
+                     int acc1, cudaStream_t st);
+
 struct BwdCtx {
   vf_unet* u;
   cudaStream_t st;
@@ -1009,18 +1017,19 @@ static void conv_backward(BwdCtx& cx, const vf_unet::TapeOp& t, const uint8_t* p
       float* db1 = t.b_idx[1] >= 0 ? pg[t.b_idx[1]] : nullptr;
       float* de = t.emb_col >= 0 ? demb : nullptr;
       const int col = t.emb_col >= 0 ? t.emb_col : 0;
+      cudaError_t le;
       if (dt == VF_BF16)
-        colsum_bias_kernel<__nv_bfloat16><<<grid, cv * py, smem, cx.st>>>((const __nv_bfloat16*)dYs, dy_ld, f.cout, out_rows_per_img, per, db0, db1, de,
-                                                                          u->last_img_row, u->E, col);
+        le = launch_pdl(colsum_bias_kernel<__nv_bfloat16>, grid, dim3(cv * py), smem, cx.st, (const __nv_bfloat16*)dYs, dy_ld, f.cout,
+                        out_rows_per_img, per, db0, db1, de, (const int*)u->last_img_row, u->E, col);
       else
-        colsum_bias_kernel<float><<<grid, cv * py, smem, cx.st>>>((const float*)dYs, dy_ld, f.cout, out_rows_per_img, per, db0, db1, de,
-                                                                  u->last_img_row, u->E, col);
+        le = launch_pdl(colsum_bias_kernel<float>, grid, dim3(cv * py), smem, cx.st, (const float*)dYs, dy_ld, f.cout, out_rows_per_img, per,
+                        db0, db1, de, (const int*)u->last_img_row, u->E, col);
+      if (le != cudaSuccess) { set_error("colsum_bias launch: %s", cudaGetErrorString(le)); cx.rc = VF_ERR_CUDA; }
     }
   }
   // ---- weight gradient into the packed scratch, then scatter to the OIHW parameter gradients
   int k_total = 0;
   for (int s = 0; s < f.n_seg; ++s) k_total += f.ksize[s] * f.ksize[s] * f.src_c[s];
-  if (!cx.dry && cx.rc == VF_OK) cudaMemsetAsync(dwp, 0, (size_t)f.cout_pad * k_total * 4, cx.st);
   {
     vf_conv_args aw = a;
     const void* dYw = dYs;
@@ -1102,12 +1111,15 @@ static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float*
   const int images = u->last_images, S = u->cfg.image_size;
   const vf_unet_config& c = u->cfg;
   // scratch: packed weight gradient (largest conv), per-image column sums, embedding-table gradient
+  // Every convolution gets its own slice of ONE zero-filled packed-gradient arena and every GroupNorm its own slice of
+  // one zero-filled reduction arena: two memsets per backward instead of one per layer, and no memset nodes between
+  // the kernels of the chain (they would break the programmatic dependent launches).
   size_t dwp_floats = 0, cs_floats = 0;
   for (auto& t : u->tape)
     if (t.kind == 0) {
       size_t k = 0;
       for (int s = 0; s < t.conv.n_seg; ++s) k += (size_t)t.conv.ksize[s] * t.conv.ksize[s] * t.conv.src_c[s];
-      dwp_floats = std::max(dwp_floats, (size_t)t.conv.cout_pad * k);
+      dwp_floats += align_up((size_t)t.conv.cout_pad * k, 64);
       cs_floats = std::max(cs_floats, (size_t)images * t.conv.cout);
     }
   float* dwp = (float*)cx.galloc(dwp_floats * 4);
@@ -1118,12 +1130,14 @@ static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float*
   float* emb_rows = (float*)cx.galloc((size_t)u->last_rows * 11 * c.inner_channel * 4);
   size_t gn_floats = 0, att_floats = 0;
   for (auto& t : u->tape) {
-    if (t.kind == 1) gn_floats = std::max(gn_floats, (size_t)images * (t.gC0 + t.gC1) * 2);
+    if (t.kind == 1) gn_floats += align_up((size_t)images * (t.gC0 + t.gC1) * 2, 64);
     if (t.kind == 2) att_floats = std::max(att_floats, (size_t)images * t.aL * 2 * t.aC * std::max(1, t.aL / 128));
   }
   float* gn_scratch = (float*)cx.galloc(gn_floats * 4);
   float* att_scratch = (float*)cx.galloc(att_floats * 4);
   if (!cx.dry) {
+    cudaMemsetAsync(dwp, 0, dwp_floats * 4, cx.st);
+    cudaMemsetAsync(gn_scratch, 0, gn_floats * 4, cx.st);
     cudaMemsetAsync(demb, 0, (size_t)u->last_rows * u->E * 4, cx.st);
     cudaMemsetAsync(dew, 0, (size_t)u->E * c.inner_channel * 4, cx.st);
     cudaMemsetAsync(deb, 0, (size_t)u->E * 4, cx.st);
@@ -1137,9 +1151,17 @@ static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float*
     if (dt == VF_BF16) grad8_to_padded_kernel<__nv_bfloat16><<<grid, 256, 0, cx.st>>>(g8, S, S, np, total, (__nv_bfloat16*)g_out);
     else grad8_to_padded_kernel<float><<<grid, 256, 0, cx.st>>>(g8, S, S, np, total, (float*)g_out);
   }
+  float* dwp_cur = dwp;
+  float* gn_cur = gn_scratch;
   for (int i = (int)u->tape.size() - 1; i >= 0 && cx.rc == VF_OK; --i) {
     const vf_unet::TapeOp& t = u->tape[i];
     if (t.kind == 0) {
+      float* dwp_l = dwp_cur;
+      {
+        size_t k = 0;
+        for (int s = 0; s < t.conv.n_seg; ++s) k += (size_t)t.conv.ksize[s] * t.conv.ksize[s] * t.conv.src_c[s];
+        dwp_cur += align_up((size_t)t.conv.cout_pad * k, 64);
+      }
       if (t.conv.out == (void*)u->last_out) {
         vf_unet::TapeOp tf = t;               // final conv: its gradient arrives PADDED with np channels
         tf.conv.out_padded = 1;
@@ -1147,19 +1169,20 @@ static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float*
         // only the real output channels have parameters: unpack / bias use the true cout below
         vf_unet::TapeOp tt = tf;
         tt.conv.cout = c.out_channel; tt.conv.cout_pad = np;
-        conv_backward(cx, tt, pkt, g_out, np, dwp, cs, pg, demb);
+        conv_backward(cx, tt, pkt, g_out, np, dwp_l, cs, pg, demb);
       } else {
         auto& g = cx.grad_of(t.conv.out);
         const int ld = t.conv.qkv_split ? 3 * t.conv.qkv_split : t.conv.out_ld;
-        conv_backward(cx, t, pkt, g.first, ld, dwp, cs, pg, demb);
+        conv_backward(cx, t, pkt, g.first, ld, dwp_l, cs, pg, demb);
       }
     } else if (t.kind == 1) {
       auto& gy = cx.grad_of(t.gdst);
       auto& g0 = cx.grad_of(t.gsrc0);
       std::pair<void*, bool>* g1 = t.gsrc1 ? &cx.grad_of(t.gsrc1) : nullptr;
-      VF_B(vf_gn_backward(t.gsrc0, t.gC0, t.gst0, t.gld0, t.gsrc1, t.gC1, t.gst1, t.gld1, dt, images, t.gH, t.gW, c.norm_groups,
-                          u->master[t.gw], u->master[t.gb], t.swish, gy.first, gn_scratch, pg[t.gw], pg[t.gb], g0.first, g0.second ? 1 : 0,
-                          g1 ? g1->first : nullptr, g1 && g1->second ? 1 : 0, (vf_stream)cx.st));
+      VF_B(gn_backward_impl(t.gsrc0, t.gC0, t.gst0, t.gld0, t.gsrc1, t.gC1, t.gst1, t.gld1, dt, images, t.gH, t.gW, c.norm_groups,
+                            u->master[t.gw], u->master[t.gb], t.swish, gy.first, gn_cur, true, pg[t.gw], pg[t.gb], g0.first, g0.second ? 1 : 0,
+                            g1 ? g1->first : nullptr, g1 && g1->second ? 1 : 0, cx.st));
+      gn_cur += align_up((size_t)images * (t.gC0 + t.gC1) * 2, 64);
       g0.second = true;
       if (g1) g1->second = true;
     } else if (t.kind == 2) {

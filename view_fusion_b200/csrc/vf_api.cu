@@ -50,9 +50,11 @@ extern "C" __attribute__((visibility("default"))) int vf_device_check(void) {
 
 // force_simt: debugging / cross-check switch (environment VF_FORCE_SIMT=1 is read by the Python tests only)
 namespace vf {
+static bool g_pdl_suspended = false;
+void pdl_set_suspended(bool s) { g_pdl_suspended = s; }     // per-kernel event timing needs serialised launches
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("VF_PDL"); return !(e && e[0] == '0'); }();
-  return on;
+  return on && !g_pdl_suspended;
 }
 }  // namespace vf
 static int g_force_simt = 0;

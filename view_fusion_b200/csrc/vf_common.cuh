@@ -44,6 +44,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 bool pdl_enabled();      // VF_PDL=0 in the environment turns the launch attribute off (vf_api.cu)
+void pdl_set_suspended(bool s);
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
@@ -55,6 +56,25 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// Row splits per image for a (splits, images) grid of a bandwidth kernel: around `want`, at most `max_splits`, chosen so
+// that splits*images CTAs fill whole waves of `resident` co-resident CTAs (a 3.03-wave grid runs as long as a 4-wave one).
+inline int wave_splits(int images, int want, int max_splits, int resident) {
+  if (max_splits < 1) max_splits = 1;
+  if (want < 1) want = 1;
+  if (want > max_splits) want = max_splits;
+  int lo = want / 2 > 0 ? want / 2 : 1, hi = want * 2 < max_splits ? want * 2 : max_splits;
+  int best = want;
+  double best_eff = -1.0;
+  for (int s = lo; s <= hi; ++s) {
+    const long ctas = (long)s * images;
+    const long waves = (ctas + resident - 1) / resident;
+    const double eff = (double)ctas / (double)(waves * resident);
+    const int d = s > want ? s - want : want - s, bd = best > want ? best - want : want - best;
+    if (eff > best_eff + 0.02 || (eff > best_eff - 0.02 && d < bd && eff >= best_eff - 1e-9)) { best = s; best_eff = eff > best_eff ? eff : best_eff; }
+  }
+  return best;
 }
 
 inline cudaStream_t as_stream(vf_stream s) { return reinterpret_cast<cudaStream_t>(s); }
