@@ -10,3 +10,12 @@ for N in (64, 128, 192, 256):
         torch.cuda.synchronize()
         cyc = out.double().mean().item()
         print(f"N {N:3d} mode {ce:4d}: {cyc / (ng * 4):7.1f} cycles/MMA", flush=True)
+
+print("weight-gradient pattern (MN-major operands, 5 accumulators):")
+for N in (64, 96):
+    for ce in (-200, -201, -202, -203, -204):
+        ng = 1600
+        _lib.check(lib.vf_debug_umma_rate(N, 3, ng, ce, 148, out.data_ptr(), _lib.stream_handle()), "rate")
+        torch.cuda.synchronize()
+        cyc = out.double().mean().item()
+        print(f"N {N:3d} mode {ce:4d}: {cyc / (ng * 4):7.1f} cycles/MMA", flush=True)

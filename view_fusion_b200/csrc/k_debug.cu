@@ -138,6 +138,28 @@ __global__ void __launch_bounds__(128) umma_rate_probe(int N, int shift_rows, in
           ptx::umma_commit(sink_bar);
         }
       }
+    } else if (commit_every <= -200 && commit_every >= -209) {
+      // weight-gradient pattern: both operands MN-major, 5 accumulators (tap pairs) whose A descriptors differ in start
+      // row and leading-dimension offset, 8 k-steps of 16 rows per 128-row chunk.  Order: -200 accumulator outer,
+      // -201 k-step outer, -202 chains of four k-steps, -203 chains of two, -204 accumulator outer with identical A
+      const uint32_t idm = ptx::make_idesc_bf16(128, N, 1, 1);
+      const int shifts[5] = {0, 2, 66, 131, 132};
+      uint64_t adp[5];
+      for (int a = 0; a < 5; ++a)
+        adp[a] = ptx::make_smem_desc(sA + (uint32_t)(commit_every == -204 ? 0 : shifts[a]) * 128u, a == 4 ? 128u : (a == 1 ? 63u * 128u : 128u), 1024);
+      const uint64_t bdm = ptx::make_smem_desc(sB, 128 * 128, 1024);
+      const uint32_t sink_bar = base + 40;
+      ptx::mbar_init(sink_bar, 1);
+      ptx::fence_barrier_init();
+      const int mode = -200 - commit_every;
+      const int chain = mode == 1 ? 1 : (mode == 2 ? 4 : (mode == 3 ? 2 : 8));
+      for (int i = 0; i < n_groups; i += 10) {           // 10 groups of 4 = 40 MMAs = one chunk
+        for (int kb = 0; kb < 8; kb += chain)
+          for (int a = 0; a < 5; ++a)
+            for (int k = kb; k < kb + chain; ++k)
+              ptx::umma_f16(tmem_d + (uint32_t)(a * N), adp[a] + (uint64_t)(k * 128), bdm + (uint64_t)(k * 128), idm, 1u);
+        ptx::umma_commit(sink_bar);
+      }
     } else if (commit_every >= 0) {
       for (int i = 0; i < n_groups; ++i) {
         ptx::umma_f16_k4(tmem_d, ad, bd, idesc, 1u);

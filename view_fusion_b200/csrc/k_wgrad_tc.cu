@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
   const int r_end = min(p.rows_total, r_begin + p.rows_per_split);
   const int nk = r_begin < r_end ? (r_end - r_begin + WG_R - 1) / WG_R : 0;
   const int nbox_x = (WG_R + 2 * sg.halo + 63) / 64;
-  const int natom_n = p.block_n / 64;
+  const int natom_n = (p.block_n + 63) / 64;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(bar_full + 8 * s, 1); ptx::mbar_init(bar_empty + 8 * s, 1); }
@@ -232,14 +232,18 @@ int conv2d_wgrad_tc(const vf_conv_args* a, const void* dy, int dy_ld, float* dwp
   p.W1 = W + 1;
   p.cout = a->cout;
   p.dwp = dwp;
-  // N tile: the largest multiple of 64 <= 256 dividing the (64-padded) output channels
+  // N tile: MN-major MMAs cost ~81 clk up to N = 160 and N/2 beyond (scripts/probe_rate.py), so the widest tile that
+  // divides the (64-padded) output channels wins: n_cols / t, a multiple of 16, at most 256 (320 -> 160, 576 -> 192)
   const int n_cols = (int)align_up((size_t)a->cout, 64);
   p.block_n = 64;
-  for (int bn = 256; bn >= 64; bn -= 64)
-    if (n_cols % bn == 0) { p.block_n = bn; break; }
+  for (int t = 1; t <= n_cols / 16; ++t)
+    if (n_cols % t == 0 && (n_cols / t) % 16 == 0 && n_cols / t <= 256) { p.block_n = n_cols / t; break; }
   p.n_tiles_n = n_cols / p.block_n;
   p.acc_max = 512 / p.block_n;
   if (p.acc_max > WG_MAX_ACC) p.acc_max = WG_MAX_ACC;
+  // Few rows (the 16x16 and 8x8 levels): the reduction is short and the output large, so parallelism should come from
+  // output tiles (one tap pair per job) rather than from row splits, whose partial sums all go through fp32 REDs
+  if (p.rows_total < 65536) p.acc_max = 1;
   p.n_seg = a->n_seg;
   int k_total = 0, halo_max = 0, jobs = 0, max_pairs = 0;
   for (int s = 0; s < a->n_seg; ++s) {
@@ -257,7 +261,7 @@ int conv2d_wgrad_tc(const vf_conv_args* a, const void* dy, int dy_ld, float* dwp
   p.k_total = k_total;
   p.x_rows = (int)align_up((size_t)WG_R + 2 * halo_max, 64);
   p.x_bytes = p.x_rows * 128;
-  p.stage_bytes = p.x_bytes + p.block_n / 64 * WG_R * 128;
+  p.stage_bytes = p.x_bytes + (p.block_n + 63) / 64 * WG_R * 128;
   p.stages = (int)((227 * 1024 - 2048) / p.stage_bytes);
   if (p.stages > 4) p.stages = 4;
   VF_REQUIRE(p.stages >= 2, "vf_conv2d_wgrad(tc): stage of %d B does not fit twice", p.stage_bytes);
