@@ -262,12 +262,12 @@ def main():
         pin = lambda x: x.contiguous().pin_memory()
         yc_p, yt_p, an_p, vc_p = pin(y_cond_h), pin(y_T_h), pin(angle_h), pin(vc)
         out_p = torch.empty_like(yt_p).pin_memory()
-        t_host = torch.full((B,), T_STEPS - 1, dtype=torch.long)
+        t_host = torch.full((B,), T_STEPS - 1, dtype=torch.long).pin_memory()
 
         def e2e_step():
             yc = yc_p.to(dev, non_blocking=True); yt = yt_p.to(dev, non_blocking=True)
-            an = an_p.to(dev, non_blocking=True); tt = t_host.to(dev, non_blocking=True)
-            y_prev, _, _ = model.p_sample(yt, yc, vc_p, an, tt, want_weights=False)
+            an = an_p.to(dev, non_blocking=True)
+            y_prev, _, _ = model.p_sample(yt, yc, vc_p, an, t_host, want_weights=False)      # t, view_count: host tensors
             out_p.copy_(y_prev, non_blocking=True)
             torch.cuda.synchronize()
 

@@ -179,6 +179,18 @@ class ViewFusion(nn.Module):
             y_t = y_t.contiguous().float()
         return y_cond, angle, y_t
 
+    def _plan_for(self, y_cond, view_count) -> "_Plan":
+        """Offsets and staging buffers of the last (view_count, shape): repeated p_sample calls of a sampling loop reuse them
+        (stream order makes the reuse safe) instead of re-allocating and re-uploading the offsets every step."""
+        vc = view_count.detach().to("cpu", torch.int64)
+        key = (tuple(vc.tolist()), tuple(y_cond.shape), str(y_cond.device), self.denoise_fn.precision)
+        cached = getattr(self, "_plan_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        plan = _Plan(self, y_cond, vc)
+        self._plan_cache = (key, plan)
+        return plan
+
     # ---------------------------------------------------------------- p_mean_variance / p_sample (:86-177)
     @torch.no_grad()
     def p_mean_variance(self, y_t, y_cond, view_count, angle, t, clip_denoised: bool):
@@ -198,14 +210,16 @@ class ViewFusion(nn.Module):
     def p_sample(self, y_t, y_cond, view_count, angle, t, clip_denoised=True, noise=None, _plan=None, _eps_out=None,
                  want_weights=True):
         y_cond, angle, y_t = self._prep(y_cond, angle, y_t)
-        plan = _plan if _plan is not None else _Plan(self, y_cond, view_count)
-        t = t.to(y_cond.device).long()
+        plan = _plan if _plan is not None else self._plan_for(y_cond, view_count)
+        # the reference's `any(t > 0)` (:176) is a host decision: a host-resident `t` answers it without touching the
+        # device; a device-resident one costs the same sync the reference pays (generate() below avoids it)
+        add_noise = bool((t > 0).any())
+        t = t.to(y_cond.device, non_blocking=True).long()
         H, W = y_t.shape[-2:]
         w = self.weighting_inference
         weights = torch.empty(plan.B, plan.max_v, 3, H, W, device=y_t.device) if (w and want_weights) else None
         logits = torch.empty(plan.images, 3, H, W, device=y_t.device) if (w and want_weights) else None
         y_prev = torch.empty_like(y_t)
-        add_noise = bool((t > 0).any())          # the reference's `any(t > 0)` (:176); generate() below avoids this sync
         if not add_noise:
             noise = None
         self._step(plan, y_t, y_cond, angle, t, y_prev, z=None if noise is None else noise.contiguous().float(),
