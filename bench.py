@@ -336,7 +336,8 @@ def main():
         yc_d, y0_d, an_d = yc_h.to(dev), y0_h.to(dev), an_h.to(dev)
         if world > 1:
             data_parallel(model)
-        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+        from view_fusion_b200.optim import FusedAdam
+        opt = FusedAdam(model.parameters(), lr=1e-4)         # torch.optim.Adam semantics, one launch
 
         def train_step(host: bool):
             if host:
@@ -376,7 +377,7 @@ def main():
             "metric": "train_samples_per_sec", "value": world * Bt / (tr_ms * 1e-3), "unit": "samples/s", "ms_per_step": tr_ms,
             "steps": args.train_steps, "scaling": "weak", "B_per_gpu": Bt, "N": N,
             "step": "zero_grad -> ViewFusion.forward (loss) -> backward (hand-written CUDA) -> "
-                    + ("flat-gradient NCCL all-reduce (mean, 4 chunks) -> " if world > 1 else "") + "torch Adam",
+                    + ("flat-gradient NCCL all-reduce (mean, 4 chunks) -> " if world > 1 else "") + "fused Adam (vf_adam_step)",
             "e2e": {"value": world * Bt / tr_e2e, "unit": "samples/s", "ms_per_step": tr_e2e * 1e3,
                     "h2d_bytes_per_step": (yc_p.numel() + y0_p.numel() + an_p.numel()) * 4, "d2h_bytes_per_step": 4},
             "flop_utilisation": round(tr_flops / (tr_ms * 1e-3) / 1e12 / pk["tf_sustained"], 4),

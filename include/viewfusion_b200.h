@@ -344,6 +344,22 @@ int vf_add_inplace(void* dst, const void* src, int dtype, size_t n_elems, vf_str
 /* [rows, 8] fp32 (vf_compose_mse's grad_out) -> [rows, ld] activation dtype, zero beyond channel 8. */
 int vf_grad8_to_act(const float* g8, size_t rows, int dtype, int ld, void* dst, vf_stream stream);
 
+/* ---- optimizer step (reference: torch.optim.Adam of experiment.py:115-120, stepped at :293) -------------
+ * One launch for all parameter tensors.  table_dev: one entry per tensor (fp32 device pointers); chunk_entry_dev /
+ * chunk_start_dev: for every vf_adam_chunk_elems()-sized chunk the entry index and the first element.  `step` is the
+ * 1-based step count used for the bias corrections (host scalar, as in torch's non-capturable Adam). */
+typedef struct vf_adam_entry {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int numel;
+  int reserved;
+} vf_adam_entry;
+int vf_adam_chunk_elems(void);
+int vf_adam_step(const vf_adam_entry* table_dev, const int* chunk_entry_dev, const int* chunk_start_dev, int n_chunks, double lr,
+                 double beta1, double beta2, double eps, double weight_decay, int step, vf_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -160,3 +160,35 @@ def test_wgrad_tcgen05_1x1_flat_rows_and_padded_columns(case):
     ref = torch.einsum("rnl,rcl->nc", dy.double().view(R, ld, S * S), x.double().view(R, cin, S * S)).float()
     assert rel(dwp.cpu()[:cout], ref[:cout]) < 1e-4
     assert float(dwp[cout:].abs().max()) == 0.0 if cout < ld else True
+
+
+def test_fused_adam_matches_torch_adam():
+    """view_fusion_b200.optim.FusedAdam vs torch.optim.Adam over several steps (odd sizes, unaligned views, weight decay)."""
+    from view_fusion_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    shapes = [(64, 6, 3, 3), (64,), (320, 640, 1, 1), (5568, 64), (7,), (4099,)]
+    flat = torch.randn(sum(int(torch.tensor(s).prod()) for s in shapes) + 3, device="cuda")
+    for wd in (0.0, 0.01):
+        ref_p = [torch.nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
+        my_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+        ref = torch.optim.Adam(ref_p, lr=3e-3, weight_decay=wd)
+        mine = FusedAdam(my_p, lr=3e-3, weight_decay=wd)
+        for it in range(5):
+            off = 3                                   # gradients are (possibly misaligned) views of one flat buffer
+            for a, b in zip(ref_p, my_p):
+                g = torch.randn_like(a)
+                a.grad = g.clone()
+                view = flat[off:off + g.numel()].view_as(g)
+                view.copy_(g)
+                b.grad = view
+                off += g.numel()
+            if it == 3:
+                for o in (ref, mine):
+                    o.param_groups[0]["lr"] = 1e-3    # scheduler-style learning-rate rewrite
+            ref.step()
+            mine.step()
+        for a, b in zip(ref_p, my_p):
+            assert rel(b, a) < 2e-6
+        sd = mine.state_dict()
+        assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 5.0
+        assert rel(mine.state[my_p[2]]["exp_avg_sq"], ref.state[ref_p[2]]["exp_avg_sq"]) < 2e-6

@@ -27,6 +27,7 @@ SYMBOLS = [
     "vf_unet_packed_t_bytes", "vf_unet_pack_weights_t", "vf_unet_backward_workspace_bytes", "vf_unet_backward",
     "vf_conv2d_wgrad", "vf_unpack_conv_wgrad", "vf_pack_conv_weight_t", "vf_gn_backward", "vf_attention_backward",
     "vf_upsample2x_backward", "vf_zero_insert2x", "vf_add_inplace", "vf_grad8_to_act",
+    "vf_adam_chunk_elems", "vf_adam_step",
 ]
 
 
@@ -136,6 +137,8 @@ def load() -> C.CDLL:
         "vf_zero_insert2x": (i, [p, i, i, i, i, i, p, p]),
         "vf_add_inplace": (i, [p, p, i, sz, p]),
         "vf_grad8_to_act": (i, [p, sz, i, i, p, p]),
+        "vf_adam_chunk_elems": (i, []),
+        "vf_adam_step": (i, [p, p, p, i, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, i, p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -811,20 +811,35 @@ __global__ void __launch_bounds__(256) colsum_bias_kernel(const T* __restrict__ 
   }
 }
 
-// [M, 8] fp32 FLAT gradient of the UNet output -> [rows_p, ld] activation dtype, PADDED, zero padding rows / channels
+// [M, 8] fp32 FLAT gradient of the UNet output -> [rows_p, ld] activation dtype, PADDED, zero padding rows / channels.
+// One thread per (padded row, group of 8 channels): 32-byte read, 16/32-byte write.
 template <typename T>
-__global__ void grad8_to_padded_kernel(const float* __restrict__ g8, int H, int W, int ld, size_t total, T* __restrict__ dst) {
-  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // over (padded row, channel)
+__global__ void __launch_bounds__(256) grad8_to_padded_kernel(const float* __restrict__ g8, int H, int W, int ld, size_t total, T* __restrict__ dst) {
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // over (padded row, channel octet)
   if (gid >= total) return;
-  const int c = (int)(gid % ld);
-  const size_t r = gid / ld;
+  const int oct = ld / 8;
+  const int o = (int)(gid % oct);
+  const size_t r = gid / oct;
   const int W1 = W + 1, P = (H + 1) * W1;
   const int rem = (int)(r % P);
   const size_t img = r / P;
   const int yy = rem / W1, xx = rem - yy * W1;
-  float v = 0.f;
-  if (yy > 0 && xx > 0 && c < 8) v = g8[((img * H + (yy - 1)) * W + (xx - 1)) * 8 + c];
-  dst[gid] = from_f<T>(v);
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  if (yy > 0 && xx > 0 && o == 0) {
+    const float4* src = reinterpret_cast<const float4*>(g8 + ((img * H + (yy - 1)) * W + (xx - 1)) * 8);
+    const float4 a = __ldg(src), b = __ldg(src + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  T* out = dst + r * (size_t)ld + o * 8;
+  if constexpr (sizeof(T) == 2) {
+    store_vec(out, v);
+  } else {
+    float lo[4] = {v[0], v[1], v[2], v[3]}, hi[4] = {v[4], v[5], v[6], v[7]};
+    store_vec(out, lo);
+    store_vec(out + 4, hi);
+  }
 }
 
 __global__ void axpy_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
@@ -1146,7 +1161,7 @@ static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float*
   const int np = u->final_npad;
   void* g_out = cx.galloc((size_t)images * (S + 1) * (S + 1) * np * es);
   if (!cx.dry) {
-    const size_t total = (size_t)images * (S + 1) * (S + 1) * np;
+    const size_t total = (size_t)images * (S + 1) * (S + 1) * (np / 8);
     const unsigned grid = (unsigned)((total + 255) / 256);
     if (dt == VF_BF16) grad8_to_padded_kernel<__nv_bfloat16><<<grid, 256, 0, cx.st>>>(g8, S, S, np, total, (__nv_bfloat16*)g_out);
     else grad8_to_padded_kernel<float><<<grid, 256, 0, cx.st>>>(g8, S, S, np, total, (float*)g_out);

@@ -232,12 +232,13 @@ class UNet(nn.Module):
             else:
                 self._gws.zero_()
             self._gws_images = self._last_images
-        total = sum(p.numel() for p in plist)
+        # every gradient starts on a 16-byte boundary of the flat buffer (vectorised optimizer / all-reduce accesses)
+        total = sum((p.numel() + 3) & ~3 for p in plist)
         flat = torch.zeros(total, dtype=torch.float32, device=dev)
         grads, off = [], 0
         for p in plist:
             grads.append(flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
+            off += (p.numel() + 3) & ~3
         arr = (C.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
         _lib.check(lib.vf_unet_backward(h, pt.data_ptr(), self._gws.data_ptr(), self._gws.numel(), grad_out8.data_ptr(), arr,
                                         _lib.stream_handle()), "vf_unet_backward")
