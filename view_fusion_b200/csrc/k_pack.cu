@@ -19,14 +19,15 @@ __global__ void img_sample_kernel(const int* __restrict__ voff, int B, int image
 // One thread per (image, pixel), consecutive threads = consecutive x: every (tap, channel) load is coalesced along the
 // image row (the 9x re-reads of a pixel hit L1), the K0 values of the pixel are staged in a conflict-free smem column
 // and leave as one contiguous K0*sizeof(T) row.
+// CC > 0: conditioning channels known at compile time -> the 9 * (CC + 3) loads are fully unrolled and independent.
 constexpr int kPackThreads = 128;
-template <typename T>
+template <typename T, int CC>
 __global__ void __launch_bounds__(kPackThreads) pack_views_kernel(const float* __restrict__ y_cond, const float* __restrict__ y_t,
                                                                   const int* __restrict__ voff, const int* __restrict__ img_sample,
                                                                   int n_max, int Cc, int H, int W, int images, int K0,
                                                                   T* __restrict__ x0) {
   constexpr int VEC = VecOf<T>::N;
-  extern __shared__ float stage[];                 // [K0][kPackThreads]
+  extern __shared__ float stage[];                 // [K0][kPackThreads + 1]
   const size_t total = (size_t)images * H * W;
   const size_t gid = (size_t)blockIdx.x * kPackThreads + threadIdx.x;
   const bool live = gid < total;
@@ -36,9 +37,12 @@ __global__ void __launch_bounds__(kPackThreads) pack_views_kernel(const float* _
   const int y = pix / W, x = pix - y * W;
   const int b = __ldg(img_sample + img);
   const int view = img - __ldg(voff + b);
+  if (CC > 0) Cc = CC;
   const int Cin = Cc + 3;
   const float* cond = y_cond + ((size_t)b * n_max + view) * Cc * H * W;
   const float* tgt = y_t + (size_t)b * 3 * H * W;
+  // staging row stride of kPackThreads + 1 floats: the transposed read-out below is bank-conflict free
+  constexpr int LD = kPackThreads + 1;
   float* col = stage + threadIdx.x;
   int k = 0;
 #pragma unroll
@@ -46,20 +50,33 @@ __global__ void __launch_bounds__(kPackThreads) pack_views_kernel(const float* _
     const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
     const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
     const size_t off = (size_t)yy * W + xx;
-    for (int c = 0; c < Cin; ++c, ++k) {
-      float val = 0.f;
-      if (in) val = c < Cc ? __ldg(cond + (size_t)c * H * W + off) : __ldg(tgt + (size_t)(c - Cc) * H * W + off);
-      col[k * kPackThreads] = val;
+    if (CC > 0) {
+      float vals[CC + 3];
+#pragma unroll
+      for (int c = 0; c < CC + 3; ++c)
+        vals[c] = in ? (c < CC ? __ldg(cond + (size_t)c * H * W + off) : __ldg(tgt + (size_t)(c - CC) * H * W + off)) : 0.f;
+#pragma unroll
+      for (int c = 0; c < CC + 3; ++c, ++k) col[k * LD] = vals[c];
+    } else {
+      for (int c = 0; c < Cin; ++c, ++k) {
+        float val = 0.f;
+        if (in) val = c < Cc ? __ldg(cond + (size_t)c * H * W + off) : __ldg(tgt + (size_t)(c - Cc) * H * W + off);
+        col[k * LD] = val;
+      }
     }
   }
-  for (; k < K0; ++k) col[k * kPackThreads] = 0.f;
-  if (!live) return;                               // (own column only: no barrier needed)
-  T* out = x0 + gid * (size_t)K0;
-  for (int k0 = 0; k0 < K0; k0 += VEC) {
+  for (; k < K0; ++k) col[k * LD] = 0.f;
+  __syncthreads();
+  // write-out: consecutive threads take consecutive 16-byte chunks of consecutive pixels -> full 128-byte lines
+  const int chunks = K0 / VEC;
+  const size_t first = (size_t)blockIdx.x * kPackThreads;
+  for (int i = threadIdx.x; i < kPackThreads * chunks; i += kPackThreads) {
+    const int pl = i / chunks, ch = i - pl * chunks;
+    if (first + pl >= total) break;
     float v[VEC];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) v[j] = col[(k0 + j) * kPackThreads];
-    store_vec(out + k0, v);
+    for (int j = 0; j < VEC; ++j) v[j] = stage[(ch * VEC + j) * LD + pl];
+    store_vec(x0 + (first + pl) * (size_t)K0 + ch * VEC, v);
   }
 }
 
@@ -151,12 +168,16 @@ extern "C" __attribute__((visibility("default"))) int vf_pack_views(const float*
   VF_LAUNCH_CHECK();
   const size_t total = (size_t)images * H * W;
   const unsigned grid = (unsigned)((total + kPackThreads - 1) / kPackThreads);
-  const size_t smem = (size_t)k0 * kPackThreads * sizeof(float);
+  const size_t smem = (size_t)k0 * (kPackThreads + 1) * sizeof(float);
   VF_REQUIRE(smem <= 48 * 1024, "vf_pack_views: k0=%d too large", k0);
-  if (x0_dtype == VF_BF16)
-    pack_views_kernel<__nv_bfloat16><<<grid, kPackThreads, smem, st>>>(y_cond, y_t, view_offset, img_sample, n_max, cond_channels, H, W, images, k0, (__nv_bfloat16*)x0);
-  else
-    pack_views_kernel<float><<<grid, kPackThreads, smem, st>>>(y_cond, y_t, view_offset, img_sample, n_max, cond_channels, H, W, images, k0, (float*)x0);
+#define VF_PACK_LAUNCH(T, CC) \
+  pack_views_kernel<T, CC><<<grid, kPackThreads, smem, st>>>(y_cond, y_t, view_offset, img_sample, n_max, cond_channels, H, W, images, k0, (T*)x0)
+  if (x0_dtype == VF_BF16) {
+    if (cond_channels == 3) VF_PACK_LAUNCH(__nv_bfloat16, 3); else if (cond_channels == 6) VF_PACK_LAUNCH(__nv_bfloat16, 6); else VF_PACK_LAUNCH(__nv_bfloat16, 0);
+  } else {
+    if (cond_channels == 3) VF_PACK_LAUNCH(float, 3); else if (cond_channels == 6) VF_PACK_LAUNCH(float, 6); else VF_PACK_LAUNCH(float, 0);
+  }
+#undef VF_PACK_LAUNCH
   VF_LAUNCH_CHECK();
   return VF_OK;
 }
