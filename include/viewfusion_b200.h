@@ -322,7 +322,8 @@ int vf_pack_conv_weight_t(const float* w_oihw, int cout, int cin, int ksize, int
 
 /* GroupNorm(+Swish) backward for dst = vf_gn_apply(src0 | src1): dy [images*P, C0+C1] PADDED.
  * dxK receives (accK == 0) or accumulates (accK != 0) the gradient of source K; dgamma/dbeta [C0+C1] fp32 are
- * accumulated; scratch: images*(C0+C1)*2 floats. */
+ * accumulated; scratch: images*(C0+C1)*2 floats.  With swish != 0 the buffer behind dy is CONSUMED: the first pass
+ * overwrites it with dy * swish'(z) so that the second pass is a pure FMA stream. */
 int vf_gn_backward(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1, const float* stats1,
                    int stats1_ld, int dtype, int images, int H, int W, int groups, const float* gamma, const float* beta, int swish,
                    const void* dy, float* scratch, float* dgamma, float* dbeta, void* dx0, int acc0, void* dx1, int acc1,

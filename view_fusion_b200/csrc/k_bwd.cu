@@ -137,6 +137,21 @@ template <> __device__ __forceinline__ float dswish_for<float>(float z) {
   const float s = 1.f / (1.f + __expf(-z));
   return s * (1.f + z * (1.f - s));
 }
+// g * swish'(z) given h = z/2:  swish'(z) = 0.5 * (1 + t + h*(1 - t*t)),  t = tanh(h)
+template <typename T> __device__ __forceinline__ float dz_swish(float g, float h);
+template <> __device__ __forceinline__ float dz_swish<float>(float g, float h) {
+  const float t = tanhf(h);
+  const float q = fmaf(h, fmaf(-t, t, 1.f), t);
+  const float gh = 0.5f * g;
+  return fmaf(gh, q, gh);
+}
+template <> __device__ __forceinline__ float dz_swish<__nv_bfloat16>(float g, float h) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  const float q = fmaf(h, fmaf(-t, t, 1.f), t);
+  const float gh = 0.5f * g;
+  return fmaf(gh, q, gh);
+}
 template <> __device__ __forceinline__ float dswish_for<__nv_bfloat16>(float z) {
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
@@ -187,7 +202,7 @@ __global__ void __launch_bounds__(kGbThreads, 2) gn_bwd_reduce_kernel(const GnBw
   pdl_launch_dependents();
   pdl_wait();
   constexpr int VEC = VecOf<T>::N;
-  constexpr int UN = kGbUnroll;    // (three rows in flight at 3 CTAs per SM measured 20 % slower)
+  constexpr int UN = kGbUnroll;    // (two or three rows in flight at 3 CTAs per SM measured 5-20 % slower)
   extern __shared__ float sm[];
   const int C = p.C0 + p.C1, CV = C / VEC;
   float* mr = sm;              // [C][2]
@@ -200,12 +215,13 @@ __global__ void __launch_bounds__(kGbThreads, 2) gn_bwd_reduce_kernel(const GnBw
   const T* src = c < p.C0 ? (const T*)p.s0 + (size_t)img * p.P * p.C0 + c : (const T*)p.s1 + (size_t)img * p.P * p.C1 + (c - p.C0);
   const int ld = c < p.C0 ? p.C0 : p.C1;
   const T* dy = (const T*)p.dy + (size_t)img * p.P * C + c;
-  // per-channel constants: z = x*cA + cD (GroupNorm output), xhat = x*cR - cM
-  float cA[VEC], cD[VEC], cR[VEC], cM[VEC], sA[VEC], sB[VEC];
+  // per-channel constants: h = z/2 = x*cA + cD with z the GroupNorm output.  The sums are taken over dz and dz*x;
+  // sum(dz * xhat) = rs * sum(dz*x) - mu*rs * sum(dz) is formed once at the end.
+  float cA[VEC], cD[VEC], sA[VEC], sB[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
     const float mu = mr[2 * (c + j)], rs = mr[2 * (c + j) + 1], ga = __ldg(p.gamma + c + j), be = __ldg(p.beta + c + j);
-    cA[j] = rs * ga; cD[j] = be - mu * rs * ga; cR[j] = rs; cM[j] = mu * rs;
+    cA[j] = 0.5f * rs * ga; cD[j] = 0.5f * (be - mu * rs * ga);
     sA[j] = sB[j] = 0.f;
   }
   const int p0 = blockIdx.x * p.rows_per_cta, p1 = min(p.P, p0 + p.rows_per_cta);
@@ -230,16 +246,23 @@ __global__ void __launch_bounds__(kGbThreads, 2) gn_bwd_reduce_kernel(const GnBw
       float x[VEC], g[VEC];
       load_vec(reinterpret_cast<const T*>(&xr[u]), x);
       load_vec(reinterpret_cast<const T*>(&gr[u]), g);
+      if (p.swish) {
+        // dz = dy * swish'(z) replaces dy in place (stored in the activation type): the apply pass then needs no
+        // transcendental at all
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        const float xh = fmaf(x[j], cR[j], -cM[j]);
-        const float dz = p.swish ? g[j] * dswish_for<T>(fmaf(x[j], cA[j], cD[j])) : g[j];
-        sA[j] += dz; sB[j] = fmaf(dz, xh, sB[j]);
+        for (int j = 0; j < VEC; ++j) g[j] = dz_swish<T>(g[j], fmaf(x[j], cA[j], cD[j]));
+        store_vec(const_cast<T*>(dy) + (size_t)(rb + u * PY) * C, g);
       }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) { sA[j] += g[j]; sB[j] = fmaf(g[j], x[j], sB[j]); }
     }
   }
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) { part[(py * C + c + j) * 2] = sA[j]; part[(py * C + c + j) * 2 + 1] = sB[j]; }
+  for (int j = 0; j < VEC; ++j) {
+    const float mu = mr[2 * (c + j)], rs = mr[2 * (c + j) + 1];
+    part[(py * C + c + j) * 2] = sA[j];
+    part[(py * C + c + j) * 2 + 1] = rs * (sB[j] - mu * sA[j]);       // sum(dz * xhat)
+  }
   __syncthreads();
   // per-image sums; gn_bwd_apply folds them into dgamma / dbeta (one CTA per image)
   float* red = p.red + (size_t)img * C * 2;
@@ -292,13 +315,13 @@ __global__ void __launch_bounds__(kGbThreads, 3) gn_bwd_apply_kernel(const GnBwd
   T* dx = first ? (T*)p.dx0 + (size_t)img * p.P * p.C0 + c : (T*)p.dx1 + (size_t)img * p.P * p.C1 + (c - p.C0);
   const bool accum = first ? p.acc0 : p.acc1;
   const T* dy = (const T*)p.dy + (size_t)img * p.P * C + c;
-  // per-channel constants: z = x*cA + cD;  dx = cA*dz + x*cB + cC  with cB = -rs*t2, cC = mu*rs*t2 - t1
-  float cA[VEC], cD[VEC], cB[VEC], cC[VEC];
+  // per-channel constants: dx = cA*dz + x*cB + cC  with cA = rs*gamma, cB = -rs*t2, cC = mu*rs*t2 - t1
+  float cA[VEC], cB[VEC], cC[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
-    const float mu = mr[2 * (c + j)], rs = mr[2 * (c + j) + 1], ga = __ldg(p.gamma + c + j), be = __ldg(p.beta + c + j);
+    const float mu = mr[2 * (c + j)], rs = mr[2 * (c + j) + 1], ga = __ldg(p.gamma + c + j);
     const float t1 = tt[2 * (c + j)], t2 = tt[2 * (c + j) + 1];
-    cA[j] = rs * ga; cD[j] = be - mu * rs * ga; cB[j] = -rs * t2; cC[j] = mu * rs * t2 - t1;
+    cA[j] = rs * ga; cB[j] = -rs * t2; cC[j] = mu * rs * t2 - t1;
   }
   const int p0 = blockIdx.x * p.rows_per_cta, p1 = min(p.P, p0 + p.rows_per_cta);
   RowWalk rw(p0 + py, PY, p.W1);
@@ -331,10 +354,7 @@ __global__ void __launch_bounds__(kGbThreads, 3) gn_bwd_apply_kernel(const GnBwd
         load_vec(reinterpret_cast<const T*>(&xr[u]), x);
         load_vec(reinterpret_cast<const T*>(&gr[u]), g);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          const float dz = p.swish ? g[j] * dswish_for<T>(fmaf(x[j], cA[j], cD[j])) : g[j];
-          o[j] = fmaf(cA[j], dz, fmaf(x[j], cB[j], cC[j]));
-        }
+        for (int j = 0; j < VEC; ++j) o[j] = fmaf(cA[j], g[j], fmaf(x[j], cB[j], cC[j]));     // g = dz (written by the reduce pass)
         if (accum) {
           float old[VEC];
           load_vec(reinterpret_cast<const T*>(&orr[u]), old);
