@@ -94,13 +94,13 @@ __global__ void __launch_bounds__(kGnThreads, 4) gn_apply_kernel(const T* __rest
 #pragma unroll
   for (int j = 0; j < VEC; ++j) { a[j] = ab[2 * (c + j)]; b[j] = ab[2 * (c + j) + 1]; }
   const int p0 = blockIdx.x * rows_per_cta, p1 = min(P, p0 + rows_per_cta);
-  constexpr int UN = 4;                              // independent 16-byte loads in flight per thread (kept packed)
-  // (yy, xx) of this thread's row advance incrementally: no integer division in the streaming loop
+  // Software pipeline: two half-batches of UN rows; while one is normalised and stored, the loads of the next are in
+  // flight (a warp never sits in a pure wait-then-compute cycle).  (yy, xx) of the thread's row advance incrementally.
+  constexpr int UN = 2;
   int yy = (p0 + py) / W1, xx = (p0 + py) - yy * W1;
   const int dy = PY / W1, dx = PY - dy * W1;
-  for (int pb = p0 + py; pb < p1; pb += UN * PY) {
-    uint4 raw[UN];
-    uint32_t padm = 0, inm = 0;
+  auto fetch = [&](int pb, uint4 (&raw)[UN], uint32_t& inm, uint32_t& padm) {
+    inm = 0; padm = 0;
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       const int p = pb + u * PY;
@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(kGnThreads, 4) gn_apply_kernel(const T* __rest
       yy += dy; xx += dx;
       if (xx >= W1) { xx -= W1; ++yy; }
     }
+  };
+  auto emit = [&](int pb, const uint4 (&raw)[UN], uint32_t inm, uint32_t padm) {
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       if (!((inm >> u) & 1u)) continue;
@@ -127,6 +129,16 @@ __global__ void __launch_bounds__(kGnThreads, 4) gn_apply_kernel(const T* __rest
       }
       store_vec(out + (size_t)(pb + u * PY) * C, v);
     }
+  };
+  uint4 ra[UN], rb2[UN];
+  uint32_t ia, pa, ib, pb2;
+  int pb = p0 + py;
+  fetch(pb, ra, ia, pa);
+  for (; pb < p1; pb += 2 * UN * PY) {
+    fetch(pb + UN * PY, rb2, ib, pb2);
+    emit(pb, ra, ia, pa);
+    fetch(pb + 2 * UN * PY, ra, ia, pa);
+    emit(pb + UN * PY, rb2, ib, pb2);
   }
 }
 
