@@ -103,7 +103,7 @@ def test_wgrad_tcgen05_vs_cuda_cores(case):
     assert rel(outs[0], ref.float()) < 1e-4, "tcgen05 weight gradient"
 
 
-@pytest.mark.parametrize("R,L,Cc", [(3, 256, 192), (2, 128, 128), (5, 256, 128), (2, 64, 128)])
+@pytest.mark.parametrize("R,L,Cc", [(3, 256, 192), (2, 128, 128), (5, 256, 128), (2, 64, 128), (3, 64, 320)])
 def test_attention_backward_bf16(R, L, Cc):
     """Attention backward (tcgen05 where the shape fits, CUDA cores otherwise) vs autograd on the same bf16 operands."""
     import math

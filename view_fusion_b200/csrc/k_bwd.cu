@@ -6,6 +6,8 @@
 //   vf_gn_backward         GroupNorm (+Swish) backward: two HBM passes (reduce, apply), two-source aware
 //   vf_attention_backward  softmax(QK^T/sqrt(C))V backward (CUDA cores)
 //   vf_upsample2x_backward / vf_zero_insert2x / vf_add_inplace / vf_grad8_to_act   small layout kernels
+#include <mutex>
+
 #include "vf_common.cuh"
 
 namespace vf {
@@ -440,6 +442,140 @@ __global__ void __launch_bounds__(256) attn_bwd_simt_kernel(const T* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// attention backward for short sequences (L = 64: the 8x8 mid block, C = 320): one CTA per image, every operand of the
+// image resident in shared memory (bf16), the five products on CUDA cores with register tiles.  No atomics, no
+// scratch: dq | dk | dv rows are written straight into dqkv.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int AL = 64;                 // tokens per image
+struct AttnL64Smem {
+  static __host__ __device__ int ldh(int C) { return C + 4; }          // bf16 row stride: (C+4)/2 words == 2 (mod 32) for C % 64 == 0
+  static __host__ __device__ size_t bytes(int C) {
+    return (size_t)3 * AL * ldh(C) * 2 + (size_t)C * (AL + 2) * 2 + (size_t)2 * AL * (AL + 1) * 4;
+  }
+};
+
+__global__ void __launch_bounds__(256) attn_bwd_l64_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ vt,
+                                                           const __nv_bfloat16* __restrict__ dO, int C, __nv_bfloat16* __restrict__ dqkv) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int LDH = AttnL64Smem::ldh(C), LDV = AL + 2, LDP = AL + 1;
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smraw);
+  __nv_bfloat16* Ks = Qs + AL * LDH;
+  __nv_bfloat16* Gs = Ks + AL * LDH;                 // dO
+  __nv_bfloat16* Vts = Gs + AL * LDH;                // [C][LDV]
+  float* Ps = reinterpret_cast<float*>(Vts + (size_t)C * LDV);
+  float* Ds = Ps + AL * LDP;
+  const int img = blockIdx.x, t = threadIdx.x;
+  const int ld = 3 * C;
+  const __nv_bfloat16* base = qkv + (size_t)img * AL * ld;
+  // ---- stage Q, K, dO rows (8-byte pieces: the padded rows are 8-byte aligned) and V^T
+  const int c4 = C / 4;
+  for (int i = t; i < AL * c4; i += 256) {
+    const int r = i / c4, c = (i - r * c4) * 4;
+    *reinterpret_cast<uint2*>(Qs + r * LDH + c) = *reinterpret_cast<const uint2*>(base + (size_t)r * ld + c);
+    *reinterpret_cast<uint2*>(Ks + r * LDH + c) = *reinterpret_cast<const uint2*>(base + (size_t)r * ld + C + c);
+    *reinterpret_cast<uint2*>(Gs + r * LDH + c) = *reinterpret_cast<const uint2*>(dO + ((size_t)img * AL + r) * C + c);
+  }
+  const __nv_bfloat16* vsrc = vt + (size_t)img * C * AL;
+  for (int i = t; i < C * (AL / 2); i += 256) {
+    const int c = i / (AL / 2), k = (i - c * (AL / 2)) * 2;
+    *reinterpret_cast<uint32_t*>(Vts + c * LDV + k) = *reinterpret_cast<const uint32_t*>(vsrc + (size_t)c * AL + k);
+  }
+  __syncthreads();
+  // ---- S = Q K^T / sqrt(C), dP = dO V^T : thread tile q = tq + 16 i, k = tk + 16 j (conflict-free smem rows)
+  const float scale = rsqrtf((float)C);
+  {
+    const int tq = t >> 4, tk = t & 15;
+    float sacc[4][4], pacc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sacc[i][j] = pacc[i][j] = 0.f;
+    for (int c = 0; c < C; c += 2) {
+      float2 q[4], g[4], kk[4], v0[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        q[i] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Qs + (tq + 16 * i) * LDH + c));
+        g[i] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Gs + (tq + 16 * i) * LDH + c));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        kk[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Ks + (tk + 16 * j) * LDH + c));
+        v0[j].x = __bfloat162float(Vts[c * LDV + tk + 16 * j]);
+        v0[j].y = __bfloat162float(Vts[(c + 1) * LDV + tk + 16 * j]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          sacc[i][j] = fmaf(q[i].x, kk[j].x, fmaf(q[i].y, kk[j].y, sacc[i][j]));
+          pacc[i][j] = fmaf(g[i].x, v0[j].x, fmaf(g[i].y, v0[j].y, pacc[i][j]));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        Ps[(tq + 16 * i) * LDP + tk + 16 * j] = sacc[i][j] * scale;
+        Ds[(tq + 16 * i) * LDP + tk + 16 * j] = pacc[i][j];
+      }
+  }
+  __syncthreads();
+  // ---- softmax rows: P, then dS = P * (dP - sum_k P dP) / sqrt(C)
+  {
+    const int warp = t >> 5, lane = t & 31;
+    for (int r = warp; r < AL; r += 8) {
+      float* prow = Ps + r * LDP;
+      float* drow = Ds + r * LDP;
+      const float s0 = prow[lane], s1 = prow[lane + 32];
+      const float m = warp_max(fmaxf(s0, s1));
+      const float e0 = __expf(s0 - m), e1 = __expf(s1 - m);
+      const float inv = 1.f / warp_sum(e0 + e1);
+      const float p0 = e0 * inv, p1 = e1 * inv;
+      const float d0 = drow[lane], d1 = drow[lane + 32];
+      const float delta = warp_sum(p0 * d0 + p1 * d1);
+      prow[lane] = p0; prow[lane + 32] = p1;
+      drow[lane] = p0 * (d0 - delta) * scale; drow[lane + 32] = p1 * (d1 - delta) * scale;
+    }
+  }
+  __syncthreads();
+  // ---- dQ = dS K, dK = dS^T Q, dV = P^T dO : work unit = (block of 8 rows, channel pair)
+  const int cp_n = C / 2;
+  __nv_bfloat16* orow = dqkv + (size_t)img * AL * ld;
+  for (int idx = t; idx < 3 * (AL / 8) * cp_n; idx += 256) {
+    const int which = idx / ((AL / 8) * cp_n);
+    const int rem = idx - which * (AL / 8) * cp_n;
+    const int rb = rem / cp_n, c = (rem - rb * cp_n) * 2;
+    float2 acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = make_float2(0.f, 0.f);
+    if (which == 0) {            // dQ[q][c] = sum_k dS[q][k] K[k][c]
+      for (int k = 0; k < AL; ++k) {
+        const float2 kv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Ks + k * LDH + c));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float w = Ds[(rb * 8 + i) * LDP + k];
+          acc[i].x = fmaf(w, kv.x, acc[i].x); acc[i].y = fmaf(w, kv.y, acc[i].y);
+        }
+      }
+    } else {                     // dK[k][c] = sum_q dS[q][k] Q[q][c];  dV[k][c] = sum_q P[q][k] dO[q][c]
+      const float* W = which == 1 ? Ds : Ps;
+      const __nv_bfloat16* X = which == 1 ? Qs : Gs;
+      for (int q = 0; q < AL; ++q) {
+        const float2 xv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(X + q * LDH + c));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float w = W[q * LDP + rb * 8 + i];
+          acc[i].x = fmaf(w, xv.x, acc[i].x); acc[i].y = fmaf(w, xv.y, acc[i].y);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      *reinterpret_cast<__nv_bfloat162*>(orow + (size_t)(rb * 8 + i) * ld + which * C + c) = __floats2bfloat162_rn(acc[i].x, acc[i].y);
+  }
+}
+
 template <typename T>
 __global__ void dkv_to_act_kernel(const float* __restrict__ dkv, int C, size_t rows, T* __restrict__ dqkv) {
   const size_t total = rows * 2 * C;
@@ -655,9 +791,19 @@ VF_API int vf_attention_backward(const void* qk, const void* vt, const void* out
   VF_REQUIRE(qk && d_out && scratch && dqkv && images > 0 && L > 0 && C > 0, "vf_attention_backward: bad args");
   if (dtype == VF_BF16 && !g_force_simt_flag && vt && out && lse && attention_bwd_tc_supported(L, C))
     return attention_bwd_tc(qk, vt, out, lse, d_out, images, L, C, scratch, dqkv, as_stream(stream));
+  cudaStream_t st = as_stream(stream);
+  if (dtype == VF_BF16 && !g_force_simt_flag && vt && L == AL && C % 64 == 0 && AttnL64Smem::bytes(C) <= 227 * 1024) {
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(attn_bwd_l64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+    VF_CUDA(attr_err);
+    attn_bwd_l64_kernel<<<images, 256, AttnL64Smem::bytes(C), st>>>((const __nv_bfloat16*)qk, (const __nv_bfloat16*)vt, (const __nv_bfloat16*)d_out,
+                                                                    C, (__nv_bfloat16*)dqkv);
+    VF_LAUNCH_CHECK();
+    return VF_OK;
+  }
   const size_t smem = (size_t)BQ * (2 * C + 2 * L) * sizeof(float);
   VF_REQUIRE(smem <= 48 * 1024, "vf_attention_backward: L=%d C=%d too large", L, C);
-  cudaStream_t st = as_stream(stream);
   VF_CUDA(cudaMemsetAsync(scratch, 0, (size_t)images * L * 2 * C * sizeof(float), st));
   dim3 grid(cdiv(L, BQ), images);
   const size_t rows = (size_t)images * L;
