@@ -92,7 +92,8 @@ struct vf_unet {
   const float* last_level = nullptr; const float* last_angle = nullptr; const int* last_img_row = nullptr;
   int last_rows = 0;
   const void* last_x0 = nullptr; float* last_out = nullptr;
-  size_t packed_t_bytes = 0;
+  size_t packed_t_bytes = 0, pack_tab_off = 0, pack_t_tab_off = 0;
+  std::vector<uint8_t> pack_cache, pack_t_cache;            // job tables as last uploaded (re-uploaded only when they change)
   bool packed_t = false;
   bool profiling = false;
   std::vector<cudaEvent_t> ev;
@@ -224,6 +225,132 @@ __global__ void add_bias_kernel(const float* a, const float* b, int n, float* ds
   if (i < n) dst[i] = a[i] + (b ? b[i] : 0.f);
 }
 
+// ---- table-driven weight packing: ONE launch derives every GEMM-ready weight tensor of a pack from the fp32 masters ----
+struct PackJob {
+  const float* src;
+  const float* src2;
+  void* dst;
+  int type;       // 0 conv K-major, 1 conv transposed + tap-flipped, 2 transposed 1x1 slice, 3 identity block, 4 bias sum, 5 fp32 copy
+  int cout, cin, kk, rows_pad, k_total, k_off, n_stride, c_off;
+  int total;      // destination elements of the job
+  int pad_;
+};
+constexpr int kPackChunk = 4096;
+
+template <typename T>
+__global__ void __launch_bounds__(256) multi_pack_kernel(const PackJob* __restrict__ jobs, const int* __restrict__ chunk_job,
+                                                         const int* __restrict__ chunk_start) {
+  const PackJob j = jobs[chunk_job[blockIdx.x]];
+  const int start = chunk_start[blockIdx.x];
+  const int end = min(j.total, start + kPackChunk);
+  T* dst = reinterpret_cast<T*>(j.dst);
+  for (int gid = start + threadIdx.x; gid < end; gid += 256) {
+    switch (j.type) {
+      case 0: {   // dst[n][k_off + tap*cin + c] = w[n][c][tap]            (vf_pack_conv_weight)
+        const int per_row = j.kk * j.cin;
+        const int n = gid / per_row, r = gid - n * per_row;
+        const int tap = r / j.cin, c = r - tap * j.cin;
+        const float v = n < j.cout ? __ldg(j.src + ((size_t)n * j.cin + c) * j.kk + tap) : 0.f;
+        dst[(size_t)n * j.k_total + j.k_off + r] = from_f<T>(v);
+        break;
+      }
+      case 1: {   // dst[c][k_off + (kk-1-tap)*n_stride + n] = w[n][c][tap]  (vf_pack_conv_weight_t)
+        const int per_row = j.kk * j.n_stride;
+        const int c = gid / per_row, r = gid - c * per_row;
+        const int tapf = r / j.n_stride, n = r - tapf * j.n_stride;
+        const int tap = j.kk - 1 - tapf;
+        const float v = (c < j.cin && n < j.cout) ? __ldg(j.src + ((size_t)n * j.cin + c) * j.kk + tap) : 0.f;
+        dst[(size_t)c * j.k_total + j.k_off + r] = from_f<T>(v);
+        break;
+      }
+      case 2: {   // dst[c][n] = w[n][c_off + c]                          (transposed slice of a 1x1 weight)
+        const int c = gid / j.cout, n = gid - c * j.cout;
+        dst[gid] = from_f<T>(__ldg(j.src + (size_t)n * j.cin + j.c_off + c));
+        break;
+      }
+      case 3: {   // identity block riding as a 1x1 K segment
+        const int n = gid / j.cout, c = gid - n * j.cout;
+        dst[(size_t)n * j.k_total + j.k_off + c] = from_f<T>(c == n ? 1.f : 0.f);
+        break;
+      }
+      case 4:     // fused bias b + b_res (fp32)
+        reinterpret_cast<float*>(j.dst)[gid] = __ldg(j.src + gid) + (j.src2 ? __ldg(j.src2 + gid) : 0.f);
+        break;
+      default:    // plain fp32 copy (embedding Linear rows)
+        reinterpret_cast<float*>(j.dst)[gid] = __ldg(j.src + gid);
+        break;
+    }
+  }
+}
+
+struct PackList {
+  std::vector<PackJob> jobs;
+  std::vector<int> chunk_job, chunk_start;
+  void add(PackJob j) {
+    if (j.total <= 0) return;
+    const int id = (int)jobs.size();
+    jobs.push_back(j);
+    for (int s0 = 0; s0 < j.total; s0 += kPackChunk) { chunk_job.push_back(id); chunk_start.push_back(s0); }
+  }
+  void conv(const float* w, int cout, int cin, int ksize, void* dst, int cout_pad, int k_total, int k_off) {
+    PackJob j{};
+    j.src = w; j.dst = dst; j.type = 0; j.cout = cout; j.cin = cin; j.kk = ksize * ksize; j.rows_pad = cout_pad; j.k_total = k_total;
+    j.k_off = k_off; j.total = cout_pad * j.kk * cin;
+    add(j);
+  }
+  void conv_t(const float* w, int cout, int cin, int ksize, void* dst, int cin_pad, int k_total, int k_off, int n_stride) {
+    PackJob j{};
+    j.src = w; j.dst = dst; j.type = 1; j.cout = cout; j.cin = cin; j.kk = ksize * ksize; j.rows_pad = cin_pad; j.k_total = k_total;
+    j.k_off = k_off; j.n_stride = n_stride; j.total = cin_pad * j.kk * n_stride;
+    add(j);
+  }
+  void slice_t(const float* w, int cout, int cin, int c_off, int c_cnt, void* dst) {
+    PackJob j{};
+    j.src = w; j.dst = dst; j.type = 2; j.cout = cout; j.cin = cin; j.c_off = c_off; j.total = c_cnt * cout;
+    add(j);
+  }
+  void identity(void* dst, int n_rows, int k_total, int k_off) {
+    PackJob j{};
+    j.dst = dst; j.type = 3; j.cout = n_rows; j.k_total = k_total; j.k_off = k_off; j.total = n_rows * n_rows;
+    add(j);
+  }
+  void bias(const float* a, const float* b, int n, void* dst) {
+    PackJob j{};
+    j.src = a; j.src2 = b; j.dst = dst; j.type = 4; j.total = n;
+    add(j);
+  }
+  void copy(const float* src, int n, void* dst) {
+    PackJob j{};
+    j.src = src; j.dst = dst; j.type = 5; j.total = n;
+    add(j);
+  }
+  size_t table_bytes() const { return align_up(jobs.size() * sizeof(PackJob), 256) + 2 * align_up(chunk_job.size() * sizeof(int), 256); }
+  // Launches the one kernel over the job table living in `region` (inside the caller's pack buffer).  The table is
+  // uploaded only when it differs from the last upload (first call, or the caller moved a parameter / the buffer):
+  // in steady state a re-pack is one memset and one launch, with no host-to-device traffic.
+  int run(std::vector<uint8_t>& cache, uint8_t* region, size_t region_bytes, int dtype, cudaStream_t st) const {
+    VF_REQUIRE(table_bytes() <= region_bytes, "weight pack: job table of %zu B exceeds the reserved %zu B", table_bytes(), region_bytes);
+    const size_t o_cj = align_up(jobs.size() * sizeof(PackJob), 256), o_cs = o_cj + align_up(chunk_job.size() * sizeof(int), 256);
+    std::vector<uint8_t> blob(table_bytes() + sizeof(void*), 0);
+    memcpy(blob.data(), jobs.data(), jobs.size() * sizeof(PackJob));
+    memcpy(blob.data() + o_cj, chunk_job.data(), chunk_job.size() * sizeof(int));
+    memcpy(blob.data() + o_cs, chunk_start.data(), chunk_start.size() * sizeof(int));
+    memcpy(blob.data() + table_bytes(), &region, sizeof(void*));            // the table's own location is part of the key
+    if (blob != cache) {
+      VF_CUDA(cudaMemcpyAsync(region, blob.data(), table_bytes(), cudaMemcpyHostToDevice, st));   // pageable: staged before returning
+      cache = blob;
+    }
+    const unsigned grid = (unsigned)chunk_job.size();
+    if (dtype == VF_BF16)
+      multi_pack_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const PackJob*)region, (const int*)(region + o_cj), (const int*)(region + o_cs));
+    else
+      multi_pack_kernel<float><<<grid, 256, 0, st>>>((const PackJob*)region, (const int*)(region + o_cj), (const int*)(region + o_cs));
+    VF_LAUNCH_CHECK();
+    return VF_OK;
+  }
+};
+constexpr size_t kPackTableBytes = 768 * 1024;      // reserved at the end of each pack buffer for the job table
+
 struct Act {
   void* p;
   int C, H, W;
@@ -347,7 +474,8 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_create(const vf_un
   u->final_w = take((size_t)16 * 9 * u->final_c * es);
   u->emb_w_off = take((size_t)u->E * ic * 4);
   u->emb_b_off = take((size_t)u->E * 4);
-  u->packed_bytes = align_up(off, 256);
+  u->pack_tab_off = align_up(off, 256);
+  u->packed_bytes = u->pack_tab_off + kPackTableBytes;
   // transposed packs (data gradients): rows = source channels, K = taps * (gradient channels)
   off = 0;
   for (auto& b : u->blocks) {
@@ -368,7 +496,8 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_create(const vf_un
       if (l.kind == 2 || l.kind == 3) l.wt = take((size_t)l.c * 9 * l.c * es);
   u->final_npad = act_dtype == VF_BF16 ? 64 : 16;
   u->final_wt = take((size_t)u->final_c * 9 * u->final_npad * es);
-  u->packed_t_bytes = align_up(off, 256);
+  u->pack_t_tab_off = align_up(off, 256);
+  u->packed_t_bytes = u->pack_t_tab_off + kPackTableBytes;
   *out = u;
   return VF_OK;
 }
@@ -401,33 +530,33 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_pack_weights(vf_un
   uint8_t* pk = reinterpret_cast<uint8_t*>(packed);
   const int dt = u->dtype;
   const vf_unet_config& c = u->cfg;
-  VF_CUDA(cudaMemsetAsync(pk, 0, u->packed_bytes, st));
-  int rc;
-#define VF_TRY(call) do { rc = (call); if (rc != VF_OK) return rc; } while (0)
-  VF_TRY(vf_pack_conv_weight(u->master[u->downs[0].w_idx], c.inner_channel, c.in_channel, 3, dt, pk + u->conv0_w, c.inner_channel, u->k0, 0, stream));
+  VF_CUDA(cudaMemsetAsync(pk, 0, u->pack_tab_off, st));          // zero padding rows / columns of every pack
+  PackList pl;
+  pl.conv(u->master[u->downs[0].w_idx], c.inner_channel, c.in_channel, 3, pk + u->conv0_w, c.inner_channel, u->k0, 0);
   for (auto& b : u->blocks) {
     const int cin = b.c0 + b.c1;
-    VF_TRY(vf_pack_conv_weight(u->master[b.c1_w], b.cout, cin, 3, dt, pk + b.w1, b.cout, 9 * cin, 0, stream));
+    pl.conv(u->master[b.c1_w], b.cout, cin, 3, pk + b.w1, b.cout, 9 * cin, 0);
     const int k2 = 9 * b.cout + cin;
-    VF_TRY(vf_pack_conv_weight(u->master[b.c2_w], b.cout, b.cout, 3, dt, pk + b.w2, b.cout, k2, 0, stream));
-    if (b.rs_w >= 0) VF_TRY(vf_pack_conv_weight(u->master[b.rs_w], b.cout, cin, 1, dt, pk + b.w2, b.cout, k2, 9 * b.cout, stream));
-    else VF_TRY(pack_identity(pk + b.w2, dt, b.cout, k2, 9 * b.cout, st));    // "h + x" (unet.py:245) as an exact 1x1 segment
-    add_bias_kernel<<<cdiv(b.cout, 128), 128, 0, st>>>(u->master[b.c2_b], b.rs_b >= 0 ? u->master[b.rs_b] : nullptr, b.cout, reinterpret_cast<float*>(pk + b.bias2));
+    pl.conv(u->master[b.c2_w], b.cout, b.cout, 3, pk + b.w2, b.cout, k2, 0);
+    if (b.rs_w >= 0) pl.conv(u->master[b.rs_w], b.cout, cin, 1, pk + b.w2, b.cout, k2, 9 * b.cout);
+    else pl.identity(pk + b.w2, b.cout, k2, 9 * b.cout);           // "h + x" (unet.py:245) as an exact 1x1 segment
+    pl.bias(u->master[b.c2_b], b.rs_b >= 0 ? u->master[b.rs_b] : nullptr, b.cout, pk + b.bias2);
     if (b.attn) {
-      VF_TRY(vf_pack_conv_weight(u->master[b.qkv_w], 3 * b.cout, b.cout, 1, dt, pk + b.wqkv, 3 * b.cout, b.cout, 0, stream));
-      VF_TRY(vf_pack_conv_weight(u->master[b.ao_w], b.cout, b.cout, 1, dt, pk + b.wout, b.cout, b.cout, 0, stream));
+      pl.conv(u->master[b.qkv_w], 3 * b.cout, b.cout, 1, pk + b.wqkv, 3 * b.cout, b.cout, 0);
+      pl.conv(u->master[b.ao_w], b.cout, b.cout, 1, pk + b.wout, b.cout, b.cout, 0);
     }
     // embedding Linear of this block -> rows [emb_col, emb_col + cout) of the concatenated matrix
-    VF_CUDA(cudaMemcpyAsync(pk + u->emb_w_off + (size_t)b.emb_col * c.inner_channel * 4, u->master[b.nf_w],
-                            (size_t)b.cout * c.inner_channel * 4, cudaMemcpyDeviceToDevice, st));
-    VF_CUDA(cudaMemcpyAsync(pk + u->emb_b_off + (size_t)b.emb_col * 4, u->master[b.nf_b], (size_t)b.cout * 4, cudaMemcpyDeviceToDevice, st));
+    pl.copy(u->master[b.nf_w], b.cout * c.inner_channel, pk + u->emb_w_off + (size_t)b.emb_col * c.inner_channel * 4);
+    pl.copy(u->master[b.nf_b], b.cout, pk + u->emb_b_off + (size_t)b.emb_col * 4);
   }
   for (auto* sec : {&u->downs, &u->mid, &u->ups})
     for (auto& l : *sec)
-      if (l.kind == 2 || l.kind == 3) VF_TRY(vf_pack_conv_weight(u->master[l.w_idx], l.c, l.c, 3, dt, pk + l.w, l.c, 9 * l.c, 0, stream));
-  VF_TRY(vf_pack_conv_weight(u->master[u->fin_w], c.out_channel, u->final_c, 3, dt, pk + u->final_w, 16, 9 * u->final_c, 0, stream));
-#undef VF_TRY
-  VF_LAUNCH_CHECK();
+      if (l.kind == 2 || l.kind == 3) pl.conv(u->master[l.w_idx], l.c, l.c, 3, pk + l.w, l.c, 9 * l.c, 0);
+  pl.conv(u->master[u->fin_w], c.out_channel, u->final_c, 3, pk + u->final_w, 16, 9 * u->final_c, 0);
+  {
+    const int rc = pl.run(u->pack_cache, pk + u->pack_tab_off, kPackTableBytes, dt, st);
+    if (rc != VF_OK) return rc;
+  }
   u->packed = true;
   return VF_OK;
 }
@@ -1260,29 +1389,30 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_pack_weights_t(vf_
   if (!u->packed) { set_error("vf_unet_pack_weights_t: call vf_unet_pack_weights first"); return VF_ERR_STATE; }
   uint8_t* pk = reinterpret_cast<uint8_t*>(packed_t);
   const int dt = u->dtype;
-  VF_CUDA(cudaMemsetAsync(pk, 0, u->packed_t_bytes, as_stream(stream)));
-  int rc;
-#define VF_TRY(call) do { rc = (call); if (rc != VF_OK) return rc; } while (0)
+  VF_CUDA(cudaMemsetAsync(pk, 0, u->pack_t_tab_off, as_stream(stream)));
+  PackList pl;
   for (auto& b : u->blocks) {
     const int cin = b.c0 + b.c1;
-    VF_TRY(vf_pack_conv_weight_t(u->master[b.c1_w], b.cout, cin, 3, dt, pk + b.wt1, cin, 9 * b.cout, 0, b.cout, stream));
-    VF_TRY(vf_pack_conv_weight_t(u->master[b.c2_w], b.cout, b.cout, 3, dt, pk + b.wt2, b.cout, 9 * b.cout, 0, b.cout, stream));
+    pl.conv_t(u->master[b.c1_w], b.cout, cin, 3, pk + b.wt1, cin, 9 * b.cout, 0, b.cout);
+    pl.conv_t(u->master[b.c2_w], b.cout, b.cout, 3, pk + b.wt2, b.cout, 9 * b.cout, 0, b.cout);
     if (b.rs_w >= 0) {
       // res_conv [cout][cin][1][1]: the x slice (channels 0..c0) and the skip slice (c0..cin) get their own transposed packs
-      VF_TRY(pack_t_slice(u->master[b.rs_w], b.cout, cin, 0, b.c0, dt, pk + b.wtr0, as_stream(stream)));
-      if (b.c1) VF_TRY(pack_t_slice(u->master[b.rs_w], b.cout, cin, b.c0, b.c1, dt, pk + b.wtr1, as_stream(stream)));
+      pl.slice_t(u->master[b.rs_w], b.cout, cin, 0, b.c0, pk + b.wtr0);
+      if (b.c1) pl.slice_t(u->master[b.rs_w], b.cout, cin, b.c0, b.c1, pk + b.wtr1);
     }
     if (b.attn) {
-      VF_TRY(vf_pack_conv_weight_t(u->master[b.qkv_w], 3 * b.cout, b.cout, 1, dt, pk + b.wtqkv, b.cout, 3 * b.cout, 0, 3 * b.cout, stream));
-      VF_TRY(vf_pack_conv_weight_t(u->master[b.ao_w], b.cout, b.cout, 1, dt, pk + b.wtout, b.cout, b.cout, 0, b.cout, stream));
+      pl.conv_t(u->master[b.qkv_w], 3 * b.cout, b.cout, 1, pk + b.wtqkv, b.cout, 3 * b.cout, 0, 3 * b.cout);
+      pl.conv_t(u->master[b.ao_w], b.cout, b.cout, 1, pk + b.wtout, b.cout, b.cout, 0, b.cout);
     }
   }
   for (auto* sec : {&u->downs, &u->mid, &u->ups})
     for (auto& l : *sec)
-      if (l.kind == 2 || l.kind == 3) VF_TRY(vf_pack_conv_weight_t(u->master[l.w_idx], l.c, l.c, 3, dt, pk + l.wt, l.c, 9 * l.c, 0, l.c, stream));
-  VF_TRY(vf_pack_conv_weight_t(u->master[u->fin_w], u->cfg.out_channel, u->final_c, 3, dt, pk + u->final_wt, u->final_c, 9 * u->final_npad, 0,
-                               u->final_npad, stream));
-#undef VF_TRY
+      if (l.kind == 2 || l.kind == 3) pl.conv_t(u->master[l.w_idx], l.c, l.c, 3, pk + l.wt, l.c, 9 * l.c, 0, l.c);
+  pl.conv_t(u->master[u->fin_w], u->cfg.out_channel, u->final_c, 3, pk + u->final_wt, u->final_c, 9 * u->final_npad, 0, u->final_npad);
+  {
+    const int rc = pl.run(u->pack_t_cache, pk + u->pack_t_tab_off, kPackTableBytes, dt, as_stream(stream));
+    if (rc != VF_OK) return rc;
+  }
   u->packed_t = true;
   return VF_OK;
 }
