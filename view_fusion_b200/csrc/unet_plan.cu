@@ -93,7 +93,7 @@ struct vf_unet {
   int last_rows = 0;
   const void* last_x0 = nullptr; float* last_out = nullptr;
   size_t packed_t_bytes = 0, pack_tab_off = 0, pack_t_tab_off = 0;
-  std::vector<uint8_t> pack_cache, pack_t_cache;            // job tables as last uploaded (re-uploaded only when they change)
+  std::vector<uint8_t> pack_cache, pack_t_cache, unpack_cache;            // job tables as last uploaded (re-uploaded only when they change)
   bool packed_t = false;
   bool profiling = false;
   std::vector<cudaEvent_t> ev;
@@ -1097,10 +1097,51 @@ int gn_backward_impl(const void* src0, int C0, const float* stats0, int stats0_l
                      const void* dy, float* scratch, bool scratch_zeroed, float* dgamma, float* dbeta, void* dx0, int acc0, void* dx1,
                      int acc1, cudaStream_t st);
 
+// ---- all packed weight gradients -> OIHW parameter gradients in ONE launch at the end of the backward -----------------
+// (every convolution owns a slice of the packed-gradient arena, so nothing has to be unpacked layer by layer)
+struct UnpackJob {
+  const float* dwp;      // packed gradient [cout][k_total] of one convolution
+  long long dw_off;      // destination = grad_base + dw_off (floats): offsets are stable across steps, the base is not
+  int cout, cin, kk, k_total, k_off, cin_total, c_off;
+  int total;
+};
+__global__ void __launch_bounds__(256) multi_unpack_kernel(const UnpackJob* __restrict__ jobs, const int* __restrict__ chunk_job,
+                                                           const int* __restrict__ chunk_start, float* __restrict__ grad_base) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const UnpackJob j = jobs[chunk_job[blockIdx.x]];
+  const int start = chunk_start[blockIdx.x];
+  const int end = min(j.total, start + kPackChunk);
+  float* dw = grad_base + j.dw_off;
+  for (int gid = start + threadIdx.x; gid < end; gid += 256) {       // over the segment's [cout][cin][kk] slice
+    const int tap = gid % j.kk;
+    const int c = (gid / j.kk) % j.cin;
+    const int n = gid / (j.kk * j.cin);
+    dw[((size_t)n * j.cin_total + j.c_off + c) * j.kk + tap] += j.dwp[(size_t)n * j.k_total + j.k_off + tap * j.cin + c];
+  }
+}
+
+static inline long long float_offset(const float* p, const float* base) {
+  return (long long)((reinterpret_cast<intptr_t>(p) - reinterpret_cast<intptr_t>(base)) / (intptr_t)sizeof(float));
+}
+
+struct UnpackList {
+  std::vector<UnpackJob> jobs;
+  std::vector<int> chunk_job, chunk_start;
+  void add(const float* dwp, int cout, int cin, int ksize, int k_total, int k_off, long long dw_off, int cin_total, int c_off) {
+    UnpackJob j{dwp, dw_off, cout, cin, ksize * ksize, k_total, k_off, cin_total, c_off, cout * cin * ksize * ksize};
+    const int id = (int)jobs.size();
+    jobs.push_back(j);
+    for (int s0 = 0; s0 < j.total; s0 += kPackChunk) { chunk_job.push_back(id); chunk_start.push_back(s0); }
+  }
+  size_t table_bytes() const { return align_up(jobs.size() * sizeof(UnpackJob), 256) + 2 * align_up(chunk_job.size() * sizeof(int), 256); }
+};
+
 struct BwdCtx {
   vf_unet* u;
   cudaStream_t st;
   uint8_t* gbase;
+  UnpackList unpack;
   size_t goff = 0, gcap = 0;
   bool dry = false;
   int rc = VF_OK;
@@ -1201,10 +1242,9 @@ static void conv_backward(BwdCtx& cx, const vf_unet::TapeOp& t, const uint8_t* p
     if (t.w_idx[s] >= 0) {
       if (s == 0 && f.src[0] == u->last_x0) {
         // first layer: the K0 columns are (tap, channel) of the im2col'd input with cin_total real channels
-        VF_B(vf_unpack_conv_wgrad(dwp, f.cout, t.cin_total[0], 3, k_total, 0, pg[t.w_idx[0]], t.cin_total[0], 0, (vf_stream)cx.st));
+        if (!cx.dry) cx.unpack.add(dwp, f.cout, t.cin_total[0], 3, k_total, 0, float_offset(pg[t.w_idx[0]], pg[0]), t.cin_total[0], 0);
       } else {
-        VF_B(vf_unpack_conv_wgrad(dwp, f.cout, f.src_c[s], f.ksize[s], k_total, koff, pg[t.w_idx[s]], t.cin_total[s], t.c_off[s],
-                                  (vf_stream)cx.st));
+        if (!cx.dry) cx.unpack.add(dwp, f.cout, f.src_c[s], f.ksize[s], k_total, koff, float_offset(pg[t.w_idx[s]], pg[0]), t.cin_total[s], t.c_off[s]);
       }
     }
     koff += kk * f.src_c[s];
@@ -1279,6 +1319,7 @@ static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float*
   }
   float* gn_scratch = (float*)cx.galloc(gn_floats * 4);
   float* att_scratch = (float*)cx.galloc(att_floats * 4);
+  uint8_t* unpack_tab = (uint8_t*)cx.galloc(kPackTableBytes);     // job table of the final multi-tensor unpack
   if (!cx.dry) {
     cudaMemsetAsync(dwp, 0, dwp_floats * 4, cx.st);
     cudaMemsetAsync(gn_scratch, 0, gn_floats * 4, cx.st);
@@ -1339,6 +1380,30 @@ static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float*
       auto& gs = cx.grad_of(t.usrc);
       VF_B(vf_upsample2x_backward(gd.first, dt, images, t.uH, t.uW, t.uC, gs.first, gs.second ? 1 : 0, (vf_stream)cx.st));
       gs.second = true;
+    }
+  }
+  // all packed weight gradients -> OIHW parameter gradients (one launch; the table is uploaded only when it changes)
+  if (!cx.dry && cx.rc == VF_OK && !cx.unpack.jobs.empty()) {
+    const UnpackList& ul = cx.unpack;
+    if (ul.table_bytes() > kPackTableBytes) {
+      set_error("vf_unet_backward: unpack table of %zu B exceeds the reserved %zu B", ul.table_bytes(), kPackTableBytes);
+      cx.rc = VF_ERR_ARG;
+    } else {
+      const size_t o_cj = align_up(ul.jobs.size() * sizeof(UnpackJob), 256), o_cs = o_cj + align_up(ul.chunk_job.size() * sizeof(int), 256);
+      std::vector<uint8_t> blob(ul.table_bytes() + sizeof(void*), 0);
+      memcpy(blob.data(), ul.jobs.data(), ul.jobs.size() * sizeof(UnpackJob));
+      memcpy(blob.data() + o_cj, ul.chunk_job.data(), ul.chunk_job.size() * sizeof(int));
+      memcpy(blob.data() + o_cs, ul.chunk_start.data(), ul.chunk_start.size() * sizeof(int));
+      memcpy(blob.data() + ul.table_bytes(), &unpack_tab, sizeof(void*));
+      if (blob != u->unpack_cache) {
+        if (cudaMemcpyAsync(unpack_tab, blob.data(), ul.table_bytes(), cudaMemcpyHostToDevice, cx.st) != cudaSuccess) cx.rc = VF_ERR_CUDA;
+        u->unpack_cache = blob;
+      }
+      if (cx.rc == VF_OK) {
+        cudaError_t le = launch_pdl(multi_unpack_kernel, dim3((unsigned)ul.chunk_job.size()), dim3(256), 0, cx.st, (const UnpackJob*)unpack_tab,
+                                    (const int*)(unpack_tab + o_cj), (const int*)(unpack_tab + o_cs), pg[0]);
+        if (le != cudaSuccess) { set_error("multi_unpack launch: %s", cudaGetErrorString(le)); cx.rc = VF_ERR_CUDA; }
+      }
     }
   }
   // embedding path: demb [rows, E] -> noise_level_mlp and the per-block Linear(ic -> Cout) parameters
