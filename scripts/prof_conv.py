@@ -64,12 +64,19 @@ for name, dbg, use_res, use_stats in variants:
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3 / NL)
     t = min(ts[1:])
-    cnt = torch.zeros(148 * 4, dtype=torch.int64, device="cuda")
+    cnt = torch.zeros(148 * 12 + 1 + 4 * 64, dtype=torch.int64, device="cuda")
     lib.vf_debug_counters(cnt.data_ptr())
-    ops.conv2d(srcs, [k for _, k in segs], w, R, S, S, cout, bias=bias, residual=res if use_res else None, want_stats=use_stats,
-               in_padded=not c["flat"], out=out, stats=stats)
+    for _ in range(6):
+        ops.conv2d(srcs, [k for _, k in segs], w, R, S, S, cout, bias=bias, residual=res if use_res else None, want_stats=use_stats,
+                   in_padded=not c["flat"], out=out, stats=stats)
     torch.cuda.synchronize()
     lib.vf_debug_counters(0)
-    cm = cnt.view(148, 4).double().mean(0).tolist()
-    print(f"{case:5s} {name:22s}: {t:7.1f} us  {flops / t / 1e6:7.1f} TFLOP/s | MMA thread kcyc: total {cm[0]/1e3:6.1f} waitA {cm[1]/1e3:6.1f} waitB {cm[2]/1e3:6.1f} waitAcc {cm[3]/1e3:6.1f}")
+    st = cnt[148 * 12 + 1: 148 * 12 + 1 + 24].view(6, 4).cpu().double()
+    setup = (st[1:, 1] - st[1:, 0]).mean().item() / 1e3; main = (st[1:, 2] - st[1:, 1]).mean().item() / 1e3
+    tear = (st[1:, 3] - st[1:, 2]).mean().item() / 1e3; gap = (st[1:, 0] - st[:-1, 3]).mean().item() / 1e3
+    period = (st[1:, 0] - st[:-1, 0]).mean().item() / 1e3
+    stamp_txt = f" | cta0 us: entry->ready {setup:5.1f} loops {main:5.1f} teardown {tear:4.1f} exit->next entry {gap:5.1f} period {period:5.1f}"
+    cm = cnt[:148 * 4].view(148, 4).double().mean(0).tolist()
+    em = cnt[148 * 4:148 * 12].view(148, 8).double().mean(0).tolist()
+    print(f"{case:5s} {name:22s}: {t:7.1f} us  {flops / t / 1e6:7.1f} TFLOP/s | MMA thread kcyc: total {cm[0]/1e3:6.1f} waitA {cm[1]/1e3:6.1f} waitB {cm[2]/1e3:6.1f} waitAcc {cm[3]/1e3:6.1f} | epi w0 kcyc: total {em[0]/1e3:6.1f} table {em[1]/1e3:5.1f} waitAcc {em[2]/1e3:6.1f} ld+pack {em[3]/1e3:5.1f} (store-wait {em[4]/1e3:5.1f}) stats {em[5]/1e3:5.1f} prep {em[6]/1e3:4.1f}{stamp_txt}")
 lib.vf_debug_flags(0)

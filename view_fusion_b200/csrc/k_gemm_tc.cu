@@ -149,6 +149,12 @@ __device__ __forceinline__ void mma_issue_loop(const TcParams& p, const MmaCtx& 
   }
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0,
                                                                 const __grid_constant__ CUtensorMap mapA1,
                                                                 const __grid_constant__ CUtensorMap mapA2,
@@ -156,6 +162,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap mapOut,
                                                                 const __grid_constant__ CUtensorMap mapRes,
                                                                 const TcParams p) {
+  // test hook: wall-clock stamps of CTA 0 (entry, after set-up + dependency wait, after the role loops, exit) per launch,
+  // appended at dbg_out[grid*12 + 1 + 4*launch ..]; dbg_out[grid*12] counts the launches
+  long long* stamps = nullptr;
+  if (p.dbg_out && blockIdx.x == 0 && threadIdx.x == 0) {
+    long long* cnt = p.dbg_out + (size_t)gridDim.x * 12;
+    const long long li = atomicAdd(reinterpret_cast<unsigned long long*>(cnt), 1ull);
+    if (li < 64) { stamps = cnt + 1 + 4 * li; stamps[0] = (long long)global_timer_ns(); }
+  }
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -197,6 +211,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_wait();                                            // set-up above overlapped the previous kernel's tail
+  if (stamps) stamps[1] = (long long)global_timer_ns();
 
   if (warp == 8) {
     // ===================== TMA producer =====================
@@ -284,12 +299,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     uint32_t res_phase = 0;
     const bool has_res = p.residual != nullptr;
     int k_idx = 0;
+    // test hook: cycle counters of epilogue warp 0 -> dbg_out[grid*4 + cta*8 + ...] = total, table, wait acc, ld+pack, store wait, stats, prep
+    const bool eprof = p.dbg_out != nullptr && et == 0;
+    long long ec[7] = {0, 0, 0, 0, 0, 0, 0}, et0 = 0;
+    const long long e_start = eprof ? clock64() : 0;
+#define VF_EP_BEGIN() do { if (eprof) et0 = clock64(); } while (0)
+#define VF_EP_END(i) do { if (eprof) ec[i] += clock64() - et0; } while (0)
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++k_idx) {
       const int set = k_idx & 1;
       const int n_tile = item / p.n_mblocks, m_blk = item - n_tile * p.n_mblocks;
       const int m0 = m_blk * BM, n0 = n_tile * p.block_n;
       const int img_first = m0 / (p.geo.in_padded ? p.geo.P : p.geo.HW);
       // bias + embedding rows of the images this block touches (built while the main loop runs)
+      VF_EP_BEGIN();
       if (!(p.dbg & 8)) {
       asm volatile("bar.sync 1, 256;" ::: "memory");     // previous item's readers are done
       for (int i = et; i < p.max_imgs * p.block_n; i += 256) {
@@ -304,6 +326,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       }
+      VF_EP_END(1);
 
       // the first unit's residual is fetched under the main loop
       RowInfo ri{};
@@ -325,10 +348,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           __syncwarp();
         }
       };
+      VF_EP_BEGIN();
       if (sub < U) prep_unit(sub, true);
+      VF_EP_END(6);
 
+      VF_EP_BEGIN();
       ptx::mbar_wait(bar_accfull + 8 * set, (uint32_t)(k_idx >> 1) & 1u);
       ptx::tc_fence_after();
+      VF_EP_END(2);
       for (int u = sub; u < U && !(p.dbg & 4); u += 2) {
         const int g = u / npanel, c0 = (u - g * npanel) * 64;
         const int width = min(64, p.block_n - c0);
@@ -342,14 +369,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           // ---------------- fast path: staged through shared memory, TMA in / TMA out ----------------
           uint8_t* tile = stg_g + lane * 128;                                // this thread's 128-byte row
           if (has_res) { ptx::mbar_wait(rbar, res_phase); res_phase ^= 1u; }
+          VF_EP_BEGIN();
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {                                   // two 32-column halves (register budget)
             uint32_t rr[2][16];
             ptx::tmem_ld16(trow + 32 * hh, rr[0]);
             ptx::tmem_ld16(trow + 32 * hh + 16, rr[1]);
             if (hh == 0 && !has_res) {                                       // the previous store must have read the tile
+              const long long ts = eprof ? clock64() : 0;
               if (lane == 0) ptx::tma_store_wait_read<0>();                  // out; overlaps with the TMEM load latency
               __syncwarp();
+              if (eprof) ec[4] += clock64() - ts;
             }
             ptx::tmem_ld_wait();
 #pragma unroll
@@ -380,6 +410,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             ptx::tma_store_2d(&mapOut, stg, n0 + c0, (int)row_base);
             ptx::tma_store_commit();
           }
+          VF_EP_END(3);
+          VF_EP_BEGIN();
           if (p.stats && !(p.dbg & 1)) {
             // column sums straight from the staging tile: lane owns channels (2*lane, 2*lane+1); conflict-free reads.
             // Padding rows were stored as zeros, so a tile inside one image is summed without any per-row test.
@@ -415,6 +447,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               }
             }
           }
+          VF_EP_END(5);
         } else if (__any_sync(0xffffffffu, valid)) {
           // ---------------- fallback: row-per-thread global accesses, 16 columns at a time ----------------
           for (int cc = 0; cc < width; cc += 16) {
@@ -476,6 +509,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar_accempty + 8 * set);
     }
+    if (eprof) {
+      ec[0] = clock64() - e_start;
+      long long* o = p.dbg_out + (size_t)gridDim.x * 4 + (size_t)blockIdx.x * 8;
+      for (int i = 0; i < 7; ++i) o[i] = ec[i];
+    }
+#undef VF_EP_BEGIN
+#undef VF_EP_END
+    if (stamps) stamps[2] = (long long)global_timer_ns();
     if (lane == 0) ptx::tma_store_wait_all<0>();     // staged stores must land before the CTA exits
   }
   __syncthreads();
@@ -483,6 +524,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
+  if (stamps) stamps[3] = (long long)global_timer_ns();
 }
 
 // ---- host side --------------------------------------------------------------------------------------
