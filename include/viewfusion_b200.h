@@ -113,6 +113,11 @@ int vf_unet_forward(vf_unet* u, const void* packed, void* workspace, size_t work
                     const void* x0, const float* level, const float* angle, int rows, const int* img_row,
                     float* out, vf_stream stream);
 
+/* Training (default, on = 1): the forward also writes what only vf_unet_backward reads (the transposed V of every
+ * attention block).  Inference (on = 0): those extras are skipped — the attention kernel takes V row-major from the qkv
+ * tensor — and vf_unet_backward after such a forward returns VF_ERR_STATE.  Activations and results are identical. */
+int vf_unet_set_stash(vf_unet* u, int on);
+
 /* Number of kernels enqueued by the last vf_unet_forward on this plan (bench.py's gpu_launches claim). */
 int vf_unet_last_launches(const vf_unet* u);
 
@@ -120,6 +125,10 @@ int vf_unet_last_launches(const vf_unet* u);
  * the roofline breakdown in bench.py.  ms[6] / counts[6] = conv, gn_stats, gn_apply, attention, upsample, embed. */
 int vf_unet_set_profiling(vf_unet* u, int on);
 int vf_unet_profile_read(vf_unet* u, float* ms_host, int* counts_host);
+/* Per-launch table of the same profiled forward, in launch order: ms[i], kind[i] (class index as above) and
+ * desc[6*i..6*i+5] = images, H, C_in (conv: total K), C_out, ksize, stride (zeros where not recorded).
+ * Returns the number of launches written (<= cap), negative on error. */
+int vf_unet_profile_launches(vf_unet* u, float* ms_host, int* kind_host, int* desc_host, int cap);
 
 /* Debug/parity tap: copies the output activation of module `name` ("downs.3", "mid.0", "ups.17", ...) of the
  * LAST vf_unet_forward on this plan into `dst` as NCHW fp32.  dst must hold images*C*H*W floats. */

@@ -24,4 +24,4 @@ for r in data:
 print(sorted(agg.items(), key=lambda x: -x[1])[:8])
 for r in sorted(data, key=lambda r: -int(r[idx["# Samples"]] or 0))[:n]:
     st = sorted(((h, int(r[idx[h]] or 0)) for h in stall_cols), key=lambda x: -x[1])[:2]
-    print(r[idx["# Samples"]].rjust(6), r[idx["Source"]][:70].ljust(70), st)
+    print(r[idx["# Samples"]].rjust(6), r[idx.get("Address", 0)][-6:], r[idx["Source"]][:70].ljust(70), st)

@@ -34,6 +34,8 @@ flops = 2 * R * S * S * cout * k_total
 variants = [("full", 0, True, True)]
 if len(sys.argv) > 2 and sys.argv[2] == "ablate":
     variants += [("no-res (typical)", 0, False, True), ("no-res dbg:no-table", 8, False, True), ("no-res-no-stats", 0, False, False), ("dbg:no-store", 2, True, True), ("dbg:no-unit-work", 4, True, True), ("dbg:no-unit-no-table", 12, True, True)]
+if len(sys.argv) > 2 and sys.argv[2] == "typical":
+    variants = [("no-res (typical)", 0, False, True)]
 if len(sys.argv) > 2 and sys.argv[2] == "sweep":
     variants = []
     for bn in sorted({b for b in (64, 96, 128, 160, 192, 256, 320) if cout % b == 0 and b <= 256}):

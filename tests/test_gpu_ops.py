@@ -237,6 +237,51 @@ def test_conv_flat_source_padded_output(lib, dtype):
     assert rel(ops.from_padded(out, R, S, S), ref) < (4e-3 if dtype == torch.bfloat16 else 5e-6)
 
 
+@pytest.mark.parametrize("R,S,Cc,cout", [(5, 16, 192, 192), (7, 8, 320, 320), (150, 16, 64, 128), (3, 32, 128, 64)])
+def test_conv_bf16_flat_to_padded_staged_epilogue(lib, R, S, Cc, cout):
+    """FLAT rows -> PADDED output through the staged TMA epilogue (32-row tiles = whole image lines of 3D tensor maps):
+    output, residual fetch and fused GroupNorm sums vs exact math; padding rows of the output stay untouched."""
+    from view_fusion_b200 import ops
+    torch.manual_seed(11)
+    dtype = torch.bfloat16
+    rnd = lambda *s: bf16r(torch.randn(*s))
+    x, w, res, bias = rnd(R, Cc, S, S), bf16r(rnd(cout, Cc, 1, 1) / math.sqrt(Cc)), rnd(R, cout, S, S), torch.randn(cout)
+    ref = F.conv2d(x, w, bias) + res
+    wp = ops.pack_conv_weight(w.cuda(), dtype)
+    out, stats = ops.conv2d([ops.to_nhwc(x, dtype).cuda()], [1], wp, R, S, S, cout, bias=bias.cuda(),
+                            residual=ops.to_padded(res, dtype, fill=float("nan")).cuda(), in_padded=False, out_padded=True,
+                            want_stats=True)
+    got = ops.from_padded(out, R, S, S).cpu()
+    assert rel(got, ref) < 4e-3
+    want = torch.stack([got.sum(dim=(2, 3)), (got * got).sum(dim=(2, 3))], dim=-1)
+    assert rel(stats, want) < 1e-5
+    pad = out.float().view(R, S + 1, S + 1, cout)
+    assert torch.isnan(pad[:, 0]).all() and torch.isnan(pad[:, :, 0]).all(), "padding rows must not be written"
+
+
+@pytest.mark.parametrize("R,S,Cc", [(5, 16, 192), (7, 8, 320), (150, 16, 64), (1, 8, 64)])
+def test_conv_bf16_padded_to_flat_gathered_source(lib, R, S, Cc):
+    """1x1 conv from a PADDED source to FLAT rows (qkv projection / data gradient of the attention output projection):
+    TMA gathers the valid pixels, so NaN padding rows of the source must not leak; q|k panels leave through the staged
+    epilogue, V transposed; the accumulate-into-existing-gradient port (residual, FLAT) is covered too."""
+    from view_fusion_b200 import ops
+    torch.manual_seed(12)
+    dtype = torch.bfloat16
+    rnd = lambda *s: bf16r(torch.randn(*s))
+    x, w = rnd(R, Cc, S, S), bf16r(rnd(3 * Cc, Cc, 1, 1) / math.sqrt(Cc))
+    ref = F.conv2d(x, w)
+    wp = ops.pack_conv_weight(w.cuda(), dtype)
+    src = ops.to_padded(x, dtype, fill=float("nan")).cuda()
+    out, vt = ops.conv2d([src], [1], wp, R, S, S, 3 * Cc, qkv_split=Cc, out_padded=False)
+    got = ops.from_nhwc(out, R, S, S).cpu()
+    assert rel(got[:, : 2 * Cc], ref[:, : 2 * Cc]) < 4e-3
+    assert rel(vt.float().cpu().view(R, Cc, S, S), ref[:, 2 * Cc:]) < 4e-3
+    # plain FLAT output + FLAT residual
+    res = rnd(R, 3 * Cc, S, S)
+    out2 = ops.conv2d([src], [1], wp, R, S, S, 3 * Cc, out_padded=False, residual=ops.to_nhwc(res, dtype).cuda())
+    assert rel(ops.from_nhwc(out2, R, S, S).cpu(), ref + res) < 4e-3
+
+
 def test_conv_bf16_final_layer_fp32_out(lib):
     from view_fusion_b200 import ops
     R, S, segs, cout = 2, 16, [(64, 3)], 6
@@ -279,6 +324,11 @@ def test_attention(lib, dtype, R, L, Cc):
         finally:
             ops.force_simt(False)
         assert rel(out, simt) < 1e-2
+        # inference variant: no transposed copy, V is read row-major from qkv as an MN-major tensor-core operand
+        out_mn = ops.attention(qd, None, R, L, Cc)
+        torch.cuda.synchronize()
+        assert rel(out_mn, ref) < 1e-2
+        assert rel(out_mn, out) < 2e-3
 
 
 def test_embed_table(lib):

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libviewfusion_b200.so")
+LIB_PATH = os.environ.get("VF_B200_LIB") or os.path.join(_HERE, "libviewfusion_b200.so")   # override: A/B builds in profiling scripts
 
 VF_F32, VF_BF16 = 0, 1
 VF_MAX_LEVELS = 8
@@ -19,7 +19,7 @@ SYMBOLS = [
     "vf_last_error", "vf_abi_version", "vf_device_check",
     "vf_unet_create", "vf_unet_destroy", "vf_unet_num_params", "vf_unet_param_info", "vf_unet_emb_channels",
     "vf_unet_packed_bytes", "vf_unet_pack_weights", "vf_unet_workspace_bytes", "vf_unet_k0", "vf_unet_forward",
-    "vf_unet_last_launches", "vf_unet_read_tap", "vf_unet_set_profiling", "vf_unet_profile_read",
+    "vf_unet_last_launches", "vf_unet_read_tap", "vf_unet_set_profiling", "vf_unet_profile_read", "vf_unet_profile_launches", "vf_unet_set_stash",
     "vf_pack_views", "vf_pack_nchw", "vf_nhwc_to_nchw", "vf_q_sample",
     "vf_compose_ddpm_step", "vf_compose_mse",
     "vf_embed", "vf_gn_stats", "vf_gn_apply", "vf_upsample2x", "vf_flat_to_padded", "vf_padded_to_flat", "vf_zero_padding", "vf_conv2d", "vf_debug_force_simt", "vf_debug_flags", "vf_debug_counters", "vf_debug_umma_shift", "vf_debug_umma_rate", "vf_debug_umma_mn", "vf_attention",
@@ -100,7 +100,9 @@ def load() -> C.CDLL:
         "vf_unet_forward": (i, [p, p, p, sz, i, p, p, p, i, p, p, p]),
         "vf_unet_last_launches": (i, [p]),
         "vf_unet_set_profiling": (i, [p, i]),
+        "vf_unet_set_stash": (i, [p, i]),
         "vf_unet_profile_read": (i, [p, C.POINTER(C.c_float), C.POINTER(i)]),
+        "vf_unet_profile_launches": (i, [p, C.POINTER(C.c_float), C.POINTER(i), C.POINTER(i), i]),
         "vf_unet_read_tap": (i, [p, p, C.c_char_p, p, C.POINTER(C.c_int64), p]),
         "vf_pack_views": (i, [p, p, p, i, i, i, i, i, i, i, i, p, p, p]),
         "vf_pack_nchw": (i, [p, i, i, i, i, i, i, p, p]),

@@ -29,7 +29,13 @@
 namespace vf {
 
 constexpr int TC_BK = 64;
-constexpr int TC_THREADS = 320;     // 8 epilogue warps + TMA producer + MMA issuer
+#ifndef VF_TC_EPI_WARPS
+#define VF_TC_EPI_WARPS 8      // 16 was measured slower (conv class 5.48 vs 4.99 ms per step): the epilogue is not latency-bound per warp
+#endif
+constexpr int TC_EPI_WARPS = VF_TC_EPI_WARPS;          // epilogue warps: TC_EPI_WARPS/4 per TMEM lane quarter
+constexpr int TC_EPI_THREADS = 32 * TC_EPI_WARPS;
+constexpr int TC_NSUB = TC_EPI_WARPS / 4;
+constexpr int TC_THREADS = TC_EPI_THREADS + 64;   // + TMA producer + MMA issuer
 constexpr int TC_ABOX = 64;        // rows per A TMA box
 constexpr int TC_MAX_STAGES = 16;
 
@@ -63,6 +69,9 @@ struct TcParams {
   long long* dbg_out;   // test hook: per-CTA cycle counters of the MMA thread [grid][4] = total, wait A, wait B, wait acc
   int dbg;        // test hook (vf_debug_flags): bit0 no stats, bit1 no store, bit2 no unit work, bit3 no bias table
   int epi_tma;    // staged TMA epilogue enabled (bf16 row-contiguous output, block_n % 64 == 0)
+  // 1x1 layers that change the row order (the attention block's qkv / out projections and their data gradients):
+  int a_lines;    // >0: the source is stored PADDED but read as FLAT rows: A boxes are (64 ch, W, 64/W lines) of a 3D map
+  int epi_lines;  // >0: FLAT rows written to a PADDED output / residual: 32-row tiles are (64 ch, W, 32/W lines) of 3D maps
 };
 
 struct MmaCtx {
@@ -149,6 +158,18 @@ __device__ __forceinline__ void mma_issue_loop(const TcParams& p, const MmaCtx& 
   }
 }
 
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {   // one F2FP: {hi, lo} -> bf16x2, round to nearest even
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// one 16-byte vector reduction instead of four scalar REDs (sum, sum of squares of two adjacent channels)
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
 __device__ __forceinline__ unsigned long long global_timer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -180,7 +201,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t bar_accfull = base + 320, bar_accempty = base + 336;
   const uint32_t tmem_slot = base + 352;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + 352);
-  float* sm_bias_all = reinterpret_cast<float*>(gbase + 1024);             // 2 x [max_imgs][block_n] (one per epilogue group)
+  float* sm_bias_all = reinterpret_cast<float*>(gbase + 1024);             // [max_imgs][block_n] bias + embedding
   const uint32_t bias_bytes = ((uint32_t)(p.max_imgs * p.block_n * 4) + 1023u) & ~1023u;
   const uint32_t ringA = base + 1024 + 2 * bias_bytes;
   const uint32_t ringB = ringA + (uint32_t)p.a_stages * (uint32_t)p.a_stage_bytes;
@@ -193,16 +214,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.a_stages; ++s) { ptx::mbar_init(bar_afull + 8 * s, 1); ptx::mbar_init(bar_aempty + 8 * s, 1); }
     for (int s = 0; s < (p.b_resident ? 1 : p.b_stages); ++s) { ptx::mbar_init(bar_bfull + 8 * s, 1); ptx::mbar_init(bar_bempty + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(bar_accfull + 8 * s, 1); ptx::mbar_init(bar_accempty + 8 * s, 256); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(bar_accfull + 8 * s, 1); ptx::mbar_init(bar_accempty + 8 * s, TC_EPI_THREADS); }
     ptx::fence_barrier_init();
   }
-  if (warp == 8 && lane == 0) {
+  if (warp == TC_EPI_WARPS && lane == 0) {
     ptx::prefetch_tmap(&mapA0);
     ptx::prefetch_tmap(&mapB);
     if (p.n_seg > 1) ptx::prefetch_tmap(&mapA1);
     if (p.n_seg > 2) ptx::prefetch_tmap(&mapA2);
   }
-  if (warp == 9) {
+  if (warp == TC_EPI_WARPS + 1) {
     ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     ptx::tmem_relinquish();
   }
@@ -213,7 +234,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   pdl_wait();                                            // set-up above overlapped the previous kernel's tail
   if (stamps) stamps[1] = (long long)global_timer_ns();
 
-  if (warp == 8) {
+  if (warp == TC_EPI_WARPS) {
     // ===================== TMA producer =====================
     if (ptx::elect_one()) {
       int as = 0, bs = 0;
@@ -240,8 +261,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const uint32_t fa = bar_afull + 8 * as;
             ptx::mbar_arrive_expect_tx(fa, (uint32_t)nbox * TC_ABOX * 128);
             const uint32_t sa = ringA + (uint32_t)as * (uint32_t)p.a_stage_bytes;
-            for (int b = 0; b < nbox; ++b)
-              ptx::tma_load_2d(sa + b * (TC_ABOX * 128), mA, fa, ch * TC_BK, m0 - sg.halo + b * TC_ABOX);
+            if (p.a_lines) {
+              // FLAT row f of the GEMM = pixel (img, y, x) of a PADDED tensor: a 64-row box is 64/W whole image lines
+              for (int b = 0; b < nbox; ++b) {
+                const int f = m0 + b * TC_ABOX, img = f / p.geo.HW, y = (f - img * p.geo.HW) / p.geo.W;
+                ptx::tma_load_3d(sa + b * (TC_ABOX * 128), mA, fa, ch * TC_BK, 0, img * (p.geo.H + 1) + y);
+              }
+            } else {
+              for (int b = 0; b < nbox; ++b)
+                ptx::tma_load_2d(sa + b * (TC_ABOX * 128), mA, fa, ch * TC_BK, m0 - sg.halo + b * TC_ABOX);
+            }
             if (++as == a_stages) { as = 0; a_par ^= 1u; }
             if (stream_b) {
               int kcol = sg.koff + ch * TC_BK;
@@ -257,7 +286,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == TC_EPI_WARPS + 1) {
     // ===================== MMA issuer =====================
     if (ptx::elect_one()) {
       MmaCtx mc{bar_afull, bar_aempty, bar_bfull, bar_bempty, bar_accfull, bar_accempty, ringA, ringB, b_bytes, tmem_base};
@@ -286,7 +315,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // (+ a TMA-fetched residual panel) in a 128B-swizzled staging tile, the tile leaves by TMA store, and the GroupNorm
     // column sums are read back from the tile: no scattered LSU traffic.
     // Fallback (fp32 / qkv / stride-2 / non-contiguous rows): row-per-thread global accesses.
-    const int q = warp & 3, sub = warp >> 2;                     // sub in {0, 1}
+    const int q = warp & 3, sub = warp >> 2;                     // sub in [0, TC_NSUB)
     const int et = threadIdx.x;                                  // 0..255
     const int npanel = (p.block_n + 63) / 64;
     const int U = p.G * npanel;                                  // <= 4
@@ -305,26 +334,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const long long e_start = eprof ? clock64() : 0;
 #define VF_EP_BEGIN() do { if (eprof) et0 = clock64(); } while (0)
 #define VF_EP_END(i) do { if (eprof) ec[i] += clock64() - et0; } while (0)
+    // bias + embedding table of an item, one value per (image of the block, channel): max_imgs * block_n <= 1024 entries
+    constexpr int TAB_PER_THREAD = (1024 + TC_EPI_THREADS - 1) / TC_EPI_THREADS;
+    float tab_next[TAB_PER_THREAD];
+    auto load_table = [&](int it) {
+      const int nt = it / p.n_mblocks, mb = it - nt * p.n_mblocks;
+      const int img0 = div_small<false>(mb * BM, p.geo.in_padded ? p.geo.P : p.geo.HW, p.geo.rcp_rows), nn0 = nt * p.block_n;
+      const float rcp_bn = 1.0f / (float)p.block_n;
+#pragma unroll
+      for (int j = 0; j < TAB_PER_THREAD; ++j) {
+        const int i = et + j * TC_EPI_THREADS;
+        float v = 0.f;
+        if (i < p.max_imgs * p.block_n) {
+          const int li = div_small<false>(i, p.block_n, rcp_bn), n = nn0 + i - li * p.block_n;
+          const int img = img0 + li;
+          if (n < p.cout) {
+            if (p.bias) v += __ldg(p.bias + n);
+            if (p.emb && img < p.geo.images) v += __ldg(p.emb + (size_t)__ldg(p.img_row + img) * p.emb_ld + n);
+          }
+        }
+        tab_next[j] = v;
+      }
+    };
+    if ((int)blockIdx.x < p.n_items && !(p.dbg & 8)) load_table(blockIdx.x);
+    // (combining the GroupNorm sums per CTA in shared memory first was tried: shared-memory float atomics cost more than
+    // the global REDs they save, 12 -> 31 kclk per CTA in the statistics section)
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++k_idx) {
       const int set = k_idx & 1;
       const int n_tile = item / p.n_mblocks, m_blk = item - n_tile * p.n_mblocks;
       const int m0 = m_blk * BM, n0 = n_tile * p.block_n;
-      const int img_first = m0 / (p.geo.in_padded ? p.geo.P : p.geo.HW);
-      // bias + embedding rows of the images this block touches (built while the main loop runs)
+      const int rows_img = p.geo.in_padded ? p.geo.P : p.geo.HW;
+      const int img_first = div_small<false>(m0, rows_img, p.geo.rcp_rows);
+      // bias + embedding rows of the images this block touches.  The values were fetched into registers during the
+      // previous item (tab_next), so only the two barriers around the smem write are on this item's critical path.
       VF_EP_BEGIN();
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");     // previous item's readers are done
       if (!(p.dbg & 8)) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");     // previous item's readers are done
-      for (int i = et; i < p.max_imgs * p.block_n; i += 256) {
-        const int li = i / p.block_n, n = n0 + i - li * p.block_n;
-        const int img = img_first + li;
-        float v = 0.f;
-        if (n < p.cout) {
-          if (p.bias) v += __ldg(p.bias + n);
-          if (p.emb && img < p.geo.images) v += __ldg(p.emb + (size_t)__ldg(p.img_row + img) * p.emb_ld + n);
+#pragma unroll
+        for (int j = 0; j < TAB_PER_THREAD; ++j) {
+          const int i = et + j * TC_EPI_THREADS;
+          if (i < p.max_imgs * p.block_n) sm_bias[i] = tab_next[j];
         }
-        sm_bias[i] = v;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
+      if (!(p.dbg & 8)) {
+        const int item_next = item + gridDim.x;
+        if (item_next < p.n_items) load_table(item_next);
       }
       VF_EP_END(1);
 
@@ -332,17 +387,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       RowInfo ri{};
       long row_base = 0;
       bool contig = false;
+      auto unit_gc = [&](int u, int& g, int& c0) {       // u = g * npanel + panel, U <= 4: no integer division
+        g = 0;
+        int pu = u;
+        while (pu >= npanel) { pu -= npanel; ++g; }
+        c0 = pu * 64;
+      };
       auto prep_unit = [&](int u, bool issue) {
-        const int g = u / npanel, c0 = (u - g * npanel) * 64;
-        ri = decode_row(p.geo, m0 + g * 128 + q * 32 + lane);
-        row_base = __shfl_sync(0xffffffffu, ri.out_row, 0);
-        contig = p.epi_tma && __all_sync(0xffffffffu, ri.out_row == row_base + lane);
+        int g, c0;
+        unit_gc(u, g, c0);
+        const int f0 = m0 + g * 128 + q * 32;
+        ri = decode_row<true>(p.geo, f0 + lane);
+        if (p.epi_lines) {
+          // FLAT rows -> PADDED output: the warp's 32 rows are 32/W whole lines of one image (3D maps, see conv2d_tc)
+          row_base = (long)ri.img * (p.geo.H + 1) + __shfl_sync(0xffffffffu, ri.pix, 0) / p.geo.W;
+          row_base = __shfl_sync(0xffffffffu, (int)row_base, 0);
+          contig = p.epi_tma && f0 < p.geo.rows_total;
+        } else {
+          row_base = __shfl_sync(0xffffffffu, ri.out_row, 0);
+          contig = p.epi_tma && __all_sync(0xffffffffu, ri.out_row == row_base + lane);
+        }
+        if (p.qkv_split > 0 && n0 + c0 >= 2 * p.qkv_split) contig = false;   // V panels leave transposed (fallback path)
         if (issue && contig) {
           if (lane == 0) {
             if (has_res) {
               ptx::tma_store_wait_read<0>();               // the staging tile's previous store has been read out
               ptx::mbar_arrive_expect_tx(rbar, 4096);
-              ptx::tma_load_2d(stg, &mapRes, rbar, n0 + c0, (int)row_base);
+              if (p.epi_lines) ptx::tma_load_3d(stg, &mapRes, rbar, n0 + c0, 0, (int)row_base);
+              else ptx::tma_load_2d(stg, &mapRes, rbar, n0 + c0, (int)row_base);
             }
           }
           __syncwarp();
@@ -356,8 +428,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       ptx::mbar_wait(bar_accfull + 8 * set, (uint32_t)(k_idx >> 1) & 1u);
       ptx::tc_fence_after();
       VF_EP_END(2);
-      for (int u = sub; u < U && !(p.dbg & 4); u += 2) {
-        const int g = u / npanel, c0 = (u - g * npanel) * 64;
+      for (int u = sub; u < U && !(p.dbg & 4); u += TC_NSUB) {
+        int g, c0;
+        unit_gc(u, g, c0);
         const int width = min(64, p.block_n - c0);
         if (u != sub) prep_unit(u, true);
         const bool valid = ri.valid;
@@ -370,11 +443,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           uint8_t* tile = stg_g + lane * 128;                                // this thread's 128-byte row
           if (has_res) { ptx::mbar_wait(rbar, res_phase); res_phase ^= 1u; }
           VF_EP_BEGIN();
+          // TMEM round trips per unit: with two warps per scheduler all 64 columns are requested at once; with four the
+          // other warps hide the latency and two 32-column halves keep the register count under the 640-thread limit
+          constexpr int NHALF = TC_EPI_WARPS > 8 ? 2 : 1, LDS_PER = 4 / NHALF, SLOTS = 8 / NHALF;
+          const uint32_t sw = (uint32_t)(lane & 7);
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {                                   // two 32-column halves (register budget)
-            uint32_t rr[2][16];
-            ptx::tmem_ld16(trow + 32 * hh, rr[0]);
-            ptx::tmem_ld16(trow + 32 * hh + 16, rr[1]);
+          for (int hh = 0; hh < NHALF; ++hh) {
+            uint32_t rr[LDS_PER][16];
+#pragma unroll
+            for (int h4 = 0; h4 < LDS_PER; ++h4) ptx::tmem_ld16(trow + (uint32_t)(hh * (64 / NHALF) + 16 * h4), rr[h4]);
             if (hh == 0 && !has_res) {                                       // the previous store must have read the tile
               const long long ts = eprof ? clock64() : 0;
               if (lane == 0) ptx::tma_store_wait_read<0>();                  // out; overlaps with the TMEM load latency
@@ -382,32 +459,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               if (eprof) ec[4] += clock64() - ts;
             }
             ptx::tmem_ld_wait();
+            // one 16-byte slot = 8 channels; the residual / padding-row cases are separate straight-line loops so the
+            // common path is (2 LDS + 8 FADD + 4 F2FP + 1 STS) per slot without selects or branches
+            if (!valid) {
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {                                 // 8 channels = one 16-byte slot
-              const int j = hh * 4 + jj;
-              uint4* slot = reinterpret_cast<uint4*>(tile + ((j ^ (lane & 7)) << 4));
-              const float4 b0 = *reinterpret_cast<const float4*>(brow + j * 8), b1 = *reinterpret_cast<const float4*>(brow + j * 8 + 4);
-              float v[8];
+              for (int jj = 0; jj < SLOTS; ++jj)                             // padding rows are stored as zeros
+                *reinterpret_cast<uint4*>(tile + (((uint32_t)(hh * SLOTS + jj) ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+            } else if (has_res) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(rr[jj >> 1][(jj & 1) * 8 + e]);
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-              if (has_res) {
+              for (int jj = 0; jj < SLOTS; ++jj) {
+                const int j = hh * SLOTS + jj;
+                uint4* slot = reinterpret_cast<uint4*>(tile + (((uint32_t)j ^ sw) << 4));
+                const float4 b0 = *reinterpret_cast<const float4*>(brow + j * 8), b1 = *reinterpret_cast<const float4*>(brow + j * 8 + 4);
                 const uint4 rv = *slot;
-                const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(rb[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+                const uint32_t* acc = &rr[jj >> 1][(jj & 1) * 8];
+                uint4 o;
+                o.x = pack_bf16x2(__uint_as_float(acc[0]) + b0.x + bf16_lo(rv.x), __uint_as_float(acc[1]) + b0.y + bf16_hi(rv.x));
+                o.y = pack_bf16x2(__uint_as_float(acc[2]) + b0.z + bf16_lo(rv.y), __uint_as_float(acc[3]) + b0.w + bf16_hi(rv.y));
+                o.z = pack_bf16x2(__uint_as_float(acc[4]) + b1.x + bf16_lo(rv.z), __uint_as_float(acc[5]) + b1.y + bf16_hi(rv.z));
+                o.w = pack_bf16x2(__uint_as_float(acc[6]) + b1.z + bf16_lo(rv.w), __uint_as_float(acc[7]) + b1.w + bf16_hi(rv.w));
+                *slot = o;
               }
-              uint4 o;
-              __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+            } else {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) ob[e] = valid ? __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]) : __floats2bfloat162_rn(0.f, 0.f);
-              *slot = o;                                                     // padding rows are stored as zeros
+              for (int jj = 0; jj < SLOTS; ++jj) {
+                const int j = hh * SLOTS + jj;
+                const float4 b0 = *reinterpret_cast<const float4*>(brow + j * 8), b1 = *reinterpret_cast<const float4*>(brow + j * 8 + 4);
+                const uint32_t* acc = &rr[jj >> 1][(jj & 1) * 8];
+                uint4 o;
+                o.x = pack_bf16x2(__uint_as_float(acc[0]) + b0.x, __uint_as_float(acc[1]) + b0.y);
+                o.y = pack_bf16x2(__uint_as_float(acc[2]) + b0.z, __uint_as_float(acc[3]) + b0.w);
+                o.z = pack_bf16x2(__uint_as_float(acc[4]) + b1.x, __uint_as_float(acc[5]) + b1.y);
+                o.w = pack_bf16x2(__uint_as_float(acc[6]) + b1.z, __uint_as_float(acc[7]) + b1.w);
+                *reinterpret_cast<uint4*>(tile + (((uint32_t)j ^ sw) << 4)) = o;
+              }
             }
           }
           ptx::fence_proxy_async();
           __syncwarp();
           if (lane == 0 && !(p.dbg & 2)) {
-            ptx::tma_store_2d(&mapOut, stg, n0 + c0, (int)row_base);
+            if (p.epi_lines) ptx::tma_store_3d(&mapOut, stg, n0 + c0, 0, (int)row_base);
+            else ptx::tma_store_2d(&mapOut, stg, n0 + c0, (int)row_base);
             ptx::tma_store_commit();
           }
           VF_EP_END(3);
@@ -427,7 +519,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               }
               if (img_lo < p.geo.images) {
                 float* sp = p.stats + ((size_t)img_lo * p.cout + n0 + c0 + 2 * lane) * 2;
-                atomicAdd(sp, s0); atomicAdd(sp + 1, q0); atomicAdd(sp + 2, s1); atomicAdd(sp + 3, q1);
+                red_add_v4(sp, s0, q0, s1, q1);
               }
             } else {
               for (int im = img_lo; im <= img_hi; ++im) {
@@ -442,7 +534,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 }
                 if (im < p.geo.images) {
                   float* sp = p.stats + ((size_t)im * p.cout + n0 + c0 + 2 * lane) * 2;
-                  atomicAdd(sp, s0); atomicAdd(sp + 1, q0); atomicAdd(sp + 2, s1); atomicAdd(sp + 3, q1);
+                  red_add_v4(sp, s0, q0, s1, q1);
                 }
               }
             }
@@ -520,7 +612,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if (lane == 0) ptx::tma_store_wait_all<0>();     // staged stores must land before the CTA exits
   }
   __syncthreads();
-  if (warp == 9) {
+  if (warp == TC_EPI_WARPS + 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
@@ -610,7 +702,7 @@ static bool pick_tiling(const TcParams& p, int cout_pad, int sms, bool epi_tma, 
       c.a_stage_bytes = (int)align_up((size_t)BM + 2 * halo_max, TC_ABOX) * 128;
       c.max_imgs = (BM + rows_per_img - 1) / rows_per_img + 1;
       const size_t bias_bytes = align_up((size_t)c.max_imgs * bn * 4, 1024);
-      const size_t fixed = 1024 + 1024 + 2 * bias_bytes + (epi_tma ? 8 * 4096 : 0);   // + staging tiles of the TMA epilogue
+      const size_t fixed = 1024 + 1024 + 2 * bias_bytes + (epi_tma ? TC_EPI_WARPS * 4096 : 0);   // + staging tiles of the TMA epilogue
       const size_t bstage = (size_t)bn * 128;
       // pipeline depth is a hard requirement (both rings run across work items): >= 2 A slabs so the next slab
       // loads under the current one's MMAs, >= 4 weight tiles so a tap never waits for its own load
@@ -644,7 +736,7 @@ static bool pick_tiling(const TcParams& p, int cout_pad, int sms, bool epi_tma, 
       }
       // the epilogue of an item overlaps the next item's main loop; the two warps of a TMEM lane quarter take alternate
       // (row tile, 64-column panel) units, ~2600 clk each with the GroupNorm sums
-      const double epi = 1500.0 + 2600.0 * ((G * ((bn + 63) / 64) + 1) / 2);
+      const double epi = 1500.0 + 2600.0 * ((G * ((bn + 63) / 64) + TC_NSUB - 1) / TC_NSUB);
       double item = cyc > bytes / kIngestBytesPerClk ? cyc : bytes / kIngestBytesPerClk;
       if (epi > item) item = epi;
       const long items = (long)((p.geo.rows_total + BM - 1) / BM) * t;
@@ -661,7 +753,14 @@ int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
   VF_REQUIRE(a->dtype == VF_BF16, "vf_conv2d(tc): bf16 activations only");
   const int H = a->H, W = a->W;
   TcParams p{};
-  p.geo = make_geom(a->images, H, W, a->in_padded, a->out_padded, a->stride == 2);
+  // A 1x1 layer from a PADDED source to a FLAT output runs as a FLAT -> FLAT GEMM: TMA gathers the valid pixels (whole
+  // image lines) out of the padded tensor, so the rows map 1:1 onto the output and the staged TMA epilogue applies.
+  const bool gather = a->n_seg == 1 && a->ksize[0] == 1 && a->in_padded && !a->out_padded && a->stride != 2 && W <= TC_ABOX &&
+                      TC_ABOX % W == 0 && H % (TC_ABOX / W) == 0 && !(g_tc_dbg & 1024);
+  const int in_padded = gather ? 0 : a->in_padded;
+  p.a_lines = gather ? W : 0;
+  p.geo = make_geom(a->images, H, W, in_padded, a->out_padded, a->stride == 2);
+  VF_REQUIRE(p.geo.rows_total < (1 << 24), "vf_conv2d(tc): %d rows exceed the 2^24 limit of the epilogue's row arithmetic", p.geo.rows_total);
   VF_REQUIRE(!p.geo.stride2 || (H % 2 == 0 && W % 2 == 0), "vf_conv2d(tc): stride 2 needs even H, W");
   VF_REQUIRE(a->cout_pad % 16 == 0, "vf_conv2d(tc): cout_pad=%d not a multiple of 16", a->cout_pad);
 
@@ -677,13 +776,21 @@ int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
     k_total += sg.ntaps * C;
   }
   const bool out_f32 = a->out_dtype == VF_F32;
-  p.epi_tma = !out_f32 && !a->qkv_split && !p.geo.stride2 && a->out_padded && a->cout_pad % 64 == 0 && a->cout == a->cout_pad &&
-              (a->in_padded || W % 32 == 0);
+  // staged TMA epilogue: the 32 output rows of an epilogue warp must be one box of the output tensor map
+  //   PADDED -> PADDED, FLAT -> FLAT: rows map 1:1 (2D maps);   FLAT -> PADDED: W % 32 == 0 (part of one line, 2D maps) or
+  //   32 % W == 0 (32/W whole lines of one image, 3D maps: p.epi_lines)
+  const bool lines = !in_padded && a->out_padded && W % 32 != 0 && 32 % W == 0 && (H * W) % 32 == 0 && !(g_tc_dbg & 1024);
+  p.epi_lines = lines ? W : 0;
+  const bool layout_ok = (in_padded && a->out_padded) || (!in_padded && !a->out_padded && !(g_tc_dbg & 1024)) ||
+                         (!in_padded && a->out_padded && (W % 32 == 0 || lines));
+  p.epi_tma = !out_f32 && (!a->qkv_split || ((2 * a->qkv_split) % 64 == 0 && !(g_tc_dbg & 1024))) && !p.geo.stride2 && layout_ok &&
+              a->cout_pad % 64 == 0 && a->cout == a->cout_pad;
   TcTiling tl;
   VF_REQUIRE(pick_tiling(p, a->cout_pad, sm_count(), p.epi_tma != 0, &tl), "vf_conv2d(tc): no tiling for cout_pad=%d W=%d", a->cout_pad, W);
   p.block_n = tl.block_n; p.G = tl.G; p.a_stages = tl.a_stages; p.b_stages = tl.b_stages; p.a_stage_bytes = tl.a_stage_bytes;
   p.b_resident = tl.b_resident;
   p.max_imgs = tl.max_imgs;
+  VF_REQUIRE(p.max_imgs * p.block_n <= 1024, "vf_conv2d(tc): bias table of %d x %d entries exceeds the epilogue's registers", p.max_imgs, p.block_n);
   p.n_tiles_n = a->cout_pad / p.block_n;
   p.n_mblocks = cdiv(p.geo.rows_total, 128 * p.G);
   p.n_items = p.n_mblocks * p.n_tiles_n;
@@ -692,11 +799,24 @@ int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
   p.idesc = ptx::make_idesc_bf16(128, p.block_n, 0, 0);
 
   CUtensorMap maps[3];
+  // (channels, x, line) view of a PADDED tensor [images*P, ld] restricted to its valid pixels: pixel (img, y, x) is row
+  // (img*(H+1) + y + 1)*(W+1) + x + 1, i.e. line img*(H+1) + y of a view that starts W+2 rows into the tensor
+  auto encode_lines = [&](CUtensorMap* m, const void* ptr, int channels, int ld, int rows_per_box) {
+    const uint64_t dims[3] = {(uint64_t)channels, (uint64_t)W, (uint64_t)a->images * (H + 1) - 1};
+    const uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)(W + 1) * ld * 2};
+    const uint32_t box[3] = {64, (uint32_t)W, (uint32_t)(rows_per_box / W)};
+    return encode_bf16_map(m, reinterpret_cast<const __nv_bfloat16*>(ptr) + (size_t)(W + 2) * ld, 3, dims, strides, box);
+  };
   for (int s = 0; s < a->n_seg; ++s) {
-    const uint64_t dims[2] = {(uint64_t)a->src_c[s], (uint64_t)p.geo.rows_total};
-    const uint64_t strides[1] = {(uint64_t)a->src_c[s] * 2};
-    const uint32_t box[2] = {TC_BK, TC_ABOX};
-    int rc = encode_bf16_map(&maps[s], a->src[s], 2, dims, strides, box);
+    int rc;
+    if (gather) {
+      rc = encode_lines(&maps[s], a->src[s], a->src_c[s], a->src_c[s], TC_ABOX);
+    } else {
+      const uint64_t dims[2] = {(uint64_t)a->src_c[s], (uint64_t)p.geo.rows_total};
+      const uint64_t strides[1] = {(uint64_t)a->src_c[s] * 2};
+      const uint32_t box[2] = {TC_BK, TC_ABOX};
+      rc = encode_bf16_map(&maps[s], a->src[s], 2, dims, strides, box);
+    }
     if (rc) return rc;
   }
   for (int s = a->n_seg; s < 3; ++s) maps[s] = maps[0];
@@ -722,8 +842,15 @@ int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
   VF_REQUIRE(!a->stats || (!p.out_f32 && !a->qkv_split), "vf_conv2d(tc): fused statistics need a plain bf16 output");
 
   CUtensorMap mapOut = mapB, mapRes = mapB;
-  if (p.epi_tma) {
-    const uint64_t out_rows = (uint64_t)a->images * (H + 1) * (W + 1);
+  if (p.epi_tma && lines) {
+    int rc = encode_lines(&mapOut, a->out, a->cout, a->out_ld, 32);
+    if (rc) return rc;
+    if (a->residual) {
+      rc = encode_lines(&mapRes, a->residual, a->cout, a->cout, 32);
+      if (rc) return rc;
+    }
+  } else if (p.epi_tma) {
+    const uint64_t out_rows = a->out_padded ? (uint64_t)a->images * (H + 1) * (W + 1) : (uint64_t)a->images * H * W;
     const uint32_t box[2] = {64, 32};
     {
       const uint64_t dims[2] = {(uint64_t)a->cout, out_rows};
@@ -746,9 +873,9 @@ int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
   VF_CUDA(attr_err);
   const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
   if (g_tc_dbg & 256)
-    fprintf(stderr, "[vf tc] rows %d W %d cout %d segs %d ktot %d | bn %d G %d a_stages %d (%d B) b_stages %d resident %d smem %zu items %d grid %d epi_tma %d\n",
+    fprintf(stderr, "[vf tc] rows %d W %d cout %d segs %d ktot %d | bn %d G %d a_stages %d (%d B) b_stages %d resident %d smem %zu items %d grid %d epi_tma %d a_lines %d epi_lines %d\n",
             p.geo.rows_total, W, a->cout, a->n_seg, k_total, p.block_n, p.G, p.a_stages, p.a_stage_bytes, p.b_stages, p.b_resident, tl.smem,
-            p.n_items, grid, p.epi_tma);
+            p.n_items, grid, p.epi_tma, p.a_lines, p.epi_lines);
   VF_CUDA(launch_pdl(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), tl.smem, st, maps[0], maps[1], maps[2], mapB, mapOut, mapRes, p));
   VF_LAUNCH_CHECK();
   return VF_OK;

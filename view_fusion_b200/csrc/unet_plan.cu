@@ -9,6 +9,7 @@
 //   * FeatureWiseAffine (:160-177): all 30 Linear layers are one table computed per sample by vf_embed and added
 //     in conv1's epilogue; conv bias, identity residual and the attention residual (:277) are epilogue adds;
 //   * the first 3x3 conv runs as a K=64 GEMM over the im2col rows written by vf_pack_views.
+#include <array>
 #include <map>
 #include <string>
 #include <vector>
@@ -96,8 +97,11 @@ struct vf_unet {
   std::vector<uint8_t> pack_cache, pack_t_cache, unpack_cache;            // job tables as last uploaded (re-uploaded only when they change)
   bool packed_t = false;
   bool profiling = false;
+  bool stash = true;             // the forward also produces what only the backward reads (V^T of the attention blocks)
+  bool last_stash = true;
   std::vector<cudaEvent_t> ev;
   std::vector<int> ev_kind;      // kind of the launch between ev[i] and ev[i+1]
+  std::vector<std::array<int, 6>> ev_desc;   // images, H, C_in (K total for conv), C_out, ksize, stride of that launch
   int ev_used = 0;
 };
 
@@ -192,10 +196,17 @@ static void prof_mark(vf_unet* u, cudaStream_t st, int kind) {
     if (cudaEventCreate(&e) != cudaSuccess) return;
     u->ev.push_back(e);
     u->ev_kind.push_back(-1);
+    u->ev_desc.push_back({0, 0, 0, 0, 0, 0});
   }
   cudaEventRecord(u->ev[u->ev_used], st);
   u->ev_kind[u->ev_used] = kind;
+  u->ev_desc[u->ev_used] = {0, 0, 0, 0, 0, 0};
   ++u->ev_used;
+}
+
+// shape of the launch that the last prof_mark opened (per-launch table of vf_unet_profile_launches)
+static void prof_describe(vf_unet* u, int images, int H, int cin, int cout, int ksize, int stride) {
+  if (u && u->profiling && u->ev_used > 0) u->ev_desc[u->ev_used - 1] = {images, H, cin, cout, ksize, stride};
 }
 
 #define VF_RUN(ex, kind, call)                                       \
@@ -575,6 +586,9 @@ static void conv_call(Exec& ex, vf_unet* u, vf_conv_args& a, const ConvMeta& m) 
   if (a.out_dtype < 0) a.out_dtype = u->dtype;
   VF_RUN(ex, K_CONV, vf_conv2d(&a, (vf_stream)ex.st));
   if (!ex.dry) {
+    int ktot = 0;
+    for (int i = 0; i < a.n_seg; ++i) ktot += a.ksize[i] * a.ksize[i] * a.src_c[i];
+    prof_describe(ex.u, a.images, a.H, ktot, a.cout, a.ksize[0], a.stride);
     vf_unet::TapeOp t{};
     t.kind = 0; t.conv = a;
     for (int i = 0; i < 3; ++i) { t.w_idx[i] = m.w_idx[i]; t.c_off[i] = m.c_off[i]; t.cin_total[i] = m.cin_total[i]; t.wt_off[i] = m.wt_off[i]; }
@@ -609,6 +623,7 @@ static Act gn_block(Exec& ex, vf_unet* u, int images, const Act& x, const Act* s
   VF_RUN(ex, K_GN_APPLY, vf_gn_apply(x.p, x.C, s0, ld0, skip ? skip->p : nullptr, C1, s1, ld1, u->dtype, images, x.H, x.W, u->cfg.norm_groups,
                                      u->master[gw], u->master[gb], swish ? 1 : 0, y.p, (vf_stream)ex.st));
   if (!ex.dry) {
+    prof_describe(ex.u, images, x.H, C, C, 0, 0);
     vf_unet::TapeOp t{};
     t.kind = 1;
     t.gsrc0 = x.p; t.gC0 = x.C; t.gst0 = s0; t.gld0 = ld0;
@@ -666,14 +681,17 @@ static Act run_resblock(Exec& ex, vf_unet* u, const uint8_t* pk, int images, con
   const int C = b.cout;
   Act n = gn_block(ex, u, images, out, nullptr, b.an_w, b.an_b, false);
   void* qkv = ex.alloc((size_t)images * HW * 3 * C * es);
+  // V^T feeds the attention backward only; without it (inference) the forward kernel reads V row-major from qkv and the
+  // whole qkv projection leaves through the staged TMA epilogue.  The workspace is always sized for the stash.
   void* vt = u->dtype == VF_BF16 ? ex.alloc((size_t)images * HW * C * es) : nullptr;
+  if (!ex.dry && !u->stash) vt = nullptr;
   {
     vf_conv_args a = conv_args_init();
     a.images = images; a.H = x.H; a.W = x.W; a.n_seg = 1;
     a.src[0] = n.p; a.src_c[0] = C; a.ksize[0] = 1;
     a.weight = pk + b.wqkv; a.cout = 3 * C; a.cout_pad = 3 * C;
     a.out = qkv; a.out_ld = 3 * C; a.out_padded = 0;          // attention works on FLAT token rows
-    if (u->dtype == VF_BF16) { a.qkv_split = C; a.out_vt = vt; }
+    if (vt) { a.qkv_split = C; a.out_vt = vt; }
     ConvMeta m;
     m.w_idx[0] = b.qkv_w; m.cin_total[0] = C; m.wt_off[0] = b.wtqkv;
     conv_call(ex, u, a, m);
@@ -836,10 +854,17 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_forward(vf_unet* u
   u->last_level = level; u->last_angle = angle; u->last_img_row = img_row; u->last_rows = rows; u->last_x0 = x0; u->last_out = out;
   ex.u = u;
   u->ev_used = 0;
+  u->last_stash = u->stash;
   int rc = walk(u, ex, reinterpret_cast<const uint8_t*>(packed), images, x0, level, angle, rows, img_row, out);
   if (u->profiling) prof_mark(u, ex.st, -1);
   u->launches = ex.launches;
   return rc;
+}
+
+extern "C" __attribute__((visibility("default"))) int vf_unet_set_stash(vf_unet* u, int on) {
+  VF_REQUIRE(u, "vf_unet_set_stash: null plan");
+  u->stash = on != 0;
+  return VF_OK;
 }
 
 extern "C" __attribute__((visibility("default"))) int vf_unet_set_profiling(vf_unet* u, int on) {
@@ -866,6 +891,21 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_profile_read(vf_un
     counts_host[k] += 1;
   }
   return VF_OK;
+}
+
+// Per-launch table of the last profiled forward: ms[i], kind[i] (kernel class) and desc[6*i..] = images, H, C_in (conv:
+// K total), C_out, ksize, stride.  Returns the number of launches (<= cap written), negative on error.
+extern "C" __attribute__((visibility("default"))) int vf_unet_profile_launches(vf_unet* u, float* ms_host, int* kind_host, int* desc_host, int cap) {
+  VF_REQUIRE(u && ms_host && kind_host && desc_host, "vf_unet_profile_launches: null args");
+  if (u->ev_used < 2) return 0;
+  VF_CUDA(cudaEventSynchronize(u->ev[u->ev_used - 1]));
+  int n = 0;
+  for (int i = 0; i + 1 < u->ev_used && n < cap; ++i, ++n) {
+    VF_CUDA(cudaEventElapsedTime(&ms_host[n], u->ev[i], u->ev[i + 1]));
+    kind_host[n] = u->ev_kind[i];
+    for (int j = 0; j < 6; ++j) desc_host[6 * n + j] = u->ev_desc[i][j];
+  }
+  return n;
 }
 
 extern "C" __attribute__((visibility("default"))) int vf_unet_read_tap(vf_unet* u, const void* workspace, const char* name, float* dst, int64_t* chw, vf_stream stream) {
@@ -1494,6 +1534,7 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_backward(vf_unet* 
                                                                      const float* grad_out8, float* const* param_grads_host, vf_stream stream) {
   VF_REQUIRE(u && packed_t && grad_workspace && grad_out8 && param_grads_host, "vf_unet_backward: null args");
   if (u->tape.empty() || !u->packed_t) { set_error("vf_unet_backward: needs a forward and vf_unet_pack_weights_t first"); return VF_ERR_STATE; }
+  if (!u->last_stash) { set_error("vf_unet_backward: the last forward ran with vf_unet_set_stash(0) (inference mode)"); return VF_ERR_STATE; }
   for (size_t i = 0; i < u->params.size(); ++i) VF_REQUIRE(param_grads_host[i], "vf_unet_backward: gradient %zu (%s) is null", i, u->params[i].name.c_str());
   {
     BwdCtx dry{u, nullptr, nullptr};

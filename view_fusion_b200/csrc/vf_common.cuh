@@ -147,6 +147,7 @@ struct RowGeom {
   int H, W, HW, W1, P, images;
   int rows_total;                    // GEMM M: images*P (PADDED sources) or images*H*W (FLAT)
   int in_padded, out_padded, stride2;
+  float rcp_rows, rcp_w;             // 1 / rows per image (P or HW), 1 / line length (W+1 or W): exact small-integer division
 };
 struct RowInfo {
   int img, pix;      // pix = y*Wo + x at the OUTPUT resolution
@@ -158,22 +159,36 @@ inline RowGeom make_geom(int images, int H, int W, int in_padded, int out_padded
   g.H = H; g.W = W; g.HW = H * W; g.W1 = W + 1; g.P = (H + 1) * (W + 1); g.images = images;
   g.in_padded = in_padded; g.out_padded = out_padded; g.stride2 = stride2;
   g.rows_total = images * (in_padded ? g.P : g.HW);
+  g.rcp_rows = 1.0f / (float)(in_padded ? g.P : g.HW);
+  g.rcp_w = 1.0f / (float)(in_padded ? g.W1 : g.W);
   return g;
 }
+// n / d for 0 <= n < 2^24 through the float reciprocal (|error| < 1 before truncation, one correction step): a few
+// instructions instead of the ~100-cycle integer division sequence on the epilogue's critical path.
+template <bool kChecked = true>
+__device__ __forceinline__ int div_small(int n, int d, float rcp) {
+  if (kChecked && n >= (1 << 24)) return n / d;
+  int q = __float2int_rz(__int2float_rn(n) * rcp);
+  const int r = n - q * d;
+  q += (r >= d) - (r < 0);
+  return q;
+}
+// kFast: the caller guarantees rows_total < 2^24 (no integer-division fallback is compiled in)
+template <bool kFast = false>
 __device__ __forceinline__ RowInfo decode_row(const RowGeom& p, int m) {
   RowInfo r;
   r.valid = m < p.rows_total;
   int img = 0, y = 0, x = 0;
   if (p.in_padded) {
-    img = m / p.P;
+    img = div_small<!kFast>(m, p.P, p.rcp_rows);
     const int rem = m - img * p.P;
-    const int yy = rem / p.W1, xx = rem - yy * p.W1;
+    const int yy = div_small<!kFast>(rem, p.W1, p.rcp_w), xx = rem - yy * p.W1;
     r.valid = r.valid && yy >= 1 && xx >= 1;
     y = yy - 1; x = xx - 1;
   } else {
-    img = m / p.HW;
+    img = div_small<!kFast>(m, p.HW, p.rcp_rows);
     const int rem = m - img * p.HW;
-    y = rem / p.W; x = rem - y * p.W;
+    y = div_small<!kFast>(rem, p.W, p.rcp_w); x = rem - y * p.W;
   }
   int Wo = p.W, Ho = p.H;
   if (p.stride2) {

@@ -116,6 +116,7 @@ class UNet(nn.Module):
         self._ws = None
         self._ws_images = 0
         self._gws = None
+        self._stash = True
         self._gws_images = -1
         self._flat_grad = None
 
@@ -254,12 +255,18 @@ class UNet(nn.Module):
         return _lib.require_device().vf_unet_k0(self._native())
 
     def run_packed(self, x0: torch.Tensor, images: int, level: torch.Tensor, angle: torch.Tensor, img_row: torch.Tensor,
-                   out: torch.Tensor) -> None:
+                   out: torch.Tensor, stash=None) -> None:
         """Enqueue one UNet forward on pre-packed input (the sampler / trainer entry)."""
         lib = _lib.require_device()
         h = self._native()
         packed = self.packed_weights()
         ws = self.workspace(images)
+        if stash is None:
+            stash = torch.is_grad_enabled()          # under no_grad nothing extra is kept for vf_unet_backward
+        stash = bool(stash)
+        if stash != self._stash:
+            _lib.check(lib.vf_unet_set_stash(h, int(stash)), "vf_unet_set_stash")
+            self._stash = stash
         _lib.check(lib.vf_unet_forward(h, packed.data_ptr(), ws.data_ptr(), ws.numel(), images, x0.data_ptr(), level.data_ptr(),
                                        angle.data_ptr(), level.numel(), img_row.data_ptr(), out.data_ptr(), _lib.stream_handle()),
                    "vf_unet_forward")
@@ -278,6 +285,17 @@ class UNet(nn.Module):
         cnt = (C.c_int * 6)()
         _lib.check(_lib.load().vf_unet_profile_read(self._native(), ms, cnt), "vf_unet_profile_read")
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
+
+    def profile_launches(self, cap: int = 1024) -> list:
+        """[(class, ms, images, H, C_in_or_K, C_out, ksize, stride)] per launch of the last profiled forward."""
+        ms = (C.c_float * cap)()
+        kind = (C.c_int * cap)()
+        desc = (C.c_int * (6 * cap))()
+        n = _lib.load().vf_unet_profile_launches(self._native(), ms, kind, desc, cap)
+        if n < 0:
+            _lib.check(n, "vf_unet_profile_launches")
+        return [(self.KERNEL_CLASSES[kind[j]] if 0 <= kind[j] < len(self.KERNEL_CLASSES) else "other", float(ms[j]),
+                 *[int(desc[6 * j + q]) for q in range(6)]) for j in range(n)]
 
     def read_tap(self, name: str) -> torch.Tensor:
         """Output activation of module `name` in the last forward, as NCHW fp32 (parity debugging)."""

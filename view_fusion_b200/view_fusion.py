@@ -309,7 +309,7 @@ class _TrainStep(torch.autograd.Function):
                    "vf_pack_views")
         unet._last_images = plan.images
         ang = angle.reshape(-1).contiguous()
-        unet.run_packed(plan.x0, plan.images, sample_gammas, ang, plan.img_sample, plan.out8)
+        unet.run_packed(plan.x0, plan.images, sample_gammas, ang, plan.img_sample, plan.out8, stash=True)   # grad mode is off in here
         loss = torch.zeros(1, dtype=torch.float32, device=y_0.device)
         grad8 = torch.empty_like(plan.out8)
         weighting = int(model.weighting_train)
