@@ -282,6 +282,27 @@ def test_conv_bf16_padded_to_flat_gathered_source(lib, R, S, Cc):
     assert rel(ops.from_nhwc(out2, R, S, S).cpu(), ref + res) < 4e-3
 
 
+@pytest.mark.parametrize("R,S,Cc", [(3, 32, 64), (40, 16, 128), (150, 8, 192), (2, 4, 64)])
+def test_conv_bf16_stride2_gathers_pixel_phases(lib, R, S, Cc):
+    """Downsample (3x3, stride 2, unet.py:195-201) over the OUTPUT pixels only: per-tap TMA gathers of the input's pixel
+    phases, zero halo from out-of-bounds fill (NaN padding rows of the source must not leak), fused GroupNorm sums.
+    S is the OUTPUT size; (2, 4, 64) does not fit the gather (4x4 outputs) and checks the full-resolution fallback."""
+    from view_fusion_b200 import ops
+    torch.manual_seed(13)
+    dtype = torch.bfloat16
+    rnd = lambda *s: bf16r(torch.randn(*s))
+    x, w, bias = rnd(R, Cc, 2 * S, 2 * S), bf16r(rnd(Cc, Cc, 3, 3) / math.sqrt(9 * Cc)), torch.randn(Cc)
+    ref = F.conv2d(x, w, bias, stride=2, padding=1)
+    wp = ops.pack_conv_weight(w.cuda(), dtype)
+    gathers = S >= 8
+    src = ops.to_padded(x, dtype, fill=float("nan") if gathers else 0.0).cuda()
+    out, stats = ops.conv2d([src], [3], wp, R, 2 * S, 2 * S, Cc, stride=2, bias=bias.cuda(), want_stats=True)
+    got = ops.from_padded(out, R, S, S).cpu()
+    assert rel(got, ref) < 4e-3
+    want = torch.stack([got.sum(dim=(2, 3)), (got * got).sum(dim=(2, 3))], dim=-1)
+    assert rel(stats, want) < 1e-5
+
+
 def test_conv_bf16_final_layer_fp32_out(lib):
     from view_fusion_b200 import ops
     R, S, segs, cout = 2, 16, [(64, 3)], 6

@@ -72,6 +72,10 @@ struct TcParams {
   // 1x1 layers that change the row order (the attention block's qkv / out projections and their data gradients):
   int a_lines;    // >0: the source is stored PADDED but read as FLAT rows: A boxes are (64 ch, W, 64/W lines) of a 3D map
   int epi_lines;  // >0: FLAT rows written to a PADDED output / residual: 32-row tiles are (64 ch, W, 32/W lines) of 3D maps
+  // stride-2 3x3 (Downsample): the GEMM runs over the OUTPUT pixels only.  K chunk = (tap, 64 channels); its A tile is
+  // gathered by TMA from the pixel phase (row parity, column parity) of the PADDED input the tap reads: four 4D maps
+  // (channels, x/2, y/2, image), tap shifts of -1 become out-of-bounds coordinates that TMA fills with zeros.
+  int s2_cchunks; // >0: Cin / 64 in that mode
 };
 
 struct MmaCtx {
@@ -179,6 +183,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0,
                                                                 const __grid_constant__ CUtensorMap mapA1,
                                                                 const __grid_constant__ CUtensorMap mapA2,
+                                                                const __grid_constant__ CUtensorMap mapA3,
                                                                 const __grid_constant__ CUtensorMap mapB,
                                                                 const __grid_constant__ CUtensorMap mapOut,
                                                                 const __grid_constant__ CUtensorMap mapRes,
@@ -221,7 +226,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     ptx::prefetch_tmap(&mapA0);
     ptx::prefetch_tmap(&mapB);
     if (p.n_seg > 1) ptx::prefetch_tmap(&mapA1);
-    if (p.n_seg > 2) ptx::prefetch_tmap(&mapA2);
+    if (p.n_seg > 2 || p.s2_cchunks) { ptx::prefetch_tmap(&mapA1); ptx::prefetch_tmap(&mapA2); }
+    if (p.s2_cchunks) ptx::prefetch_tmap(&mapA3);
   }
   if (warp == TC_EPI_WARPS + 1) {
     ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -261,7 +267,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const uint32_t fa = bar_afull + 8 * as;
             ptx::mbar_arrive_expect_tx(fa, (uint32_t)nbox * TC_ABOX * 128);
             const uint32_t sa = ringA + (uint32_t)as * (uint32_t)p.a_stage_bytes;
-            if (p.a_lines) {
+            if (p.s2_cchunks) {
+              // output pixel (y, x), tap (kh, kw) reads input pixel (2y + kh - 1, 2x + kw - 1): phase (kh != 1, kw != 1),
+              // shifted by -1 in the half-resolution grid when kh == 0 / kw == 0
+              const int tap = ch / p.s2_cchunks, cc = ch - tap * p.s2_cchunks;
+              const int kh = tap / 3, kw = tap - 3 * kh;
+              const int ph = (kh != 1 ? 2 : 0) + (kw != 1 ? 1 : 0);
+              const CUtensorMap* mP = ph == 0 ? &mapA0 : (ph == 1 ? &mapA1 : (ph == 2 ? &mapA2 : &mapA3));
+              for (int b = 0; b < nbox; ++b) {
+                const int f = m0 + b * TC_ABOX, img = f / p.geo.HW, y = (f - img * p.geo.HW) / p.geo.W;
+                ptx::tma_load_4d(sa + b * (TC_ABOX * 128), mP, fa, cc * TC_BK, kw == 0 ? -1 : 0, y - (kh == 0 ? 1 : 0), img);
+              }
+            } else if (p.a_lines) {
               // FLAT row f of the GEMM = pixel (img, y, x) of a PADDED tensor: a 64-row box is 64/W whole image lines
               for (int b = 0; b < nbox; ++b) {
                 const int f = m0 + b * TC_ABOX, img = f / p.geo.HW, y = (f - img * p.geo.HW) / p.geo.W;
@@ -751,15 +768,20 @@ static bool pick_tiling(const TcParams& p, int cout_pad, int sms, bool epi_tma, 
 
 int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
   VF_REQUIRE(a->dtype == VF_BF16, "vf_conv2d(tc): bf16 activations only");
-  const int H = a->H, W = a->W;
   TcParams p{};
+  // Downsample (3x3, stride 2): GEMM rows are the output pixels (FLAT order at half resolution), see TcParams::s2_cchunks
+  const int Wo2 = a->W / 2, Ho2 = a->H / 2;
+  const bool s2 = a->stride == 2 && a->n_seg == 1 && a->ksize[0] == 3 && a->in_padded && a->out_padded && a->H % 2 == 0 && a->W % 2 == 0 &&
+                  Wo2 <= TC_ABOX && TC_ABOX % Wo2 == 0 && Ho2 % (TC_ABOX / Wo2) == 0 && a->src_c[0] % TC_BK == 0 && !(g_tc_dbg & 1024);
+  const int H = s2 ? Ho2 : a->H, W = s2 ? Wo2 : a->W;      // resolution of the GEMM rows
   // A 1x1 layer from a PADDED source to a FLAT output runs as a FLAT -> FLAT GEMM: TMA gathers the valid pixels (whole
   // image lines) out of the padded tensor, so the rows map 1:1 onto the output and the staged TMA epilogue applies.
   const bool gather = a->n_seg == 1 && a->ksize[0] == 1 && a->in_padded && !a->out_padded && a->stride != 2 && W <= TC_ABOX &&
                       TC_ABOX % W == 0 && H % (TC_ABOX / W) == 0 && !(g_tc_dbg & 1024);
-  const int in_padded = gather ? 0 : a->in_padded;
+  const int in_padded = (gather || s2) ? 0 : a->in_padded;
   p.a_lines = gather ? W : 0;
-  p.geo = make_geom(a->images, H, W, in_padded, a->out_padded, a->stride == 2);
+  p.s2_cchunks = s2 ? a->src_c[0] / TC_BK : 0;
+  p.geo = make_geom(a->images, H, W, in_padded, a->out_padded, a->stride == 2 && !s2);
   VF_REQUIRE(p.geo.rows_total < (1 << 24), "vf_conv2d(tc): %d rows exceed the 2^24 limit of the epilogue's row arithmetic", p.geo.rows_total);
   VF_REQUIRE(!p.geo.stride2 || (H % 2 == 0 && W % 2 == 0), "vf_conv2d(tc): stride 2 needs even H, W");
   VF_REQUIRE(a->cout_pad % 16 == 0, "vf_conv2d(tc): cout_pad=%d not a multiple of 16", a->cout_pad);
@@ -774,6 +796,9 @@ int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
     sg.C = C; sg.nchunks = C / TC_BK; sg.ntaps = a->ksize[s] * a->ksize[s]; sg.koff = k_total;
     sg.halo = a->ksize[s] == 3 ? W + 2 : 0;
     k_total += sg.ntaps * C;
+    if (s2) {   // nine taps x C/64 chunks, each with its own gathered A tile: a 1x1-like segment over K = 9C ([tap][cin] weight order)
+      sg.C = 9 * C; sg.nchunks = 9 * C / TC_BK; sg.ntaps = 1; sg.halo = 0;
+    }
   }
   const bool out_f32 = a->out_dtype == VF_F32;
   // staged TMA epilogue: the 32 output rows of an epilogue warp must be one box of the output tensor map
@@ -798,7 +823,7 @@ int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
   while (p.tmem_cols < 2 * p.G * p.block_n) p.tmem_cols *= 2;
   p.idesc = ptx::make_idesc_bf16(128, p.block_n, 0, 0);
 
-  CUtensorMap maps[3];
+  CUtensorMap maps[3], maps4[4];
   // (channels, x, line) view of a PADDED tensor [images*P, ld] restricted to its valid pixels: pixel (img, y, x) is row
   // (img*(H+1) + y + 1)*(W+1) + x + 1, i.e. line img*(H+1) + y of a view that starts W+2 rows into the tensor
   auto encode_lines = [&](CUtensorMap* m, const void* ptr, int channels, int ld, int rows_per_box) {
@@ -807,7 +832,20 @@ int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
     const uint32_t box[3] = {64, (uint32_t)W, (uint32_t)(rows_per_box / W)};
     return encode_bf16_map(m, reinterpret_cast<const __nv_bfloat16*>(ptr) + (size_t)(W + 2) * ld, 3, dims, strides, box);
   };
-  for (int s = 0; s < a->n_seg; ++s) {
+  if (s2) {
+    // phase (py, px): input pixels (2*yh + py, 2*xh + px) = PADDED rows base + img*P + yh*2(Win+1) + xh*2
+    const int Win = a->W, Hin = a->H, C = a->src_c[0];
+    for (int ph = 0; ph < 4; ++ph) {
+      const int py = ph >> 1, px = ph & 1;
+      const uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wo2, (uint64_t)Ho2, (uint64_t)a->images};
+      const uint64_t strides[3] = {(uint64_t)2 * C * 2, (uint64_t)2 * (Win + 1) * C * 2, (uint64_t)(Hin + 1) * (Win + 1) * C * 2};
+      const uint32_t box[4] = {TC_BK, (uint32_t)Wo2, (uint32_t)(TC_ABOX / Wo2), 1};
+      const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(a->src[0]) + ((size_t)(py + 1) * (Win + 1) + px + 1) * C;
+      int rc = encode_bf16_map(&maps4[ph], base, 4, dims, strides, box);
+      if (rc) return rc;
+    }
+  }
+  for (int s = 0; s < a->n_seg && !s2; ++s) {
     int rc;
     if (gather) {
       rc = encode_lines(&maps[s], a->src[s], a->src_c[s], a->src_c[s], TC_ABOX);
@@ -819,7 +857,8 @@ int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
     }
     if (rc) return rc;
   }
-  for (int s = a->n_seg; s < 3; ++s) maps[s] = maps[0];
+  for (int s = a->n_seg; s < 3 && !s2; ++s) maps[s] = maps[0];
+  if (s2) { maps[0] = maps4[0]; maps[1] = maps4[1]; maps[2] = maps4[2]; } else maps4[3] = maps[0];
   CUtensorMap mapB;
   {
     const uint64_t dims[2] = {(uint64_t)k_total, (uint64_t)a->cout_pad};
@@ -876,7 +915,7 @@ int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
     fprintf(stderr, "[vf tc] rows %d W %d cout %d segs %d ktot %d | bn %d G %d a_stages %d (%d B) b_stages %d resident %d smem %zu items %d grid %d epi_tma %d a_lines %d epi_lines %d\n",
             p.geo.rows_total, W, a->cout, a->n_seg, k_total, p.block_n, p.G, p.a_stages, p.a_stage_bytes, p.b_stages, p.b_resident, tl.smem,
             p.n_items, grid, p.epi_tma, p.a_lines, p.epi_lines);
-  VF_CUDA(launch_pdl(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), tl.smem, st, maps[0], maps[1], maps[2], mapB, mapOut, mapRes, p));
+  VF_CUDA(launch_pdl(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), tl.smem, st, maps[0], maps[1], maps[2], maps4[3], mapB, mapOut, mapRes, p));
   VF_LAUNCH_CHECK();
   return VF_OK;
 }

@@ -17,6 +17,11 @@
 #include "vf_common.cuh"
 
 namespace vf {
+extern int g_force_simt_flag;     // vf_api.cu: CUDA-core cross-check mode
+int tc_debug_flags();             // k_gemm_tc.cu: test hooks of the tcgen05 convolution
+}
+
+namespace vf {
 
 int pack_identity(void* dst, int dtype, int n_rows, int k_total, int k_off, cudaStream_t st);
 
@@ -756,8 +761,11 @@ static int walk(vf_unet* u, Exec& ex, const uint8_t* pk, int images, const void*
       x = run_resblock(ex, u, pk, images, u->blocks[l.rb], x, nullptr, emb, img_row);
     } else {   // Downsample: conv3x3 stride 2                                              unet.py:195-201
       Act y = new_act(ex, u, images, l.c, x.H / 2, x.W / 2, true);
-      // x is a raw convolution output: its padding rows were never written, and this 3x3 reads them as the zero halo
-      VF_RUN(ex, K_UPSAMPLE, vf_zero_padding(x.p, u->dtype, images, x.H, x.W, x.C, (vf_stream)ex.st));
+      // x is a raw convolution output whose padding rows were never written.  The tcgen05 stride-2 path gathers pixel
+      // phases by TMA and gets its zero halo from out-of-bounds fill, so only the CUDA-core path and the training
+      // backward (the weight gradient reads x with its halo) need real zeros there.
+      if (u->dtype != VF_BF16 || u->stash || vf::tc_debug_flags() != 0 || vf::g_force_simt_flag)
+        VF_RUN(ex, K_UPSAMPLE, vf_zero_padding(x.p, u->dtype, images, x.H, x.W, x.C, (vf_stream)ex.st));
       vf_conv_args a = conv_args_init();
       a.images = images; a.H = x.H; a.W = x.W; a.n_seg = 1; a.stride = 2;
       a.src[0] = x.p; a.src_c[0] = l.c; a.ksize[0] = 3;
