@@ -131,6 +131,7 @@ struct GnBwdParams {
   float* red;            // [images][C][2]
   float* dgamma; float* dbeta;
   void* dx0; int acc0; void* dx1; int acc1;
+  GnColsum cs;           // optional (cs.db / cs.demb non-null): closed-form column sums of dx0 (single-source case)
 };
 
 // d/dz [z * sigmoid(z)]; the bf16 path takes sigmoid from one tanh.approx like the forward kernel
@@ -305,6 +306,16 @@ __global__ void __launch_bounds__(kGbThreads, 3) gn_bwd_apply_kernel(const GnBwd
       for (int j = 0; j < gs; ++j) { S1 += raw[2 * (g0 + j)]; S2 += raw[2 * (g0 + j) + 1]; }
       tt[2 * ch] = mr[2 * ch + 1] * S1 * inv_n;
       tt[2 * ch + 1] = mr[2 * ch + 1] * S2 * inv_n;
+      if (blockIdx.x == 0 && (p.cs.db || p.cs.demb)) {
+        // sum over the image's pixels of dx = cA*dz + cB*x + cC (constants as below): the bias / embedding gradient of the
+        // convolution that produced x, without reading dx back
+        const float mu = mr[2 * ch], rs = mr[2 * ch + 1], ga = __ldg(p.gamma + ch);
+        const float t1 = tt[2 * ch], t2 = tt[2 * ch + 1];
+        const float sum_dz = __ldg(red + 2 * ch), sum_x = __ldg(p.st0 + ((size_t)img * p.ld0 + ch) * 2);
+        const float v = rs * ga * sum_dz - rs * t2 * sum_x + (mu * rs * t2 - t1) * (float)p.HW;
+        if (p.cs.db) atomicAdd(p.cs.db + ch, v);
+        if (p.cs.demb) atomicAdd(p.cs.demb + (size_t)__ldg(p.cs.img_row + img) * p.cs.emb_ld + p.cs.col + ch, v);
+      }
     }
   }
   __syncthreads();
@@ -730,7 +741,7 @@ namespace vf {
 int gn_backward_impl(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1, const float* stats1,
                      int stats1_ld, int dtype, int images, int H, int W, int groups, const float* gamma, const float* beta, int swish,
                      const void* dy, float* scratch, bool scratch_zeroed, float* dgamma, float* dbeta, void* dx0, int acc0, void* dx1,
-                     int acc1, cudaStream_t st) {
+                     int acc1, cudaStream_t st, const GnColsum* colsum) {
   VF_REQUIRE(src0 && stats0 && gamma && beta && dy && scratch && dgamma && dbeta && dx0, "vf_gn_backward: null args");
   if (!src1) C1 = 0;
   VF_REQUIRE(C1 == 0 || (stats1 && dx1), "vf_gn_backward: second source needs stats and dx");
@@ -742,6 +753,10 @@ int gn_backward_impl(const void* src0, int C0, const float* stats0, int stats0_l
   p.HW = H * W; p.W1 = W + 1; p.P = (H + 1) * (W + 1); p.groups = groups; p.swish = swish;
   p.gamma = gamma; p.beta = beta; p.dy = dy; p.red = scratch; p.dgamma = dgamma; p.dbeta = dbeta;
   p.dx0 = dx0; p.acc0 = acc0; p.dx1 = dx1; p.acc1 = acc1;
+  if (colsum) {
+    VF_REQUIRE(C1 == 0 && !acc0, "vf_gn_backward: closed-form column sums need a single source and a fresh dx");
+    p.cs = *colsum;
+  }
   const int CV = C / vec, PY = kGbThreads / CV > 0 ? kGbThreads / CV : 1;
   const int threads = CV * PY;
   // (Processing large layers in L2-sized image groups so that the apply pass re-reads x / dy from L2 was measured
@@ -777,7 +792,7 @@ VF_API int vf_gn_backward(const void* src0, int C0, const float* stats0, int sta
                           const void* dy, float* scratch, float* dgamma, float* dbeta, void* dx0, int acc0, void* dx1, int acc1,
                           vf_stream stream) {
   return vf::gn_backward_impl(src0, C0, stats0, stats0_ld, src1, C1, stats1, stats1_ld, dtype, images, H, W, groups, gamma, beta, swish, dy,
-                              scratch, false, dgamma, dbeta, dx0, acc0, dx1, acc1, as_stream(stream));
+                              scratch, false, dgamma, dbeta, dx0, acc0, dx1, acc1, as_stream(stream), nullptr);
 }
 
 namespace vf {

@@ -1143,7 +1143,7 @@ __global__ void __launch_bounds__(256) embed_bwd_params_kernel(const float* __re
 int gn_backward_impl(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1, const float* stats1,
                      int stats1_ld, int dtype, int images, int H, int W, int groups, const float* gamma, const float* beta, int swish,
                      const void* dy, float* scratch, bool scratch_zeroed, float* dgamma, float* dbeta, void* dx0, int acc0, void* dx1,
-                     int acc1, cudaStream_t st);
+                     int acc1, cudaStream_t st, const GnColsum* colsum);
 
 // ---- all packed weight gradients -> OIHW parameter gradients in ONE launch at the end of the backward -----------------
 // (every convolution owns a slice of the packed-gradient arena, so nothing has to be unpacked layer by layer)
@@ -1219,7 +1219,7 @@ struct BwdCtx {
   } while (0)
 
 static void conv_backward(BwdCtx& cx, const vf_unet::TapeOp& t, const uint8_t* pkt, const void* dY, int dy_ld, float* dwp, float* cs,
-                          float* const* pg, float* demb) {
+                          float* const* pg, float* demb, bool skip_colsum = false) {
   vf_unet* u = cx.u;
   const vf_conv_args& f = t.conv;
   const int dt = u->dtype;
@@ -1237,7 +1237,7 @@ static void conv_backward(BwdCtx& cx, const vf_unet::TapeOp& t, const uint8_t* p
   }
   const int out_rows_per_img = a.out_padded ? (H + 1) * (W + 1) : H * W;
   // ---- bias / embedding gradients: per-image column sums of dY
-  if (t.b_idx[0] >= 0 || t.emb_col >= 0) {
+  if ((t.b_idx[0] >= 0 || t.emb_col >= 0) && !skip_colsum) {
     if (!cx.dry && cx.rc == VF_OK) {
       const int vec = dt == VF_BF16 ? 8 : 4;
       const int cv = (f.cout + vec - 1) / vec;
@@ -1386,6 +1386,7 @@ static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float*
   }
   float* dwp_cur = dwp;
   float* gn_cur = gn_scratch;
+  int colsum_done = -1;          // tape index of the convolution whose bias / embedding gradients the GroupNorm backward produced
   for (int i = (int)u->tape.size() - 1; i >= 0 && cx.rc == VF_OK; --i) {
     const vf_unet::TapeOp& t = u->tape[i];
     if (t.kind == 0) {
@@ -1406,15 +1407,30 @@ static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float*
       } else {
         auto& g = cx.grad_of(t.conv.out);
         const int ld = t.conv.qkv_split ? 3 * t.conv.qkv_split : t.conv.out_ld;
-        conv_backward(cx, t, pkt, g.first, ld, dwp_l, cs, pg, demb);
+        conv_backward(cx, t, pkt, g.first, ld, dwp_l, cs, pg, demb, colsum_done == i);
       }
     } else if (t.kind == 1) {
       auto& gy = cx.grad_of(t.gdst);
       auto& g0 = cx.grad_of(t.gsrc0);
       std::pair<void*, bool>* g1 = t.gsrc1 ? &cx.grad_of(t.gsrc1) : nullptr;
+      // The first convolution of a ResnetBlock (the one with the embedding add) feeds this GroupNorm and nothing else, so
+      // its bias / embedding gradients (per-image column sums of dx) come out of the GroupNorm backward in closed form and
+      // conv_backward skips its pass over dY.
+      GnColsum csum{};
+      bool fused_cs = false;
+      if (i > 0 && !t.gsrc1 && !g0.second) {
+        const vf_unet::TapeOp& pc = u->tape[i - 1];
+        if (pc.kind == 0 && pc.conv.out == t.gsrc0 && pc.emb_col >= 0 && pc.b_idx[1] < 0 && pc.conv.stride == 1 && pc.conv.cout == t.gC0 &&
+            !(vf::tc_debug_flags() & 2048)) {
+          csum.db = (!cx.dry && pc.b_idx[0] >= 0) ? pg[pc.b_idx[0]] : nullptr;      // the sizing walk has no gradient table
+          csum.demb = demb; csum.img_row = (const int*)u->last_img_row; csum.emb_ld = u->E; csum.col = pc.emb_col;
+          fused_cs = true;
+          colsum_done = i - 1;
+        }
+      }
       VF_B(gn_backward_impl(t.gsrc0, t.gC0, t.gst0, t.gld0, t.gsrc1, t.gC1, t.gst1, t.gld1, dt, images, t.gH, t.gW, c.norm_groups,
                             u->master[t.gw], u->master[t.gb], t.swish, gy.first, gn_cur, true, pg[t.gw], pg[t.gb], g0.first, g0.second ? 1 : 0,
-                            g1 ? g1->first : nullptr, g1 && g1->second ? 1 : 0, cx.st));
+                            g1 ? g1->first : nullptr, g1 && g1->second ? 1 : 0, cx.st, fused_cs ? &csum : nullptr));
       gn_cur += align_up((size_t)images * (t.gC0 + t.gC1) * 2, 64);
       g0.second = true;
       if (g1) g1->second = true;

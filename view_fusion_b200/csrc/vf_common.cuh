@@ -149,6 +149,14 @@ struct RowGeom {
   int in_padded, out_padded, stride2;
   float rcp_rows, rcp_w;             // 1 / rows per image (P or HW), 1 / line length (W+1 or W): exact small-integer division
 };
+// Bias / embedding gradient of the convolution that produced a GroupNorm input, emitted by the GroupNorm backward itself:
+// dx = cA*dz + cB*x + cC per (image, channel), so sum_pixels dx = cA*sum(dz) + cB*sum(x) + cC*HW needs no pass over dx.
+struct GnColsum {
+  float* db;            // [C] bias gradient (+=) or NULL
+  float* demb;          // embedding-table gradient [rows, emb_ld] (+= at column col) or NULL
+  const int* img_row;   // [images] embedding row of each image
+  int emb_ld, col;
+};
 struct RowInfo {
   int img, pix;      // pix = y*Wo + x at the OUTPUT resolution
   bool valid;
