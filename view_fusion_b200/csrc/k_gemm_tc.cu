@@ -373,7 +373,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         tab_next[j] = v;
       }
     };
-    if ((int)blockIdx.x < p.n_items && !(p.dbg & 8)) load_table(blockIdx.x);
+    if (p.emb != nullptr && (int)blockIdx.x < p.n_items && !(p.dbg & 8)) load_table(blockIdx.x);
+    int tab_n_tile = -1;
     // (combining the GroupNorm sums per CTA in shared memory first was tried: shared-memory float atomics cost more than
     // the global REDs they save, 12 -> 31 kclk per CTA in the statistics section)
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++k_idx) {
@@ -382,21 +383,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const int m0 = m_blk * BM, n0 = n_tile * p.block_n;
       const int rows_img = p.geo.in_padded ? p.geo.P : p.geo.HW;
       const int img_first = div_small<false>(m0, rows_img, p.geo.rcp_rows);
-      // bias + embedding rows of the images this block touches.  The values were fetched into registers during the
-      // previous item (tab_next), so only the two barriers around the smem write are on this item's critical path.
+      // bias + embedding rows of the images this block touches.  With an embedding the table changes with every item: its
+      // values were fetched into registers during the previous item (tab_next), so only the two barriers around the smem
+      // write are on this item's critical path.  Without one it is the bias of the N tile: rebuilt only when the CTA moves
+      // to another N tile, and the epilogue warps run from item to item without meeting at a barrier.
       VF_EP_BEGIN();
-      asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");     // previous item's readers are done
-      if (!(p.dbg & 8)) {
+      if (p.emb != nullptr || n_tile != tab_n_tile) {
+        if (p.emb == nullptr && !(p.dbg & 8)) load_table(item);
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");     // previous item's readers are done
+        if (!(p.dbg & 8)) {
 #pragma unroll
-        for (int j = 0; j < TAB_PER_THREAD; ++j) {
-          const int i = et + j * TC_EPI_THREADS;
-          if (i < p.max_imgs * p.block_n) sm_bias[i] = tab_next[j];
+          for (int j = 0; j < TAB_PER_THREAD; ++j) {
+            const int i = et + j * TC_EPI_THREADS;
+            if (i < p.max_imgs * p.block_n) sm_bias[i] = tab_next[j];
+          }
         }
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
-      if (!(p.dbg & 8)) {
-        const int item_next = item + gridDim.x;
-        if (item_next < p.n_items) load_table(item_next);
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
+        tab_n_tile = n_tile;
+        if (p.emb != nullptr && !(p.dbg & 8)) {
+          const int item_next = item + gridDim.x;
+          if (item_next < p.n_items) load_table(item_next);
+        }
       }
       VF_EP_END(1);
 
