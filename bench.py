@@ -42,7 +42,7 @@ T_STEPS = 2000
 # algorithmic work per view-image forward
 GFLOP_PER_VIEW = 20.994
 GFLOP_CONV_PER_VIEW = 2 * (9.595 + 0.723)        # conv3x3 + conv1x1 MACs -> FLOPs (attention core excluded)
-CONV_DRAM_BYTES_PER_STEP = 7.354e9                # measured once with ncu at B=28, N=6 (profiles/r01_ncu_full_conv.txt)
+CONV_DRAM_BYTES_PER_STEP = 7.362e9                # measured with ncu at B=28, N=6 (profiles/r01_ncu_full_v6_conv.txt: 6.04 GB read + 1.32 GB written)
 COMPOSE_BYTES_PER_SAMPLE = lambda n: n * 4096 * 32 + 2 * 3 * 4096 * 4
 
 
@@ -309,7 +309,7 @@ def main():
             roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
                     "traffic": CONV_DRAM_BYTES_PER_STEP / conv_n if (B, N) == (28, 6) else None,
                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum over the 84 conv launches of one "
-                                      "step (profiles/r01_ncu_full_conv.txt), per launch",
+                                      "step (profiles/r01_ncu_full_v6_conv.txt), per launch",
                     "kernel": "conv_tc_kernel", "launches_per_step": conv_n,
                     "flops_per_launch": flops / conv_n, "avg_launch_ms": conv_ms / conv_n,
                     "peak_source": f"{pk['src']} sustained bf16 (kernel timed inside a long step)"}

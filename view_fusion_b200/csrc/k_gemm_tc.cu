@@ -17,8 +17,10 @@
 //   * (block_n, G) are chosen per layer by a small cost model of ingest bytes vs MMA cycles vs wave quantisation.
 // Up to three K segments accumulate into the same tile (3x3 conv over h + 1x1 res_conv over x and the skip tensor),
 // fusing the ResnetBlock's residual projection (unet.py:245) and the decoder's torch.cat (unet.py:134).
-// Warp roles: warps 0-15 epilogue (TMEM -> registers -> smem -> TMA store, + GroupNorm partial sums), warp 16 TMA
-// producer, warp 17 MMA issuer + TMEM allocator.
+// Warp roles: warps 0..TC_EPI_WARPS-1 (8) epilogue (TMEM -> registers -> smem -> TMA store, + GroupNorm partial sums), then
+// one TMA producer warp and one MMA issuer + TMEM allocator warp.
+// 1x1 layers that change the row order and the stride-2 Downsample run on the same kernel through other tensor maps
+// (TcParams::a_lines / epi_lines / s2_cchunks).
 #include <cuda.h>
 
 #include <mutex>
