@@ -183,8 +183,8 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=28, help="samples per GPU (small-v100.yaml batch_size)")
     ap.add_argument("--views", type=int, default=6)
@@ -192,7 +192,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--train-batch", type=int, default=28, help="training samples per GPU (weak scaling)")
-    ap.add_argument("--train-steps", type=int, default=10)
+    ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--no-train", action="store_true", help="skip the training-throughput leg")
     args = ap.parse_args()
 
