@@ -238,12 +238,18 @@ typedef struct vf_conv_args {
   int dtype;                 /* VF_F32 -> CUDA-core kernel, VF_BF16 -> tcgen05 kernel */
   int images, H, W;          /* spatial size of the SOURCES (the output is H/2 x W/2 when stride == 2) */
   int in_padded;             /* row order of every source: 1 PADDED, 0 FLAT (FLAT only with ksize 1) */
-  int out_padded;            /* row order of out / residual / stats rows */
+  int out_padded;            /* row order of out / residual / stats rows.  1x1 layers may change the order: PADDED -> FLAT
+                              * gathers the valid pixels through the source's tensor map, FLAT -> PADDED stores whole image
+                              * lines through the output's; padding rows of a PADDED output are never written */
   int n_seg;                 /* 1..3 K-segments accumulated into the same output tile */
   const void* src[3];        /* [rows, src_c[i]] */
   int src_c[3];
   int ksize[3];              /* 1 or 3 (only segment 0 may be 3) */
-  int stride;                /* 1, or 2 = Downsample: computed at source resolution, even pixels kept */
+  int stride;                /* 1, or 2 = Downsample (3x3, single segment).  The tcgen05 path computes the H/2 x W/2 output
+                              * pixels only: TMA gathers the pixel phases of the PADDED source and supplies the zero halo
+                              * by out-of-bounds fill (padding rows of the source are not read) when W/2 divides 64;
+                              * otherwise, and on the CUDA-core path, it is computed at source resolution with the even
+                              * pixels kept and the source's padding rows must hold zeros */
   const void* weight;        /* [Cout_pad, K_total] K-major in `dtype`; K_total = sum ksize^2 * src_c */
   int cout;                  /* logical output channels */
   int cout_pad;              /* rows of `weight` (multiple of 16) */
@@ -282,7 +288,8 @@ int vf_debug_umma_shift(const void* A, int rows, const void* B, int shift_rows, 
 
 /* Single-head self-attention core (unet.py:267-274): O = softmax(Q K^T / sqrt(C)) V per image.
  *   qk  : [images*L, 3C] rows hold q in [0,C), k in [C,2C) (v columns unused when vt != NULL)
- *   vt  : [images, C, L] V transposed (bf16 tensor-core path) or NULL (fp32 path reads v from qk)
+ *   vt  : [images, C, L] V transposed, or NULL: v is read row-major from columns [2C,3C) of qk (the tensor-core path
+ *         then uses it as an MN-major operand; inference mode, nothing is written for the backward)
  *   out : [images*L, C]
  *   lse : optional [images*L] fp32, written by the tensor-core path for vf_attention_backward: log2 of the softmax
  *         denominator in the scaled domain, P = exp2(s * log2(e)/sqrt(C) - lse).  NULL when not training. */
