@@ -8,6 +8,8 @@
 //   vf_upsample2x_backward / vf_zero_insert2x / vf_add_inplace / vf_grad8_to_act   small layout kernels
 #include <mutex>
 
+#include <cstdlib>
+
 #include "vf_common.cuh"
 
 namespace vf {
@@ -765,6 +767,8 @@ int gn_backward_impl(const void* src0, int C0, const float* stats0, int stats0_l
   int want = cdiv(148 * 8, group);
   int max_splits = p.P / (PY * 4) > 0 ? p.P / (PY * 4) : 1;
   int splits = wave_splits(group, want, max_splits, 148 * 3);
+  if (latency_bound_layer(p.P, C) && !getenv("VF_GN_OLD_SPLITS"))
+    splits = latency_splits(group, p.P, kGbUnroll * PY, max_splits, 148 * 2, 3.0, 0.8);   // the reduce pass runs 2 CTAs per SM
   p.rows_per_cta = cdiv(p.P, splits);
   splits = cdiv(p.P, p.rows_per_cta);
   if (!scratch_zeroed) VF_CUDA(cudaMemsetAsync(scratch, 0, (size_t)images * C * 2 * sizeof(float), st));

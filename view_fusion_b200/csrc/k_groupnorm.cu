@@ -8,6 +8,8 @@
 //                 torch.cat((x, skip), 1) (unet.py:134) is never materialised un-normalised.
 //   vf_gn_stats : stand-alone statistics pass (API completeness / tests; the plan uses the fused sums).
 // Algorithmic bytes (bf16): apply 4 B/elem, stats 2 B/elem.
+#include <cstdlib>
+
 #include "vf_common.cuh"
 
 namespace vf {
@@ -219,6 +221,8 @@ static GnGeom gn_geom(int C, int vec, int HW, int images) {   // HW = rows per i
   int want = cdiv(148 * 16, images > 0 ? images : 1);
   int max_splits = HW / (PY * 4) > 0 ? HW / (PY * 4) : 1;
   g.splits = wave_splits(images > 0 ? images : 1, want, max_splits, 148 * 4);
+  if (latency_bound_layer(HW, C) && !getenv("VF_GN_OLD_SPLITS"))
+    g.splits = latency_splits(images > 0 ? images : 1, HW, 2 * PY, max_splits, 148 * 4, 3.0, 0.8);   // UN = 2 rows per half-batch
   g.pix_per_cta = cdiv(HW, g.splits);
   g.splits = cdiv(HW, g.pix_per_cta);
   return g;

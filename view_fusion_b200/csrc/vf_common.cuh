@@ -77,6 +77,29 @@ inline int wave_splits(int images, int want, int max_splits, int resident) {
   return best;
 }
 
+// Row splits for SMALL layers of the same kind of kernel.  There a CTA's fixed cost (the statistics prologue: two
+// dependent global round trips, two barriers and the per-group loops, ~3 us) rivals its streaming time, so filling the
+// machine with many short CTAs multiplies the prologue by the number of waves (ncu: 25 us for the 33 MB of a 16x16 192-
+// channel GroupNorm backward pass in 4 waves).  Model: time = waves * (t_pro + iterations * t_iter), t_iter = one memory
+// round trip per unrolled row batch; the fewest CTAs win ties.
+inline int latency_splits(int images, int rows, int rows_per_iter, int max_splits, int resident, double t_pro_us, double t_iter_us) {
+  if (max_splits < 1) max_splits = 1;
+  if (rows_per_iter < 1) rows_per_iter = 1;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int s = 1; s <= max_splits; ++s) {
+    const long ctas = (long)s * images;
+    const long waves = (ctas + resident - 1) / resident;
+    const int rpc = (rows + s - 1) / s;
+    const int iters = (rpc + rows_per_iter - 1) / rows_per_iter;
+    const double cost = (double)waves * (t_pro_us + iters * t_iter_us);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+// layers up to 32x32 x 256 channels per image (<= 94 MB per tensor at 168 view-images) are scheduled by latency_splits
+inline bool latency_bound_layer(int rows_per_img, int C) { return (long)rows_per_img * C <= 1089L * 256; }
+
 inline cudaStream_t as_stream(vf_stream s) { return reinterpret_cast<cudaStream_t>(s); }
 inline size_t dtype_size(int dt) { return dt == VF_BF16 ? 2 : 4; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
