@@ -87,3 +87,39 @@ def test_no_weighting_ablation_mean_over_views():
     y_prev, logits, weights = m.p_sample(y_t.cuda(), y_cond.cuda(), view_count, angle.cuda(), t.cuda(), noise=z.cuda(), _eps_out=eps)
     assert rel(eps, eps_ref) < 1e-4 and rel(y_prev, y_ref) < 1e-4
     assert logits is None and weights is None
+
+
+def test_autoregressive_driver_equals_reference_loop_on_device():
+    """view_fusion_b200.drivers.autoregressive_orbit (one conditioning buffer of the final size, generated views written
+    in place, view_count selecting the live prefix) against the reference's loop that re-concatenates y_cond every step
+    (experiment.py:516-545), both through `model(..., generate=True)` with the model's own noise; 16-step schedule."""
+    import contextlib
+    import io
+    from view_fusion_b200 import UNet, ViewFusion, drivers
+    cfg = O.TINY
+    S = cfg["image_size"]
+    beta = {"train": dict(O.BETA_TRAIN, num_timesteps=16)}
+
+    def make():
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = ViewFusion(UNet(**cfg, precision="fp32"), beta).cuda()
+        m.set_new_noise_schedule(device="cuda", phase="train")
+        return m
+
+    m1, m2 = make(), make()
+    first = torch.rand(2, 1, 3, S, S, generator=torch.Generator().manual_seed(3)).cuda()
+    n = 3
+    torch.manual_seed(5)
+    cond, samples = drivers.autoregressive_orbit(m1, first, n_targets=n)
+    torch.manual_seed(5)
+    ref = first.clone()
+    for count in range(1, n + 1):
+        vc = torch.full((2,), count)
+        angle = torch.full((2, 1), 2 * math.pi / n * count, device="cuda")
+        *_, gen = m2(y_cond=ref, view_count=vc, angle=angle, generate=True)
+        ref = torch.cat((ref, gen[:, None]), dim=1)
+    torch.cuda.synchronize()
+    assert cond.shape == ref.shape == (2, n + 1, 3, S, S) and samples.shape == (n, 2, 3, S, S)
+    assert torch.isfinite(cond).all()
+    assert rel(cond, ref) < 1e-5, rel(cond, ref)
