@@ -377,6 +377,15 @@ int vf_adam_chunk_elems(void);
 int vf_adam_step(const vf_adam_entry* table_dev, const int* chunk_entry_dev, const int* chunk_start_dev, int n_chunks, double lr,
                  double beta1, double beta2, double eps, double weight_decay, int step, vf_stream stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Evaluation metrics on the device (utils/metrics.py:6-12, called from experiment.py:349-356): PSNR and SSIM (the
+ * algorithm of pytorch_msssim.ssim(..., data_range=1.0, size_average=False): 11-tap Gaussian, sigma 1.5, VALID windows)
+ * of generated vs target, both (B, C, H, W) fp32 NCHW.  psnr / ssim: [B] fp32, overwritten.  H, W >= 11; the two planes
+ * and their five filtered copies must fit in shared memory (up to ~94 x 94 pixels).
+ * ---------------------------------------------------------------------------------------------------- */
+int vf_eval_metrics(const float* generated, const float* target, int B, int C, int H, int W, float* psnr, float* ssim,
+                    vf_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

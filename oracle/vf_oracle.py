@@ -422,6 +422,33 @@ def psnr(a: Tensor, b: Tensor) -> Tensor:
     return 20 * torch.log10(1.0 / torch.sqrt(mse))
 
 
+def ssim(a: Tensor, b: Tensor, data_range: float = 1.0, win_size: int = 11, win_sigma: float = 1.5) -> Tensor:
+    """utils/metrics.py:11-12 = pytorch_msssim.ssim(a, b, data_range=1.0, size_average=False) -> (B,).
+
+    pytorch-msssim is a third-party dependency that is absent from this image (pinned ==1.0.0 in the reference's
+    environment.yml:196), so this restates its published algorithm — PARITY UNPINNED for this function: 1-D Gaussian window
+    (size 11, sigma 1.5, normalised to sum 1), applied separably along H then W as a VALID depth-wise convolution (no
+    padding) to x, y, x*x, y*y, x*y; C1 = (0.01 L)^2, C2 = (0.03 L)^2;
+    cs = (2 s_xy + C2) / (s_xx + s_yy + C2), ssim_map = (2 mu_x mu_y + C1) / (mu_x^2 + mu_y^2 + C1) * cs;
+    mean of the map per (image, channel), then mean over channels."""
+    C = a.shape[1]
+    coords = torch.arange(win_size, dtype=torch.float32) - win_size // 2
+    g = torch.exp(-(coords ** 2) / (2 * win_sigma ** 2))
+    g = (g / g.sum()).to(a.dtype)
+
+    def filt(x):
+        x = F.conv2d(x, g.view(1, 1, -1, 1).repeat(C, 1, 1, 1), groups=C)      # along H
+        return F.conv2d(x, g.view(1, 1, 1, -1).repeat(C, 1, 1, 1), groups=C)   # along W
+
+    K1, K2 = 0.01, 0.03
+    C1, C2 = (K1 * data_range) ** 2, (K2 * data_range) ** 2
+    mu1, mu2 = filt(a), filt(b)
+    s11, s22, s12 = filt(a * a) - mu1 * mu1, filt(b * b) - mu2 * mu2, filt(a * b) - mu1 * mu2
+    cs = (2 * s12 + C2) / (s11 + s22 + C2)
+    m = (2 * mu1 * mu2 + C1) / (mu1 * mu1 + mu2 * mu2 + C1) * cs
+    return m.flatten(2).mean(-1).mean(1)
+
+
 # --------------------------------------------------------------------------------------
 # synthetic NMR-shaped inputs (SURVEY.md §8d)
 # --------------------------------------------------------------------------------------

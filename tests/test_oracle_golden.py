@@ -121,3 +121,32 @@ def test_generate_contract_shapes():
     sv, mv = int(bt["view_count"].sum()), int(bt["view_count"].max())
     assert ret.shape == (2, 9, 3, 16, 16) and la.shape == (sv, 8, 3, 16, 16) and wa.shape == (2, 8, mv, 3, 16, 16)
     assert torch.equal(last, y)
+
+
+def test_ssim_restatement_against_bruteforce_float64():
+    """O.ssim (pytorch-msssim 1.0.0's published algorithm; the package is absent here, so parity is unpinned) against a
+    direct float64 evaluation of the same definition, plus the properties any SSIM has."""
+    import numpy as np
+    g = torch.Generator().manual_seed(4)
+    a = torch.rand(2, 3, 20, 24, generator=g)
+    b = (a + 0.1 * torch.randn(2, 3, 20, 24, generator=g)).clamp(0, 1)
+    got = O.ssim(a, b)
+    k = np.arange(11) - 5
+    w = np.exp(-(k ** 2) / (2 * 1.5 ** 2)); w /= w.sum()
+    w2 = np.outer(w, w)
+    an, bn = a.double().numpy(), b.double().numpy()
+    want = np.zeros(2)
+    for n in range(2):
+        for c in range(3):
+            vals = []
+            for i in range(20 - 10):
+                for j in range(24 - 10):
+                    x, y = an[n, c, i:i + 11, j:j + 11], bn[n, c, i:i + 11, j:j + 11]
+                    mx, my = (w2 * x).sum(), (w2 * y).sum()
+                    sxx, syy, sxy = (w2 * x * x).sum() - mx * mx, (w2 * y * y).sum() - my * my, (w2 * x * y).sum() - mx * my
+                    vals.append((2 * mx * my + 1e-4) / (mx * mx + my * my + 1e-4) * (2 * sxy + 9e-4) / (sxx + syy + 9e-4))
+            want[n] += np.mean(vals) / 3
+    assert np.allclose(got.numpy(), want, atol=2e-6)
+    assert torch.allclose(O.ssim(a, a), torch.ones(2), atol=1e-6)
+    assert torch.allclose(O.ssim(a, b), O.ssim(b, a), atol=1e-6)
+    assert bool((got < 1).all())
