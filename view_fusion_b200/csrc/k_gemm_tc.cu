@@ -775,13 +775,22 @@ static bool pick_tiling(const TcParams& p, int cout_pad, int sms, bool epi_tma, 
   return found;
 }
 
+// Whether the stride-2 3x3 convolution of a PADDED [images*(H+1)*(W+1), C] source runs in the phase-gather mode (which
+// never reads the source's padding rows) or in the full-resolution fallback (which needs zeros there).  The plan asks
+// this before deciding to skip vf_zero_padding in inference.
+bool conv2d_tc_stride2_gathers(int H, int W, int C) {
+  const int Wo2 = W / 2, Ho2 = H / 2;
+  return H % 2 == 0 && W % 2 == 0 && Wo2 >= 1 && Wo2 <= TC_ABOX && TC_ABOX % Wo2 == 0 && Ho2 % (TC_ABOX / Wo2) == 0 && C % TC_BK == 0 &&
+         !(g_tc_dbg & 1024);
+}
+
 int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
   VF_REQUIRE(a->dtype == VF_BF16, "vf_conv2d(tc): bf16 activations only");
   TcParams p{};
   // Downsample (3x3, stride 2): GEMM rows are the output pixels (FLAT order at half resolution), see TcParams::s2_cchunks
   const int Wo2 = a->W / 2, Ho2 = a->H / 2;
-  const bool s2 = a->stride == 2 && a->n_seg == 1 && a->ksize[0] == 3 && a->in_padded && a->out_padded && a->H % 2 == 0 && a->W % 2 == 0 &&
-                  Wo2 <= TC_ABOX && TC_ABOX % Wo2 == 0 && Ho2 % (TC_ABOX / Wo2) == 0 && a->src_c[0] % TC_BK == 0 && !(g_tc_dbg & 1024);
+  const bool s2 = a->stride == 2 && a->n_seg == 1 && a->ksize[0] == 3 && a->in_padded && a->out_padded &&
+                  conv2d_tc_stride2_gathers(a->H, a->W, a->src_c[0]);
   const int H = s2 ? Ho2 : a->H, W = s2 ? Wo2 : a->W;      // resolution of the GEMM rows
   // A 1x1 layer from a PADDED source to a FLAT output runs as a FLAT -> FLAT GEMM: TMA gathers the valid pixels (whole
   // image lines) out of the padded tensor, so the rows map 1:1 onto the output and the staged TMA epilogue applies.

@@ -19,6 +19,7 @@
 namespace vf {
 extern int g_force_simt_flag;     // vf_api.cu: CUDA-core cross-check mode
 int tc_debug_flags();             // k_gemm_tc.cu: test hooks of the tcgen05 convolution
+bool conv2d_tc_stride2_gathers(int H, int W, int C);
 }
 
 namespace vf {
@@ -764,7 +765,7 @@ static int walk(vf_unet* u, Exec& ex, const uint8_t* pk, int images, const void*
       // x is a raw convolution output whose padding rows were never written.  The tcgen05 stride-2 path gathers pixel
       // phases by TMA and gets its zero halo from out-of-bounds fill, so only the CUDA-core path and the training
       // backward (the weight gradient reads x with its halo) need real zeros there.
-      if (u->dtype != VF_BF16 || u->stash || vf::tc_debug_flags() != 0 || vf::g_force_simt_flag)
+      if (u->dtype != VF_BF16 || u->stash || vf::tc_debug_flags() != 0 || vf::g_force_simt_flag || !vf::conv2d_tc_stride2_gathers(x.H, x.W, x.C))
         VF_RUN(ex, K_UPSAMPLE, vf_zero_padding(x.p, u->dtype, images, x.H, x.W, x.C, (vf_stream)ex.st));
       vf_conv_args a = conv_args_init();
       a.images = images; a.H = x.H; a.W = x.W; a.n_seg = 1; a.stride = 2;
