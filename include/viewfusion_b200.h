@@ -268,6 +268,12 @@ typedef struct vf_conv_args {
 
 int vf_conv2d(const vf_conv_args* a, vf_stream stream);
 
+/* Test hooks (host arithmetic only, usable without a device): the row splits per image the GroupNorm forward /
+ * backward kernels would be launched with for `images` images of H x W x C (small layers are scheduled by
+ * a latency model).  Return the split count (threads per CTA through threads_out), negative for unsupported shapes. */
+int vf_debug_gn_splits(int images, int H, int W, int C, int dtype, int* threads_out);
+int vf_debug_gn_bwd_splits(int images, int H, int W, int C, int dtype);
+
 /* Test hook: route VF_BF16 vf_conv2d / vf_attention through the CUDA-core kernels (same bf16 storage, fp32
  * accumulation) so the tcgen05 kernels can be cross-checked on the device.  Never enabled by the product path. */
 void vf_debug_force_simt(int on);

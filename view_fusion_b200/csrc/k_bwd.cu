@@ -740,6 +740,16 @@ VF_API int vf_unpack_conv_wgrad(const float* dwp, int cout, int cin, int ksize, 
 }
 
 namespace vf {
+// row splits per image of the two GroupNorm backward passes (one grid for both)
+static int gn_bwd_splits(int images, int P, int C, int PY) {
+  const int want = cdiv(148 * 8, images);
+  const int max_splits = P / (PY * 4) > 0 ? P / (PY * 4) : 1;
+  int splits = wave_splits(images, want, max_splits, 148 * 3);
+  if (latency_bound_layer(P, C) && !getenv("VF_GN_OLD_SPLITS"))
+    splits = latency_splits(images, P, kGbUnroll * PY, max_splits, 148 * 2, 3.0, 0.8);   // the reduce pass runs 2 CTAs per SM
+  return splits;
+}
+
 int gn_backward_impl(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1, const float* stats1,
                      int stats1_ld, int dtype, int images, int H, int W, int groups, const float* gamma, const float* beta, int swish,
                      const void* dy, float* scratch, bool scratch_zeroed, float* dgamma, float* dbeta, void* dx0, int acc0, void* dx1,
@@ -764,11 +774,7 @@ int gn_backward_impl(const void* src0, int C0, const float* stats0, int stats0_l
   // (Processing large layers in L2-sized image groups so that the apply pass re-reads x / dy from L2 was measured
   // 25 % slower than whole-batch launches: the smaller grids lose more than the L2 hits win.)
   const int group = images;
-  int want = cdiv(148 * 8, group);
-  int max_splits = p.P / (PY * 4) > 0 ? p.P / (PY * 4) : 1;
-  int splits = wave_splits(group, want, max_splits, 148 * 3);
-  if (latency_bound_layer(p.P, C) && !getenv("VF_GN_OLD_SPLITS"))
-    splits = latency_splits(group, p.P, kGbUnroll * PY, max_splits, 148 * 2, 3.0, 0.8);   // the reduce pass runs 2 CTAs per SM
+  int splits = gn_bwd_splits(group, p.P, C, PY);
   p.rows_per_cta = cdiv(p.P, splits);
   splits = cdiv(p.P, p.rows_per_cta);
   if (!scratch_zeroed) VF_CUDA(cudaMemsetAsync(scratch, 0, (size_t)images * C * 2 * sizeof(float), st));
@@ -790,6 +796,14 @@ int gn_backward_impl(const void* src0, int C0, const float* stats0, int stats0_l
   return VF_OK;
 }
 }  // namespace vf
+
+// Test hook (host only): row splits the GroupNorm backward would launch with.
+VF_API int vf_debug_gn_bwd_splits(int images, int H, int W, int C, int dtype) {
+  const int vec = dtype == VF_BF16 ? 8 : 4;
+  if (images <= 0 || H <= 0 || W <= 0 || C <= 0 || C % vec || C / vec > vf::kGbThreads) return -1;
+  const int CV = C / vec, PY = vf::kGbThreads / CV > 0 ? vf::kGbThreads / CV : 1;
+  return vf::gn_bwd_splits(images, (H + 1) * (W + 1), C, PY);
+}
 
 VF_API int vf_gn_backward(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1, const float* stats1,
                           int stats1_ld, int dtype, int images, int H, int W, int groups, const float* gamma, const float* beta, int swish,

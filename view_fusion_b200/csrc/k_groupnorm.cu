@@ -233,6 +233,15 @@ static GnGeom gn_geom(int C, int vec, int HW, int images) {   // HW = rows per i
 
 }  // namespace vf
 
+// Test hook (host only, no device needed): the (row splits, threads) the GroupNorm forward would launch with.
+extern "C" __attribute__((visibility("default"))) int vf_debug_gn_splits(int images, int H, int W, int C, int dtype, int* threads_out) {
+  const int vec = dtype == VF_BF16 ? 8 : 4;
+  if (images <= 0 || H <= 0 || W <= 0 || C <= 0 || C % vec || C / vec > vf::kGnThreads) return -1;
+  const vf::GnGeom g = vf::gn_geom(C, vec, (H + 1) * (W + 1), images);
+  if (threads_out) *threads_out = g.threads;
+  return g.splits;
+}
+
 extern "C" __attribute__((visibility("default"))) int vf_gn_stats(const void* src0, int C0, const void* src1, int C1, int dtype, int images, int H, int W,
                            float* stats, vf_stream stream) {
   using namespace vf;
