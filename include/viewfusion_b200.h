@@ -392,6 +392,13 @@ int vf_adam_step(const vf_adam_entry* table_dev, const int* chunk_entry_dev, con
 int vf_eval_metrics(const float* generated, const float* target, int B, int C, int H, int W, float* psnr, float* ssim,
                     vf_stream stream);
 
+/* Input path (data/nmr_dataset.py:10-52, `process_sample`, for a whole batch): views (B, V, H, W, C) uint8 HWC as
+ * decoded from the dataset, perm (B, V) int32 = the per-object view permutation (np.random.shuffle in the reference).
+ *   target (B, C, H, W) = views[b, perm[b,0]] / 255;  cond (B, V-1, C, H, W) = views[b, perm[b,1:]] / 255;
+ *   angle (B) = 2 pi / V * perm[b,0]        — all fp32, NCHW, bit-exact with the host computation. */
+int vf_prepare_batch_u8(const uint8_t* views, const int* perm, int B, int V, int C, int H, int W, float* target, float* cond,
+                        float* angle, vf_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -449,6 +449,18 @@ def ssim(a: Tensor, b: Tensor, data_range: float = 1.0, win_size: int = 11, win_
     return m.flatten(2).mean(-1).mean(1)
 
 
+def process_batch_u8(views_u8: np.ndarray, perm: np.ndarray) -> Dict[str, np.ndarray]:
+    """data/nmr_dataset.py:10-52 (`process_sample`) for a batch, with the view permutation given instead of drawn:
+    views_u8 (B, V, H, W, C) uint8 as decoded from the dataset (webdataset's "rgb" decoder = uint8 / 255 in float32),
+    perm (B, V) = the shuffled `images_idx`.  Returns target (B,C,H,W), cond (B,V-1,C,H,W), angle (B,1), all float32."""
+    B, V = perm.shape
+    images = views_u8.astype(np.float32) / np.float32(255.0)                 # "rgb" decode
+    images = np.transpose(images, (0, 1, 4, 2, 3))                           # v h w c -> v c h w        (:15)
+    shuffled = np.stack([images[b, perm[b]] for b in range(B)])              # cond_images = images[images_idx]  (:17-18)
+    angle = (2 * np.pi / V * perm[:, :1]).astype(np.float32)                 # (:20-24)
+    return {"target": shuffled[:, 0], "cond": shuffled[:, 1:], "angle": angle}
+
+
 # --------------------------------------------------------------------------------------
 # synthetic NMR-shaped inputs (SURVEY.md §8d)
 # --------------------------------------------------------------------------------------

@@ -150,3 +150,20 @@ def test_ssim_restatement_against_bruteforce_float64():
     assert torch.allclose(O.ssim(a, a), torch.ones(2), atol=1e-6)
     assert torch.allclose(O.ssim(a, b), O.ssim(b, a), atol=1e-6)
     assert bool((got < 1).all())
+
+
+def test_process_batch_restatement_matches_reference_semantics():
+    """O.process_batch_u8 against the literal per-sample steps of data/nmr_dataset.py:10-24, 43 with the same permutation."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    views = rng.integers(0, 256, size=(2, 24, 6, 5, 3), dtype=np.uint8)
+    perm = np.stack([rng.permutation(24) for _ in range(2)])
+    got = O.process_batch_u8(views, perm)
+    for b in range(2):
+        images = np.stack([views[b, i].astype("f") / 255.0 for i in range(24)], 0).astype(np.float32)   # decode("rgb") + np.stack
+        images = np.transpose(images, (0, 3, 1, 2))
+        cond_images = images[perm[b]]
+        assert np.array_equal(got["target"][b], cond_images[0])
+        assert np.array_equal(got["cond"][b], cond_images[1:])
+        assert got["angle"][b, 0] == np.asarray([2 * np.pi / 24 * perm[b, 0]]).astype(np.float32)[0]
+    assert got["cond"].shape == (2, 23, 3, 6, 5) and got["target"].dtype == np.float32
