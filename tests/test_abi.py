@@ -73,3 +73,27 @@ def test_bad_config_is_an_error_not_a_crash(lib):
     h = ctypes.c_void_p()
     assert lib.vf_unet_create(ctypes.byref(c), _lib.VF_BF16, ctypes.byref(h)) == -1
     assert b"norm_groups" in lib.vf_last_error() or b"channels" in lib.vf_last_error()
+
+
+def _declared_arity():
+    """{function: number of parameters} parsed from the header's prototypes."""
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(vf_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", src, flags=re.S):
+        name, args = m.group(1), m.group(2).strip()
+        out[name] = 0 if args in ("", "void") else args.count(",") + 1
+    return out
+
+
+def test_ctypes_signatures_have_the_declared_arity(lib):
+    """A binding with the wrong number of arguments would still 'work' through ctypes and corrupt the call."""
+    arity = _declared_arity()
+    checked = 0
+    for name, n in arity.items():
+        fn = getattr(lib, name)
+        if fn.argtypes is None:
+            continue
+        assert len(fn.argtypes) == n, f"{name}: header declares {n} parameters, _lib.py binds {len(fn.argtypes)}"
+        checked += 1
+    assert checked >= 40
