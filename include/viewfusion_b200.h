@@ -272,6 +272,11 @@ int vf_conv2d(const vf_conv_args* a, vf_stream stream);
  * backward kernels would be launched with for `images` images of H x W x C (small layers are scheduled by
  * a latency model).  Return the split count (threads per CTA through threads_out), negative for unsupported shapes. */
 int vf_debug_gn_splits(int images, int H, int W, int C, int dtype, int* threads_out);
+/* Same for the tcgen05 convolution: the host-side plan for `a` (pointers are not dereferenced, nothing is launched).
+ * out[16] = block_n, G (128-row accumulators per item), A stages, B stages, weights resident, dynamic smem bytes, TMEM
+ * columns, work items, grid, staged TMA epilogue, gathered-source mode (W), line-map epilogue (W), stride-2 gather chunks
+ * (Cin/64), GEMM rows, bias-table images, K. */
+int vf_debug_conv_tiling(const vf_conv_args* a, int* out16);
 int vf_debug_gn_bwd_splits(int images, int H, int W, int C, int dtype);
 
 /* Test hook: route VF_BF16 vf_conv2d / vf_attention through the CUDA-core kernels (same bf16 storage, fp32

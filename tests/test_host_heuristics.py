@@ -55,3 +55,49 @@ def test_large_layers_keep_the_wave_filling_rule():
 def test_unsupported_shapes_are_rejected():
     assert _fwd(168, 16, 100)[0] < 0                    # channels not a multiple of the 16-byte vector
     assert _bwd(0, 16, 192) < 0
+
+
+# ---- tcgen05 convolution: host-side plan (vf_debug_conv_tiling) over every layer shape of the benchmark UNet ----------
+def _conv_plans(images=168):
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("tiling_table", os.path.join(os.path.dirname(__file__), "..", "scripts", "tiling_table.py"))
+    tt = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tt)
+    return [(name, S, segs, cout, kw, tt.plan(images, S, segs, cout, **kw)) for name, S, segs, cout, kw in tt.benchmark_layers()]
+
+
+def test_conv_plans_respect_the_hardware_limits():
+    for name, S, segs, cout, kw, p in _conv_plans():
+        cout_pad = kw.get("cout_pad", cout)
+        assert p["smem"] <= 227 * 1024, name
+        assert p["tmem"] <= 512 and p["tmem"] >= 2 * p["G"] * p["bn"] and p["tmem"] & (p["tmem"] - 1) == 0, name   # two accumulator sets
+        assert cout_pad % p["bn"] == 0 and p["bn"] % 16 == 0 and p["bn"] <= 256, name
+        assert 1 <= p["G"] <= 4 and p["aS"] >= 2 and p["bS"] >= 1, name
+        assert 1 <= p["grid"] <= SMS and p["grid"] == min(p["items"], SMS), name                                  # persistent CTAs, one per SM
+        assert p["imgs"] * p["bn"] <= 1024, name                                                                   # bias table fits the epilogue's registers
+        assert p["K"] == sum(c * k * k for c, k in segs), name
+        assert p["items"] == math.ceil(p["rows"] / (128 * p["G"])) * (cout_pad // p["bn"]), name
+
+
+def test_conv_modes_follow_the_layer_kind():
+    plans = {name: p for name, *_, p in _conv_plans()}
+    # every bf16-output layer leaves through the staged TMA epilogue; the fp32 final layer cannot
+    assert all(p["epi"] == 1 for n, p in plans.items() if not n.startswith("final"))
+    assert plans["final 64->6 (fp32 out)"]["epi"] == 0
+    # PADDED -> FLAT 1x1 (qkv): the source is gathered as whole image lines, GEMM rows are the valid pixels only
+    for n, W, rows in [("qkv 192 (inference)", 16, 168 * 256), ("qkv 192 (training)", 16, 168 * 256), ("qkv 320", 8, 168 * 64)]:
+        assert plans[n]["aL"] == W and plans[n]["rows"] == rows and plans[n]["eL"] == 0
+    # FLAT -> PADDED 1x1 (attention out-projection): 32-row tiles are whole lines of the padded output
+    assert plans["attn out 192"]["eL"] == 16 and plans["attn out 320"]["eL"] == 8
+    assert plans["conv0 (im2col 1x1, FLAT in)"]["eL"] == 0                     # W = 64: part of one line, plain 2D map
+    # Downsample: output pixels only, one gathered A tile per (tap, 64 channels)
+    for n, S, Cc in [("down 64", 64, 64), ("down 128", 32, 128), ("down 192", 16, 192)]:
+        assert plans[n]["s2"] == Cc // 64 and plans[n]["rows"] == 168 * (S // 2) ** 2 and plans[n]["K"] == 9 * Cc
+    # 3x3 layers run over PADDED rows
+    assert plans["64->64 conv1"]["rows"] == 168 * 65 * 65 and plans["320->320 conv1"]["rows"] == 168 * 81
+
+
+def test_conv_plan_scales_down_to_a_single_image():
+    for name, S, segs, cout, kw, p in _conv_plans(images=1):
+        assert p["items"] >= 1 and p["grid"] >= 1 and p["smem"] <= 227 * 1024, name

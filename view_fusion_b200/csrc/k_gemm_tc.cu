@@ -784,6 +784,10 @@ bool conv2d_tc_stride2_gathers(int H, int W, int C) {
          !(g_tc_dbg & 1024);
 }
 
+// Test hook (vf_debug_conv_tiling): when set, conv2d_tc stops after the host-side planning (geometry, mode selection,
+// tiling) and reports it here instead of encoding tensor maps and launching.
+static thread_local int* g_tc_plan_out = nullptr;
+
 int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
   VF_REQUIRE(a->dtype == VF_BF16, "vf_conv2d(tc): bf16 activations only");
   TcParams p{};
@@ -840,6 +844,13 @@ int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.G * p.block_n) p.tmem_cols *= 2;
   p.idesc = ptx::make_idesc_bf16(128, p.block_n, 0, 0);
+  if (g_tc_plan_out) {
+    int* o = g_tc_plan_out;
+    o[0] = p.block_n; o[1] = p.G; o[2] = p.a_stages; o[3] = p.b_stages; o[4] = p.b_resident; o[5] = (int)tl.smem; o[6] = p.tmem_cols;
+    o[7] = p.n_items; o[8] = p.n_items < sm_count() ? p.n_items : sm_count(); o[9] = p.epi_tma; o[10] = p.a_lines; o[11] = p.epi_lines;
+    o[12] = p.s2_cchunks; o[13] = p.geo.rows_total; o[14] = p.max_imgs; o[15] = k_total;
+    return VF_OK;
+  }
 
   CUtensorMap maps[3], maps4[4];
   // (channels, x, line) view of a PADDED tensor [images*P, ld] restricted to its valid pixels: pixel (img, y, x) is row
@@ -938,4 +949,20 @@ int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
   return VF_OK;
 }
 
+int conv2d_tc_plan(const vf_conv_args* a, int* out16) {
+  g_tc_plan_out = out16;
+  const int rc = conv2d_tc(a, nullptr);
+  g_tc_plan_out = nullptr;
+  return rc;
+}
+
 }  // namespace vf
+
+// Test hook (host arithmetic only, usable without a device): the plan vf_conv2d's tcgen05 path would use for `a` (pointers
+// are not dereferenced).  out[16] = block_n, G, a_stages, b_stages, weights resident, smem bytes, TMEM columns, work items,
+// grid, staged epilogue, gathered-source lines, line-map epilogue, stride-2 gather chunks, GEMM rows, bias-table images, K.
+extern "C" __attribute__((visibility("default"))) int vf_debug_conv_tiling(const vf_conv_args* a, int* out16) {
+  using namespace vf;
+  VF_REQUIRE(a && out16, "vf_debug_conv_tiling: null args");
+  return conv2d_tc_plan(a, out16);
+}
