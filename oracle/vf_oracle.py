@@ -15,6 +15,11 @@ it, and (a) asserts this restatement agrees with it, (b) writes the reference's
 outputs to `tests/golden/*.npz`.  `tests/test_oracle_golden.py` re-checks the
 oracle against those committed reference outputs on any machine.
 
+Two helpers outside `model/` are restated as well: `process_batch_u8` (data/nmr_dataset.py:10-52,
+checked against the literal per-sample steps in tests/test_oracle_golden.py) and `ssim` — the reference calls
+pytorch-msssim 1.0.0, which is absent from this image, so that ONE function restates the package's published
+algorithm and its parity is UNPINNED (cross-checked against a float64 brute-force evaluation of the definition only).
+
 Everything is written functionally over a flat ``state_dict`` (reference key
 layout) so it shares no module code with the product.
 Each function cites the reference lines it restates.
