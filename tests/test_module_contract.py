@@ -69,3 +69,15 @@ def test_no_cpu_fallback():
     net = UNet(**O.TINY)
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 6, 16, 16), torch.zeros(1, 1), torch.zeros(1, 1))
+
+
+def test_no_cpu_fallback_in_metrics_and_inputs():
+    """The eval metrics and the input path are CUDA-only too: on a machine without a B200 (or with CPU tensors) they raise."""
+    from view_fusion_b200 import inputs, metrics
+    a = torch.rand(2, 3, 16, 16)
+    with pytest.raises(RuntimeError):
+        metrics.compute_psnr(a, a)
+    with pytest.raises(RuntimeError):
+        metrics.compute_ssim(a, a)
+    with pytest.raises(RuntimeError):
+        inputs.prepare_batch(torch.zeros(1, 2, 4, 4, 3, dtype=torch.uint8), torch.zeros(1, 2, dtype=torch.long))
