@@ -7,7 +7,12 @@ per GPU, N=6 conditioning views (168 view-images through the shared UNet per ste
   step   = ONE reverse-diffusion step over the batch: view stacking -> UNet over all views -> softmax-over-views
            composition -> DDPM posterior update (ViewFusion.p_sample's work).  Every one of the T steps of
            `generate` is this same work, so   views/s = n_gpus * B / (T * seconds_per_step).
-  value  = device-timed (CUDA events), inputs resident in HBM.
+  value  = device-timed (CUDA events), inputs resident in HBM: K consecutive steps of the reverse loop run through the
+           public `ViewFusion.generate(..., steps=[T-1, T-2, ...])`; K = T is literally one full generate().
+  generate_full = ONE real `model(y_cond=, view_count=, angle=, generate=True)` call (all T = 2000 steps, the call
+           experiment.py:337-342 makes), timed on the device and by wall clock, next to the K-step extrapolation.
+  library_baseline = the same step run by the library kernels torch dispatches on this GPU (cuDNN / cuBLAS / ATen through
+           the functional restatement of the reference graph): fp32 with TF32 off, and bf16 autocast + channels_last.
   e2e    = the same metric through the public API `ViewFusion.p_sample` with HOST buffers: every step copies
            y_cond / y_t / angle / view_count from pinned host memory and reads y_{t-1} back.
   roofline      = the dominant kernel class (tcgen05 implicit-GEMM convolution): algorithmic conv FLOPs per
@@ -42,7 +47,22 @@ T_STEPS = 2000
 # algorithmic work per view-image forward
 GFLOP_PER_VIEW = 20.994
 GFLOP_CONV_PER_VIEW = 2 * (9.595 + 0.723)        # conv3x3 + conv1x1 MACs -> FLOPs (attention core excluded)
-CONV_DRAM_BYTES_PER_STEP = 7.362e9                # measured with ncu at B=28, N=6 (profiles/r01_ncu_full_v6_conv.txt: 6.04 GB read + 1.32 GB written)
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the round's `ncu --set full` capture (scripts/ncu_traffic.py writes
+    profiles/conv_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum averaged over the captured launches); None when
+    no capture of this round is committed (ncu cannot run inside the timed bench)."""
+    p = os.path.join(ROOT, "profiles", "conv_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+# algorithmic HBM bytes of the conv class per view-image: every conv reads its sources once and writes its output once (bf16);
+# weights are L2-resident.  From the layer table (Appendix A/B): sum over the 84 launches of (Cin_total + Cout) * H*W * 2 B.
+CONV_ALGO_BYTES_PER_VIEW = 52.06e6
 COMPOSE_BYTES_PER_SAMPLE = lambda n: n * 4096 * 32 + 2 * 3 * 4096 * 4
 
 
@@ -160,6 +180,126 @@ def cpu_train_rate(B, N, steps, warmup, threads):
     return B / sec, sec
 
 
+
+# --------------------------------------------------------------------------------------------------
+# same-box LIBRARY baseline: the reference graph through torch's own CUDA kernels (cuDNN / cuBLAS / ATen)
+# --------------------------------------------------------------------------------------------------
+def library_baseline(B, N, dev, steps=5, warmup=2):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import vf_oracle as O
+    out = {}
+    sd0 = O.init_state_dict(O.SMALL_V100, 0, prefix="denoise_fn.")
+    sched = {k: v.to(dev) for k, v in O.make_schedule(**O.BETA_TRAIN).items()}
+    y_cond, y, angle, vc = synthetic(B, N)
+    y_cond, y, angle = y_cond.to(dev), y.to(dev), angle.to(dev)
+    z = torch.randn(B, 3, 64, 64, device=dev)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    try:
+        for mode in ("fp32_no_tf32", "bf16_autocast_channels_last"):
+            bf = mode.startswith("bf16")
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+            sd = {k: (v.to(dev).contiguous(memory_format=torch.channels_last) if (bf and v.dim() == 4) else v.to(dev)) for k, v in sd0.items()}
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf):
+                yy = y
+                for j in range(warmup + steps):
+                    if j == warmup:
+                        ev[0].record()
+                    t = torch.full((B,), T_STEPS - 1 - j, dtype=torch.long, device=dev)
+                    yy = O.p_sample(sd, O.SMALL_V100, sched, yy.float(), y_cond, vc, angle, t, z)[0]
+                ev[1].record()
+            torch.cuda.synchronize()
+            ms = ev[0].elapsed_time(ev[1]) / steps
+            out[mode] = {"ms_per_step": ms, "views_per_sec": B / (T_STEPS * ms * 1e-3)}
+            del sd
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    torch.cuda.empty_cache()
+    out["what"] = (f"reference graph (oracle/vf_oracle.py functional restatement) on this GPU through torch {torch.__version__} library kernels, "
+                   f"B={B} N={N}, {steps} timed p_sample steps after {warmup} warm-up, cudnn.benchmark on; includes torch's host overhead")
+    return out
+
+
+def compose_roofline(model, dev, B=1024, N=6, iters=10):
+    """The fused composition + DDPM kernel alone at a batch that fills the machine: algorithmic bytes / event time."""
+    import ctypes as C
+    from view_fusion_b200 import _lib
+    lib = _lib.require_device()
+    out8 = torch.randn(B * N * 4096, 8, device=dev)
+    y_t, y_prev = torch.randn(B, 3, 64, 64, device=dev), torch.empty(B, 3, 64, 64, device=dev)
+    off = (torch.arange(B + 1, dtype=torch.int32) * N).to(dev)
+    t32 = torch.full((B,), 1000, dtype=torch.int32, device=dev)
+    a = _lib.ComposeArgs()
+    a.unet_out, a.view_offset, a.t, a.y_t, a.y_prev = out8.data_ptr(), off.data_ptr(), t32.data_ptr(), y_t.data_ptr(), y_prev.data_ptr()
+    a.seed, a.offset, a.add_noise, a.clip_denoised, a.weighting, a.B, a.H, a.W, a.max_v = 1234, 1, 1, 1, 1, B, 64, 64, N
+    sched = model._schedule_struct()
+    st = _lib.stream_handle()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for j in range(iters + 3):
+        if j == 3:
+            ev[0].record()
+        _lib.check(lib.vf_compose_ddpm_step(C.byref(a), C.byref(sched), st), "compose")
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / iters
+    nbytes = B * COMPOSE_BYTES_PER_SAMPLE(N)
+    pk = peaks()
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    return {"kernel": "compose_ddpm_kernel", "B": B, "N": N, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+            "frac": gbs / pk["hbm"], "bytes_per_launch": nbytes, "avg_launch_ms": ms,
+            "note": f"input ({B * N * 4096 * 32 / 1e6:.0f} MB) exceeds the 126 MB L2; fp32 [.,8] UNet output rows as produced by the final conv"}
+
+
+def extra_configs(model, dev, steps, rank):
+    """BASELINE.json configs 4 and 5: extrapolation N = 12 / 24 at B = 12 (experiment.py:472-514, vis batch size :212) and the
+    autoregressive orbit at B = 1, count = 1..24 (experiment.py:516-578).  Per-step device time over `steps` consecutive
+    reverse steps through generate(); the orbit time is the sum over the 24 growing conditioning sets of T * step(count)."""
+    out = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    host0 = None
+    for n in (12, 24):
+        y_cond, y_T, angle, vc = synthetic(12, n, seed=77 + n)
+        y_cond, y_T, angle = y_cond.to(dev), y_T.to(dev), angle.to(dev)
+        ts = [T_STEPS - 1 - j for j in range(steps)]
+        model.generate(y_cond, vc, angle, y_t=y_T, steps=ts[:3])
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record()
+        model.generate(y_cond, vc, angle, y_t=y_T, steps=ts)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[f"extrapolation_N{n}_B12"] = {"ms_per_step": ms, "views_per_sec": 12 / (T_STEPS * ms * 1e-3), "view_images_per_step": 12 * n}
+    # autoregressive: B = 1, the conditioning set grows from 1 to 24 views
+    y_cond, y_T, angle, _ = synthetic(1, 24, seed=5)
+    y_cond, y_T, angle = y_cond.to(dev), y_T.to(dev), angle.to(dev)
+    per_count, host_ms = {}, {}
+    total_s = 0.0
+    ts = [T_STEPS - 1 - j for j in range(steps)]
+    for count in range(1, 25):
+        vc = torch.full((1,), count, dtype=torch.long)
+        model.generate(y_cond, vc, angle, y_t=y_T, steps=ts[:3])
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        h0 = time.perf_counter()
+        e0.record()
+        model.generate(y_cond, vc, angle, y_t=y_T, steps=ts)
+        e1.record()
+        h1 = time.perf_counter()                  # host time to ENQUEUE the steps (no sync yet)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        per_count[count] = round(ms, 4)
+        host_ms[count] = round((h1 - h0) * 1e3 / steps, 4)
+        total_s += T_STEPS * ms * 1e-3
+    out["autoregressive_B1"] = {"seconds_per_24_view_orbit": total_s, "ms_per_step_by_view_count": per_count,
+                                "host_enqueue_ms_per_step_by_view_count": host_ms,
+                                "how": f"sum over count = 1..24 of T * (device ms per step at that count, {steps} consecutive steps each); "
+                                       "host_enqueue = wall time generate() needs to issue a step (must stay below the device time)"}
+    return out
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -194,6 +334,9 @@ def main():
     ap.add_argument("--train-batch", type=int, default=28, help="training samples per GPU (weak scaling)")
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--no-train", action="store_true", help="skip the training-throughput leg")
+    ap.add_argument("--no-full-generate", action="store_true", help="skip the real T=2000 generate() run (~13 s)")
+    ap.add_argument("--no-library-baseline", action="store_true", help="skip the torch library-kernel comparison on this GPU")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the autoregressive (C4) / extrapolation (C5) legs")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -223,31 +366,24 @@ def main():
     y_cond_h, y_T_h, angle_h, vc = synthetic(B, N, seed=1234 + rank)
     y_cond, y_t, angle = y_cond_h.to(dev), y_T_h.to(dev), angle_h.to(dev)
 
-    from view_fusion_b200.view_fusion import _Plan
-    plan = _Plan(model, y_cond, vc)
-    bufs = [y_t, torch.empty_like(y_t)]
-    t = torch.empty(B, dtype=torch.long, device=dev)
-
-    def step(j):
-        i = T_STEPS - 1 - (j % T_STEPS)
-        t.fill_(i)
-        model._step(plan, bufs[j & 1], y_cond, angle, t, bufs[(j + 1) & 1], add_noise=i > 0)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def run_steps(first_t, k, y_start):
+        """k consecutive reverse steps t = first_t, first_t - 1, ... through the public generate() (wraps below 0)."""
+        ts = [(first_t - j) % T_STEPS for j in range(k)]
+        return model.generate(y_cond, vc, angle, y_t=y_start, steps=ts)[0]
+
     with torch.no_grad():
-        for j in range(args.warmup):
-            step(j)
-        launches_per_step = model.denoise_fn.last_launches() + 2 + 1      # + pack_views (2 kernels) + compose
+        y_w = run_steps(T_STEPS - 1, args.warmup, y_t)
+        launches_per_step = model.denoise_fn.last_launches() + model.step_overhead_launches()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local_rank) as clk:
             e0.record()
-            for j in range(args.steps):
-                step(args.warmup + j)
+            y_k = run_steps(T_STEPS - 1 - args.warmup, args.steps, y_w)
             e1.record()
             barrier()
         ms = e0.elapsed_time(e1)
@@ -257,6 +393,29 @@ def main():
             ms = float(tm)
         ms_step = ms / args.steps
         value = world * B / (T_STEPS * ms_step * 1e-3)
+        assert bool(torch.isfinite(y_k).all())
+
+        # ---- one REAL full-T generate() through the module call the reference's experiment makes ------------------
+        gen_full = None
+        if not args.no_full_generate:
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0 = time.perf_counter()
+            g0.record()
+            y_fin, ret_arr, logit_arr, weight_arr, last = model(y_cond=y_cond, view_count=vc, angle=angle, generate=True)
+            g1.record()
+            barrier()
+            wall = time.perf_counter() - w0
+            gsec = g0.elapsed_time(g1) * 1e-3
+            if world > 1:
+                tm = torch.tensor([gsec, wall], device=dev)
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                gsec, wall = float(tm[0]), float(tm[1])
+            assert tuple(ret_arr.shape) == (B, 9, 3, 64, 64) and bool(torch.isfinite(y_fin).all())
+            gen_full = {"value": world * B / gsec, "unit": "views/s", "seconds": gsec, "wall_seconds": wall, "T": T_STEPS,
+                        "ms_per_step": gsec * 1e3 / T_STEPS, "ratio_to_k_step_value": (world * B / gsec) / value,
+                        "api": "ViewFusion.forward(y_cond, view_count, angle, generate=True): T reverse steps + 8 weight/logit snapshots"}
+            del y_fin, ret_arr, logit_arr, weight_arr, last
 
         # ---- e2e through the public API with host buffers -------------------------------------------------
         pin = lambda x: x.contiguous().pin_memory()
@@ -294,7 +453,7 @@ def main():
             model.denoise_fn.set_profiling(True)
             acc = {}
             for j in range(3):
-                step(j)
+                run_steps(T_STEPS - 1 - j, 1, y_t)
                 pr = model.denoise_fn.profile()
                 if j > 0:
                     for k, (m_, c_) in pr.items():
@@ -302,14 +461,15 @@ def main():
                         a_[0] += m_ / 2; a_[1] = c_
             model.denoise_fn.set_profiling(False)
             pk = peaks()
+            tr_ = ncu_traffic()
             conv_ms, conv_n = acc["conv"]
             images = B * N
             flops = GFLOP_CONV_PER_VIEW * 1e9 * images
             ach = flops / (conv_ms * 1e-3) / 1e12
             roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                    "traffic": CONV_DRAM_BYTES_PER_STEP / conv_n if (B, N) == (28, 6) else None,
-                    "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum over the 84 conv launches of one "
-                                      "step (profiles/r01_ncu_full_v6_conv.txt), per launch",
+                    "traffic": (tr_.get("bytes_per_launch") if (tr_ and (B, N) == (28, 6)) else None),
+                    "traffic_source": (tr_.get("source") if tr_ else "no ncu capture committed for this round"),
+                    "algorithmic_bytes_per_launch": CONV_ALGO_BYTES_PER_VIEW * images / conv_n,
                     "kernel": "conv_tc_kernel", "launches_per_step": conv_n,
                     "flops_per_launch": flops / conv_n, "avg_launch_ms": conv_ms / conv_n,
                     "peak_source": f"{pk['src']} sustained bf16 (kernel timed inside a long step)"}
@@ -322,11 +482,21 @@ def main():
             classes["hbm_peak_GBps"] = pk["hbm"]
             classes["step_flop_utilisation"] = round(GFLOP_PER_VIEW * 1e9 * images / (ms_step * 1e-3) / 1e12 / pk["tf_sustained"], 4)
 
+    lib_base = roof_compose = extra = None
+    if rank == 0 and world == 1:
+        with torch.no_grad():
+            roof_compose = compose_roofline(model, dev)
+            if not args.no_extra_configs:
+                extra = extra_configs(model, dev, max(10, min(args.steps, 40)), rank)
+        model.release_buffers()
+        torch.cuda.empty_cache()
+        if not args.no_library_baseline:
+            lib_base = library_baseline(B, N, dev)
+
     # ---- training leg: zero_grad -> forward -> backward (+ gradient all-reduce) -> Adam ------------------------
     train = None
     if not args.no_train:
         from view_fusion_b200.distributed import data_parallel
-        del plan, bufs
         torch.cuda.empty_cache()
         Bt = args.train_batch
         yc_h, eps_h, an_h, vct = synthetic(Bt, N, seed=4321 + rank)
@@ -413,6 +583,10 @@ def main():
             "gpu_launches_per_step": launches_per_step,
             "clocks": clk.summary(),
             "roofline": roof,
+            "roofline_compose": roof_compose,
+            "generate_full": gen_full,
+            "library_baseline": lib_base,
+            "extra_configs": extra,
             "kernel_classes": classes,
             "cpu_baseline": cpu,
             "train": train,

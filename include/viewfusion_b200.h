@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define VF_ABI_VERSION 1
+#define VF_ABI_VERSION 2
 
 typedef enum vf_status {
   VF_OK = 0,
@@ -109,9 +109,20 @@ size_t vf_unet_workspace_bytes(const vf_unet* u, int max_images);
  *   out      : [images*H*W, 8] fp32, channels 0..out_channel-1 valid (NHWC, padded to 8)
  */
 int vf_unet_k0(const vf_unet* u);
+int vf_unet_act_dtype(const vf_unet* u);   /* VF_F32 / VF_BF16 given to vf_unet_create */
 int vf_unet_forward(vf_unet* u, const void* packed, void* workspace, size_t workspace_bytes, int images,
                     const void* x0, const float* level, const float* angle, int rows, const int* img_row,
                     float* out, vf_stream stream);
+
+/* Arena layout capacity.  vf_unet_forward / vf_unet_backward size every buffer of their bump-allocated workspaces for
+ * max(capacity, images) view-images, so with a workspace of vf_unet_workspace_bytes(u, capacity) bytes the position of every
+ * buffer — and with it the zero padding rows the caller established by zero-filling the workspace once — stays put when the
+ * batch size or the view counts change from call to call (the reference draws view_count per step, experiment.py:277).
+ * The backward workspace (vf_unet_backward_workspace_bytes) follows the layout of the last forward. */
+int vf_unet_set_capacity(vf_unet* u, int max_images);
+/* Monotonic counter bumped by every vf_unet_forward on this plan: vf_unet_backward differentiates the LAST forward, so a
+ * caller that stashed a forward checks this before running its backward. */
+unsigned long long vf_unet_forward_generation(const vf_unet* u);
 
 /* Training (default, on = 1): the forward also writes what only vf_unet_backward reads (the transposed V of every
  * attention block).  Inference (on = 0): those extras are skipped — the attention kernel takes V row-major from the qkv
@@ -175,7 +186,7 @@ typedef struct vf_compose_args {
   const float* z;            /* (B,3,H,W) injected N(0,1) draw, or NULL -> Philox(seed, offset) in-kernel */
   uint64_t seed;
   uint64_t offset;
-  int add_noise;             /* the reference's `any(t > 0)` (view_fusion.py:176), decided by the caller */
+  int add_noise;             /* the reference's `any(t > 0)` (view_fusion.py:176): 0 / 1 decided by the caller, 2 = read from `step` */
   int clip_denoised;
   int weighting;             /* 1: softmax over views (6-channel UNet); 0: plain mean (ablation, :141-150) */
   int B, H, W;
@@ -183,7 +194,53 @@ typedef struct vf_compose_args {
   float* weights_out;        /* optional (B,max_v,3,H,W): softmax weights, zero in padded slots */
   int max_v;
   float* logits_out;         /* optional (images,3,H,W): un-padded logits (p_sample's 2nd return value) */
+  const struct vf_step_record* step; /* optional DEVICE record written by vf_step_prepare: when set, add_noise == 2 takes the
+                                * `any(t > 0)` decision from step->any_t_positive, the Philox offset from step->noise_offset and
+                                * (seed == 0) the seed from step->seed
+                                * (nothing about the step is baked into the launch: CUDA-graph replays advance on the device) */
 } vf_compose_args;
+
+/* Device-resident state of a reverse loop (view_fusion.py:196-206), so that one captured CUDA graph can be replayed for every
+ * step: vf_step_prepare reads t_state[b], publishes the step's constants and (advance != 0) decrements t_state / bumps the
+ * noise counter for the next replay. */
+typedef struct vf_step_record {
+  int any_t_positive;              /* the reference's `any(t > 0)` over the batch (view_fusion.py:176) */
+  int reserved;
+  unsigned long long noise_offset; /* Philox offset of this step's draw */
+  unsigned long long seed;         /* Philox seed of the loop (copied from noise_ctr[1]) */
+} vf_step_record;
+
+/*   t_state [B] int32 (in/out), noise_ctr [2] u64 = {Philox offset (in/out), seed} (may be NULL), gammas [T] ->
+ *   level [B] = gammas[t] (the UNet's noise-level input, view_fusion.py:98), t_cur [B] = t, rec = the step record */
+int vf_step_prepare(int* t_state, int B, const float* gammas, int num_timesteps, int advance, unsigned long long* noise_ctr,
+                    float* level, int* t_cur, vf_step_record* rec, vf_stream stream);
+
+/* One whole reverse step, enqueued on `stream` without any host decision (graph-capturable): vf_step_prepare -> vf_pack_views ->
+ * vf_unet_forward -> vf_compose_ddpm_step.  This is ViewFusion.p_sample (view_fusion.py:166-177) over a batch whose time-steps
+ * live on the device. */
+typedef struct vf_sample_step_args {
+  const void* packed;              /* vf_unet_pack_weights output */
+  void* workspace;                 /* vf_unet_workspace_bytes(u, capacity) bytes */
+  size_t workspace_bytes;
+  const float* y_cond;             /* (B, n_max, cond_channels, H, W) fp32 */
+  int B, n_max, cond_channels, H, W, images;
+  const int* view_offset;          /* [B+1] int32 */
+  const float* angle;              /* [B] fp32 */
+  const float* y_t;                /* (B,3,H,W) */
+  float* y_prev;                   /* (B,3,H,W); may alias y_t (in-place reverse loop) */
+  int* t_state;                    /* [B] int32 device */
+  int advance;                     /* != 0: t_state[b] = max(t-1, 0) and ++noise_ctr after use */
+  unsigned long long* noise_ctr;   /* [2] device {offset, seed}, or NULL with z */
+  uint64_t seed;                   /* != 0: Philox seed by value; 0: the device-resident noise_ctr[1] (replayed graphs) */
+  const float* z;                  /* injected draw or NULL */
+  int add_noise;                   /* 0 never, 1 always, 2 iff any t > 0 (decided on the device) */
+  int clip_denoised, weighting;
+  void* x0; int* img_sample; float* unet_out;      /* staging: [images*H*W, K0] act dtype, [images], [images*H*W, 8] fp32 */
+  float* level; int* t_cur; vf_step_record* rec;   /* [B], [B], [1] device scratch */
+  float* eps_out; float* weights_out; float* logits_out; int max_v;   /* optional outputs as in vf_compose_args */
+  vf_schedule sched;
+} vf_sample_step_args;
+int vf_p_sample_step(vf_unet* u, const vf_sample_step_args* a, vf_stream stream);
 
 int vf_compose_ddpm_step(const vf_compose_args* a, const vf_schedule* s, vf_stream stream);
 
@@ -371,6 +428,19 @@ int vf_zero_insert2x(const void* dy, int dtype, int images, int H, int W, int C,
 int vf_add_inplace(void* dst, const void* src, int dtype, size_t n_elems, vf_stream stream);
 /* [rows, 8] fp32 (vf_compose_mse's grad_out) -> [rows, ld] activation dtype, zero beyond channel 8. */
 int vf_grad8_to_act(const float* g8, size_t rows, int dtype, int ld, void* dst, vf_stream stream);
+
+/* Bias / embedding gradients of one convolution (autograd of unet.py:214 bias and :176 FeatureWiseAffine add): per-image column
+ * sums of dy [images*rows_per_img, ld] (padding rows must hold zeros), first `cout` columns:
+ *   db0[n], db1[n] += sum_rows dy[row][n]   (either may be NULL);   demb[img_row[img]][col + n] += sum_rows(img) dy[row][n]  (or NULL). */
+int vf_colsum_bias(const void* dy, int dtype, int images, int rows_per_img, int ld, int cout, float* db0, float* db1, float* demb,
+                   const int* img_row, int emb_ld, int col, vf_stream stream);
+
+/* Backward of vf_embed (autograd of unet.py:115-116, 27-32, 165-176): demb [rows, E] = gradient of the embedding table.
+ * dew [E, ic] and deb [E] are OVERWRITTEN with the gradients of the concatenated per-block Linear weights / biases; the
+ * noise_level_mlp gradients dw0 [4ic, ic], db0 [4ic], dw2 [ic, 4ic], db2 [ic] are ACCUMULATED.  rowbuf: rows*11*ic floats. */
+int vf_embed_backward(const float* level, const float* angle, int rows, int inner_channel, const float* w0, const float* b0,
+                      const float* w2, const float* b2, const float* emb_w, int E, const float* demb, float* rowbuf, float* dew,
+                      float* deb, float* dw0, float* db0, float* dw2, float* db2, vf_stream stream);
 
 /* ---- optimizer step (reference: torch.optim.Adam of experiment.py:115-120, stepped at :293) -------------
  * One launch for all parameter tensors.  table_dev: one entry per tensor (fp32 device pointers); chunk_entry_dev /

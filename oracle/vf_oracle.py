@@ -222,7 +222,7 @@ def make_schedule(**beta_kw) -> SD:
 def positional_encoding(level: Tensor, dim: int) -> Tensor:
     """unet.py:147-157.  level (R,1) -> (R,1,dim): [sin(l*f_k), cos(l*f_k)], f_k = 1e4^(-k/count)."""
     count = dim // 2
-    step = torch.arange(count, dtype=level.dtype) / count
+    step = torch.arange(count, dtype=level.dtype, device=level.device) / count
     enc = level.unsqueeze(1) * torch.exp(-math.log(1e4) * step.unsqueeze(0))
     return torch.cat([torch.sin(enc), torch.cos(enc)], dim=-1)
 
@@ -318,7 +318,7 @@ def stack_views(y_cond: Tensor, y_t: Tensor, view_count: Tensor, angle: Tensor, 
     """view_fusion.py:95-115 / :244-263: first V_b views of each sample, target/level/angle repeated."""
     vc = [int(v) for v in view_count.tolist()]
     cond = torch.cat([y_cond[b, :v] for b, v in enumerate(vc)], dim=0)
-    rep = torch.tensor(vc, dtype=torch.long)
+    rep = torch.tensor(vc, dtype=torch.long, device=y_t.device)
     x = torch.cat([cond, torch.repeat_interleave(y_t, rep, dim=0)], dim=1)
     return x, torch.repeat_interleave(angle, rep, dim=0), torch.repeat_interleave(level, rep, dim=0)
 

@@ -37,3 +37,22 @@ def build_model(cfg, seed, precision, weighting=True):
 
 def bf16r(x):
     return x.to(torch.bfloat16).float()
+
+
+# ---- recorded margins: every parity number the GPU tests measure goes to one text file (copied to profiles/ per round) ----
+_MARGIN_FILE = os.environ.get("VF_MARGINS_FILE") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                 "gpurun_out", "parity_margins.txt")
+
+
+def margin(name, value, bar, higher_is_better=False):
+    """Append `name value bar margin` to the margins file and return whether the bar is met (NaN never passes)."""
+    value = float(value)
+    ok = (value > bar) if higher_is_better else (value < bar)
+    ratio = (value / bar) if higher_is_better else (bar / value if value > 0 else float("inf"))
+    try:
+        os.makedirs(os.path.dirname(_MARGIN_FILE), exist_ok=True)
+        with open(_MARGIN_FILE, "a") as fh:
+            fh.write(f"{name:<78s} measured {value:11.4e}  bar {'>' if higher_is_better else '<'} {bar:9.3e}  margin x{ratio:7.2f}  {'ok' if ok else 'FAIL'}\n")
+    except OSError:
+        pass
+    return ok

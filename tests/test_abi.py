@@ -32,7 +32,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.vf_abi_version() == 1
+    assert lib.vf_abi_version() == 2
     assert isinstance(lib.vf_last_error(), bytes)
 
 

@@ -1,0 +1,80 @@
+"""GPU: the HEADLINE configuration (small-v100 UNet, 64x64, N = 6 conditioning views) against the live CPU oracle.
+
+BASELINE.json quotes its metric on N = 6; the committed goldens are N = 3 (tests/golden/psample_small_n3.npz) and the
+full-size tests (B = 28) can only compare the CUDA path with itself, so this file pins N = 6 at a batch the oracle
+finishes in seconds (B = 2: 12 view-images, ~0.2 s per step on the host).  Reference semantics: model/view_fusion.py:86-177.
+Bars (BASELINE.json north_star): composed noise prediction within 1e-2 relative (bf16) / 1e-4 (fp32 mode), view-weight
+argmax identical.  Every measured number is appended to the margins file (gpu_util.margin).
+"""
+import math
+
+import pytest
+import torch
+
+import vf_oracle as O
+from gpu_util import build_model, margin, rel
+
+pytestmark = pytest.mark.gpu
+
+B, N = 2, 6
+
+
+def _inputs(seed):
+    g = torch.Generator().manual_seed(seed)
+    y_cond = torch.rand(B, N, 3, 64, 64, generator=g)
+    y_t = torch.randn(B, 3, 64, 64, generator=g)
+    angle = (2 * math.pi / 24) * torch.randint(0, 24, (B, 1), generator=g).float()
+    z = torch.randn(B, 3, 64, 64, generator=g)
+    return y_cond, y_t, angle, torch.full((B,), N, dtype=torch.long), z
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_p_sample_n6_vs_oracle(prec, tol):
+    cfg = O.SMALL_V100
+    m, sd = build_model(cfg, 7, prec)
+    sched = O.make_schedule(**O.BETA_TRAIN)
+    y_cond, y_t, angle, vc, z = _inputs(1234)
+    ok = True
+    for tv in (1999, 1000, 1, 0):
+        t = torch.full((B,), tv, dtype=torch.long)
+        # at small t the reverse process sits near the data manifold: start from a q_sample of a clean image, not from N(0, I)
+        g = float(sched["gammas"][tv])
+        y_in = math.sqrt(g) * y_cond[:, 0] + math.sqrt(1 - g) * y_t
+        with torch.no_grad():
+            y_ref, eps_ref, logits_ref, w_ref = O.p_sample(sd, cfg, sched, y_in, y_cond, vc, angle, t, z)
+        eps = torch.empty(B, 3, 64, 64, device="cuda")
+        y_prev, logits, w = m.p_sample(y_in.cuda(), y_cond.cuda(), vc, angle.cuda(), t.cuda(), noise=z.cuda(), _eps_out=eps)
+        ok &= margin(f"headline N=6 B=2 small-v100 {prec} t={tv}: composed eps rel-L2 vs oracle", rel(eps, eps_ref), tol)
+        ok &= margin(f"headline N=6 B=2 small-v100 {prec} t={tv}: y_(t-1) rel-L2 vs oracle", rel(y_prev, y_ref), tol)
+        ok &= margin(f"headline N=6 B=2 small-v100 {prec} t={tv}: view weights rel-L2 vs oracle", rel(w, w_ref), 1e-4 if prec == "fp32" else 2e-2)
+        assert w.shape == w_ref.shape and logits.shape == logits_ref.shape
+        if prec == "fp32":
+            assert torch.equal(w.cpu().argmax(1), w_ref.argmax(1)), "view-weight argmax must be identical in fp32 mode"
+        else:
+            top2 = w_ref.topk(2, dim=1).values
+            clear = (top2[:, 0] - top2[:, 1]) > 0.02          # random-init logits are near-ties
+            same = w.cpu().argmax(1) == w_ref.argmax(1)
+            assert bool(same[clear].all())
+            margin(f"headline N=6 B=2 small-v100 bf16 t={tv}: argmax agreement over ALL pixels (near-ties included)",
+                   float(same.float().mean()), 0.9, higher_is_better=True)
+    assert ok, "see the margins file"
+
+
+def test_closed_loop_bf16_psnr_vs_oracle():
+    """bf16 closed loop: 50 consecutive reverse steps from t = 49 (where the clamp and the noise scale matter), both sides
+    fed their OWN previous output and the same injected noise; stated bound: PSNR of the final view vs the oracle > 35 dB."""
+    cfg = O.SMALL_V100
+    m, sd = build_model(cfg, 7, "bf16")
+    sched = O.make_schedule(**O.BETA_TRAIN)
+    y_cond, y_t, angle, vc, _ = _inputs(77)
+    steps = list(range(49, -1, -1))
+    g = float(sched["gammas"][steps[0]])
+    y_start = math.sqrt(g) * y_cond[:, 0] + math.sqrt(1 - g) * y_t
+    zs = O.normal_draws(len(steps), (B, 3, 64, 64), seed=5)
+    with torch.no_grad():
+        y_ref, *_ = O.generate(sd, cfg, sched, y_cond, vc, angle, y_start, zs, steps=steps)
+    y, *_ = m.generate(y_cond.cuda(), vc, angle.cuda(), y_t=y_start.cuda(), noise_steps=zs, steps=steps)
+    psnr = float(O.psnr(y.cpu().clamp(0, 1), y_ref.clamp(0, 1)).min())
+    ok = margin("closed loop 50 steps (t=49..0) N=6 B=2 small-v100 bf16: PSNR(final view, oracle) dB", psnr, 35.0, higher_is_better=True)
+    ok &= margin("closed loop 50 steps (t=49..0) N=6 B=2 small-v100 bf16: final y rel-L2 vs oracle", rel(y, y_ref), 1e-2)
+    assert ok

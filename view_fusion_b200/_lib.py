@@ -19,14 +19,14 @@ SYMBOLS = [
     "vf_last_error", "vf_abi_version", "vf_device_check",
     "vf_unet_create", "vf_unet_destroy", "vf_unet_num_params", "vf_unet_param_info", "vf_unet_emb_channels",
     "vf_unet_packed_bytes", "vf_unet_pack_weights", "vf_unet_workspace_bytes", "vf_unet_k0", "vf_unet_forward",
-    "vf_unet_last_launches", "vf_unet_read_tap", "vf_unet_set_profiling", "vf_unet_profile_read", "vf_unet_profile_launches", "vf_unet_set_stash",
+    "vf_unet_last_launches", "vf_unet_read_tap", "vf_unet_set_profiling", "vf_unet_profile_read", "vf_unet_profile_launches", "vf_unet_set_stash", "vf_unet_set_capacity", "vf_unet_forward_generation",
     "vf_pack_views", "vf_pack_nchw", "vf_nhwc_to_nchw", "vf_q_sample",
-    "vf_compose_ddpm_step", "vf_compose_mse",
+    "vf_compose_ddpm_step", "vf_compose_mse", "vf_step_prepare", "vf_p_sample_step", "vf_unet_act_dtype",
     "vf_embed", "vf_gn_stats", "vf_gn_apply", "vf_upsample2x", "vf_flat_to_padded", "vf_padded_to_flat", "vf_zero_padding", "vf_conv2d", "vf_debug_force_simt", "vf_debug_flags", "vf_debug_counters", "vf_debug_umma_shift", "vf_debug_umma_rate", "vf_debug_umma_mn", "vf_attention",
     "vf_pack_conv_weight",
     "vf_unet_packed_t_bytes", "vf_unet_pack_weights_t", "vf_unet_backward_workspace_bytes", "vf_unet_backward",
     "vf_conv2d_wgrad", "vf_unpack_conv_wgrad", "vf_pack_conv_weight_t", "vf_gn_backward", "vf_attention_backward",
-    "vf_upsample2x_backward", "vf_zero_insert2x", "vf_add_inplace", "vf_grad8_to_act",
+    "vf_upsample2x_backward", "vf_zero_insert2x", "vf_add_inplace", "vf_grad8_to_act", "vf_colsum_bias", "vf_embed_backward",
     "vf_adam_chunk_elems", "vf_adam_step", "vf_eval_metrics", "vf_prepare_batch_u8", "vf_debug_gn_splits", "vf_debug_gn_bwd_splits", "vf_debug_conv_tiling",
 ]
 
@@ -55,6 +55,21 @@ class ComposeArgs(C.Structure):
         ("add_noise", C.c_int), ("clip_denoised", C.c_int), ("weighting", C.c_int),
         ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
         ("eps_out", C.c_void_p), ("weights_out", C.c_void_p), ("max_v", C.c_int), ("logits_out", C.c_void_p),
+        ("step", C.c_void_p),
+    ]
+
+
+class SampleStepArgs(C.Structure):
+    _fields_ = [
+        ("packed", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("y_cond", C.c_void_p), ("B", C.c_int), ("n_max", C.c_int), ("cond_channels", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("images", C.c_int), ("view_offset", C.c_void_p), ("angle", C.c_void_p), ("y_t", C.c_void_p), ("y_prev", C.c_void_p),
+        ("t_state", C.c_void_p), ("advance", C.c_int), ("noise_ctr", C.c_void_p), ("seed", C.c_uint64), ("z", C.c_void_p),
+        ("add_noise", C.c_int), ("clip_denoised", C.c_int), ("weighting", C.c_int),
+        ("x0", C.c_void_p), ("img_sample", C.c_void_p), ("unet_out", C.c_void_p),
+        ("level", C.c_void_p), ("t_cur", C.c_void_p), ("rec", C.c_void_p),
+        ("eps_out", C.c_void_p), ("weights_out", C.c_void_p), ("logits_out", C.c_void_p), ("max_v", C.c_int),
+        ("sched", Schedule),
     ]
 
 
@@ -101,6 +116,8 @@ def load() -> C.CDLL:
         "vf_unet_last_launches": (i, [p]),
         "vf_unet_set_profiling": (i, [p, i]),
         "vf_unet_set_stash": (i, [p, i]),
+        "vf_unet_set_capacity": (i, [p, i]),
+        "vf_unet_forward_generation": (C.c_ulonglong, [p]),
         "vf_unet_profile_read": (i, [p, C.POINTER(C.c_float), C.POINTER(i)]),
         "vf_eval_metrics": (i, [p, p, i, i, i, i, p, p, p]),
         "vf_prepare_batch_u8": (i, [p, p, i, i, i, i, i, p, p, p, p]),
@@ -115,6 +132,9 @@ def load() -> C.CDLL:
         "vf_q_sample": (i, [p, p, p, i, i, p, p]),
         "vf_compose_ddpm_step": (i, [C.POINTER(ComposeArgs), C.POINTER(Schedule), p]),
         "vf_compose_mse": (i, [p, p, p, i, i, i, i, p, p, p, f, p]),
+        "vf_step_prepare": (i, [p, i, p, i, i, p, p, p, p, p]),
+        "vf_p_sample_step": (i, [p, C.POINTER(SampleStepArgs), p]),
+        "vf_unet_act_dtype": (i, [p]),
         "vf_embed": (i, [p, p, i, i, p, p, p, p, p, p, i, p, p]),
         "vf_gn_stats": (i, [p, i, p, i, i, i, i, i, p, p]),
         "vf_gn_apply": (i, [p, i, p, i, p, i, p, i, i, i, i, i, i, p, p, i, p, p]),
@@ -144,6 +164,8 @@ def load() -> C.CDLL:
         "vf_zero_insert2x": (i, [p, i, i, i, i, i, p, p]),
         "vf_add_inplace": (i, [p, p, i, sz, p]),
         "vf_grad8_to_act": (i, [p, sz, i, i, p, p]),
+        "vf_colsum_bias": (i, [p, i, i, i, i, i, p, p, p, p, i, i, p]),
+        "vf_embed_backward": (i, [p, p, i, i, p, p, p, p, p, i, p, p, p, p, p, p, p, p, p]),
         "vf_adam_chunk_elems": (i, []),
         "vf_adam_step": (i, [p, p, p, i, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, i, p]),
     }
@@ -151,7 +173,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.vf_abi_version() != 1:
+    if lib.vf_abi_version() != 2:
         raise RuntimeError("libviewfusion_b200.so: ABI version mismatch")
     _lib = lib
     return lib

@@ -310,10 +310,7 @@ int attention_bwd_tc(const void* qkv, const void* vt, const void* out, const flo
   }
   const size_t smem = 1024 + 1024 + 4 * (size_t)p.tile_bytes + 2 * 128 * 128;
   VF_REQUIRE(smem <= 227 * 1024, "vf_attention_backward(tc): L=%d C=%d need %zu B of shared memory", L, C, smem);
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
-  VF_CUDA(attr_err);
+  VF_SET_MAX_SMEM(attn_bwd_tc_kernel, 227 * 1024);
   attn_bwd_tc_kernel<<<images * p.nblk, AB_THREADS, smem, st>>>(mapQKV, mapDO, mapVT, p);
   VF_LAUNCH_CHECK();
   const size_t total = rows * (size_t)(2 * C / 8);

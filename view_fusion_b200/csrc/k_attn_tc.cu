@@ -305,10 +305,7 @@ int attention_tc(const void* qk, const void* vt, int images, int L, int C, void*
     int rc = encode_bf16_map(&mapVT, vt, 2, dims, strides, box);
     if (rc) return rc;
   }
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
-  VF_CUDA(attr_err);
+  VF_SET_MAX_SMEM(attn_tc_kernel, 227 * 1024);
   VF_CUDA(launch_pdl(attn_tc_kernel, dim3(cdiv(p.M, 128)), dim3(ATT_THREADS), smem, st, mapQK, mapVT, p));
   VF_LAUNCH_CHECK();
   return VF_OK;

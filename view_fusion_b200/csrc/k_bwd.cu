@@ -826,10 +826,7 @@ VF_API int vf_attention_backward(const void* qk, const void* vt, const void* out
     return attention_bwd_tc(qk, vt, out, lse, d_out, images, L, C, scratch, dqkv, as_stream(stream));
   cudaStream_t st = as_stream(stream);
   if (dtype == VF_BF16 && !g_force_simt_flag && vt && L == AL && C % 64 == 0 && AttnL64Smem::bytes(C) <= 227 * 1024) {
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(attn_bwd_l64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
-    VF_CUDA(attr_err);
+    VF_SET_MAX_SMEM(attn_bwd_l64_kernel, 227 * 1024);
     attn_bwd_l64_kernel<<<images, 256, AttnL64Smem::bytes(C), st>>>((const __nv_bfloat16*)qk, (const __nv_bfloat16*)vt, (const __nv_bfloat16*)d_out,
                                                                     C, (__nv_bfloat16*)dqkv);
     VF_LAUNCH_CHECK();

@@ -95,20 +95,23 @@ __global__ void __launch_bounds__(256) compose_ddpm_kernel(const ComposeParams p
   const int t = __ldg(a.t + b);
   const float A = __ldg(p.s.sqrt_recip_gammas + t), Bm = __ldg(p.s.sqrt_recipm1_gammas + t);
   const float c1 = __ldg(p.s.posterior_mean_coef1 + t), c2 = __ldg(p.s.posterior_mean_coef2 + t);
-  const float sigma = a.add_noise ? expf(0.5f * __ldg(p.s.posterior_log_variance_clipped + t)) : 0.f;
+  // the `any(t > 0)` decision and the Philox offset come from the launch arguments or, in a replayed CUDA graph, from the
+  // device-resident step record that vf_step_prepare wrote
+  const bool add_noise = a.add_noise == 2 ? (a.step != nullptr && a.step->any_t_positive != 0) : a.add_noise != 0;
+  const float sigma = add_noise ? expf(0.5f * __ldg(p.s.posterior_log_variance_clipped + t)) : 0.f;
   const size_t o = (size_t)b * 3 * HW + pix;
   float z[3] = {0.f, 0.f, 0.f};
-  if (a.add_noise) {
+  if (add_noise) {
     if (a.z) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) z[c] = __ldg(a.z + o + (size_t)c * HW);
     } else {
-      normal3(a.seed, a.offset, (uint64_t)b * HW + pix, z);
+      normal3((a.step && a.seed == 0) ? a.step->seed : a.seed, a.step ? a.step->noise_offset : a.offset, (uint64_t)b * HW + pix, z);
     }
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float yt = __ldg(a.y_t + o + (size_t)c * HW);
+    const float yt = a.y_t[o + (size_t)c * HW];            // plain load: y_prev may alias y_t (in-place reverse loop)
     float y0 = A * yt - Bm * eps[c];
     if (a.clip_denoised) y0 = fminf(fmaxf(y0, -1.f), 1.f);
     const float mean = c1 * y0 + c2 * yt;

@@ -933,12 +933,7 @@ int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
       if (rc) return rc;
     }
   }
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-  });
-  VF_CUDA(attr_err);
+  VF_SET_MAX_SMEM(conv_tc_kernel, kSmemBudget);
   const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
   if (g_tc_dbg & 256)
     fprintf(stderr, "[vf tc] rows %d W %d cout %d segs %d ktot %d | bn %d G %d a_stages %d (%d B) b_stages %d resident %d smem %zu items %d grid %d epi_tma %d a_lines %d epi_lines %d\n",

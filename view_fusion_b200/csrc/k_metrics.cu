@@ -109,10 +109,7 @@ extern "C" __attribute__((visibility("default"))) int vf_eval_metrics(const floa
   const size_t smem = ((size_t)2 * H * W + (size_t)5 * (H - MT_WIN + 1) * W) * sizeof(float);
   constexpr size_t kMaxDyn = 226 * 1024;      // 227 KB per CTA minus the kernel's static reduction scratch
   VF_REQUIRE(smem <= kMaxDyn, "vf_eval_metrics: %dx%d planes need %zu B of shared memory", H, W, smem);
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); });
-  VF_CUDA(attr_err);
+  VF_SET_MAX_SMEM(metrics_kernel, 226 * 1024);
   cudaStream_t st = as_stream(stream);
   MetricParams p{};
   p.x = generated; p.y = target; p.C = C; p.H = H; p.W = W; p.mse_sum = psnr; p.ssim = ssim;

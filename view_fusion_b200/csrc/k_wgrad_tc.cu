@@ -291,10 +291,7 @@ int conv2d_wgrad_tc(const vf_conv_args* a, const void* dy, int dy_ld, float* dwp
     int rc = encode_bf16_map(&mapDY, dy, 2, dims, strides, box);
     if (rc) return rc;
   }
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
-  VF_CUDA(attr_err);
+  VF_SET_MAX_SMEM(conv_wgrad_tc_kernel, 227 * 1024);
   const size_t smem = 2048 + (size_t)p.stages * p.stage_bytes;
   dim3 grid(splits, jobs);
   VF_CUDA(launch_pdl(conv_wgrad_tc_kernel, grid, dim3(WG_THREADS), smem, st, maps[0], maps[1], maps[2], mapDY, p));

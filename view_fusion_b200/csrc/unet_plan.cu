@@ -77,6 +77,9 @@ struct vf_unet {
   struct Tap { size_t off; int C, H, W; int dtype; int ld; };
   std::map<std::string, Tap> taps;
   int last_images = 0;
+  int capacity = 0;               // arena layout is computed for max(capacity, images) view-images (vf_unet_set_capacity)
+  int last_layout = 0;            // layout image count of the last forward (the backward lays its arena out the same way)
+  unsigned long long fwd_gen = 0; // forward generation: bumped by every vf_unet_forward (vf_unet_forward_generation)
   // optional per-kernel-class timing of one forward (CUDA events around every launch; perturbs overlap, so it is
   // only enabled for the roofline breakdown, never for the throughput measurement)
   // training tape: what the last forward did, in order (replayed in reverse by vf_unet_backward)
@@ -177,6 +180,7 @@ struct Exec {
   cudaStream_t st;
   int rc = VF_OK;
   int launches = 0;
+  int alloc_images = 0;          // image count the buffers are SIZED for (>= the images processed): keeps the arena layout fixed
   vf_unet* u = nullptr;
   float* stats_base = nullptr;   // GroupNorm statistics arena (zeroed once per forward)
   size_t stats_used = 0;         // floats
@@ -376,8 +380,9 @@ struct Act {
 
 static Act new_act(Exec& ex, const vf_unet* u, int images, int C, int H, int W, bool want_stats) {
   // spatial activations live in the PADDED row order: images * (H+1) * (W+1) rows
-  Act a{ex.alloc((size_t)images * (H + 1) * (W + 1) * C * (u->dtype == VF_BF16 ? 2 : 4)), C, H, W, nullptr};
-  if (want_stats) a.stats = ex.alloc_stats((size_t)images * C * 2);
+  const int li = ex.alloc_images > images ? ex.alloc_images : images;
+  Act a{ex.alloc((size_t)li * (H + 1) * (W + 1) * C * (u->dtype == VF_BF16 ? 2 : 4)), C, H, W, nullptr};
+  if (want_stats) a.stats = ex.alloc_stats((size_t)li * C * 2);
   return a;
 }
 
@@ -527,6 +532,7 @@ extern "C" __attribute__((visibility("default"))) void vf_unet_destroy(vf_unet* 
 extern "C" __attribute__((visibility("default"))) int vf_unet_num_params(const vf_unet* u) { return u ? (int)u->params.size() : 0; }
 extern "C" __attribute__((visibility("default"))) int vf_unet_emb_channels(const vf_unet* u) { return u ? u->E : 0; }
 extern "C" __attribute__((visibility("default"))) int vf_unet_k0(const vf_unet* u) { return u ? u->k0 : 0; }
+extern "C" __attribute__((visibility("default"))) int vf_unet_act_dtype(const vf_unet* u) { return u ? u->dtype : -1; }
 extern "C" __attribute__((visibility("default"))) size_t vf_unet_packed_bytes(const vf_unet* u) { return u ? u->packed_bytes : 0; }
 extern "C" __attribute__((visibility("default"))) int vf_unet_last_launches(const vf_unet* u) { return u ? u->launches : 0; }
 
@@ -621,7 +627,7 @@ static Act gn_block(Exec& ex, vf_unet* u, int images, const Act& x, const Act* s
   const float *s0 = x.stats, *s1 = skip ? skip->stats : nullptr;
   int ld0 = x.C, ld1 = C1;
   if (!x.stats || (skip && !skip->stats)) {
-    float* st = ex.alloc_stats((size_t)images * C * 2);
+    float* st = ex.alloc_stats((size_t)(ex.alloc_images > images ? ex.alloc_images : images) * C * 2);
     VF_RUN(ex, K_GN_STATS, vf_gn_stats(x.p, x.C, skip ? skip->p : nullptr, C1, u->dtype, images, x.H, x.W, st, (vf_stream)ex.st));
     s0 = st; s1 = st + 2 * x.C; ld0 = ld1 = C;
   }
@@ -645,6 +651,7 @@ static Act run_resblock(Exec& ex, vf_unet* u, const uint8_t* pk, int images, con
   const int HW = x.H * x.W;
   const size_t es = k_elems(u);
   const int cin = b.c0 + b.c1;
+  const size_t li = (size_t)(ex.alloc_images > images ? ex.alloc_images : images);   // buffers are sized for the layout image count
   // block1: GN -> Swish -> conv3x3 (+bias +embedding)                                   unet.py:242-243
   Act a1 = gn_block(ex, u, images, x, skip, b.g1_w, b.g1_b, true);
   Act h1 = new_act(ex, u, images, b.cout, x.H, x.W, true);
@@ -686,10 +693,10 @@ static Act run_resblock(Exec& ex, vf_unet* u, const uint8_t* pk, int images, con
   // SelfAttention: GN -> qkv 1x1 -> softmax(QK^T/sqrt(C)) V -> out 1x1 (+bias) + input     unet.py:258-277
   const int C = b.cout;
   Act n = gn_block(ex, u, images, out, nullptr, b.an_w, b.an_b, false);
-  void* qkv = ex.alloc((size_t)images * HW * 3 * C * es);
+  void* qkv = ex.alloc(li * HW * 3 * C * es);
   // V^T feeds the attention backward only; without it (inference) the forward kernel reads V row-major from qkv and the
   // whole qkv projection leaves through the staged TMA epilogue.  The workspace is always sized for the stash.
-  void* vt = u->dtype == VF_BF16 ? ex.alloc((size_t)images * HW * C * es) : nullptr;
+  void* vt = u->dtype == VF_BF16 ? ex.alloc(li * HW * C * es) : nullptr;
   if (!ex.dry && !u->stash) vt = nullptr;
   {
     vf_conv_args a = conv_args_init();
@@ -702,8 +709,8 @@ static Act run_resblock(Exec& ex, vf_unet* u, const uint8_t* pk, int images, con
     m.w_idx[0] = b.qkv_w; m.cin_total[0] = C; m.wt_off[0] = b.wtqkv;
     conv_call(ex, u, a, m);
   }
-  Act o{ex.alloc((size_t)images * HW * C * es), C, x.H, x.W, nullptr};   // FLAT
-  float* lse = reinterpret_cast<float*>(ex.alloc((size_t)images * HW * 4));
+  Act o{ex.alloc(li * HW * C * es), C, x.H, x.W, nullptr};   // FLAT
+  float* lse = reinterpret_cast<float*>(ex.alloc(li * HW * 4));
   VF_RUN(ex, K_ATTN, vf_attention(qkv, vt, u->dtype, images, HW, C, o.p, lse, (vf_stream)ex.st));
   if (!ex.dry) {
     vf_unet::TapeOp t{};
@@ -735,7 +742,7 @@ static int walk(vf_unet* u, Exec& ex, const uint8_t* pk, int images, const void*
     if (!ex.dry) u->taps[name] = vf_unet::Tap{(size_t)((uint8_t*)a.p - ex.base), a.C, a.H, a.W, u->dtype, a.C};
   };
   // embedding table [rows, E]
-  float* emb = reinterpret_cast<float*>(ex.alloc((size_t)rows * u->E * 4));
+  float* emb = reinterpret_cast<float*>(ex.alloc((size_t)(ex.alloc_images > rows ? ex.alloc_images : rows) * u->E * 4));
   if (!ex.dry) { u->last_emb = emb; u->emb_w_dev = reinterpret_cast<const float*>(pk + u->emb_w_off); }
   VF_RUN(ex, K_EMBED, vf_embed(level, angle, rows, c.inner_channel, u->master[u->mlp_w0], u->master[u->mlp_b0], u->master[u->mlp_w2],
                          u->master[u->mlp_b2], reinterpret_cast<const float*>(pk + u->emb_w_off),
@@ -834,6 +841,7 @@ extern "C" __attribute__((visibility("default"))) size_t vf_unet_workspace_bytes
   if (!u || max_images <= 0) return 0;
   Exec ex{true, nullptr};
   ex.st = nullptr;
+  ex.alloc_images = max_images;
   walk(const_cast<vf_unet*>(u), ex, nullptr, max_images, nullptr, nullptr, nullptr, max_images, nullptr, nullptr);
   return align_up(ex.off, 256) + ex.stats_used * 4 + 256;
 }
@@ -847,9 +855,15 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_forward(vf_unet* u
   Exec ex{false, reinterpret_cast<uint8_t*>(workspace)};
   ex.st = as_stream(stream);
   ex.cap = workspace_bytes;
+  // every buffer is sized for max(capacity, images) view-images, so the arena layout (hence the zero padding rows the
+  // caller established once) does not move when the batch / view counts change from call to call
+  ex.alloc_images = u->capacity > images ? u->capacity : images;
+  u->last_layout = ex.alloc_images;
+  ++u->fwd_gen;
   {
     Exec dry{true, nullptr};
     dry.st = nullptr;
+    dry.alloc_images = ex.alloc_images;
     walk(u, dry, nullptr, images, nullptr, nullptr, nullptr, rows, nullptr, nullptr);
     const size_t act = align_up(dry.off, 256), need = act + dry.stats_used * 4;
     VF_REQUIRE(need <= workspace_bytes, "vf_unet_forward: workspace too small (%zu < %zu)", workspace_bytes, need);
@@ -869,6 +883,13 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_forward(vf_unet* u
   u->launches = ex.launches;
   return rc;
 }
+
+extern "C" __attribute__((visibility("default"))) int vf_unet_set_capacity(vf_unet* u, int max_images) {
+  VF_REQUIRE(u && max_images >= 0, "vf_unet_set_capacity: bad args");
+  u->capacity = max_images;
+  return VF_OK;
+}
+extern "C" __attribute__((visibility("default"))) unsigned long long vf_unet_forward_generation(const vf_unet* u) { return u ? u->fwd_gen : 0; }
 
 extern "C" __attribute__((visibility("default"))) int vf_unet_set_stash(vf_unet* u, int on) {
   VF_REQUIRE(u, "vf_unet_set_stash: null plan");
@@ -1186,12 +1207,25 @@ struct UnpackList {
   size_t table_bytes() const { return align_up(jobs.size() * sizeof(UnpackJob), 256) + 2 * align_up(chunk_job.size() * sizeof(int), 256); }
 };
 
+// Backward of vf_embed (two launches, no atomics): demb [rows, E] -> dew [E, ic] / deb [E] (overwritten) and += into the
+// noise_level_mlp gradients.  rowbuf: rows * 11 * ic floats of scratch.
+static int embed_backward_launch(const float* level, const float* angle, int rows, int ic, const float* w0, const float* b0, const float* w2,
+                                 const float* b2, const float* emb_w, int E, const float* demb, float* rowbuf, float* dew, float* deb, float* dw0,
+                                 float* db0, float* dw2, float* db2, cudaStream_t st) {
+  embed_bwd_rows_kernel<<<rows, 256, (size_t)(14 * ic) * sizeof(float), st>>>(level, angle, ic, w0, b0, w2, b2, emb_w, E, demb, rowbuf);
+  const size_t total = (size_t)E * ic + E + (size_t)8 * ic * ic + 5 * ic;
+  embed_bwd_params_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(rowbuf, demb, rows, ic, E, dew, deb, dw0, db0, dw2, db2);
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}
+
 struct BwdCtx {
   vf_unet* u;
   cudaStream_t st;
   uint8_t* gbase;
   UnpackList unpack;
   size_t goff = 0, gcap = 0;
+  size_t li = 0;             // layout image count (u->last_layout): buffers are sized for it, kernels run over u->last_images
   bool dry = false;
   int rc = VF_OK;
   std::map<const void*, std::pair<void*, bool>> grads;     // forward tensor -> (gradient buffer, written?)
@@ -1219,6 +1253,29 @@ struct BwdCtx {
     if (!cx.dry && cx.rc == VF_OK) cx.rc = (call);  \
   } while (0)
 
+// One launch: per-image column sums of dY [images*rows_per_img, ld] (first `cout` columns) added into db0 / db1 [cout] and
+// into demb[img_row[img]][col + n].
+static int colsum_bias_launch(const void* dy, int dt, int images, int rows_per_img, int ld, int cout, float* db0, float* db1, float* demb,
+                              const int* img_row, int emb_ld, int col, cudaStream_t st) {
+  const int vec = dt == VF_BF16 ? 8 : 4;
+  const int cv = (cout + vec - 1) / vec;
+  VF_REQUIRE(cv >= 1 && cv <= 256 && ld % vec == 0, "colsum_bias: cout=%d ld=%d", cout, ld);
+  const int py = 256 / cv;
+  int per = py * 4 * 8;                                   // >= 8 unrolled iterations per thread
+  if (per < 512) per = 512;
+  dim3 grid(cdiv(rows_per_img, per), images);
+  const size_t smem = (size_t)py * cv * vec * sizeof(float);
+  cudaError_t le;
+  if (dt == VF_BF16)
+    le = launch_pdl(colsum_bias_kernel<__nv_bfloat16>, grid, dim3(cv * py), smem, st, (const __nv_bfloat16*)dy, ld, cout, rows_per_img, per, db0, db1,
+                    demb, img_row, emb_ld, col);
+  else
+    le = launch_pdl(colsum_bias_kernel<float>, grid, dim3(cv * py), smem, st, (const float*)dy, ld, cout, rows_per_img, per, db0, db1, demb, img_row,
+                    emb_ld, col);
+  if (le != cudaSuccess) { set_error("colsum_bias launch: %s", cudaGetErrorString(le)); return VF_ERR_CUDA; }
+  return VF_OK;
+}
+
 static void conv_backward(BwdCtx& cx, const vf_unet::TapeOp& t, const uint8_t* pkt, const void* dY, int dy_ld, float* dwp, float* cs,
                           float* const* pg, float* demb, bool skip_colsum = false) {
   vf_unet* u = cx.u;
@@ -1231,7 +1288,7 @@ static void conv_backward(BwdCtx& cx, const vf_unet::TapeOp& t, const uint8_t* p
   const int images = f.images;
   if (f.stride == 2) {
     // Downsample: scatter dY (H/2 x W/2) onto the even pixels of a zeroed H x W grid -> stride-1 problems at source resolution
-    void* z = cx.galloc((size_t)images * (H + 1) * (W + 1) * dy_ld * es);
+    void* z = cx.galloc(cx.li * (H + 1) * (W + 1) * dy_ld * es);
     VF_B(vf_zero_insert2x(dY, dt, images, H / 2, W / 2, dy_ld, z, (vf_stream)cx.st));
     dYs = z;
     a.stride = 1;
@@ -1240,25 +1297,11 @@ static void conv_backward(BwdCtx& cx, const vf_unet::TapeOp& t, const uint8_t* p
   // ---- bias / embedding gradients: per-image column sums of dY
   if ((t.b_idx[0] >= 0 || t.emb_col >= 0) && !skip_colsum) {
     if (!cx.dry && cx.rc == VF_OK) {
-      const int vec = dt == VF_BF16 ? 8 : 4;
-      const int cv = (f.cout + vec - 1) / vec;
-      const int py = 256 / cv;
-      int per = py * 4 * 8;                                   // >= 8 unrolled iterations per thread
-      if (per < 512) per = 512;
-      dim3 grid(cdiv(out_rows_per_img, per), images);
-      const size_t smem = (size_t)py * cv * vec * sizeof(float);
       float* db0 = t.b_idx[0] >= 0 ? pg[t.b_idx[0]] : nullptr;
       float* db1 = t.b_idx[1] >= 0 ? pg[t.b_idx[1]] : nullptr;
       float* de = t.emb_col >= 0 ? demb : nullptr;
       const int col = t.emb_col >= 0 ? t.emb_col : 0;
-      cudaError_t le;
-      if (dt == VF_BF16)
-        le = launch_pdl(colsum_bias_kernel<__nv_bfloat16>, grid, dim3(cv * py), smem, cx.st, (const __nv_bfloat16*)dYs, dy_ld, f.cout,
-                        out_rows_per_img, per, db0, db1, de, (const int*)u->last_img_row, u->E, col);
-      else
-        le = launch_pdl(colsum_bias_kernel<float>, grid, dim3(cv * py), smem, cx.st, (const float*)dYs, dy_ld, f.cout, out_rows_per_img, per,
-                        db0, db1, de, (const int*)u->last_img_row, u->E, col);
-      if (le != cudaSuccess) { set_error("colsum_bias launch: %s", cudaGetErrorString(le)); cx.rc = VF_ERR_CUDA; }
+      cx.rc = colsum_bias_launch(dYs, dt, images, out_rows_per_img, dy_ld, f.cout, db0, db1, de, (const int*)u->last_img_row, u->E, col, cx.st);
     }
   }
   // ---- weight gradient into the packed scratch, then scatter to the OIHW parameter gradients
@@ -1273,11 +1316,11 @@ static void conv_backward(BwdCtx& cx, const vf_unet::TapeOp& t, const uint8_t* p
       // 1x1 convolution between the two row orders (qkv, attention out-projection, first layer): bring dY into the
       // row order of X so the tensor-core weight-gradient GEMM sees one row index on both operands
       if (a.in_padded) {
-        void* z = cx.galloc((size_t)images * (H + 1) * (W + 1) * dy_ld * es);
+        void* z = cx.galloc(cx.li * (H + 1) * (W + 1) * dy_ld * es);
         VF_B(vf_flat_to_padded(dYs, dt, images, H, W, dy_ld, z, (vf_stream)cx.st));
         dYw = z;
       } else {
-        void* z = cx.galloc((size_t)images * H * W * dy_ld * es);
+        void* z = cx.galloc(cx.li * H * W * dy_ld * es);
         VF_B(vf_padded_to_flat(dYs, dt, images, H, W, dy_ld, z, (vf_stream)cx.st));
         dYw = z;
       }
@@ -1353,18 +1396,18 @@ static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float*
       size_t k = 0;
       for (int s = 0; s < t.conv.n_seg; ++s) k += (size_t)t.conv.ksize[s] * t.conv.ksize[s] * t.conv.src_c[s];
       dwp_floats += align_up((size_t)t.conv.cout_pad * k, 64);
-      cs_floats = std::max(cs_floats, (size_t)images * t.conv.cout);
+      cs_floats = std::max(cs_floats, cx.li * t.conv.cout);
     }
   float* dwp = (float*)cx.galloc(dwp_floats * 4);
   float* cs = (float*)cx.galloc(cs_floats * 4);
-  float* demb = (float*)cx.galloc((size_t)u->last_rows * u->E * 4);
+  float* demb = (float*)cx.galloc(cx.li * u->E * 4);
   float* dew = (float*)cx.galloc((size_t)u->E * c.inner_channel * 4);
   float* deb = (float*)cx.galloc((size_t)u->E * 4);
-  float* emb_rows = (float*)cx.galloc((size_t)u->last_rows * 11 * c.inner_channel * 4);
+  float* emb_rows = (float*)cx.galloc(cx.li * 11 * c.inner_channel * 4);
   size_t gn_floats = 0, att_floats = 0;
   for (auto& t : u->tape) {
-    if (t.kind == 1) gn_floats += align_up((size_t)images * (t.gC0 + t.gC1) * 2, 64);
-    if (t.kind == 2) att_floats = std::max(att_floats, (size_t)images * t.aL * 2 * t.aC * std::max(1, t.aL / 128));
+    if (t.kind == 1) gn_floats += align_up(cx.li * (t.gC0 + t.gC1) * 2, 64);
+    if (t.kind == 2) att_floats = std::max(att_floats, cx.li * t.aL * 2 * t.aC * std::max(1, t.aL / 128));
   }
   float* gn_scratch = (float*)cx.galloc(gn_floats * 4);
   float* att_scratch = (float*)cx.galloc(att_floats * 4);
@@ -1378,7 +1421,7 @@ static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float*
   }
   // gradient of the UNet output -> PADDED activation-dtype matrix with final_npad channels
   const int np = u->final_npad;
-  void* g_out = cx.galloc((size_t)images * (S + 1) * (S + 1) * np * es);
+  void* g_out = cx.galloc(cx.li * (S + 1) * (S + 1) * np * es);
   if (!cx.dry) {
     const size_t total = (size_t)images * (S + 1) * (S + 1) * (np / 8);
     const unsigned grid = (unsigned)((total + 255) / 256);
@@ -1432,7 +1475,7 @@ static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float*
       VF_B(gn_backward_impl(t.gsrc0, t.gC0, t.gst0, t.gld0, t.gsrc1, t.gC1, t.gst1, t.gld1, dt, images, t.gH, t.gW, c.norm_groups,
                             u->master[t.gw], u->master[t.gb], t.swish, gy.first, gn_cur, true, pg[t.gw], pg[t.gb], g0.first, g0.second ? 1 : 0,
                             g1 ? g1->first : nullptr, g1 && g1->second ? 1 : 0, cx.st, fused_cs ? &csum : nullptr));
-      gn_cur += align_up((size_t)images * (t.gC0 + t.gC1) * 2, 64);
+      gn_cur += align_up(cx.li * (t.gC0 + t.gC1) * 2, 64);
       g0.second = true;
       if (g1) g1->second = true;
     } else if (t.kind == 2) {
@@ -1476,12 +1519,9 @@ static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float*
     const int ic = c.inner_channel;
     const uint8_t* pk = nullptr; (void)pk;
     const int rows = u->last_rows;
-    embed_bwd_rows_kernel<<<rows, 256, (size_t)(14 * ic) * sizeof(float), cx.st>>>(
-        u->last_level, u->last_angle, ic, u->master[u->mlp_w0], u->master[u->mlp_b0], u->master[u->mlp_w2], u->master[u->mlp_b2],
-        u->emb_w_dev, u->E, demb, emb_rows);
-    const size_t total = (size_t)u->E * ic + u->E + (size_t)8 * ic * ic + 5 * ic;
-    embed_bwd_params_kernel<<<(unsigned)((total + 255) / 256), 256, 0, cx.st>>>(emb_rows, demb, rows, ic, u->E, dew, deb, pg[u->mlp_w0],
-                                                                               pg[u->mlp_b0], pg[u->mlp_w2], pg[u->mlp_b2]);
+    cx.rc = embed_backward_launch(u->last_level, u->last_angle, rows, ic, u->master[u->mlp_w0], u->master[u->mlp_b0], u->master[u->mlp_w2],
+                                  u->master[u->mlp_b2], u->emb_w_dev, u->E, demb, emb_rows, dew, deb, pg[u->mlp_w0], pg[u->mlp_b0], pg[u->mlp_w2],
+                                  pg[u->mlp_b2], cx.st);
     for (auto& b : u->blocks) {
       const size_t nw = (size_t)b.cout * ic;
       axpy_f32_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, cx.st>>>(pg[b.nf_w], dew + (size_t)b.emb_col * ic, nw);
@@ -1551,6 +1591,7 @@ extern "C" __attribute__((visibility("default"))) size_t vf_unet_backward_worksp
   if (!u || u->tape.empty()) return 0;
   BwdCtx cx{u, nullptr, nullptr};
   cx.dry = true;
+  cx.li = (size_t)(u->last_layout > u->last_images ? u->last_layout : u->last_images);
   backward_walk(cx, nullptr, nullptr, nullptr);
   return align_up(cx.goff, 256) + 256;
 }
@@ -1564,12 +1605,34 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_backward(vf_unet* 
   {
     BwdCtx dry{u, nullptr, nullptr};
     dry.dry = true;
+    dry.li = (size_t)(u->last_layout > u->last_images ? u->last_layout : u->last_images);
     backward_walk(dry, nullptr, nullptr, nullptr);
     VF_REQUIRE(dry.goff <= grad_workspace_bytes, "vf_unet_backward: workspace too small (%zu < %zu)", grad_workspace_bytes, dry.goff);
   }
   BwdCtx cx{u, as_stream(stream), reinterpret_cast<uint8_t*>(grad_workspace)};
   cx.gcap = grad_workspace_bytes;
+  cx.li = (size_t)(u->last_layout > u->last_images ? u->last_layout : u->last_images);
   int rc = backward_walk(cx, reinterpret_cast<const uint8_t*>(packed_t), grad_out8, param_grads_host);
   if (rc == VF_OK) VF_LAUNCH_CHECK();
   return rc;
+}
+
+// ---- stage-level exports of two backward helpers (unit parity; the plan calls the same launchers) ----------------------
+extern "C" __attribute__((visibility("default"))) int vf_colsum_bias(const void* dy, int dtype, int images, int rows_per_img, int ld, int cout,
+                                                                   float* db0, float* db1, float* demb, const int* img_row, int emb_ld, int col,
+                                                                   vf_stream stream) {
+  VF_REQUIRE(dy && images > 0 && rows_per_img > 0 && cout > 0 && (db0 || db1 || demb), "vf_colsum_bias: bad args");
+  VF_REQUIRE(!demb || img_row, "vf_colsum_bias: demb needs img_row");
+  return vf::colsum_bias_launch(dy, dtype, images, rows_per_img, ld, cout, db0, db1, demb, img_row, emb_ld, col, as_stream(stream));
+}
+
+extern "C" __attribute__((visibility("default"))) int vf_embed_backward(const float* level, const float* angle, int rows, int inner_channel,
+                                                                      const float* w0, const float* b0, const float* w2, const float* b2,
+                                                                      const float* emb_w, int E, const float* demb, float* rowbuf, float* dew,
+                                                                      float* deb, float* dw0, float* db0, float* dw2, float* db2, vf_stream stream) {
+  VF_REQUIRE(level && angle && w0 && b0 && w2 && b2 && emb_w && demb && rowbuf && dew && deb && dw0 && db0 && dw2 && db2 && rows > 0 && E > 0,
+             "vf_embed_backward: null args");
+  VF_REQUIRE(inner_channel > 0 && inner_channel % 4 == 0 && inner_channel <= 256, "vf_embed_backward: inner_channel=%d", inner_channel);
+  return vf::embed_backward_launch(level, angle, rows, inner_channel, w0, b0, w2, b2, emb_w, E, demb, rowbuf, dew, deb, dw0, db0, dw2, db2,
+                                   as_stream(stream));
 }

@@ -106,6 +106,24 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 int sm_count();
 
+// True exactly once per (call site, CUDA device): kernel attributes (opt-in shared memory) are per-device state, so a
+// process that drives several GPUs must set them on each one.
+struct PerDeviceOnce {
+  unsigned long long mask = 0;
+  bool first() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) return true;
+    const unsigned long long bit = 1ull << (d & 63);
+    const unsigned long long old = __atomic_fetch_or(&mask, bit, __ATOMIC_ACQ_REL);
+    return !(old & bit);
+  }
+};
+#define VF_SET_MAX_SMEM(kernel, bytes)                                                                          \
+  do {                                                                                                          \
+    static ::vf::PerDeviceOnce _once;                                                                           \
+    if (_once.first()) VF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+  } while (0)
+
 // ---- device-side scalar/vector helpers -------------------------------------------------------------
 template <typename T> struct VecOf;            // 16-byte vector of T
 template <> struct VecOf<float> { static constexpr int N = 4; };

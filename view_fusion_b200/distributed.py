@@ -83,8 +83,12 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0, group: Optional[
     """Start-up parameter broadcast (what the DDP constructor does, experiment.py:105-107)."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
-    for p in module.parameters():
-        dist.broadcast(p.data, src=src, group=group)
+    with torch.no_grad():
+        for p in module.parameters():
+            dist.broadcast(p.detach(), src=src, group=group)     # shares p's version counter (p.data would not)
+    for m in module.modules():
+        if hasattr(m, "invalidate_packed"):
+            m.invalidate_packed()                                  # derived bf16 weight packs follow the new masters
 
 
 def data_parallel(model, group: Optional[dist.ProcessGroup] = None, chunks: int = 4):

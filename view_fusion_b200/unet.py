@@ -114,11 +114,14 @@ class UNet(nn.Module):
         self._packed_t = None
         self._packed_t_key = None
         self._ws = None
-        self._ws_images = 0
+        self._capacity = 0            # view-images the workspaces are laid out for (grows, never shrinks)
         self._gws = None
         self._stash = True
-        self._gws_images = -1
         self._flat_grad = None
+        self._plist = None
+        self._fwd_gen = 0
+        self._accumulate = False
+        self._profiling = False
 
     # ------------------------------------------------------------------------------------------
     def _native(self):
@@ -153,6 +156,7 @@ class UNet(nn.Module):
             if len(names) != len(mine):
                 raise RuntimeError("plan/module parameter count mismatch")
             self._param_names = names
+            self._plist = [mine[n] for n in names]
         return self._plan
 
     def __del__(self):
@@ -170,8 +174,7 @@ class UNet(nn.Module):
         """GEMM-ready weight cache; refreshed whenever a master parameter changed (optimizer step, load_state_dict)."""
         lib = _lib.require_device()
         h = self._native()
-        params = dict(self.named_parameters())
-        plist = [params[n] for n in self._param_names]
+        plist = self._params_in_order()
         key = tuple((p.data_ptr(), p._version) for p in plist)
         if self._packed is None or key != self._packed_key:
             for p in plist:
@@ -186,25 +189,57 @@ class UNet(nn.Module):
         return self._packed
 
     def workspace(self, images: int) -> torch.Tensor:
+        """Zero-filled arena of the forward.  Padding rows of convolution outputs are never written and must read as zeros
+        (3x3 halos, weight-gradient reductions), so the LAYOUT must not move between calls: the library sizes every buffer for
+        the capacity (`vf_unet_set_capacity`), not for the current image count — a different batch size or different view
+        counts (the reference draws view_count per step, experiment.py:277) reuse the same zeroed arena without a memset.  A
+        larger request grows the capacity and allocates a fresh zero-filled arena (and drops the backward's)."""
         lib = _lib.require_device()
         h = self._native()
-        dev = next(self.parameters()).device
-        # zero-filled, and re-zeroed when the image count (hence the layout) changes: padding rows of convolution
-        # outputs are never written and must read as zeros (3x3 halos, weight-gradient reductions)
-        if self._ws is None or self._ws_images != images or self._ws.device != dev:
-            nbytes = lib.vf_unet_workspace_bytes(h, images)
-            if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
-                self._ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
-            else:
-                self._ws.zero_()
-            self._ws_images = images
+        dev = self._params_in_order()[0].device
+        if self._ws is None or images > self._capacity or self._ws.device != dev:
+            cap = max(self._capacity, images)
+            _lib.check(lib.vf_unet_set_capacity(h, cap), "vf_unet_set_capacity")
+            self._ws = self._gws = None               # release before allocating the larger arenas
+            self._ws = torch.zeros(lib.vf_unet_workspace_bytes(h, cap), dtype=torch.uint8, device=dev)
+            self._capacity = cap
         return self._ws
+
+    def grad_accumulation(self, on: bool) -> None:
+        """Micro-batching: with `on`, a backward whose parameters still hold the previous backward's flat-buffer gradients adds
+        into that buffer natively (one launch chain, no 400 per-tensor adds); `optimizer.zero_grad(set_to_none=True)` starts over."""
+        self._accumulate = bool(on)
+
+    def release_buffers(self) -> None:
+        """Drop the workspaces (they are re-created, zero-filled, on the next call)."""
+        self._ws = self._gws = None
+        self._capacity = 0
+        if self._plan is not None:
+            _lib.check(_lib.load().vf_unet_set_capacity(self._plan, 0), "vf_unet_set_capacity")
+
+    def invalidate_packed(self) -> None:
+        """Force a re-pack of the GEMM-ready weights on the next forward (after writes that bypass the version counter,
+        e.g. `.data` updates)."""
+        self._packed_key = None
+        self._packed_t_key = None
 
     # ---------------------------------------------------------------- training support
     def _params_in_order(self):
         self._native()
-        params = dict(self.named_parameters())
-        return [params[n] for n in self._param_names]
+        pl = self._plist
+        # .to(device) / load_state_dict keep the Parameter objects; a re-registered parameter (assign=True, module surgery)
+        # is caught by checking the two ends of the table
+        if pl is None or pl[0] is not self._param_by_name(self._param_names[0]) or pl[-1] is not self._param_by_name(self._param_names[-1]):
+            mine = dict(self.named_parameters())
+            pl = self._plist = [mine[n] for n in self._param_names]
+        return pl
+
+    def _param_by_name(self, name: str):
+        m = self
+        parts = name.split(".")
+        for q in parts[:-1]:
+            m = m._modules[q]
+        return m._parameters[parts[-1]]
 
     def packed_weights_t(self) -> torch.Tensor:
         """Transposed packs for the data gradients; refreshed together with the forward packs."""
@@ -226,16 +261,24 @@ class UNet(nn.Module):
         plist = self._params_in_order()
         pt = self.packed_weights_t()
         dev = plist[0].device
-        nbytes = lib.vf_unet_backward_workspace_bytes(h)
-        if self._gws is None or self._gws.numel() < nbytes or self._gws_images != self._last_images or self._gws.device != dev:
-            if self._gws is None or self._gws.numel() < nbytes or self._gws.device != dev:
-                self._gws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
-            else:
-                self._gws.zero_()
-            self._gws_images = self._last_images
+        nbytes = lib.vf_unet_backward_workspace_bytes(h)          # laid out for the capacity, like the forward arena
+        if self._gws is None or self._gws.numel() < nbytes or self._gws.device != dev:
+            self._gws = None
+            self._gws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
         # every gradient starts on a 16-byte boundary of the flat buffer (vectorised optimizer / all-reduce accesses)
-        total = sum((p.numel() + 3) & ~3 for p in plist)
-        flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        # micro-batch accumulation (grad_accumulation(True)): when every .grad still IS its slice of the previous flat buffer,
+        # the library adds into that buffer and autograd gets nothing to add a second time
+        accumulate = False
+        if self._accumulate and self._flat_grad is not None and self._flat_grad.device == dev:
+            g0, g1 = plist[0].grad, plist[-1].grad
+            accumulate = (g0 is not None and g1 is not None and g0.data_ptr() == self._flat_grad.data_ptr()
+                          and g1.data_ptr() + g1.numel() * 4 <= self._flat_grad.data_ptr() + self._flat_grad.numel() * 4
+                          and g1.data_ptr() > self._flat_grad.data_ptr())
+        if accumulate:
+            flat = self._flat_grad                    # micro-batch accumulation: the library adds into the same buffer
+        else:
+            total = sum((p.numel() + 3) & ~3 for p in plist)
+            flat = torch.zeros(total, dtype=torch.float32, device=dev)
         grads, off = [], 0
         for p in plist:
             grads.append(flat[off:off + p.numel()].view_as(p))
@@ -245,10 +288,10 @@ class UNet(nn.Module):
                                         _lib.stream_handle()), "vf_unet_backward")
         self._flat_grad = flat
         sync = getattr(self, "_grad_sync", None)
-        if sync is not None:
+        if sync is not None and not getattr(self, "_no_sync", False):
             from .distributed import allreduce_mean_
             allreduce_mean_(flat, sync[0], sync[1])      # the one collective of the path (training gradient mean)
-        return plist, grads
+        return plist, grads, accumulate
 
     @property
     def k0(self) -> int:
@@ -270,6 +313,16 @@ class UNet(nn.Module):
         _lib.check(lib.vf_unet_forward(h, packed.data_ptr(), ws.data_ptr(), ws.numel(), images, x0.data_ptr(), level.data_ptr(),
                                        angle.data_ptr(), level.numel(), img_row.data_ptr(), out.data_ptr(), _lib.stream_handle()),
                    "vf_unet_forward")
+        self._fwd_gen = int(lib.vf_unet_forward_generation(h))
+
+    def forward_generation(self) -> int:
+        """Counter of forwards run on the native plan: the backward differentiates the LAST one."""
+        return int(_lib.load().vf_unet_forward_generation(self._native()))
+
+    def set_stash(self, stash: bool) -> None:
+        if bool(stash) != self._stash:
+            _lib.check(_lib.load().vf_unet_set_stash(self._native(), int(bool(stash))), "vf_unet_set_stash")
+            self._stash = bool(stash)
 
     def last_launches(self) -> int:
         return _lib.load().vf_unet_last_launches(self._native())
@@ -278,6 +331,7 @@ class UNet(nn.Module):
 
     def set_profiling(self, on: bool) -> None:
         _lib.check(_lib.load().vf_unet_set_profiling(self._native(), int(on)), "vf_unet_set_profiling")
+        self._profiling = bool(on)
 
     def profile(self) -> dict:
         """{class: (ms, launches)} of the last forward run with profiling on (synchronises)."""
@@ -306,6 +360,7 @@ class UNet(nn.Module):
         S = self.config["image_size"]
         cmax = 2 * self.config["inner_channel"] * max(self.config["channel_mults"])
         buf = torch.empty(self._last_images * cmax * S * S, dtype=torch.float32, device=self._ws.device)
+        # taps are addressed inside the CURRENT workspace: the last forward must have used it
         _lib.check(lib.vf_unet_read_tap(h, self._ws.data_ptr(), name.encode(), buf.data_ptr(), chw, _lib.stream_handle()), "vf_unet_read_tap")
         c, hh, ww = chw[0], chw[1], chw[2]
         return buf[: self._last_images * c * hh * ww].view(self._last_images, c, hh, ww).clone()
@@ -322,21 +377,24 @@ class UNet(nn.Module):
         S = self.config["image_size"]
         if (H, W) != (S, S) or Cin != self.config["in_channel"]:
             raise ValueError(f"expected input (R,{self.config['in_channel']},{S},{S}), got {tuple(x.shape)}")
+        if self._params_in_order()[0].device != x.device:
+            raise RuntimeError(f"UNet parameters live on {self._params_in_order()[0].device}, the input on {x.device}")
         x = x.contiguous().float()
-        k0 = self.k0
-        es = 2 if self.precision == "bf16" else 4
-        x0 = torch.empty(R * H * W * k0 * es, dtype=torch.uint8, device=x.device)
-        st = _lib.stream_handle()
-        _lib.check(lib.vf_pack_nchw(x.data_ptr(), R, Cin, H, W, k0, self.act_dtype, x0.data_ptr(), st), "vf_pack_nchw")
-        level = time.reshape(-1).contiguous().float()
-        ang = angle.reshape(-1).contiguous().float()
-        if level.numel() != R or ang.numel() != R:
-            raise ValueError("angle and time must be (R, 1)")
-        img_row = torch.arange(R, dtype=torch.int32, device=x.device)
-        out8 = torch.empty(R * H * W * 8, dtype=torch.float32, device=x.device)
-        self._last_images = R
-        self.run_packed(x0, R, level, ang, img_row, out8)
-        oc = self.config["out_channel"]
-        out = torch.empty(R, oc, H, W, dtype=torch.float32, device=x.device)
-        _lib.check(lib.vf_nhwc_to_nchw(out8.data_ptr(), 8, R, oc, H, W, out.data_ptr(), st), "vf_nhwc_to_nchw")
+        with torch.cuda.device(x.device):          # launches follow the tensors' device, not the caller's current one
+            k0 = self.k0
+            es = 2 if self.precision == "bf16" else 4
+            x0 = torch.empty(R * H * W * k0 * es, dtype=torch.uint8, device=x.device)
+            st = _lib.stream_handle()
+            _lib.check(lib.vf_pack_nchw(x.data_ptr(), R, Cin, H, W, k0, self.act_dtype, x0.data_ptr(), st), "vf_pack_nchw")
+            level = time.to(x.device).reshape(-1).contiguous().float()
+            ang = angle.to(x.device).reshape(-1).contiguous().float()
+            if level.numel() != R or ang.numel() != R:
+                raise ValueError("angle and time must be (R, 1)")
+            img_row = torch.arange(R, dtype=torch.int32, device=x.device)
+            out8 = torch.empty(R * H * W * 8, dtype=torch.float32, device=x.device)
+            self._last_images = R
+            self.run_packed(x0, R, level, ang, img_row, out8)
+            oc = self.config["out_channel"]
+            out = torch.empty(R, oc, H, W, dtype=torch.float32, device=x.device)
+            _lib.check(lib.vf_nhwc_to_nchw(out8.data_ptr(), 8, R, oc, H, W, out.data_ptr(), st), "vf_nhwc_to_nchw")
         return out
