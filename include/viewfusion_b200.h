@@ -273,9 +273,19 @@ int vf_gn_stats(const void* src0, int C0, const void* src1, int C1, int dtype, i
  * with exact zeros in the padding rows.
  * statsX: per (image, channel) {sum, sum of squares} of source X, rows of statsX_ld channels ([images, ld, 2]);
  * they come from vf_gn_stats or from the producing convolution's epilogue (vf_conv_args::stats). */
+typedef struct vf_gn_shift {   /* source 0 is stored WITHOUT the per-(image, channel) constant  s[img][c] = bias[c] + emb[img_row[img]][c]  */
+  const float* bias;           /* [C0] or NULL */
+  const float* emb;            /* [rows, emb_ld] (column offset already applied) or NULL */
+  const int* img_row;          /* [images], needed with emb */
+  int emb_ld;
+} vf_gn_shift;
+/* `shift` (may be NULL): the normalisation is applied to src0 + s without s ever being added in memory — the statistics of
+ * src0 (raw sums) are shifted in closed form, sum(x+s) = S1 + HW*s, sum((x+s)^2) = S2 + 2*s*S1 + HW*s^2, and s folds into the
+ * per-channel FMA.  The plan uses it for ResnetBlock.block1's bias and the FeatureWiseAffine add (unet.py:242-243, :176),
+ * whose only consumer is block2's GroupNorm: the convolution epilogue then adds nothing. */
 int vf_gn_apply(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1,
                 const float* stats1, int stats1_ld, int dtype, int images, int H, int W, int groups, const float* gamma,
-                const float* beta, int swish, void* dst, vf_stream stream);
+                const float* beta, int swish, void* dst, const vf_gn_shift* shift, vf_stream stream);
 
 /* Nearest-neighbour x2 up-sampling (unet.py:188): PADDED (H, W) -> PADDED (2H, 2W), zero padding rows. */
 int vf_upsample2x(const void* src, int dtype, int images, int H, int W, int C, void* dst, vf_stream stream);
@@ -344,16 +354,6 @@ void vf_debug_flags(int flags);
 /* Test hook: device buffer [148*4] int64 receiving the tcgen05 conv's MMA-thread cycle counters (NULL = off). */
 void vf_debug_counters(long long* dev_buf);
 
-/* Hardware probe (tests only): out[i][n] = sum_k A[shift_rows + i][k] * B[n][k] through ONE TMA-loaded, 128B-swizzled
- * smem tile and a tcgen05 descriptor whose start is shifted by `shift_rows` rows. A [rows>=256, 64] bf16, B [64, 64]. */
-/* Hardware probe: cycles for n_groups x 4 back-to-back tcgen05.mma (M=128, N, K=16) issued by one thread per CTA. */
-int vf_debug_umma_rate(int N, int shift_rows, int n_groups, int commit_every, int grid, long long* cycles_out, vf_stream stream);
-/* Hardware probe: MN-major operands: out[m][n] = sum_{k<64} A[k][m] * B[shift_rows + k][n] (A [.,128], B [.,64] bf16). */
-int vf_debug_umma_mn(const void* A, int rowsA, const void* B, int rowsB, int shift_rows, int lbo_bytes, int sbo_bytes, float* out,
-                     vf_stream stream);
-int vf_debug_umma_shift(const void* A, int rows, const void* B, int shift_rows, int use_base_offset, float* out,
-                        vf_stream stream);
-
 /* Single-head self-attention core (unet.py:267-274): O = softmax(Q K^T / sqrt(C)) V per image.
  *   qk  : [images*L, 3C] rows hold q in [0,C), k in [C,2C) (v columns unused when vt != NULL)
  *   vt  : [images, C, L] V transposed, or NULL: v is read row-major from columns [2C,3C) of qk (the tensor-core path
@@ -407,11 +407,12 @@ int vf_pack_conv_weight_t(const float* w_oihw, int cout, int cin, int ksize, int
 /* GroupNorm(+Swish) backward for dst = vf_gn_apply(src0 | src1): dy [images*P, C0+C1] PADDED.
  * dxK receives (accK == 0) or accumulates (accK != 0) the gradient of source K; dgamma/dbeta [C0+C1] fp32 are
  * accumulated; scratch: images*(C0+C1)*2 floats.  With swish != 0 the buffer behind dy is CONSUMED: the first pass
- * overwrites it with dy * swish'(z) so that the second pass is a pure FMA stream. */
+ * overwrites it with dy * swish'(z) so that the second pass is a pure FMA stream.  `shift` as in vf_gn_apply (dx0 is the
+ * gradient w.r.t. src0 + s, which equals the gradient w.r.t. src0). */
 int vf_gn_backward(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1, const float* stats1,
                    int stats1_ld, int dtype, int images, int H, int W, int groups, const float* gamma, const float* beta, int swish,
                    const void* dy, float* scratch, float* dgamma, float* dbeta, void* dx0, int acc0, void* dx1, int acc1,
-                   vf_stream stream);
+                   const vf_gn_shift* shift, vf_stream stream);
 
 /* Backward of vf_attention: d_out [images*L, C] -> dqkv [images*L, 3C] (dq | dk | dv).
  *   out, lse : the forward results (tensor-core path: bf16, L in {128, 256}, C in {128, 192}; otherwise unused / NULL

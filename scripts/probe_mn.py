@@ -10,7 +10,7 @@ for lbo, sbo in ((8192, 1024), (1024, 8192), (16, 1024), (8192, 2048)):
     for shift in (0, 8, 1, 3, 17):
         out = torch.zeros(128, 64, device="cuda")
         try:
-            _lib.check(lib.vf_debug_umma_mn(Ad.data_ptr(), 64, Bd.data_ptr(), 192, shift, lbo, sbo, out.data_ptr(), _lib.stream_handle()), "mn")
+            _lib.check(_lib.load_probes().vf_debug_umma_mn(Ad.data_ptr(), 64, Bd.data_ptr(), 192, shift, lbo, sbo, out.data_ptr(), _lib.stream_handle()), "mn")
             torch.cuda.synchronize()
         except Exception as e:
             print("ERR", lbo, sbo, shift, str(e)[:80]); break

@@ -6,7 +6,7 @@ out = torch.zeros(148, dtype=torch.int64, device="cuda")
 for N in (64, 128, 192, 256):
     for ce in (0, -2, -100, -101):
         ng = 1600
-        _lib.check(lib.vf_debug_umma_rate(N, 3, ng, ce, 148, out.data_ptr(), _lib.stream_handle()), "rate")
+        _lib.check(_lib.load_probes().vf_debug_umma_rate(N, 3, ng, ce, 148, out.data_ptr(), _lib.stream_handle()), "rate")
         torch.cuda.synchronize()
         cyc = out.double().mean().item()
         print(f"N {N:3d} mode {ce:4d}: {cyc / (ng * 4):7.1f} cycles/MMA", flush=True)
@@ -15,7 +15,7 @@ print("weight-gradient pattern (MN-major operands, 5 accumulators):")
 for N in (64, 96):
     for ce in (-200, -201, -202, -203, -204):
         ng = 1600
-        _lib.check(lib.vf_debug_umma_rate(N, 3, ng, ce, 148, out.data_ptr(), _lib.stream_handle()), "rate")
+        _lib.check(_lib.load_probes().vf_debug_umma_rate(N, 3, ng, ce, 148, out.data_ptr(), _lib.stream_handle()), "rate")
         torch.cuda.synchronize()
         cyc = out.double().mean().item()
         print(f"N {N:3d} mode {ce:4d}: {cyc / (ng * 4):7.1f} cycles/MMA", flush=True)

@@ -31,6 +31,18 @@ def test_header_symbols_exported(lib):
     assert sorted(_lib.SYMBOLS) == decl, "view_fusion_b200/_lib.py binds a different symbol set than the header declares"
 
 
+def test_probe_library_is_separate(lib):
+    """The tcgen05 hardware probes ship in their own library: the product .so must not export them."""
+    from view_fusion_b200 import _lib
+    probes = _lib.load_probes()
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "viewfusion_b200_probes.h")).read(), flags=re.S)
+    decl = sorted(set(re.findall(r"\b(vf_debug_[a-z0-9_]+)\s*\(", src)))
+    assert decl == sorted(_lib.PROBE_SYMBOLS)
+    for s in decl:
+        assert hasattr(probes, s)
+        assert not hasattr(lib, s), f"{s} must not be exported by the product library"
+
+
 def test_abi_version_and_error_string(lib):
     assert lib.vf_abi_version() == 2
     assert isinstance(lib.vf_last_error(), bytes)

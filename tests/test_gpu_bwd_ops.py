@@ -70,7 +70,7 @@ def test_groupnorm_swish_backward(lib, dtype, C0, C1, S, swish, acc):
     gm, bt = gamma.cuda(), beta.cuda()
     _lib.check(lib.vf_gn_backward(s0.data_ptr(), C0, st.data_ptr(), Cc, _lib.ptr(s1), C1, st.data_ptr() + 8 * C0 if C1 else 0, Cc, _dt(dtype),
                                   R, S, S, groups, gm.data_ptr(), bt.data_ptr(), int(swish), dyp.data_ptr(), scratch.data_ptr(), dgm.data_ptr(),
-                                  dbt.data_ptr(), dx0.data_ptr(), int(acc), _lib.ptr(dx1), int(acc), _lib.stream_handle()), "vf_gn_backward")
+                                  dbt.data_ptr(), dx0.data_ptr(), int(acc), _lib.ptr(dx1), int(acc), None, _lib.stream_handle()), "vf_gn_backward")
     torch.cuda.synchronize()
     tag = f"gn_backward {'bf16' if dtype == torch.bfloat16 else 'fp32'} C={C0}+{C1} {S}x{S} swish={int(swish)} acc={int(acc)}"
     tol_x, tol_p = (1e-2, 5e-3) if dtype == torch.bfloat16 else (2e-5, 2e-5)
@@ -84,6 +84,52 @@ def test_groupnorm_swish_backward(lib, dtype, C0, C1, S, swish, acc):
     if not acc:      # gradients of padding rows are exact zeros (the weight-gradient GEMMs read them)
         pad = dx0.float().view(R, S + 1, S + 1, C0)
         assert float(pad[:, 0].abs().max()) == 0.0 and float(pad[:, :, 0].abs().max()) == 0.0
+    assert ok
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C0,S", [(64, 16), (320, 8), (128, 32)])
+def test_groupnorm_deferred_bias_and_embedding(lib, dtype, C0, S):
+    """vf_gn_shift: ResnetBlock.block1's bias and FeatureWiseAffine add (unet.py:243, :176) are never added in memory; the
+    GroupNorm of block2 (forward and backward) acts on h + bias[c] + emb[img_row[img]][c] in closed form.  Checked against
+    fp64 autograd of GroupNorm+Swish applied to the explicitly shifted tensor."""
+    from view_fusion_b200 import _lib, ops
+    torch.manual_seed(C0 + S)
+    R, groups, rows, E, col = 4, 32, 3, C0 + 40, 8
+    rnd = (lambda *s: bf16r(torch.randn(*s))) if dtype == torch.bfloat16 else (lambda *s: torch.randn(*s))
+    h = rnd(R, C0, S, S) * 1.3 + 0.2
+    h = bf16r(h) if dtype == torch.bfloat16 else h
+    bias, emb = torch.randn(C0) * 0.5, torch.randn(rows, E)
+    img_row = torch.randint(0, rows, (R,), dtype=torch.int32)
+    gamma, beta = torch.rand(C0) + 0.5, torch.randn(C0) * 0.1
+    dy = rnd(R, C0, S, S)
+    shift_ref = (bias[None, :] + emb[img_row.long(), col:col + C0]).double()
+    a0 = h.double().requires_grad_(True)
+    gd, bd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    y = F.group_norm(a0 + shift_ref[:, :, None, None], groups, gd, bd, eps=1e-5)
+    y = y * torch.sigmoid(y)
+    y.backward(dy.double())
+    s0 = ops.to_padded(h, dtype, fill=float("nan")).cuda()
+    st = ops.gn_stats(s0, None, R, S, S)                      # raw sums of the STORED tensor (what the conv epilogue emits)
+    bd_, ed_, ir_ = bias.cuda(), emb.cuda(), img_row.cuda()
+    sh = ops.gn_shift(bd_, ed_[:, col:], ir_)
+    sh.emb_ld = E
+    gm, bt = gamma.cuda(), beta.cuda()
+    out = ops.gn_apply(s0, None, R, S, S, groups, st, gm, bt, True, shift=sh)
+    tag = f"gn deferred bias+emb {'bf16' if dtype == torch.bfloat16 else 'fp32'} C={C0} {S}x{S}"
+    ok = margin(f"{tag}: forward rel-L2 vs fp64", rel(ops.from_padded(out, R, S, S), y.detach().float()), 4e-3 if dtype == torch.bfloat16 else 5e-6)
+    dyp = ops.to_padded(dy, dtype, fill=float("nan")).cuda()
+    dx0 = torch.full((R * (S + 1) * (S + 1), C0), float("nan")).to(dtype).cuda()
+    scratch = torch.empty(R * C0 * 2, device="cuda")
+    dgm, dbt = torch.zeros(C0, device="cuda"), torch.zeros(C0, device="cuda")
+    _lib.check(lib.vf_gn_backward(s0.data_ptr(), C0, st.data_ptr(), C0, 0, 0, 0, 0, _dt(dtype), R, S, S, groups, gm.data_ptr(), bt.data_ptr(), 1,
+                                  dyp.data_ptr(), scratch.data_ptr(), dgm.data_ptr(), dbt.data_ptr(), dx0.data_ptr(), 0, 0, 0, C.byref(sh),
+                                  _lib.stream_handle()), "vf_gn_backward")
+    torch.cuda.synchronize()
+    tol_x, tol_p = (1e-2, 5e-3) if dtype == torch.bfloat16 else (2e-5, 2e-5)
+    ok &= margin(f"{tag}: dx rel-L2 vs fp64 autograd", rel(ops.from_padded(dx0, R, S, S), a0.grad.float()), tol_x)
+    ok &= margin(f"{tag}: dgamma rel-L2", rel(dgm, gd.grad.float()), tol_p)
+    ok &= margin(f"{tag}: dbeta rel-L2", rel(dbt, bd.grad.float()), tol_p)
     assert ok
 
 

@@ -49,7 +49,14 @@ def test_p_sample_n6_vs_oracle(prec, tol):
         ok &= margin(f"headline N=6 B=2 small-v100 {prec} t={tv}: view weights rel-L2 vs oracle", rel(w, w_ref), 1e-4 if prec == "fp32" else 2e-2)
         assert w.shape == w_ref.shape and logits.shape == logits_ref.shape
         if prec == "fp32":
-            assert torch.equal(w.cpu().argmax(1), w_ref.argmax(1)), "view-weight argmax must be identical in fp32 mode"
+            # identical argmax wherever the reference's two largest weights differ by more than fp32 noise: with six views and
+            # random-init logits a handful of pixels are exact near-ties (gap < 1e-5) where no two fp32 evaluations agree
+            top2 = w_ref.topk(2, dim=1).values
+            clear = (top2[:, 0] - top2[:, 1]) > 1e-5
+            same = w.cpu().argmax(1) == w_ref.argmax(1)
+            assert bool(same[clear].all()), "view-weight argmax must be identical in fp32 mode"
+            ok &= margin(f"headline N=6 B=2 small-v100 fp32 t={tv}: argmax agreement over ALL pixels (exact near-ties included)",
+                         float(same.float().mean()), 0.9999, higher_is_better=True)
         else:
             top2 = w_ref.topk(2, dim=1).values
             clear = (top2[:, 0] - top2[:, 1]) > 0.02          # random-init logits are near-ties

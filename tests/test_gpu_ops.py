@@ -424,7 +424,7 @@ def test_probe_shifted_umma_descriptor(lib):
     for shift in (0, 8, 64, 1, 3, 7, 9, 65, 67):
         for bo in (0, 1):
             out = torch.zeros(128, 64, device="cuda")
-            _lib.check(lib.vf_debug_umma_shift(Ad.data_ptr(), 512, Bd.data_ptr(), shift, bo, out.data_ptr(), _lib.stream_handle()), "probe")
+            _lib.check(_lib.load_probes().vf_debug_umma_shift(Ad.data_ptr(), 512, Bd.data_ptr(), shift, bo, out.data_ptr(), _lib.stream_handle()), "probe")
             torch.cuda.synchronize()
             ref = A[shift:shift + 128] @ B.t()
             res[(shift, bo)] = rel(out, ref)

@@ -22,7 +22,7 @@ SYMBOLS = [
     "vf_unet_last_launches", "vf_unet_read_tap", "vf_unet_set_profiling", "vf_unet_profile_read", "vf_unet_profile_launches", "vf_unet_set_stash", "vf_unet_set_capacity", "vf_unet_forward_generation",
     "vf_pack_views", "vf_pack_nchw", "vf_nhwc_to_nchw", "vf_q_sample",
     "vf_compose_ddpm_step", "vf_compose_mse", "vf_step_prepare", "vf_p_sample_step", "vf_unet_act_dtype",
-    "vf_embed", "vf_gn_stats", "vf_gn_apply", "vf_upsample2x", "vf_flat_to_padded", "vf_padded_to_flat", "vf_zero_padding", "vf_conv2d", "vf_debug_force_simt", "vf_debug_flags", "vf_debug_counters", "vf_debug_umma_shift", "vf_debug_umma_rate", "vf_debug_umma_mn", "vf_attention",
+    "vf_embed", "vf_gn_stats", "vf_gn_apply", "vf_upsample2x", "vf_flat_to_padded", "vf_padded_to_flat", "vf_zero_padding", "vf_conv2d", "vf_debug_force_simt", "vf_debug_flags", "vf_debug_counters", "vf_attention",
     "vf_pack_conv_weight",
     "vf_unet_packed_t_bytes", "vf_unet_pack_weights_t", "vf_unet_backward_workspace_bytes", "vf_unet_backward",
     "vf_conv2d_wgrad", "vf_unpack_conv_wgrad", "vf_pack_conv_weight_t", "vf_gn_backward", "vf_attention_backward",
@@ -57,6 +57,10 @@ class ComposeArgs(C.Structure):
         ("eps_out", C.c_void_p), ("weights_out", C.c_void_p), ("max_v", C.c_int), ("logits_out", C.c_void_p),
         ("step", C.c_void_p),
     ]
+
+
+class GnShift(C.Structure):
+    _fields_ = [("bias", C.c_void_p), ("emb", C.c_void_p), ("img_row", C.c_void_p), ("emb_ld", C.c_int)]
 
 
 class SampleStepArgs(C.Structure):
@@ -137,7 +141,7 @@ def load() -> C.CDLL:
         "vf_unet_act_dtype": (i, [p]),
         "vf_embed": (i, [p, p, i, i, p, p, p, p, p, p, i, p, p]),
         "vf_gn_stats": (i, [p, i, p, i, i, i, i, i, p, p]),
-        "vf_gn_apply": (i, [p, i, p, i, p, i, p, i, i, i, i, i, i, p, p, i, p, p]),
+        "vf_gn_apply": (i, [p, i, p, i, p, i, p, i, i, i, i, i, i, p, p, i, p, C.POINTER(GnShift), p]),
         "vf_upsample2x": (i, [p, i, i, i, i, i, p, p]),
         "vf_zero_padding": (i, [p, i, i, i, i, i, p]),
         "vf_flat_to_padded": (i, [p, i, i, i, i, i, p, p]),
@@ -146,9 +150,6 @@ def load() -> C.CDLL:
         "vf_debug_force_simt": (None, [i]),
         "vf_debug_flags": (None, [i]),
         "vf_debug_counters": (None, [p]),
-        "vf_debug_umma_rate": (i, [i, i, i, i, i, p, p]),
-        "vf_debug_umma_mn": (i, [p, i, p, i, i, i, i, p, p]),
-        "vf_debug_umma_shift": (i, [p, i, p, i, i, p, p]),
         "vf_attention": (i, [p, p, i, i, i, i, p, p, p]),
         "vf_pack_conv_weight": (i, [p, i, i, i, i, p, i, i, i, p]),
         "vf_unet_packed_t_bytes": (sz, [p]),
@@ -158,7 +159,7 @@ def load() -> C.CDLL:
         "vf_conv2d_wgrad": (i, [C.POINTER(ConvArgs), p, i, p, p]),
         "vf_unpack_conv_wgrad": (i, [p, i, i, i, i, i, p, i, i, p]),
         "vf_pack_conv_weight_t": (i, [p, i, i, i, i, p, i, i, i, i, p]),
-        "vf_gn_backward": (i, [p, i, p, i, p, i, p, i, i, i, i, i, i, p, p, i, p, p, p, p, p, i, p, i, p]),
+        "vf_gn_backward": (i, [p, i, p, i, p, i, p, i, i, i, i, i, i, p, p, i, p, p, p, p, p, i, p, i, C.POINTER(GnShift), p]),
         "vf_attention_backward": (i, [p, p, p, p, p, i, i, i, i, p, p, p]),
         "vf_upsample2x_backward": (i, [p, i, i, i, i, i, p, i, p]),
         "vf_zero_insert2x": (i, [p, i, i, i, i, i, p, p]),
@@ -177,6 +178,28 @@ def load() -> C.CDLL:
         raise RuntimeError("libviewfusion_b200.so: ABI version mismatch")
     _lib = lib
     return lib
+
+
+PROBES_PATH = os.path.join(_HERE, "libviewfusion_b200_probes.so")
+PROBE_SYMBOLS = ["vf_debug_umma_shift", "vf_debug_umma_rate", "vf_debug_umma_mn"]      # include/viewfusion_b200_probes.h
+_probes = None
+
+
+def load_probes() -> C.CDLL:
+    """The probe library (tests / scripts only): product objects + csrc/k_debug.cu.  The product package never calls this."""
+    global _probes
+    if _probes is None:
+        if not os.path.exists(PROBES_PATH):
+            raise RuntimeError(f"{PROBES_PATH} is missing: build it with `python -m view_fusion_b200.build`")
+        lib = C.CDLL(PROBES_PATH)
+        p, i = C.c_void_p, C.c_int
+        for name, args in {"vf_debug_umma_rate": [i, i, i, i, i, p, p], "vf_debug_umma_mn": [p, i, p, i, i, i, i, p, p],
+                           "vf_debug_umma_shift": [p, i, p, i, i, p, p]}.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = i, args
+        lib.vf_last_error.restype = C.c_char_p
+        _probes = lib
+    return _probes
 
 
 def check(rc: int, what: str = "") -> None:

@@ -1,4 +1,6 @@
-"""In-tree build of the C-ABI library `libviewfusion_b200.so` (nvcc, sm_100a only).
+"""In-tree build of the C-ABI library `libviewfusion_b200.so` (nvcc, sm_100a only), plus
+`libviewfusion_b200_probes.so` = the same objects + `csrc/k_debug.cu` (tcgen05 hardware probes used by tests and scripts; never
+loaded by the product package).
 
     python -m view_fusion_b200.build            # incremental
     python -m view_fusion_b200.build --force
@@ -17,6 +19,8 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libviewfusion_b200.so")
+OUT_PROBES = os.path.join(HERE, "libviewfusion_b200_probes.so")    # product objects + hardware probes: tests / scripts only
+PROBE_SOURCES = ("k_debug.cu",)
 BUILD = os.path.join(CSRC, "_build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -66,12 +70,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     hdr = _headers_digest()
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         res = list(ex.map(lambda s: _compile(s, hdr, force, verbose), _sources()))
-    objs = [o for o, _ in res]
-    if any(c for _, c in res) or not os.path.exists(OUT) or force:
-        cmd = [NVCC, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    srcs = _sources()
+    objs = [o for (o, _), src in zip(res, srcs) if src not in PROBE_SOURCES]          # the product library carries no probes
+    objs_all = [o for o, _ in res]
+    changed = any(c for _, c in res)
+    for out, ob in ((OUT, objs), (OUT_PROBES, objs_all)):
+        if changed or not os.path.exists(out) or force:
+            cmd = [NVCC, "-shared", "-o", out, *ob, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return OUT
 
 

@@ -134,6 +134,7 @@ struct GnBwdParams {
   float* dgamma; float* dbeta;
   void* dx0; int acc0; void* dx1; int acc1;
   GnColsum cs;           // optional (cs.db / cs.demb non-null): closed-form column sums of dx0 (single-source case)
+  vf_gn_shift sh;        // optional: source 0 is stored without a per-(image, channel) constant (vf_gn_apply)
 };
 
 // d/dz [z * sigmoid(z)]; the bf16 path takes sigmoid from one tanh.approx like the forward kernel
@@ -172,14 +173,34 @@ __device__ __forceinline__ void gn_group_stats(const GnBwdParams& p, int img, fl
   const float inv_n = 1.f / ((float)gs * (float)p.HW);
   const float* sa = p.st0 + (size_t)img * p.ld0 * 2;
   const float* sb = p.st1 ? p.st1 + (size_t)img * p.ld1 * 2 : nullptr;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) raw[i] = i < 2 * p.C0 ? __ldg(sa + i) : __ldg(sb + (i - 2 * p.C0));
+  const bool shifted = p.sh.bias != nullptr || p.sh.emb != nullptr;
+  const float* sh_emb = p.sh.emb ? p.sh.emb + (size_t)__ldg(p.sh.img_row + img) * p.sh.emb_ld : nullptr;
+  if (!shifted) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) raw[i] = i < 2 * p.C0 ? __ldg(sa + i) : __ldg(sb + (i - 2 * p.C0));
+  } else {
+    // source 0 was normalised as x + s (vf_gn_shift): shift its raw sums the way the forward did
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+      float S1, S2;
+      if (ch < p.C0) {
+        S1 = __ldg(sa + 2 * ch); S2 = __ldg(sa + 2 * ch + 1);
+        const float sv = gn_shift_value(p.sh, sh_emb, ch);
+        S2 = fmaf(2.f * sv, S1, S2) + (float)p.HW * sv * sv;
+        S1 = fmaf((float)p.HW, sv, S1);
+      } else {
+        S1 = __ldg(sb + 2 * (ch - p.C0)); S2 = __ldg(sb + 2 * (ch - p.C0) + 1);
+      }
+      raw[2 * ch] = S1; raw[2 * ch + 1] = S2;
+    }
+  }
   __syncthreads();
   for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
     const int g0 = ch / gs * gs;
     float s = 0.f, q = 0.f;
     for (int j = 0; j < gs; ++j) { s += raw[2 * (g0 + j)]; q += raw[2 * (g0 + j) + 1]; }
-    const float mean = s * inv_n;
+    float mean = s * inv_n;
     const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+    // every later use of the mean is (x - mean) with the STORED x: with a shift that is x - (mean - s)
+    if (shifted && ch < p.C0) mean -= gn_shift_value(p.sh, sh_emb, ch);
     mr[2 * ch] = mean;
     mr[2 * ch + 1] = rsqrtf(var + 1e-5f);
   }
@@ -753,7 +774,7 @@ static int gn_bwd_splits(int images, int P, int C, int PY) {
 int gn_backward_impl(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1, const float* stats1,
                      int stats1_ld, int dtype, int images, int H, int W, int groups, const float* gamma, const float* beta, int swish,
                      const void* dy, float* scratch, bool scratch_zeroed, float* dgamma, float* dbeta, void* dx0, int acc0, void* dx1,
-                     int acc1, cudaStream_t st, const GnColsum* colsum) {
+                     int acc1, cudaStream_t st, const GnColsum* colsum, const vf_gn_shift* shift) {
   VF_REQUIRE(src0 && stats0 && gamma && beta && dy && scratch && dgamma && dbeta && dx0, "vf_gn_backward: null args");
   if (!src1) C1 = 0;
   VF_REQUIRE(C1 == 0 || (stats1 && dx1), "vf_gn_backward: second source needs stats and dx");
@@ -768,6 +789,10 @@ int gn_backward_impl(const void* src0, int C0, const float* stats0, int stats0_l
   if (colsum) {
     VF_REQUIRE(C1 == 0 && !acc0, "vf_gn_backward: closed-form column sums need a single source and a fresh dx");
     p.cs = *colsum;
+  }
+  if (shift) {
+    VF_REQUIRE(!shift->emb || shift->img_row, "vf_gn_backward: shift.emb needs img_row");
+    p.sh = *shift;
   }
   const int CV = C / vec, PY = kGbThreads / CV > 0 ? kGbThreads / CV : 1;
   const int threads = CV * PY;
@@ -808,9 +833,9 @@ VF_API int vf_debug_gn_bwd_splits(int images, int H, int W, int C, int dtype) {
 VF_API int vf_gn_backward(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1, const float* stats1,
                           int stats1_ld, int dtype, int images, int H, int W, int groups, const float* gamma, const float* beta, int swish,
                           const void* dy, float* scratch, float* dgamma, float* dbeta, void* dx0, int acc0, void* dx1, int acc1,
-                          vf_stream stream) {
+                          const vf_gn_shift* shift, vf_stream stream) {
   return vf::gn_backward_impl(src0, C0, stats0, stats0_ld, src1, C1, stats1, stats1_ld, dtype, images, H, W, groups, gamma, beta, swish, dy,
-                              scratch, false, dgamma, dbeta, dx0, acc0, dx1, acc1, as_stream(stream), nullptr);
+                              scratch, false, dgamma, dbeta, dx0, acc0, dx1, acc1, as_stream(stream), nullptr, shift);
 }
 
 namespace vf {

@@ -182,6 +182,9 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 
+// kDbg = false is the PRODUCTION instantiation: cycle counters, wall-clock stamps and the ablation bits of vf_debug_flags are
+// compiled out; kDbg = true is launched only while a test hook (vf_debug_flags / vf_debug_counters) is armed.
+template <bool kDbg>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0,
                                                                 const __grid_constant__ CUtensorMap mapA1,
                                                                 const __grid_constant__ CUtensorMap mapA2,
@@ -193,7 +196,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   // test hook: wall-clock stamps of CTA 0 (entry, after set-up + dependency wait, after the role loops, exit) per launch,
   // appended at dbg_out[grid*12 + 1 + 4*launch ..]; dbg_out[grid*12] counts the launches
   long long* stamps = nullptr;
-  if (p.dbg_out && blockIdx.x == 0 && threadIdx.x == 0) {
+  const int dbg = kDbg ? p.dbg : 0;
+  if (kDbg && p.dbg_out && blockIdx.x == 0 && threadIdx.x == 0) {
     long long* cnt = p.dbg_out + (size_t)gridDim.x * 12;
     const long long li = atomicAdd(reinterpret_cast<unsigned long long*>(cnt), 1ull);
     if (li < 64) { stamps = cnt + 1 + 4 * li; stamps[0] = (long long)global_timer_ns(); }
@@ -309,13 +313,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // ===================== MMA issuer =====================
     if (ptx::elect_one()) {
       MmaCtx mc{bar_afull, bar_aempty, bar_bfull, bar_bempty, bar_accfull, bar_accempty, ringA, ringB, b_bytes, tmem_base};
-      const bool prof = p.dbg_out != nullptr;
+      const bool prof = kDbg && p.dbg_out != nullptr;
       // one instantiation per (row-tile count, weights resident?, cycle counters?): the loop body is a few scalar
       // instructions per tap so the tensor pipe, not this thread, sets the pace
 #define VF_MMA_CASE(GG)                                                                       \
   case GG:                                                                                    \
-    if (p.b_resident) { if (prof) mma_issue_loop<GG, true, true>(p, mc); else mma_issue_loop<GG, true, false>(p, mc); }    \
-    else { if (prof) mma_issue_loop<GG, false, true>(p, mc); else mma_issue_loop<GG, false, false>(p, mc); }               \
+    if (p.b_resident) { if (kDbg && prof) mma_issue_loop<GG, true, kDbg>(p, mc); else mma_issue_loop<GG, true, false>(p, mc); }    \
+    else { if (kDbg && prof) mma_issue_loop<GG, false, kDbg>(p, mc); else mma_issue_loop<GG, false, false>(p, mc); }               \
     break;
       switch (p.G) {
         VF_MMA_CASE(1)
@@ -346,9 +350,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     __syncwarp();
     uint32_t res_phase = 0;
     const bool has_res = p.residual != nullptr;
+    const bool has_tab = p.bias != nullptr || p.emb != nullptr;      // false: nothing is added in the epilogue (deferred to the consumer)
     int k_idx = 0;
     // test hook: cycle counters of epilogue warp 0 -> dbg_out[grid*4 + cta*8 + ...] = total, table, wait acc, ld+pack, store wait, stats, prep
-    const bool eprof = p.dbg_out != nullptr && et == 0;
+    const bool eprof = kDbg && p.dbg_out != nullptr && et == 0;
     long long ec[7] = {0, 0, 0, 0, 0, 0, 0}, et0 = 0;
     const long long e_start = eprof ? clock64() : 0;
 #define VF_EP_BEGIN() do { if (eprof) et0 = clock64(); } while (0)
@@ -375,7 +380,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         tab_next[j] = v;
       }
     };
-    if (p.emb != nullptr && (int)blockIdx.x < p.n_items && !(p.dbg & 8)) load_table(blockIdx.x);
+    if (p.emb != nullptr && (int)blockIdx.x < p.n_items && !(dbg & 8)) load_table(blockIdx.x);
     int tab_n_tile = -1;
     // (combining the GroupNorm sums per CTA in shared memory first was tried: shared-memory float atomics cost more than
     // the global REDs they save, 12 -> 31 kclk per CTA in the statistics section)
@@ -390,10 +395,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       // write are on this item's critical path.  Without one it is the bias of the N tile: rebuilt only when the CTA moves
       // to another N tile, and the epilogue warps run from item to item without meeting at a barrier.
       VF_EP_BEGIN();
-      if (p.emb != nullptr || n_tile != tab_n_tile) {
-        if (p.emb == nullptr && !(p.dbg & 8)) load_table(item);
+      if (has_tab && (p.emb != nullptr || n_tile != tab_n_tile)) {
+        if (p.emb == nullptr && !(dbg & 8)) load_table(item);
         asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");     // previous item's readers are done
-        if (!(p.dbg & 8)) {
+        if (!(dbg & 8)) {
 #pragma unroll
           for (int j = 0; j < TAB_PER_THREAD; ++j) {
             const int i = et + j * TC_EPI_THREADS;
@@ -402,7 +407,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
         tab_n_tile = n_tile;
-        if (p.emb != nullptr && !(p.dbg & 8)) {
+        if (p.emb != nullptr && !(dbg & 8)) {
           const int item_next = item + gridDim.x;
           if (item_next < p.n_items) load_table(item_next);
         }
@@ -454,7 +459,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       ptx::mbar_wait(bar_accfull + 8 * set, (uint32_t)(k_idx >> 1) & 1u);
       ptx::tc_fence_after();
       VF_EP_END(2);
-      for (int u = sub; u < U && !(p.dbg & 4); u += TC_NSUB) {
+      for (int u = sub; u < U && !(dbg & 4); u += TC_NSUB) {
         int g, c0;
         unit_gc(u, g, c0);
         const int width = min(64, p.block_n - c0);
@@ -506,7 +511,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 o.w = pack_bf16x2(__uint_as_float(acc[6]) + b1.z + bf16_lo(rv.w), __uint_as_float(acc[7]) + b1.w + bf16_hi(rv.w));
                 *slot = o;
               }
-            } else {
+            } else if (has_tab) {
 #pragma unroll
               for (int jj = 0; jj < SLOTS; ++jj) {
                 const int j = hh * SLOTS + jj;
@@ -519,18 +524,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 o.w = pack_bf16x2(__uint_as_float(acc[6]) + b1.z, __uint_as_float(acc[7]) + b1.w);
                 *reinterpret_cast<uint4*>(tile + (((uint32_t)j ^ sw) << 4)) = o;
               }
+            } else {
+              // nothing to add (bias / embedding deferred into the consumer's GroupNorm): 4 F2FP + 1 STS per slot
+#pragma unroll
+              for (int jj = 0; jj < SLOTS; ++jj) {
+                const int j = hh * SLOTS + jj;
+                const uint32_t* acc = &rr[jj >> 1][(jj & 1) * 8];
+                uint4 o;
+                o.x = pack_bf16x2(__uint_as_float(acc[0]), __uint_as_float(acc[1]));
+                o.y = pack_bf16x2(__uint_as_float(acc[2]), __uint_as_float(acc[3]));
+                o.z = pack_bf16x2(__uint_as_float(acc[4]), __uint_as_float(acc[5]));
+                o.w = pack_bf16x2(__uint_as_float(acc[6]), __uint_as_float(acc[7]));
+                *reinterpret_cast<uint4*>(tile + (((uint32_t)j ^ sw) << 4)) = o;
+              }
             }
           }
           ptx::fence_proxy_async();
           __syncwarp();
-          if (lane == 0 && !(p.dbg & 2)) {
+          if (lane == 0 && !(dbg & 2)) {
             if (p.epi_lines) ptx::tma_store_3d(&mapOut, stg, n0 + c0, 0, (int)row_base);
             else ptx::tma_store_2d(&mapOut, stg, n0 + c0, (int)row_base);
             ptx::tma_store_commit();
           }
           VF_EP_END(3);
           VF_EP_BEGIN();
-          if (p.stats && !(p.dbg & 1)) {
+          if (p.stats && !(dbg & 1)) {
             // column sums straight from the staging tile: lane owns channels (2*lane, 2*lane+1); conflict-free reads.
             // Padding rows were stored as zeros, so a tile inside one image is summed without any per-row test.
             const uint8_t* col = stg_g + (lane & 3) * 4;
@@ -576,7 +594,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const bool act = valid && (n < p.cout || p.out_f32);  // structured: the warp reconverges before the next tcgen05.ld
             float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = act ? __uint_as_float(rr[j]) + brow[cc + j] : 0.f;
+            for (int j = 0; j < 16; ++j) v[j] = act ? __uint_as_float(rr[j]) + (has_tab ? brow[cc + j] : 0.f) : 0.f;
             if (act && p.residual) {
               const __nv_bfloat16* rp = p.residual + (size_t)ri.out_row * p.cout + n;
               float r0[8], r1[8];
@@ -933,13 +951,18 @@ int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
       if (rc) return rc;
     }
   }
-  VF_SET_MAX_SMEM(conv_tc_kernel, kSmemBudget);
   const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
   if (g_tc_dbg & 256)
     fprintf(stderr, "[vf tc] rows %d W %d cout %d segs %d ktot %d | bn %d G %d a_stages %d (%d B) b_stages %d resident %d smem %zu items %d grid %d epi_tma %d a_lines %d epi_lines %d\n",
             p.geo.rows_total, W, a->cout, a->n_seg, k_total, p.block_n, p.G, p.a_stages, p.a_stage_bytes, p.b_stages, p.b_resident, tl.smem,
             p.n_items, grid, p.epi_tma, p.a_lines, p.epi_lines);
-  VF_CUDA(launch_pdl(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), tl.smem, st, maps[0], maps[1], maps[2], maps4[3], mapB, mapOut, mapRes, p));
+  if (g_tc_dbg != 0 || g_tc_dbg_out != nullptr) {          // a test hook is armed: the instrumented instantiation
+    VF_SET_MAX_SMEM(conv_tc_kernel<true>, kSmemBudget);
+    VF_CUDA(launch_pdl(conv_tc_kernel<true>, dim3(grid), dim3(TC_THREADS), tl.smem, st, maps[0], maps[1], maps[2], maps4[3], mapB, mapOut, mapRes, p));
+  } else {
+    VF_SET_MAX_SMEM(conv_tc_kernel<false>, kSmemBudget);
+    VF_CUDA(launch_pdl(conv_tc_kernel<false>, dim3(grid), dim3(TC_THREADS), tl.smem, st, maps[0], maps[1], maps[2], maps4[3], mapB, mapOut, mapRes, p));
+  }
   VF_LAUNCH_CHECK();
   return VF_OK;
 }

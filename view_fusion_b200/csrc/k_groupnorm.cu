@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(kGnThreads, 4) gn_apply_kernel(const T* __rest
                                                               const float* __restrict__ st0, int ld0,
                                                               const float* __restrict__ st1, int ld1,
                                                               const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, T* __restrict__ dst) {
+                                                              const float* __restrict__ beta, T* __restrict__ dst, const vf_gn_shift sh) {
   constexpr int VEC = VecOf<T>::N;
   pdl_launch_dependents();
   pdl_wait();                                        // the statistics and the sources come from the previous kernels
@@ -123,16 +123,35 @@ __global__ void __launch_bounds__(kGnThreads, 4) gn_apply_kernel(const T* __rest
   // two barriers, the per-group loops) overlaps that load instead of preceding it (measured neutral on B200 at 168
   // view-images: 1.64 ms per step either way; kept because it removes a dependency, not for a number).
   // one coalesced load of the image's (sum, sumsq) pairs; the per-group loops then run out of shared memory
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) raw[i] = i < 2 * C0 ? __ldg(sa + i) : __ldg(sb + (i - 2 * C0));
+  const bool shifted = sh.bias != nullptr || sh.emb != nullptr;
+  const float* sh_emb = sh.emb ? sh.emb + (size_t)__ldg(sh.img_row + img) * sh.emb_ld : nullptr;
+  if (!shifted) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) raw[i] = i < 2 * C0 ? __ldg(sa + i) : __ldg(sb + (i - 2 * C0));
+  } else {
+    // source 0 is stored without its per-(image, channel) constant s: shift its raw sums in closed form
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+      float S1, S2;
+      if (ch < C0) {
+        S1 = __ldg(sa + 2 * ch); S2 = __ldg(sa + 2 * ch + 1);
+        const float sv = gn_shift_value(sh, sh_emb, ch);
+        S2 = fmaf(2.f * sv, S1, S2) + (float)HW * sv * sv;
+        S1 = fmaf((float)HW, sv, S1);
+      } else {
+        S1 = __ldg(sb + 2 * (ch - C0)); S2 = __ldg(sb + 2 * (ch - C0) + 1);
+      }
+      raw[2 * ch] = S1; raw[2 * ch + 1] = S2;
+    }
+  }
   __syncthreads();
   for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
     const int g0 = ch / gs * gs;
     float s = 0.f, q = 0.f;
     for (int j = 0; j < gs; ++j) { s += raw[2 * (g0 + j)]; q += raw[2 * (g0 + j) + 1]; }   // a group may straddle the two sources
-    const float mean = s * inv_n;
+    float mean = s * inv_n;
     const float var = fmaxf(q * inv_n - mean * mean, 0.f);
     const float rstd = rsqrtf(var + 1e-5f);
     const float a = rstd * __ldg(gamma + ch);
+    if (shifted && ch < C0) mean -= gn_shift_value(sh, sh_emb, ch);     // (x + s - mean) = x - (mean - s)
     ab[2 * ch] = a;
     ab[2 * ch + 1] = __ldg(beta + ch) - mean * a;
   }
@@ -264,8 +283,11 @@ extern "C" __attribute__((visibility("default"))) int vf_gn_stats(const void* sr
 
 extern "C" __attribute__((visibility("default"))) int vf_gn_apply(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1,
                            const float* stats1, int stats1_ld, int dtype, int images, int H, int W, int groups,
-                           const float* gamma, const float* beta, int swish, void* dst, vf_stream stream) {
+                           const float* gamma, const float* beta, int swish, void* dst, const vf_gn_shift* shift, vf_stream stream) {
   using namespace vf;
+  vf_gn_shift sh{};
+  if (shift) sh = *shift;
+  VF_REQUIRE(!sh.emb || sh.img_row, "vf_gn_apply: shift.emb needs img_row");
   VF_REQUIRE(src0 && stats0 && gamma && beta && dst && images > 0 && H > 0 && W > 0 && C0 > 0, "vf_gn_apply: bad args");
   if (!src1) C1 = 0;
   VF_REQUIRE(C1 == 0 || stats1, "vf_gn_apply: second source needs statistics");
@@ -280,7 +302,7 @@ extern "C" __attribute__((visibility("default"))) int vf_gn_apply(const void* sr
   const size_t smem = 4 * C * sizeof(float);
   cudaStream_t st = as_stream(stream);
 #define VF_GN_LAUNCH(T, SW) \
-  VF_CUDA(launch_pdl(gn_apply_kernel<T, SW>, grid, dim3(g.threads), smem, st, (const T*)src0, C0, (const T*)src1, C1, H * W, W + 1, P, groups, g.pix_per_cta, stats0, stats0_ld, C1 ? stats1 : nullptr, stats1_ld, gamma, beta, (T*)dst))
+  VF_CUDA(launch_pdl(gn_apply_kernel<T, SW>, grid, dim3(g.threads), smem, st, (const T*)src0, C0, (const T*)src1, C1, H * W, W + 1, P, groups, g.pix_per_cta, stats0, stats0_ld, C1 ? stats1 : nullptr, stats1_ld, gamma, beta, (T*)dst, sh))
   if (dtype == VF_BF16) { if (swish) VF_GN_LAUNCH(__nv_bfloat16, true); else VF_GN_LAUNCH(__nv_bfloat16, false); }
   else { if (swish) VF_GN_LAUNCH(float, true); else VF_GN_LAUNCH(float, false); }
 #undef VF_GN_LAUNCH

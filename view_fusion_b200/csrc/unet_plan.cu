@@ -91,6 +91,7 @@ struct vf_unet {
     int emb_col, nf_w, nf_b;           // embedding columns added in the epilogue (-1: none)
     size_t wt_off[3];                  // transposed weight pack per segment in packed_t (SIZE_MAX: no data gradient)
     const void* gsrc0; const void* gsrc1; int gC0, gC1; const float* gst0; const float* gst1; int gld0, gld1; int gw, gb, swish;
+    vf_gn_shift gshift;               // deferred bias + embedding of source 0 (all-null: none)
     void* gdst; int gH, gW;
     const void* qkv; const void* vt; void* o; float* lse; int aC, aL;
     const void* usrc; void* udst; int uH, uW, uC;
@@ -376,6 +377,10 @@ struct Act {
   void* p;
   int C, H, W;
   float* stats;   // [images, C, 2] sum / sum-of-squares written by the producing conv's epilogue, or null
+  // deferred additive constant: the tensor is stored WITHOUT bias[c] + emb[img_row[img]][c]; its one consumer (a GroupNorm)
+  // folds it into the normalisation (vf_gn_shift)
+  const float* sh_bias = nullptr;
+  const float* sh_emb = nullptr;
 };
 
 static Act new_act(Exec& ex, const vf_unet* u, int images, int C, int H, int W, bool want_stats) {
@@ -621,7 +626,7 @@ static vf_conv_args conv_args_init() {
 
 // GroupNorm (+Swish) of cat(x, skip) -> new activation.  Statistics come from the producers' epilogues when
 // available, otherwise from a separate vf_gn_stats pass.
-static Act gn_block(Exec& ex, vf_unet* u, int images, const Act& x, const Act* skip, int gw, int gb, bool swish) {
+static Act gn_block(Exec& ex, vf_unet* u, int images, const Act& x, const Act* skip, int gw, int gb, bool swish, const int* img_row = nullptr) {
   const int C1 = skip ? skip->C : 0;
   const int C = x.C + C1;
   const float *s0 = x.stats, *s1 = skip ? skip->stats : nullptr;
@@ -632,8 +637,10 @@ static Act gn_block(Exec& ex, vf_unet* u, int images, const Act& x, const Act* s
     s0 = st; s1 = st + 2 * x.C; ld0 = ld1 = C;
   }
   Act y = new_act(ex, u, images, C, x.H, x.W, false);
+  vf_gn_shift shift{};
+  if (x.sh_bias || x.sh_emb) { shift.bias = x.sh_bias; shift.emb = x.sh_emb; shift.img_row = img_row; shift.emb_ld = u->E; }
   VF_RUN(ex, K_GN_APPLY, vf_gn_apply(x.p, x.C, s0, ld0, skip ? skip->p : nullptr, C1, s1, ld1, u->dtype, images, x.H, x.W, u->cfg.norm_groups,
-                                     u->master[gw], u->master[gb], swish ? 1 : 0, y.p, (vf_stream)ex.st));
+                                     u->master[gw], u->master[gb], swish ? 1 : 0, y.p, &shift, (vf_stream)ex.st));
   if (!ex.dry) {
     prof_describe(ex.u, images, x.H, C, C, 0, 0);
     vf_unet::TapeOp t{};
@@ -641,6 +648,7 @@ static Act gn_block(Exec& ex, vf_unet* u, int images, const Act& x, const Act* s
     t.gsrc0 = x.p; t.gC0 = x.C; t.gst0 = s0; t.gld0 = ld0;
     t.gsrc1 = skip ? skip->p : nullptr; t.gC1 = C1; t.gst1 = s1; t.gld1 = ld1;
     t.gw = gw; t.gb = gb; t.swish = swish ? 1 : 0; t.gdst = y.p; t.gH = x.H; t.gW = x.W;
+    t.gshift = shift;
     u->tape.push_back(t);
   }
   return y;
@@ -660,8 +668,9 @@ static Act run_resblock(Exec& ex, vf_unet* u, const uint8_t* pk, int images, con
     a.images = images; a.H = x.H; a.W = x.W; a.n_seg = 1;
     a.src[0] = a1.p; a.src_c[0] = cin; a.ksize[0] = 3;
     a.weight = pk + b.w1; a.cout = b.cout; a.cout_pad = b.cout;
-    a.bias = ex.dry ? nullptr : u->master[b.c1_b];
-    a.emb = emb ? emb + b.emb_col : nullptr; a.img_row = img_row; a.emb_ld = u->E;
+    // bias + FeatureWiseAffine add (unet.py:243, :176) are NOT applied here: h1 feeds block2's GroupNorm and nothing else, so
+    // the per-(image, channel) constant folds into that normalisation (vf_gn_shift) and this epilogue adds nothing
+    if (!ex.dry) { h1.sh_bias = u->master[b.c1_b]; h1.sh_emb = emb ? emb + b.emb_col : nullptr; }
     a.out = h1.p; a.out_ld = b.cout; a.stats = h1.stats;
     ConvMeta m;
     m.w_idx[0] = b.c1_w; m.cin_total[0] = cin; m.b_idx[0] = b.c1_b; m.wt_off[0] = b.wt1;
@@ -669,7 +678,7 @@ static Act run_resblock(Exec& ex, vf_unet* u, const uint8_t* pk, int images, con
     conv_call(ex, u, a, m);
   }
   // block2: GN -> Swish -> conv3x3, + res_conv(x) or + x                                 unet.py:244-245
-  Act a2 = gn_block(ex, u, images, h1, nullptr, b.g2_w, b.g2_b, true);
+  Act a2 = gn_block(ex, u, images, h1, nullptr, b.g2_w, b.g2_b, true, img_row);
   Act out = new_act(ex, u, images, b.cout, x.H, x.W, true);
   {
     vf_conv_args a = conv_args_init();
@@ -1165,7 +1174,7 @@ __global__ void __launch_bounds__(256) embed_bwd_params_kernel(const float* __re
 int gn_backward_impl(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1, const float* stats1,
                      int stats1_ld, int dtype, int images, int H, int W, int groups, const float* gamma, const float* beta, int swish,
                      const void* dy, float* scratch, bool scratch_zeroed, float* dgamma, float* dbeta, void* dx0, int acc0, void* dx1,
-                     int acc1, cudaStream_t st, const GnColsum* colsum);
+                     int acc1, cudaStream_t st, const GnColsum* colsum, const vf_gn_shift* shift);
 
 // ---- all packed weight gradients -> OIHW parameter gradients in ONE launch at the end of the backward -----------------
 // (every convolution owns a slice of the packed-gradient arena, so nothing has to be unpacked layer by layer)
@@ -1474,7 +1483,7 @@ static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float*
       }
       VF_B(gn_backward_impl(t.gsrc0, t.gC0, t.gst0, t.gld0, t.gsrc1, t.gC1, t.gst1, t.gld1, dt, images, t.gH, t.gW, c.norm_groups,
                             u->master[t.gw], u->master[t.gb], t.swish, gy.first, gn_cur, true, pg[t.gw], pg[t.gb], g0.first, g0.second ? 1 : 0,
-                            g1 ? g1->first : nullptr, g1 && g1->second ? 1 : 0, cx.st, fused_cs ? &csum : nullptr));
+                            g1 ? g1->first : nullptr, g1 && g1->second ? 1 : 0, cx.st, fused_cs ? &csum : nullptr, &t.gshift));
       gn_cur += align_up(cx.li * (t.gC0 + t.gC1) * 2, 64);
       g0.second = true;
       if (g1) g1->second = true;

@@ -198,6 +198,12 @@ struct GnColsum {
   const int* img_row;   // [images] embedding row of each image
   int emb_ld, col;
 };
+// s[img][ch] of a vf_gn_shift (emb_row = emb + img_row[img] * emb_ld, or NULL)
+__device__ __forceinline__ float gn_shift_value(const vf_gn_shift& sh, const float* emb_row, int ch) {
+  float v = sh.bias ? __ldg(sh.bias + ch) : 0.f;
+  if (emb_row) v += __ldg(emb_row + ch);
+  return v;
+}
 struct RowInfo {
   int img, pix;      // pix = y*Wo + x at the OUTPUT resolution
   bool valid;

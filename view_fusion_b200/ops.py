@@ -118,7 +118,15 @@ def gn_stats(src0, src1, images, H, W):
     return stats
 
 
-def gn_apply(src0, src1, images, H, W, groups, stats, gamma, beta, swish=True, stats1=None):
+def gn_shift(bias=None, emb=None, img_row=None):
+    """vf_gn_shift for source 0: stored without bias[c] + emb[img_row[img]][c] (keep the tensors alive during the call)."""
+    s = _lib.GnShift()
+    s.bias, s.emb, s.img_row = _lib.ptr(bias), _lib.ptr(emb), _lib.ptr(img_row)
+    s.emb_ld = 0 if emb is None else emb.shape[1]
+    return s
+
+
+def gn_apply(src0, src1, images, H, W, groups, stats, gamma, beta, swish=True, stats1=None, shift=None):
     """PADDED in, PADDED out.  stats: [images, C0+C1, 2] (from gn_stats), or per-source [images, C0, 2] + stats1."""
     lib = _lib.require_device()
     C0, C1 = src0.shape[1], (0 if src1 is None else src1.shape[1])
@@ -128,7 +136,8 @@ def gn_apply(src0, src1, images, H, W, groups, stats, gamma, beta, swish=True, s
     else:
         s0, ld0, s1, ld1 = stats.data_ptr(), stats.shape[1], stats1.data_ptr(), stats1.shape[1]
     _lib.check(lib.vf_gn_apply(src0.data_ptr(), C0, s0, ld0, _lib.ptr(src1), C1, s1 if C1 else 0, ld1, _dt(src0), images, H, W, groups,
-                               gamma.data_ptr(), beta.data_ptr(), int(swish), dst.data_ptr(), _lib.stream_handle()), "vf_gn_apply")
+                               gamma.data_ptr(), beta.data_ptr(), int(swish), dst.data_ptr(), None if shift is None else C.byref(shift),
+                               _lib.stream_handle()), "vf_gn_apply")
     return dst
 
 
