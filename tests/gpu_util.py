@@ -56,3 +56,17 @@ def margin(name, value, bar, higher_is_better=False):
     except OSError:
         pass
     return ok
+
+
+def argmax_agrees(w, w_ref, gap):
+    """View-weight argmax (over the view axis, per pixel and channel) identical wherever the reference's two largest weights
+    differ by more than `gap`.  Random-init logits are near-ties: fp32 mode uses gap = 1e-5 (a few pixels are
+    ties below fp32 noise, where two fp32 evaluations — or two runs of the atomically accumulated GroupNorm sums — disagree),
+    bf16 mode 2e-2.  Returns (all decided pixels agree, fraction of ALL pixels that agree)."""
+    w, w_ref = w.detach().float().cpu(), w_ref.detach().float().cpu()
+    same = w.argmax(1) == w_ref.argmax(1)
+    if w_ref.shape[1] < 2:
+        return bool(same.all()), 1.0
+    top2 = w_ref.topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > gap
+    return bool(same[clear].all()), float(same.float().mean())

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 import vf_oracle as O
-from gpu_util import build_model, rel
+from gpu_util import argmax_agrees, build_model, rel
 
 pytestmark = pytest.mark.gpu
 
@@ -43,7 +43,8 @@ def test_extrapolation_views_p_sample(prec, tol, nmax, vc):
         assert float(weights[b, v:].abs().max()) == 0.0 if v < max(vc) else True
         assert torch.allclose(weights[b, :v].sum(0).cpu(), torch.ones(3, 64, 64), atol=1e-5)
     if prec == "fp32":
-        assert torch.equal(weights.cpu().argmax(1), w_ref.argmax(1))
+        ok, frac = argmax_agrees(weights, w_ref, 1e-5)
+        assert ok and frac > 0.9995, frac
         assert rel(weights, w_ref) < 1e-4
 
 

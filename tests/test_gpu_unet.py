@@ -4,7 +4,7 @@ import pytest
 import torch
 
 import vf_oracle as O
-from gpu_util import TOY64, build_model, load, rel
+from gpu_util import TOY64, argmax_agrees, build_model, load, rel
 
 pytestmark = pytest.mark.gpu
 
@@ -63,8 +63,9 @@ def test_p_sample_trajectory_vs_reference_golden(golden_dir, tag, cfg, prec, tol
     assert logits.shape == g["logits_last"].shape and weights.shape == g["weights_last"].shape
     assert rel(weights, g["weights_last"]) < (1e-4 if prec == "fp32" else 2e-2)
     if prec == "fp32":
-        # view-weight argmax identical (per pixel, per channel) in fp32 mode
-        assert torch.equal(weights.cpu().argmax(1), g["weights_last"].argmax(1))
+        # view-weight argmax identical (per pixel, per channel) in fp32 mode, exact ties below fp32 noise aside
+        ok, frac = argmax_agrees(weights, g["weights_last"], 1e-5)
+        assert ok and frac > 0.9995, frac
     else:
         # bf16: random-init logits are near-ties -> compare where the reference's top-2 gap is clear
         ref = g["weights_last"]

@@ -18,15 +18,15 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libviewfusion_b200.so")
+OUT = os.environ.get("VF_B200_OUT") or os.path.join(HERE, "libviewfusion_b200.so")      # A/B builds: VF_B200_OUT + VF_NVCC_EXTRA
 OUT_PROBES = os.path.join(HERE, "libviewfusion_b200_probes.so")    # product objects + hardware probes: tests / scripts only
 PROBE_SOURCES = ("k_debug.cu",)
-BUILD = os.path.join(CSRC, "_build")
+BUILD = os.path.join(CSRC, os.environ.get("VF_B200_BUILD_DIR", "_build"))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("VF_NVCC_EXTRA", "").split()
 
 
 def _sources():
@@ -74,7 +74,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = [o for (o, _), src in zip(res, srcs) if src not in PROBE_SOURCES]          # the product library carries no probes
     objs_all = [o for o, _ in res]
     changed = any(c for _, c in res)
-    for out, ob in ((OUT, objs), (OUT_PROBES, objs_all)):
+    targets = ((OUT, objs),) if os.environ.get("VF_B200_OUT") else ((OUT, objs), (OUT_PROBES, objs_all))     # A/B builds: product library only
+    for out, ob in targets:
         if changed or not os.path.exists(out) or force:
             cmd = [NVCC, "-shared", "-o", out, *ob, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
             r = subprocess.run(cmd, capture_output=True, text=True)

@@ -350,7 +350,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     __syncwarp();
     uint32_t res_phase = 0;
     const bool has_res = p.residual != nullptr;
-    const bool has_tab = p.bias != nullptr || p.emb != nullptr;      // false: nothing is added in the epilogue (deferred to the consumer)
+    // false: nothing is added in the epilogue (bias / embedding deferred to the consumer) and the table is never built; the
+    // residual path reads the table unconditionally (zeros when there is no bias)
+    const bool has_tab = p.bias != nullptr || p.emb != nullptr || p.residual != nullptr;
     int k_idx = 0;
     // test hook: cycle counters of epilogue warp 0 -> dbg_out[grid*4 + cta*8 + ...] = total, table, wait acc, ld+pack, store wait, stats, prep
     const bool eprof = kDbg && p.dbg_out != nullptr && et == 0;

@@ -164,9 +164,13 @@ __device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); 
 // x * sigmoid(x) with sigmoid = 0.5 * tanh(0.5 x) + 0.5: one MUFU op per element (tanh.approx, rel. error 2^-11, well
 // below the bf16 rounding of the stored result) instead of ex2 + rcp.  The SiLU pass is otherwise MUFU-bound.
 __device__ __forceinline__ float silu_fast(float x) {
+#ifdef VF_SILU_EXACT      // A/B build: 2 MUFU (ex2 + rcp), relative error ~1e-7 instead of 2^-11
+  return __fdividef(x, 1.f + __expf(-x));
+#else
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
   return x * fmaf(0.5f, t, 0.5f);
+#endif
 }
 template <typename T> __device__ __forceinline__ float silu_for(float x);
 template <> __device__ __forceinline__ float silu_for<float>(float x) { return silu(x); }
