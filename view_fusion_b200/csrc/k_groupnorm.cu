@@ -14,6 +14,11 @@
 
 namespace vf {
 
+bool gn_stream_enabled();
+int gn_apply_stream(const void* src0, int C0, const float* stats0, int ld0, const void* src1, int C1, const float* stats1, int ld1, int dtype,
+                    int images, int H, int W, int groups, const float* gamma, const float* beta, int swish, void* dst, const vf_gn_shift& sh,
+                    cudaStream_t st);
+
 constexpr int kGnThreads = 256;
 
 // block = (CV channel-vectors) x (PY row lanes); every thread keeps sums for its fixed 16-byte channel vector
@@ -297,10 +302,14 @@ extern "C" __attribute__((visibility("default"))) int vf_gn_apply(const void* sr
   const int C = C0 + C1, P = (H + 1) * (W + 1);
   VF_REQUIRE(groups > 0 && C % groups == 0, "vf_gn_apply: C=%d not divisible by groups=%d", C, groups);
   VF_REQUIRE(C / vec <= kGnThreads, "vf_gn_apply: C=%d too large", C);
+  cudaStream_t st = as_stream(stream);
+  if (gn_stream_enabled()) {         // persistent TMA-fed streaming kernel (k_gn_stream.cu); 1 = shape not supported there
+    const int rc = gn_apply_stream(src0, C0, stats0, stats0_ld, src1, C1, stats1, stats1_ld, dtype, images, H, W, groups, gamma, beta, swish, dst, sh, st);
+    if (rc <= 0) return rc;
+  }
   GnGeom g = gn_geom(C, vec, P, images);
   dim3 grid(g.splits, images);
   const size_t smem = 4 * C * sizeof(float);
-  cudaStream_t st = as_stream(stream);
 #define VF_GN_LAUNCH(T, SW) \
   VF_CUDA(launch_pdl(gn_apply_kernel<T, SW>, grid, dim3(g.threads), smem, st, (const T*)src0, C0, (const T*)src1, C1, H * W, W + 1, P, groups, g.pix_per_cta, stats0, stats0_ld, C1 ? stats1 : nullptr, stats1_ld, gamma, beta, (T*)dst, sh))
   if (dtype == VF_BF16) { if (swish) VF_GN_LAUNCH(__nv_bfloat16, true); else VF_GN_LAUNCH(__nv_bfloat16, false); }
