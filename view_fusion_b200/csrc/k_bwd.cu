@@ -761,11 +761,6 @@ VF_API int vf_unpack_conv_wgrad(const float* dwp, int cout, int cin, int ksize, 
 }
 
 namespace vf {
-bool gn_stream_enabled();
-int gn_backward_stream(const void* src0, int C0, const float* stats0, int ld0, const void* src1, int C1, const float* stats1, int ld1, int dtype,
-                       int images, int H, int W, int groups, const float* gamma, const float* beta, int swish, const void* dy, float* scratch,
-                       float* dgamma, float* dbeta, void* dx0, int acc0, void* dx1, int acc1, const GnColsum* colsum, const vf_gn_shift& sh,
-                       cudaStream_t st);
 // row splits per image of the two GroupNorm backward passes (one grid for both)
 static int gn_bwd_splits(int images, int P, int C, int PY) {
   const int want = cdiv(148 * 8, images);
@@ -800,11 +795,6 @@ int gn_backward_impl(const void* src0, int C0, const float* stats0, int stats0_l
     p.sh = *shift;
   }
   if (!scratch_zeroed) VF_CUDA(cudaMemsetAsync(scratch, 0, (size_t)images * C * 2 * sizeof(float), st));
-  if (gn_stream_enabled()) {         // persistent TMA-fed streaming kernels (k_gn_stream.cu): dy is NOT consumed on this path
-    const int rc = gn_backward_stream(src0, C0, stats0, stats0_ld, src1, C1, stats1, stats1_ld, dtype, images, H, W, groups, gamma, beta, swish,
-                                      dy, scratch, dgamma, dbeta, dx0, acc0, dx1, acc1, colsum, p.sh, st);
-    if (rc <= 0) return rc;
-  }
   const int CV = C / vec, PY = kGbThreads / CV > 0 ? kGbThreads / CV : 1;
   const int threads = CV * PY;
   // (Processing large layers in L2-sized image groups so that the apply pass re-reads x / dy from L2 was measured

@@ -14,11 +14,6 @@
 
 namespace vf {
 
-bool gn_stream_enabled();
-int gn_apply_stream(const void* src0, int C0, const float* stats0, int ld0, const void* src1, int C1, const float* stats1, int ld1, int dtype,
-                    int images, int H, int W, int groups, const float* gamma, const float* beta, int swish, void* dst, const vf_gn_shift& sh,
-                    cudaStream_t st);
-
 constexpr int kGnThreads = 256;
 
 // block = (CV channel-vectors) x (PY row lanes); every thread keeps sums for its fixed 16-byte channel vector
@@ -303,10 +298,6 @@ extern "C" __attribute__((visibility("default"))) int vf_gn_apply(const void* sr
   VF_REQUIRE(groups > 0 && C % groups == 0, "vf_gn_apply: C=%d not divisible by groups=%d", C, groups);
   VF_REQUIRE(C / vec <= kGnThreads, "vf_gn_apply: C=%d too large", C);
   cudaStream_t st = as_stream(stream);
-  if (gn_stream_enabled()) {         // persistent TMA-fed streaming kernel (k_gn_stream.cu); 1 = shape not supported there
-    const int rc = gn_apply_stream(src0, C0, stats0, stats0_ld, src1, C1, stats1, stats1_ld, dtype, images, H, W, groups, gamma, beta, swish, dst, sh, st);
-    if (rc <= 0) return rc;
-  }
   GnGeom g = gn_geom(C, vec, P, images);
   dim3 grid(g.splits, images);
   const size_t smem = 4 * C * sizeof(float);
