@@ -334,6 +334,9 @@ def main():
     ap.add_argument("--train-batch", type=int, default=28, help="training samples per GPU (weak scaling)")
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--no-train", action="store_true", help="skip the training-throughput leg")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling training leg (global batch 160)")
+    ap.add_argument("--global-batch", type=int, default=160, help="strong scaling: global batch (medium-a100-4.yaml:35)")
+    ap.add_argument("--micro-batch", type=int, default=40, help="strong scaling: samples per forward/backward on one GPU")
     ap.add_argument("--no-full-generate", action="store_true", help="skip the real T=2000 generate() run (~13 s)")
     ap.add_argument("--no-library-baseline", action="store_true", help="skip the torch library-kernel comparison on this GPU")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the autoregressive (C4) / extrapolation (C5) legs")
@@ -547,12 +550,62 @@ def main():
             "metric": "train_samples_per_sec", "value": world * Bt / (tr_ms * 1e-3), "unit": "samples/s", "ms_per_step": tr_ms,
             "steps": args.train_steps, "scaling": "weak", "B_per_gpu": Bt, "N": N,
             "step": "zero_grad -> ViewFusion.forward (loss) -> backward (hand-written CUDA) -> "
-                    + ("flat-gradient NCCL all-reduce (mean, 4 chunks) -> " if world > 1 else "") + "fused Adam (vf_adam_step)",
+                    + ("[NCCL all-reduce (AVG) of each of 4 backward phases' gradient slice, issued as the phase is enqueued and "
+                       "overlapped with the remaining phases] -> " if world > 1 else "") + "fused Adam (vf_adam_step)",
             "e2e": {"value": world * Bt / tr_e2e, "unit": "samples/s", "ms_per_step": tr_e2e * 1e3,
                     "h2d_bytes_per_step": (yc_p.numel() + y0_p.numel() + an_p.numel()) * 4, "d2h_bytes_per_step": 4},
             "flop_utilisation": round(tr_flops / (tr_ms * 1e-3) / 1e12 / pk["tf_sustained"], 4),
             "loss": float(last),
         }
+        # ---- strong scaling (BASELINE config C3, medium-a100-4.yaml:35): GLOBAL batch 160 split over the ranks; a rank's share
+        # runs as micro-batches of <= 40 samples whose gradients accumulate natively in the flat buffer, and only the last
+        # micro-batch's backward exchanges them (no_sync on the others)
+        if not args.no_strong:
+            import contextlib as _cl
+            from view_fusion_b200.distributed import no_sync
+            G = args.global_batch
+            per = G // world
+            micro = min(args.micro_batch, per)
+            n_micro = per // micro
+            per = micro * n_micro
+            ycs, _, ans, vcs = synthetic(per, N, seed=777 + rank)
+            y0s = torch.rand(per, 3, 64, 64, generator=torch.Generator().manual_seed(55 + rank))
+            ycs, y0s, ans = ycs.to(dev), y0s.to(dev), ans.to(dev)
+            model.denoise_fn.grad_accumulation(True)
+
+            def strong_step():
+                opt.zero_grad(set_to_none=True)
+                tot = None
+                for m in range(n_micro):
+                    sl = slice(m * micro, (m + 1) * micro)
+                    ctx = no_sync(model) if (world > 1 and m < n_micro - 1) else _cl.nullcontext()
+                    with ctx:
+                        loss = model(y_cond=ycs[sl], view_count=vcs[sl], angle=ans[sl], y_0=y0s[sl]) * (1.0 / n_micro)
+                        loss.backward()
+                    tot = loss.detach() if tot is None else tot + loss.detach()
+                opt.step()
+                return tot
+
+            for _ in range(2):
+                strong_step()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ks = max(3, args.train_steps // 2)
+            e0.record()
+            for _ in range(ks):
+                ls = strong_step()
+            e1.record()
+            barrier()
+            st_ms = e0.elapsed_time(e1) / ks
+            if world > 1:
+                tm = torch.tensor([st_ms], device=dev)
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                st_ms = float(tm)
+            model.denoise_fn.grad_accumulation(False)
+            train["strong"] = {"metric": "train_samples_per_sec", "scaling": "strong", "global_batch": per * world, "B_per_gpu": per,
+                               "micro_batch": micro, "micro_batches_per_step": n_micro, "ms_per_step": st_ms,
+                               "value": per * world / (st_ms * 1e-3), "steps": ks, "loss": float(ls),
+                               "flop_utilisation": round(3 * GFLOP_PER_VIEW * 1e9 * per * N / (st_ms * 1e-3) / 1e12 / pk["tf_sustained"], 4)}
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             sps, sec = cpu_train_rate(2, N, steps=2, warmup=1, threads=threads)

@@ -394,6 +394,16 @@ int vf_unet_backward(vf_unet* u, const void* packed_t, void* grad_workspace, siz
  * dy: gradient of the forward output, [out rows, dy_ld] in fwd->dtype with zero padding rows. */
 int vf_conv2d_wgrad(const vf_conv_args* fwd, const void* dy, int dy_ld, float* dwp, vf_stream stream);
 
+/* The same backward in n_phases + 1 calls (phase = 0 .. n_phases, in order, same arguments), for overlapping the data-parallel
+ * gradient exchange with the rest of the backward (reference: DistributedDataParallel's bucketed all-reduce, experiment.py:104-107).
+ * The reversed tape is cut into n_phases runs of roughly equal parameter bytes; after phase k returns, every gradient whose
+ * parameter has param_phase[i] == k is completely enqueued on `stream`; the embedding MLP and the per-block Linear parameters
+ * (gradients complete only at the very end) have param_phase == n_phases and are produced by the last call.
+ * vf_unet_backward_plan (after a forward: it follows the recorded tape) fills param_phase[vf_unet_num_params()]. */
+int vf_unet_backward_plan(vf_unet* u, int n_phases, int* param_phase_out);
+int vf_unet_backward_phase(vf_unet* u, const void* packed_t, void* grad_workspace, size_t grad_workspace_bytes, const float* grad_out8,
+                           float* const* param_grads_host, int phase, int n_phases, vf_stream stream);
+
 /* dw_oihw[n][c_off + c][tap] += dwp[n][k_off + tap*cin + c]: packed gradient of one K-segment -> its channel slice of an
  * OIHW parameter gradient with cin_total input channels. */
 int vf_unpack_conv_wgrad(const float* dwp, int cout, int cin, int ksize, int k_total, int k_off, float* dw_oihw, int cin_total,

@@ -124,3 +124,49 @@ def test_autoregressive_driver_equals_reference_loop_on_device():
     assert cond.shape == ref.shape == (2, n + 1, 3, S, S) and samples.shape == (n, 2, 3, S, S)
     assert torch.isfinite(cond).all()
     assert rel(cond, ref) < 1e-4, rel(cond, ref)     # fp32 mode; GroupNorm sums are order-dependent to rounding
+
+
+def test_reference_written_checkpoint_computes_the_reference_function(golden_dir):
+    """tests/golden/ref_checkpoint_micro.pt was written by the reference's own Checkpoint.save after two real Adam steps
+    (oracle/make_ckpt_golden.py).  Loaded strict into the drop-in module, the UNet must reproduce the reference module's
+    forward on the stored inputs (fp32 mode 1e-4, bf16 mode 3e-2 on the raw UNet output)."""
+    import contextlib
+    import io
+    import os
+    import numpy as np
+    from view_fusion_b200 import UNet, ViewFusion
+    from view_fusion_b200.interop import load_checkpoint
+    from gpu_util import BETA, margin
+    micro = dict(in_channel=6, out_channel=6, inner_channel=32, norm_groups=32, channel_mults=(1,), attn_res=(16,), res_blocks=1, image_size=16)
+    g = np.load(os.path.join(golden_dir, "ref_checkpoint_micro_io.npz"))
+    x, ang, lvl, ref = (torch.from_numpy(g[k]) for k in ("x", "angle", "level", "out"))
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ViewFusion(UNet(**micro, precision="fp32"), BETA)
+    m.set_new_noise_schedule(device="cpu", phase="train")
+    rest = load_checkpoint(os.path.join(golden_dir, "ref_checkpoint_micro.pt"), m, map_location="cpu")
+    assert rest["it"] == 2
+    m = m.cuda()
+    out = m.denoise_fn(x.cuda(), ang.cuda(), lvl.cuda())
+    assert margin("reference-written checkpoint -> drop-in UNet forward, fp32 mode: rel-L2 vs the reference module", rel(out, ref), 1e-4)
+
+
+def test_relative_variant_in_channel_9(golden_dir):
+    """configs/relative-small-v100-4.yaml:22: in_channel 9 (six channels per conditioning view + the 3-channel target): the view
+    stacking, the first layer's im2col (K0 = 9 * 9 = 81 -> 128) and the rest of the path vs the live oracle, fp32 mode."""
+    cfg = dict(O.TINY, in_channel=9)
+    m, sd = build_model(cfg, 6, "fp32")
+    sched = O.make_schedule(**O.BETA_TRAIN)
+    S = cfg["image_size"]
+    g = torch.Generator().manual_seed(8)
+    B, N = 2, 3
+    y_cond = torch.rand(B, N, 6, S, S, generator=g)
+    y_t = torch.randn(B, 3, S, S, generator=g)
+    angle = torch.rand(B, 1, generator=g)
+    z = torch.randn(B, 3, S, S, generator=g)
+    vc = torch.tensor([3, 2])
+    t = torch.tensor([1500, 2])
+    with torch.no_grad():
+        y_ref, eps_ref, _, w_ref = O.p_sample(sd, cfg, sched, y_t, y_cond, vc, angle, t, z)
+    eps = torch.empty(B, 3, S, S, device="cuda")
+    y_prev, logits, weights = m.p_sample(y_t.cuda(), y_cond.cuda(), vc, angle.cuda(), t.cuda(), noise=z.cuda(), _eps_out=eps)
+    assert rel(eps, eps_ref) < 1e-4 and rel(y_prev, y_ref) < 1e-4 and rel(weights, w_ref) < 1e-4

@@ -146,3 +146,44 @@ def test_micro_batch_accumulation_equals_one_big_batch():
     assert p0.grad.data_ptr() == buf.data_ptr()
     assert margin("micro-batch accumulation (bf16): accumulated gradient vs sum of separate backwards rel-L2", rel(buf, g_a + g_b), 1e-2)
     m.denoise_fn.grad_accumulation(False)
+
+
+def test_phased_backward_equals_single_call():
+    """vf_unet_backward_phase (the backward in n + 1 calls, for overlapping the data-parallel all-reduce) against vf_unet_backward:
+    same gradients, phase-major flat layout, every phase's parameters contiguous."""
+    m, _ = build_model(O.TINY, 4, "fp32")
+    S = 16
+    g = torch.Generator().manual_seed(1)
+    B = 3
+    kw = dict(y_cond=torch.rand(B, 3, 3, S, S, generator=g).cuda(), view_count=torch.tensor([3, 1, 2]), angle=torch.rand(B, 1, generator=g).cuda(),
+              y_0=torch.rand(B, 3, S, S, generator=g).cuda(), noise=torch.randn(B, 3, S, S, generator=g).cuda(),
+              t=torch.randint(1, 2000, (B,), generator=g), u=torch.rand(B, 1, generator=g))
+
+    def run():
+        m.zero_grad(set_to_none=True)
+        m(**kw).backward()
+        torch.cuda.synchronize()
+        return {n: p.grad.detach().clone() for n, p in m.denoise_fn.named_parameters()}
+
+    ref = run()
+    unet = m.denoise_fn
+    unet._grad_sync = (None, 4)            # 4 phases; no process group: the all-reduce calls are no-ops, the phasing is real
+    unet._layout_cache = None
+    got = run()
+    order, bounds = unet._grad_layout(4)
+    assert len(bounds) == 5 and bounds[-1][1] == unet._flat_grad.numel()
+    assert all(b[1] > b[0] for b in bounds), "every phase owns parameters"
+    worst = max(rel(got[n], ref[n]) for n in ref if float(ref[n].norm()) > 0)
+    assert margin("phased backward (4 + 1 calls) vs single call, fp32: worst per-parameter rel-L2", worst, 2e-5)
+    # the last phase holds exactly the embedding parameters
+    names = [n for n, _ in unet.named_parameters()]
+    plist = unet._params_in_order()
+    pos = {id(p): i for i, p in enumerate(plist)}
+    import ctypes as C
+    from view_fusion_b200 import _lib
+    ph = (C.c_int * len(plist))()
+    _lib.check(_lib.load().vf_unet_backward_plan(unet._native(), 4, ph), "plan")
+    late = {unet._param_names[i] for i in range(len(plist)) if ph[i] == 4}
+    assert all(("noise_func" in n or n.startswith("noise_level_mlp")) for n in late) and len(late) == 4 + 2 * sum(1 for n in names if n.endswith("noise_func.noise_func.0.weight"))
+    unet._grad_sync = None
+    unet._layout_cache = None

@@ -81,3 +81,40 @@ def test_missing_model_entry_is_an_error(tmp_path):
     torch.save({"optimizer": {}}, path)
     with pytest.raises(KeyError):
         load_checkpoint(path, _model(5))
+
+
+# ---- a file written by the reference's OWN code (oracle/make_ckpt_golden.py: model/unet.py + model/view_fusion.py +
+# utils/checkpoint.py:Checkpoint.save + torch.optim.Adam + utils/schedulers.py:LrScheduler, run unmodified) -------------------
+MICRO = dict(in_channel=6, out_channel=6, inner_channel=32, norm_groups=32, channel_mults=(1,), attn_res=(16,), res_blocks=1, image_size=16)
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_file_written_by_the_reference_checkpoint_class_loads_strict():
+    import numpy as np
+    from view_fusion_b200.optim import LrScheduler
+    torch.manual_seed(99)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ViewFusion(UNet(**MICRO, precision="fp32"), BETA)
+    m.set_new_noise_schedule(device="cpu", phase="train")
+    opt = FusedAdam(m.parameters(), lr=1.0)
+    raw = torch.load(os.path.join(GOLD, "ref_checkpoint_micro.pt"), map_location="cpu", weights_only=False)
+    assert set(raw) == {"model", "optimizer", "it", "t", "run_id", "best_psnr"}
+    assert list(raw["model"]) == list(m.state_dict()), "state_dict key order of the drop-in == the reference module's"
+    rest = load_checkpoint(os.path.join(GOLD, "ref_checkpoint_micro.pt"), m, opt, map_location="cpu")     # strict=True
+    assert rest == {"it": 2, "t": 1.5, "run_id": "ref-run", "best_psnr": 17.25}
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, raw["model"][k]), k
+    io_ = np.load(os.path.join(GOLD, "ref_checkpoint_micro_io.npz"))
+    assert abs(opt.param_groups[0]["lr"] - float(io_["lrs"][-1])) < 1e-12      # the scheduler's last value travels with the file
+    n_state = 0
+    for i, p in enumerate(m.parameters()):
+        st, ref = opt.state[p], raw["optimizer"]["state"][i]
+        assert float(st["step"]) == 2.0 and torch.equal(st["exp_avg"], ref["exp_avg"]) and torch.equal(st["exp_avg_sq"], ref["exp_avg_sq"])
+        n_state += 1
+    assert n_state == len(raw["optimizer"]["state"])
+    # LrScheduler parity (utils/schedulers.py:1-14) on the probe iterations the reference evaluated
+    a = io_["lr_args"]
+    s = LrScheduler(peak_lr=float(a[0]), peak_it=int(a[1]), decay_rate=float(a[2]), decay_it=int(a[3]))
+    for it, want in zip(io_["lr_probe_it"], io_["lr_probe"]):
+        assert s.get_cur_lr(int(it)) == float(want)
+    assert s.apply(opt, 9) == opt.param_groups[0]["lr"] == float(io_["lr_probe"][4])

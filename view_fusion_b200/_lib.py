@@ -24,7 +24,7 @@ SYMBOLS = [
     "vf_compose_ddpm_step", "vf_compose_mse", "vf_step_prepare", "vf_p_sample_step", "vf_unet_act_dtype",
     "vf_embed", "vf_gn_stats", "vf_gn_apply", "vf_upsample2x", "vf_flat_to_padded", "vf_padded_to_flat", "vf_zero_padding", "vf_conv2d", "vf_debug_force_simt", "vf_debug_flags", "vf_debug_counters", "vf_attention",
     "vf_pack_conv_weight",
-    "vf_unet_packed_t_bytes", "vf_unet_pack_weights_t", "vf_unet_backward_workspace_bytes", "vf_unet_backward",
+    "vf_unet_packed_t_bytes", "vf_unet_pack_weights_t", "vf_unet_backward_workspace_bytes", "vf_unet_backward", "vf_unet_backward_plan", "vf_unet_backward_phase",
     "vf_conv2d_wgrad", "vf_unpack_conv_wgrad", "vf_pack_conv_weight_t", "vf_gn_backward", "vf_attention_backward",
     "vf_upsample2x_backward", "vf_zero_insert2x", "vf_add_inplace", "vf_grad8_to_act", "vf_colsum_bias", "vf_embed_backward",
     "vf_adam_chunk_elems", "vf_adam_step", "vf_eval_metrics", "vf_prepare_batch_u8", "vf_debug_gn_splits", "vf_debug_gn_bwd_splits", "vf_debug_conv_tiling",
@@ -156,6 +156,8 @@ def load() -> C.CDLL:
         "vf_unet_pack_weights_t": (i, [p, p, p]),
         "vf_unet_backward_workspace_bytes": (sz, [p]),
         "vf_unet_backward": (i, [p, p, p, sz, p, C.POINTER(p), p]),
+        "vf_unet_backward_plan": (i, [p, i, C.POINTER(i)]),
+        "vf_unet_backward_phase": (i, [p, p, p, sz, p, C.POINTER(p), i, i, p]),
         "vf_conv2d_wgrad": (i, [C.POINTER(ConvArgs), p, i, p, p]),
         "vf_unpack_conv_wgrad": (i, [p, i, i, i, i, i, p, i, i, p]),
         "vf_pack_conv_weight_t": (i, [p, i, i, i, i, p, i, i, i, i, p]),

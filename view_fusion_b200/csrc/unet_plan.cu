@@ -80,6 +80,8 @@ struct vf_unet {
   int capacity = 0;               // arena layout is computed for max(capacity, images) view-images (vf_unet_set_capacity)
   int last_layout = 0;            // layout image count of the last forward (the backward lays its arena out the same way)
   unsigned long long fwd_gen = 0; // forward generation: bumped by every vf_unet_forward (vf_unet_forward_generation)
+  void* bw_state = nullptr;       // vf::BwdCtx of a phased backward in flight (vf_unet_backward_phase)
+  std::vector<int> bw_phase_stop; // its phase boundaries
   // optional per-kernel-class timing of one forward (CUDA events around every launch; perturbs overlap, so it is
   // only enabled for the roofline breakdown, never for the throughput measurement)
   // training tape: what the last forward did, in order (replayed in reverse by vf_unet_backward)
@@ -529,8 +531,10 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_create(const vf_un
   return VF_OK;
 }
 
+namespace vf { void bw_state_free(vf_unet* u); }
 extern "C" __attribute__((visibility("default"))) void vf_unet_destroy(vf_unet* u) {
   if (!u) return;
+  vf::bw_state_free(u);
   for (auto e : u->ev) cudaEventDestroy(e);
   delete u;
 }
@@ -1238,6 +1242,15 @@ struct BwdCtx {
   bool dry = false;
   int rc = VF_OK;
   std::map<const void*, std::pair<void*, bool>> grads;     // forward tensor -> (gradient buffer, written?)
+  // resumable walk (vf_unet_backward_phase): scratch pointers and the position in the reversed tape
+  float *dwp = nullptr, *cs = nullptr, *demb = nullptr, *dew = nullptr, *deb = nullptr, *emb_rows = nullptr, *gn_scratch = nullptr, *att_scratch = nullptr;
+  uint8_t* unpack_tab = nullptr;
+  void* g_out = nullptr;
+  float* dwp_cur = nullptr;
+  float* gn_cur = nullptr;
+  int colsum_done = -1;          // tape index of the convolution whose bias / embedding gradients the GroupNorm backward produced
+  int next_op = -1;              // next tape index to differentiate (counts down to 0)
+  size_t chunks_done = 0;        // unpack chunks already launched
   void* galloc(size_t bytes) {
     goff = align_up(goff, 256);
     void* p = dry ? nullptr : gbase + goff;
@@ -1389,12 +1402,21 @@ static void conv_backward(BwdCtx& cx, const vf_unet::TapeOp& t, const uint8_t* p
 
 namespace vf {
 
-static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float* const* pg) {
+// fixed layout of the unpack job table inside its reserved region: jobs | chunk -> job | chunk -> first element
+constexpr size_t kUnpackJobsBytes = 96 * 1024, kUnpackChunkBytes = 320 * 1024;
+static_assert(kUnpackJobsBytes + 2 * kUnpackChunkBytes <= kPackTableBytes, "unpack table regions");
+
+// ---- the backward as a resumable walk: begin -> ops (reversed tape, possibly in several calls) -> unpack -> finish ------
+static void bw_begin(BwdCtx& cx, const float* g8) {
   vf_unet* u = cx.u;
   const int dt = u->dtype;
   const size_t es = dtype_size(dt);
   const int images = u->last_images, S = u->cfg.image_size;
   const vf_unet_config& c = u->cfg;
+  float *&dwp = cx.dwp, *&cs = cx.cs, *&demb = cx.demb, *&dew = cx.dew, *&deb = cx.deb, *&emb_rows = cx.emb_rows, *&gn_scratch = cx.gn_scratch,
+        *&att_scratch = cx.att_scratch;
+  uint8_t*& unpack_tab = cx.unpack_tab;
+  void*& g_out = cx.g_out;
   // scratch: packed weight gradient (largest conv), per-image column sums, embedding-table gradient
   // Every convolution gets its own slice of ONE zero-filled packed-gradient arena and every GroupNorm its own slice of
   // one zero-filled reduction arena: two memsets per backward instead of one per layer, and no memset nodes between
@@ -1407,20 +1429,20 @@ static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float*
       dwp_floats += align_up((size_t)t.conv.cout_pad * k, 64);
       cs_floats = std::max(cs_floats, cx.li * t.conv.cout);
     }
-  float* dwp = (float*)cx.galloc(dwp_floats * 4);
-  float* cs = (float*)cx.galloc(cs_floats * 4);
-  float* demb = (float*)cx.galloc(cx.li * u->E * 4);
-  float* dew = (float*)cx.galloc((size_t)u->E * c.inner_channel * 4);
-  float* deb = (float*)cx.galloc((size_t)u->E * 4);
-  float* emb_rows = (float*)cx.galloc(cx.li * 11 * c.inner_channel * 4);
+  dwp = (float*)cx.galloc(dwp_floats * 4);
+  cs = (float*)cx.galloc(cs_floats * 4);
+  demb = (float*)cx.galloc(cx.li * u->E * 4);
+  dew = (float*)cx.galloc((size_t)u->E * c.inner_channel * 4);
+  deb = (float*)cx.galloc((size_t)u->E * 4);
+  emb_rows = (float*)cx.galloc(cx.li * 11 * c.inner_channel * 4);
   size_t gn_floats = 0, att_floats = 0;
   for (auto& t : u->tape) {
     if (t.kind == 1) gn_floats += align_up(cx.li * (t.gC0 + t.gC1) * 2, 64);
     if (t.kind == 2) att_floats = std::max(att_floats, cx.li * t.aL * 2 * t.aC * std::max(1, t.aL / 128));
   }
-  float* gn_scratch = (float*)cx.galloc(gn_floats * 4);
-  float* att_scratch = (float*)cx.galloc(att_floats * 4);
-  uint8_t* unpack_tab = (uint8_t*)cx.galloc(kPackTableBytes);     // job table of the final multi-tensor unpack
+  gn_scratch = (float*)cx.galloc(gn_floats * 4);
+  att_scratch = (float*)cx.galloc(att_floats * 4);
+  unpack_tab = (uint8_t*)cx.galloc(kPackTableBytes);     // job table of the multi-tensor unpack launches
   if (!cx.dry) {
     cudaMemsetAsync(dwp, 0, dwp_floats * 4, cx.st);
     cudaMemsetAsync(gn_scratch, 0, gn_floats * 4, cx.st);
@@ -1430,17 +1452,34 @@ static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float*
   }
   // gradient of the UNet output -> PADDED activation-dtype matrix with final_npad channels
   const int np = u->final_npad;
-  void* g_out = cx.galloc(cx.li * (S + 1) * (S + 1) * np * es);
+  g_out = cx.galloc(cx.li * (S + 1) * (S + 1) * np * es);
   if (!cx.dry) {
     const size_t total = (size_t)images * (S + 1) * (S + 1) * (np / 8);
     const unsigned grid = (unsigned)((total + 255) / 256);
     if (dt == VF_BF16) grad8_to_padded_kernel<__nv_bfloat16><<<grid, 256, 0, cx.st>>>(g8, S, S, np, total, (__nv_bfloat16*)g_out);
     else grad8_to_padded_kernel<float><<<grid, 256, 0, cx.st>>>(g8, S, S, np, total, (float*)g_out);
   }
-  float* dwp_cur = dwp;
-  float* gn_cur = gn_scratch;
-  int colsum_done = -1;          // tape index of the convolution whose bias / embedding gradients the GroupNorm backward produced
-  for (int i = (int)u->tape.size() - 1; i >= 0 && cx.rc == VF_OK; --i) {
+  cx.dwp_cur = dwp;
+  cx.gn_cur = gn_scratch;
+  cx.colsum_done = -1;
+  cx.next_op = (int)u->tape.size() - 1;
+  cx.chunks_done = 0;
+}
+
+// differentiate tape ops next_op, next_op - 1, ..., stop_at
+static void bw_run_ops(BwdCtx& cx, const uint8_t* pkt, float* const* pg, int stop_at) {
+  vf_unet* u = cx.u;
+  const int dt = u->dtype;
+  const int images = u->last_images;
+  const vf_unet_config& c = u->cfg;
+  const int np = u->final_npad;
+  float *&dwp_cur = cx.dwp_cur, *&gn_cur = cx.gn_cur;
+  int& colsum_done = cx.colsum_done;
+  float* const cs = cx.cs;
+  float* const demb = cx.demb;
+  float* const att_scratch = cx.att_scratch;
+  void* const g_out = cx.g_out;
+  for (int& i = cx.next_op; i >= stop_at && cx.rc == VF_OK; --i) {
     const vf_unet::TapeOp& t = u->tape[i];
     if (t.kind == 0) {
       float* dwp_l = dwp_cur;
@@ -1499,30 +1538,54 @@ static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float*
       gs.second = true;
     }
   }
-  // all packed weight gradients -> OIHW parameter gradients (one launch; the table is uploaded only when it changes)
-  if (!cx.dry && cx.rc == VF_OK && !cx.unpack.jobs.empty()) {
-    const UnpackList& ul = cx.unpack;
-    if (ul.table_bytes() > kPackTableBytes) {
-      set_error("vf_unet_backward: unpack table of %zu B exceeds the reserved %zu B", ul.table_bytes(), kPackTableBytes);
-      cx.rc = VF_ERR_ARG;
-    } else {
-      const size_t o_cj = align_up(ul.jobs.size() * sizeof(UnpackJob), 256), o_cs = o_cj + align_up(ul.chunk_job.size() * sizeof(int), 256);
-      std::vector<uint8_t> blob(ul.table_bytes() + sizeof(void*), 0);
-      memcpy(blob.data(), ul.jobs.data(), ul.jobs.size() * sizeof(UnpackJob));
-      memcpy(blob.data() + o_cj, ul.chunk_job.data(), ul.chunk_job.size() * sizeof(int));
-      memcpy(blob.data() + o_cs, ul.chunk_start.data(), ul.chunk_start.size() * sizeof(int));
-      memcpy(blob.data() + ul.table_bytes(), &unpack_tab, sizeof(void*));
-      if (blob != u->unpack_cache) {
-        if (cudaMemcpyAsync(unpack_tab, blob.data(), ul.table_bytes(), cudaMemcpyHostToDevice, cx.st) != cudaSuccess) cx.rc = VF_ERR_CUDA;
-        u->unpack_cache = blob;
-      }
-      if (cx.rc == VF_OK) {
-        cudaError_t le = launch_pdl(multi_unpack_kernel, dim3((unsigned)ul.chunk_job.size()), dim3(256), 0, cx.st, (const UnpackJob*)unpack_tab,
-                                    (const int*)(unpack_tab + o_cj), (const int*)(unpack_tab + o_cs), pg[0]);
-        if (le != cudaSuccess) { set_error("multi_unpack launch: %s", cudaGetErrorString(le)); cx.rc = VF_ERR_CUDA; }
-      }
-    }
+}
+
+// packed weight gradients produced since the last call -> OIHW parameter gradients (one launch).  The job table has a fixed
+// layout in its region and is identical from step to step, so in steady state nothing is uploaded: only slices that differ
+// from what the device already holds are copied.
+static void bw_flush_unpack(BwdCtx& cx, float* const* pg) {
+  vf_unet* u = cx.u;
+  if (cx.dry || cx.rc != VF_OK) return;
+  const UnpackList& ul = cx.unpack;
+  const size_t n_chunks = ul.chunk_job.size();
+  if (n_chunks <= cx.chunks_done) return;
+  if (ul.jobs.size() * sizeof(UnpackJob) > kUnpackJobsBytes || n_chunks * sizeof(int) > kUnpackChunkBytes) {
+    set_error("vf_unet_backward: unpack table (%zu jobs, %zu chunks) exceeds its reserved region", ul.jobs.size(), n_chunks);
+    cx.rc = VF_ERR_ARG;
+    return;
   }
+  uint8_t* tab = cx.unpack_tab;
+  std::vector<uint8_t>& cache = u->unpack_cache;           // host image of the device table + the table's address
+  if (cache.size() != kPackTableBytes + sizeof(void*) || memcmp(cache.data() + kPackTableBytes, &tab, sizeof(void*)) != 0) {
+    cache.assign(kPackTableBytes + sizeof(void*), 0xFF);   // other location (or first use): nothing on the device is valid
+    memcpy(cache.data() + kPackTableBytes, &tab, sizeof(void*));
+  }
+  auto sync_slice = [&](size_t off, const void* src, size_t bytes) {
+    if (bytes == 0 || cx.rc != VF_OK) return;
+    if (memcmp(cache.data() + off, src, bytes) == 0) return;
+    if (cudaMemcpyAsync(tab + off, src, bytes, cudaMemcpyHostToDevice, cx.st) != cudaSuccess) { cx.rc = VF_ERR_CUDA; return; }   // pageable: staged before returning
+    memcpy(cache.data() + off, src, bytes);
+  };
+  sync_slice(0, ul.jobs.data(), ul.jobs.size() * sizeof(UnpackJob));
+  sync_slice(kUnpackJobsBytes + cx.chunks_done * sizeof(int), ul.chunk_job.data() + cx.chunks_done, (n_chunks - cx.chunks_done) * sizeof(int));
+  sync_slice(kUnpackJobsBytes + kUnpackChunkBytes + cx.chunks_done * sizeof(int), ul.chunk_start.data() + cx.chunks_done,
+             (n_chunks - cx.chunks_done) * sizeof(int));
+  if (cx.rc != VF_OK) return;
+  cudaError_t le = launch_pdl(multi_unpack_kernel, dim3((unsigned)(n_chunks - cx.chunks_done)), dim3(256), 0, cx.st, (const UnpackJob*)tab,
+                              (const int*)(tab + kUnpackJobsBytes) + cx.chunks_done,
+                              (const int*)(tab + kUnpackJobsBytes + kUnpackChunkBytes) + cx.chunks_done, pg[0]);
+  if (le != cudaSuccess) { set_error("multi_unpack launch: %s", cudaGetErrorString(le)); cx.rc = VF_ERR_CUDA; }
+  cx.chunks_done = n_chunks;
+}
+
+// embedding path (always last: every ResnetBlock feeds it)
+static void bw_finish(BwdCtx& cx, float* const* pg) {
+  vf_unet* u = cx.u;
+  const vf_unet_config& c = u->cfg;
+  float* const demb = cx.demb;
+  float* const dew = cx.dew;
+  float* const deb = cx.deb;
+  float* const emb_rows = cx.emb_rows;
   // embedding path: demb [rows, E] -> noise_level_mlp and the per-block Linear(ic -> Cout) parameters
   if (!cx.dry && cx.rc == VF_OK) {
     const int ic = c.inner_channel;
@@ -1538,7 +1601,55 @@ static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float*
     }
     if (cudaGetLastError() != cudaSuccess) { set_error("vf_unet_backward: embedding backward launch failed"); cx.rc = VF_ERR_CUDA; }
   }
+}
+
+static int backward_walk(BwdCtx& cx, const uint8_t* pkt, const float* g8, float* const* pg) {
+  bw_begin(cx, g8);
+  bw_run_ops(cx, pkt, pg, 0);
+  bw_flush_unpack(cx, pg);
+  bw_finish(cx, pg);
   return cx.rc;
+}
+
+// ---- phases for overlapping the data-parallel gradient exchange with the rest of the backward ---------------------------
+// The reversed tape is cut into n_phases runs of (roughly) equal parameter bytes; a parameter belongs to the phase whose ops
+// produce its gradient, the embedding MLP and the per-block Linear(ic -> Cout) parameters to the extra last phase n_phases
+// (their gradients are complete only after every block was differentiated).  phase_stop[k] = lowest tape index of phase k.
+static void plan_phases(const vf_unet* u, int n_phases, std::vector<int>& phase_stop, std::vector<int>& param_phase) {
+  const int np = (int)u->params.size();
+  auto numel = [&](int idx) { size_t n = 1; for (int d = 0; d < u->params[idx].ndim; ++d) n *= (size_t)u->params[idx].shape[d]; return n; };
+  param_phase.assign(np, n_phases);
+  std::vector<size_t> op_bytes(u->tape.size(), 0);
+  std::vector<char> seen(np, 0);
+  size_t total = 0;
+  auto touch = [&](int idx, size_t& acc) { if (idx >= 0 && !seen[idx]) { seen[idx] = 1; acc += numel(idx); } };
+  for (int i = (int)u->tape.size() - 1; i >= 0; --i) {
+    const vf_unet::TapeOp& t = u->tape[i];
+    size_t b = 0;
+    if (t.kind == 0) { for (int sgi = 0; sgi < 3; ++sgi) touch(t.w_idx[sgi], b); touch(t.b_idx[0], b); touch(t.b_idx[1], b); }
+    if (t.kind == 1) { touch(t.gw, b); touch(t.gb, b); }
+    op_bytes[i] = b;
+    total += b;
+  }
+  phase_stop.assign(n_phases, 0);
+  std::fill(seen.begin(), seen.end(), 0);
+  size_t acc = 0;
+  int ph = 0;
+  for (int i = (int)u->tape.size() - 1; i >= 0; --i) {
+    const vf_unet::TapeOp& t = u->tape[i];
+    auto mark = [&](int idx) { if (idx >= 0 && !seen[idx]) { seen[idx] = 1; param_phase[idx] = ph; } };
+    if (t.kind == 0) { for (int sgi = 0; sgi < 3; ++sgi) mark(t.w_idx[sgi]); mark(t.b_idx[0]); mark(t.b_idx[1]); }
+    if (t.kind == 1) { mark(t.gw); mark(t.gb); }
+    acc += op_bytes[i];
+    // a GroupNorm that emits the bias gradient of the convolution below it (closed-form column sums) must stay in that
+    // convolution's phase: cut only after a convolution
+    const bool cut_ok = t.kind == 0;
+    if (ph < n_phases - 1 && cut_ok && acc * (size_t)n_phases >= total * (size_t)(ph + 1)) {
+      phase_stop[ph] = i;
+      ++ph;
+    }
+  }
+  for (int k = ph; k < n_phases; ++k) phase_stop[k] = 0;
 }
 
 }  // namespace vf
@@ -1644,4 +1755,63 @@ extern "C" __attribute__((visibility("default"))) int vf_embed_backward(const fl
   VF_REQUIRE(inner_channel > 0 && inner_channel % 4 == 0 && inner_channel <= 256, "vf_embed_backward: inner_channel=%d", inner_channel);
   return vf::embed_backward_launch(level, angle, rows, inner_channel, w0, b0, w2, b2, emb_w, E, demb, rowbuf, dew, deb, dw0, db0, dw2, db2,
                                    as_stream(stream));
+}
+
+// ---- phased backward: the same walk in n_phases + 1 calls, so that the caller can start the gradient exchange of a phase's
+// parameters (NCCL all-reduce over NVLink) while the next phases are still running --------------------------------------
+namespace vf {
+void bw_state_free(vf_unet* u) {
+  if (u && u->bw_state) { delete reinterpret_cast<BwdCtx*>(u->bw_state); u->bw_state = nullptr; }
+}
+}  // namespace vf
+
+extern "C" __attribute__((visibility("default"))) int vf_unet_backward_plan(vf_unet* u, int n_phases, int* param_phase_out) {
+  VF_REQUIRE(u && param_phase_out && n_phases >= 1 && n_phases <= 64, "vf_unet_backward_plan: bad args");
+  if (u->tape.empty()) { set_error("vf_unet_backward_plan: needs a forward first (the plan follows the recorded tape)"); return VF_ERR_STATE; }
+  std::vector<int> stop, phase;
+  vf::plan_phases(u, n_phases, stop, phase);
+  for (size_t i = 0; i < phase.size(); ++i) param_phase_out[i] = phase[i];
+  return VF_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int vf_unet_backward_phase(vf_unet* u, const void* packed_t, void* grad_workspace,
+                                                                           size_t grad_workspace_bytes, const float* grad_out8,
+                                                                           float* const* param_grads_host, int phase, int n_phases,
+                                                                           vf_stream stream) {
+  VF_REQUIRE(u && packed_t && grad_workspace && grad_out8 && param_grads_host, "vf_unet_backward_phase: null args");
+  VF_REQUIRE(n_phases >= 1 && n_phases <= 64 && phase >= 0 && phase <= n_phases, "vf_unet_backward_phase: phase %d of %d", phase, n_phases);
+  if (phase == 0) {
+    if (u->tape.empty() || !u->packed_t) { set_error("vf_unet_backward_phase: needs a forward and vf_unet_pack_weights_t first"); return VF_ERR_STATE; }
+    if (!u->last_stash) { set_error("vf_unet_backward_phase: the last forward ran with vf_unet_set_stash(0) (inference mode)"); return VF_ERR_STATE; }
+    for (size_t i = 0; i < u->params.size(); ++i) VF_REQUIRE(param_grads_host[i], "vf_unet_backward_phase: gradient %zu (%s) is null", i, u->params[i].name.c_str());
+    {
+      BwdCtx dry{u, nullptr, nullptr};
+      dry.dry = true;
+      dry.li = (size_t)(u->last_layout > u->last_images ? u->last_layout : u->last_images);
+      backward_walk(dry, nullptr, nullptr, nullptr);
+      VF_REQUIRE(dry.goff <= grad_workspace_bytes, "vf_unet_backward_phase: workspace too small (%zu < %zu)", grad_workspace_bytes, dry.goff);
+    }
+    vf::bw_state_free(u);
+    BwdCtx* cx = new BwdCtx{u, as_stream(stream), reinterpret_cast<uint8_t*>(grad_workspace)};
+    cx->gcap = grad_workspace_bytes;
+    cx->li = (size_t)(u->last_layout > u->last_images ? u->last_layout : u->last_images);
+    u->bw_state = cx;
+    std::vector<int> phase_of;
+    vf::plan_phases(u, n_phases, u->bw_phase_stop, phase_of);
+    vf::bw_begin(*cx, grad_out8);
+  }
+  BwdCtx* cx = reinterpret_cast<BwdCtx*>(u->bw_state);
+  if (!cx || (int)u->bw_phase_stop.size() != n_phases) { set_error("vf_unet_backward_phase: phases must be called in order 0..n_phases"); return VF_ERR_STATE; }
+  cx->st = as_stream(stream);
+  if (phase < n_phases) {
+    vf::bw_run_ops(*cx, reinterpret_cast<const uint8_t*>(packed_t), param_grads_host, u->bw_phase_stop[phase]);
+    vf::bw_flush_unpack(*cx, param_grads_host);
+  } else {
+    if (cx->next_op >= 0) { vf::bw_run_ops(*cx, reinterpret_cast<const uint8_t*>(packed_t), param_grads_host, 0); vf::bw_flush_unpack(*cx, param_grads_host); }
+    vf::bw_finish(*cx, param_grads_host);
+  }
+  int rc = cx->rc;
+  if (phase == n_phases || rc != VF_OK) vf::bw_state_free(u);
+  if (rc == VF_OK) VF_LAUNCH_CHECK();
+  return rc;
 }

@@ -70,13 +70,28 @@ def allreduce_mean_(flat: torch.Tensor, group: Optional[dist.ProcessGroup] = Non
     world = dist.get_world_size(group)
     if world == 1:
         return flat
-    works = []
-    for s, e in reversed(chunk_bounds(flat.numel(), chunks)):
-        works.append(dist.all_reduce(flat[s:e], op=dist.ReduceOp.SUM, group=group, async_op=True))
-    for w in works:
-        w.wait()
-    flat.mul_(1.0 / world)
+    waits = [allreduce_mean_async(flat[s:e], group) for s, e in reversed(chunk_bounds(flat.numel(), chunks))]
+    for w in waits:
+        w()
     return flat
+
+
+def allreduce_mean_async(t: torch.Tensor, group: Optional[dist.ProcessGroup] = None):
+    """Start the in-place mean of `t` over the ranks; returns a callable that makes the current stream (or the host, for CPU
+    backends) wait for it.  NCCL averages in the collective itself (ReduceOp.AVG: no separate scaling pass); the collective is
+    ordered after everything already enqueued on the current stream and runs on NCCL's own stream."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return lambda: None
+    world = dist.get_world_size(group)
+    if t.is_cuda and dist.get_backend(group) == "nccl":
+        w = dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group, async_op=True)
+        return w.wait
+    w = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+    def finish():
+        w.wait()
+        t.mul_(1.0 / world)
+    return finish
 
 
 def broadcast_parameters(module: torch.nn.Module, src: int = 0, group: Optional[dist.ProcessGroup] = None) -> None:
@@ -98,5 +113,22 @@ def data_parallel(model, group: Optional[dist.ProcessGroup] = None, chunks: int 
     `loss.backward()` then leaves rank-averaged gradients in `param.grad`."""
     unet = getattr(model, "denoise_fn", model)
     broadcast_parameters(unet, 0, group)
-    unet._grad_sync = (group, int(chunks))
+    unet._grad_sync = (group, int(chunks))        # chunks = backward phases whose all-reduce overlaps the rest of the backward
+    unet._layout_cache = None
     return model
+
+
+class no_sync:
+    """Context manager: backwards inside it skip the gradient exchange (micro-batch accumulation; DDP.no_sync of the reference's
+    wrapper).  The last micro-batch runs outside and exchanges the accumulated gradients."""
+
+    def __init__(self, model):
+        self.unet = getattr(model, "denoise_fn", model)
+
+    def __enter__(self):
+        self.unet._no_sync = True
+        return self
+
+    def __exit__(self, *a):
+        self.unet._no_sync = False
+        return False

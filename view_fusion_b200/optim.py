@@ -91,3 +91,27 @@ class FusedAdam(torch.optim.Optimizer):
             # the kernel wrote through raw pointers: tell autograd / the packed-weight cache that the parameters changed
             torch.autograd.graph.increment_version(ps)
         return loss
+
+
+class LrScheduler:
+    """Learning-rate schedule of the reference's training loop (utils/schedulers.py:1-14, used at experiment.py:115-120 and
+    :265-267): linear warm-up to `peak_lr` over `peak_it` iterations, then `peak_lr * decay_rate ** ((it - peak_it) / decay_it)`.
+    Same constructor, same `get_cur_lr(it)`; `apply(optimizer, it)` is the three-line rewrite of `param_groups[i]["lr"]` the
+    reference's loop does every iteration (FusedAdam reads the value at the next step)."""
+
+    def __init__(self, peak_lr=4e-4, peak_it=10000, decay_rate=0.5, decay_it=100000):
+        self.peak_lr = peak_lr
+        self.peak_it = peak_it
+        self.decay_rate = decay_rate
+        self.decay_it = decay_it
+
+    def get_cur_lr(self, it):
+        if it < self.peak_it:
+            return self.peak_lr * (it / self.peak_it)
+        return self.peak_lr * (self.decay_rate ** ((it - self.peak_it) / self.decay_it))
+
+    def apply(self, optimizer, it):
+        lr = self.get_cur_lr(it)
+        for group in optimizer.param_groups:
+            group["lr"] = lr
+        return lr

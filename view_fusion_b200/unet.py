@@ -122,6 +122,7 @@ class UNet(nn.Module):
         self._fwd_gen = 0
         self._accumulate = False
         self._profiling = False
+        self._flat_layout = 0
 
     # ------------------------------------------------------------------------------------------
     def _native(self):
@@ -266,32 +267,68 @@ class UNet(nn.Module):
             self._gws = None
             self._gws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
         # every gradient starts on a 16-byte boundary of the flat buffer (vectorised optimizer / all-reduce accesses)
+        sync = getattr(self, "_grad_sync", None)
+        syncing = sync is not None and not getattr(self, "_no_sync", False)
+        n_ph = int(sync[1]) if sync is not None else 0
+        order, bounds = self._grad_layout(n_ph)       # parameter order inside the flat buffer (+ slice of every phase)
         # micro-batch accumulation (grad_accumulation(True)): when every .grad still IS its slice of the previous flat buffer,
         # the library adds into that buffer and autograd gets nothing to add a second time
         accumulate = False
-        if self._accumulate and self._flat_grad is not None and self._flat_grad.device == dev:
-            g0, g1 = plist[0].grad, plist[-1].grad
-            accumulate = (g0 is not None and g1 is not None and g0.data_ptr() == self._flat_grad.data_ptr()
-                          and g1.data_ptr() + g1.numel() * 4 <= self._flat_grad.data_ptr() + self._flat_grad.numel() * 4
-                          and g1.data_ptr() > self._flat_grad.data_ptr())
-        if accumulate:
-            flat = self._flat_grad                    # micro-batch accumulation: the library adds into the same buffer
-        else:
-            total = sum((p.numel() + 3) & ~3 for p in plist)
-            flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        grads, off = [], 0
-        for p in plist:
-            grads.append(flat[off:off + p.numel()].view_as(p))
+        if self._accumulate and self._flat_grad is not None and self._flat_grad.device == dev and self._flat_layout == n_ph:
+            g0 = plist[order[0]].grad
+            accumulate = g0 is not None and g0.data_ptr() == self._flat_grad.data_ptr()
+        total = bounds[-1][1] if bounds else sum((p.numel() + 3) & ~3 for p in plist)
+        flat = self._flat_grad if accumulate else torch.zeros(total, dtype=torch.float32, device=dev)
+        grads, off = [None] * len(plist), 0
+        for i in order:
+            p = plist[i]
+            grads[i] = flat[off:off + p.numel()].view_as(p)
             off += (p.numel() + 3) & ~3
         arr = (C.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
-        _lib.check(lib.vf_unet_backward(h, pt.data_ptr(), self._gws.data_ptr(), self._gws.numel(), grad_out8.data_ptr(), arr,
-                                        _lib.stream_handle()), "vf_unet_backward")
+        st = _lib.stream_handle()
+        if n_ph == 0:
+            _lib.check(lib.vf_unet_backward(h, pt.data_ptr(), self._gws.data_ptr(), self._gws.numel(), grad_out8.data_ptr(), arr, st),
+                       "vf_unet_backward")
+        else:
+            # data parallel: the backward runs in n_ph + 1 phases; the all-reduce of a phase's slice of the flat gradient is issued
+            # the moment that phase is enqueued, so NCCL (its own stream, ordered after the work enqueued so far) exchanges the
+            # decoder-side gradients over NVLink while the encoder-side layers are still being differentiated
+            from .distributed import allreduce_mean_async
+            works = []
+            for k in range(n_ph + 1):
+                _lib.check(lib.vf_unet_backward_phase(h, pt.data_ptr(), self._gws.data_ptr(), self._gws.numel(), grad_out8.data_ptr(), arr,
+                                                      k, n_ph, st), "vf_unet_backward_phase")
+                if syncing and bounds[k][1] > bounds[k][0]:
+                    works.append(allreduce_mean_async(flat[bounds[k][0]:bounds[k][1]], sync[0]))
+            for w in works:
+                w()
         self._flat_grad = flat
-        sync = getattr(self, "_grad_sync", None)
-        if sync is not None and not getattr(self, "_no_sync", False):
-            from .distributed import allreduce_mean_
-            allreduce_mean_(flat, sync[0], sync[1])      # the one collective of the path (training gradient mean)
+        self._flat_layout = n_ph
         return plist, grads, accumulate
+
+    def _grad_layout(self, n_ph: int):
+        """Order of the parameters inside the flat gradient buffer and the [start, end) float range of every backward phase.
+        n_ph == 0: parameter order, one range.  Otherwise phase-major (vf_unet_backward_plan: phase k = k-th run of the reversed
+        tape, phase n_ph = embedding parameters), so that each phase's gradients are ONE contiguous all-reduce."""
+        cached = getattr(self, "_layout_cache", None)
+        if cached is not None and cached[0] == n_ph:
+            return cached[1], cached[2]
+        plist = self._params_in_order()
+        if n_ph == 0:
+            order, bounds = list(range(len(plist))), []
+        else:
+            ph = (C.c_int * len(plist))()
+            _lib.check(_lib.load().vf_unet_backward_plan(self._native(), n_ph, ph), "vf_unet_backward_plan")
+            order = sorted(range(len(plist)), key=lambda i: (ph[i], i))
+            bounds, off = [], 0
+            for k in range(n_ph + 1):
+                start = off
+                for i in order:
+                    if ph[i] == k:
+                        off += (plist[i].numel() + 3) & ~3
+                bounds.append((start, off))
+        self._layout_cache = (n_ph, order, bounds)
+        return order, bounds
 
     @property
     def k0(self) -> int:
