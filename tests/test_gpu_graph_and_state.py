@@ -173,7 +173,12 @@ def test_phased_backward_equals_single_call():
     order, bounds = unet._grad_layout(4)
     assert len(bounds) == 5 and bounds[-1][1] == unet._flat_grad.numel()
     assert all(b[1] > b[0] for b in bounds), "every phase owns parameters"
-    worst = max(rel(got[n], ref[n]) for n in ref if float(ref[n].norm()) > 0)
+    # gradients that are analytically zero (the bias of a convolution feeding a GroupNorm whose groups hold ONE channel: C = 32,
+    # 32 groups) come out as 1e-10 rounding noise: compare those on the scale of the largest gradient, the others relatively
+    big = max(float(v.norm()) for v in ref.values())
+    live = [n for n in ref if float(ref[n].norm()) > 1e-6 * big]
+    assert all(float(got[n].norm()) < 1e-5 * big for n in ref if n not in live)
+    worst = max(rel(got[n], ref[n]) for n in live)
     assert margin("phased backward (4 + 1 calls) vs single call, fp32: worst per-parameter rel-L2", worst, 2e-5)
     # the last phase holds exactly the embedding parameters
     names = [n for n, _ in unet.named_parameters()]

@@ -169,9 +169,13 @@ extern "C" __attribute__((visibility("default"))) int vf_pack_views(const float*
   const size_t total = (size_t)images * H * W;
   const unsigned grid = (unsigned)((total + kPackThreads - 1) / kPackThreads);
   const size_t smem = (size_t)k0 * (kPackThreads + 1) * sizeof(float);
-  VF_REQUIRE(smem <= 48 * 1024, "vf_pack_views: k0=%d too large", k0);
-#define VF_PACK_LAUNCH(T, CC) \
-  pack_views_kernel<T, CC><<<grid, kPackThreads, smem, st>>>(y_cond, y_t, view_offset, img_sample, n_max, cond_channels, H, W, images, k0, (T*)x0)
+  VF_REQUIRE(smem <= 160 * 1024, "vf_pack_views: k0=%d too large", k0);
+  // K0 = 64 (in_channel 6) stages 33 KB; the relative variant (in_channel 9, K0 = 128) needs 66 KB: opt in above 48 KB
+#define VF_PACK_LAUNCH(T, CC)                                                          \
+  do {                                                                                 \
+    if (smem > 48 * 1024) VF_SET_MAX_SMEM((pack_views_kernel<T, CC>), 160 * 1024);     \
+    pack_views_kernel<T, CC><<<grid, kPackThreads, smem, st>>>(y_cond, y_t, view_offset, img_sample, n_max, cond_channels, H, W, images, k0, (T*)x0); \
+  } while (0)
   if (x0_dtype == VF_BF16) {
     if (cond_channels == 3) VF_PACK_LAUNCH(__nv_bfloat16, 3); else if (cond_channels == 6) VF_PACK_LAUNCH(__nv_bfloat16, 6); else VF_PACK_LAUNCH(__nv_bfloat16, 0);
   } else {
