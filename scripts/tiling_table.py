@@ -8,7 +8,7 @@ from view_fusion_b200 import _lib
 NAMES = ["bn", "G", "aS", "bS", "res", "smem", "tmem", "items", "grid", "epi", "aL", "eL", "s2", "rows", "imgs", "K"]
 
 
-def plan(images, S, segs, cout, stride=1, in_padded=1, out_padded=1, qkv_split=0, cout_pad=None, out_f32=False):
+def plan(images, S, segs, cout, stride=1, in_padded=1, out_padded=1, qkv_split=0, cout_pad=None, out_f32=False, name=""):
     a = _lib.ConvArgs()
     a.dtype, a.images, a.H, a.W, a.n_seg = _lib.VF_BF16, images, S, S, len(segs)
     a.in_padded, a.out_padded, a.stride = in_padded, out_padded, stride
@@ -16,6 +16,12 @@ def plan(images, S, segs, cout, stride=1, in_padded=1, out_padded=1, qkv_split=0
         a.src_c[i], a.ksize[i] = c, k
     a.cout, a.cout_pad = cout, cout_pad or cout
     a.out_dtype, a.out_ld, a.qkv_split = (_lib.VF_F32 if out_f32 else _lib.VF_BF16), (8 if out_f32 else cout), qkv_split
+    # planning only looks at WHETHER the epilogue has a bias / statistics to handle (never dereferenced): every layer of the UNet
+    # except the qkv projections has a bias; every bf16 output except qkv feeds a GroupNorm (fused statistics)
+    if "qkv" not in name:
+        a.bias = 1
+        if not out_f32:
+            a.stats = 1
     out = (C.c_int * 16)()
     rc = _lib.load().vf_debug_conv_tiling(C.byref(a), out)
     if rc != 0:
@@ -56,5 +62,5 @@ if __name__ == "__main__":
     images = int(sys.argv[1]) if len(sys.argv) > 1 else 168
     print(f"{'layer':34s} " + " ".join(f"{n:>6s}" for n in NAMES) + "   waves")
     for name, S, segs, cout, kw in benchmark_layers():
-        p = plan(images, S, segs, cout, **kw)
+        p = plan(images, S, segs, cout, name=name, **kw)
         print(f"{name:34s} " + " ".join(f"{p[n]:6d}" for n in NAMES) + f"   {p['items'] / 148:5.2f}")

@@ -259,7 +259,7 @@ def test_conv_bf16_flat_to_padded_staged_epilogue(lib, R, S, Cc, cout):
     assert torch.isnan(pad[:, 0]).all() and torch.isnan(pad[:, :, 0]).all(), "padding rows must not be written"
 
 
-@pytest.mark.parametrize("R,S,Cc", [(5, 16, 192), (7, 8, 320), (150, 16, 64), (1, 8, 64)])
+@pytest.mark.parametrize("R,S,Cc", [(5, 16, 192), (7, 8, 320), (150, 16, 64), (1, 8, 64), (150, 16, 192)])   # the last one runs with a pinned N tile per CTA
 def test_conv_bf16_padded_to_flat_gathered_source(lib, R, S, Cc):
     """1x1 conv from a PADDED source to FLAT rows (qkv projection / data gradient of the attention output projection):
     TMA gathers the valid pixels, so NaN padding rows of the source must not leak; q|k panels leave through the staged

@@ -23,6 +23,7 @@
 // (TcParams::a_lines / epi_lines / s2_cchunks).
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "tc_ptx.cuh"
@@ -39,7 +40,8 @@ constexpr int TC_EPI_THREADS = 32 * TC_EPI_WARPS;
 constexpr int TC_NSUB = TC_EPI_WARPS / 4;
 constexpr int TC_THREADS = TC_EPI_THREADS + 64;   // + TMA producer + MMA issuer
 constexpr int TC_ABOX = 64;        // rows per A TMA box
-constexpr int TC_MAX_STAGES = 16;
+constexpr int TC_MAX_STAGES = 16;      // weight ring
+constexpr int TC_MAX_A_STAGES = 8;     // activation ring
 
 struct TcSeg {
   int C;
@@ -53,7 +55,9 @@ struct TcParams {
   RowGeom geo;
   int G, block_n, n_tiles_n, n_mblocks, n_items;
   int a_stage_bytes, a_stages, b_stages;
-  int b_resident;                 // the CTA's whole weight tile stays in smem (b_stages == taps * chunks); single N tile
+  int b_resident;                 // the CTA's whole weight tile stays in smem (b_stages == taps * chunks)
+  int n_fixed;                    // >0 (= n_tiles_n, with b_resident): every CTA keeps ONE N tile (blockIdx % n_fixed) resident and
+                                  // walks M blocks only, so layers with several N tiles also load their weights once per CTA
   int tmem_cols, max_imgs;
   int n_seg;
   TcSeg seg[3];
@@ -82,6 +86,7 @@ struct TcParams {
 
 struct MmaCtx {
   uint32_t bar_afull, bar_aempty, bar_bfull, bar_bempty, bar_accfull, bar_accempty, ringA, ringB, b_bytes, tmem_base;
+  int it_first, it_stride, it_end;      // this CTA's work items: it_first, it_first + it_stride, ... < it_end
 };
 
 // The single MMA-issuing thread.  tcgen05.mma is asynchronous, but the tensor pipe only stays busy if the scalar work
@@ -124,7 +129,7 @@ __device__ __forceinline__ void mma_issue_loop(const TcParams& p, const MmaCtx& 
     }
   };
 
-  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+  for (int item = c.it_first; item < c.it_end; item += c.it_stride) {
     if (RESIDENT) bd = bd_base;
     if (PROF) t0 = clock64();
     ptx::mbar_wait(c.bar_accempty + 8 * set, acc_par);
@@ -208,16 +213,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* gbase = smem_raw + (base - raw);
   // header (1 KB): barriers + tmem pointer; bias/emb table; A ring; B ring
-  const uint32_t bar_afull = base, bar_aempty = base + 32, bar_bfull = base + 64, bar_bempty = base + 192;
-  const uint32_t bar_accfull = base + 320, bar_accempty = base + 336;
-  const uint32_t tmem_slot = base + 352;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + 352);
+  // header: A full / empty (8 stages each), B full / empty (16 each), accumulator full / empty, TMEM slot, per-warp residual barriers
+  const uint32_t bar_afull = base, bar_aempty = base + 64, bar_bfull = base + 128, bar_bempty = base + 256;
+  const uint32_t bar_accfull = base + 384, bar_accempty = base + 400;
+  const uint32_t tmem_slot = base + 416;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + 416);
   float* sm_bias_all = reinterpret_cast<float*>(gbase + 1024);             // [max_imgs][block_n] bias + embedding
   const uint32_t bias_bytes = ((uint32_t)(p.max_imgs * p.block_n * 4) + 1023u) & ~1023u;
   const uint32_t ringA = base + 1024 + 2 * bias_bytes;
   const uint32_t ringB = ringA + (uint32_t)p.a_stages * (uint32_t)p.a_stage_bytes;
   const uint32_t b_bytes = (uint32_t)p.block_n * TC_BK * 2;
   const int BM = 128 * p.G;
+  // work items of this CTA.  Generic: item = blockIdx, blockIdx + grid, ... over (N tile major, M block minor).  Fixed-N-tile mode:
+  // the CTA owns N tile blockIdx % n_fixed (its weights stay resident) and strides over the M blocks with the CTAs of that tile.
+  int it_first = blockIdx.x, it_stride = gridDim.x, it_end = p.n_items;
+  if (p.n_fixed > 0) {
+    const int nt = (int)blockIdx.x % p.n_fixed, rank = (int)blockIdx.x / p.n_fixed;
+    it_stride = ((int)gridDim.x - nt + p.n_fixed - 1) / p.n_fixed;
+    it_first = nt * p.n_mblocks + rank;
+    it_end = (nt + 1) * p.n_mblocks;
+    if (rank >= p.n_mblocks) it_first = it_end;
+  }
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -257,11 +273,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         for (int s = 0; s < p.n_seg; ++s)
           for (int ch = 0; ch < p.seg[s].nchunks; ++ch)
             for (int tap = 0; tap < p.seg[s].ntaps; ++tap, ++bt)
-              ptx::tma_load_2d(ringB + bt * b_bytes, &mapB, bar_bfull, p.seg[s].koff + tap * p.seg[s].C + ch * TC_BK, 0);
+              ptx::tma_load_2d(ringB + bt * b_bytes, &mapB, bar_bfull, p.seg[s].koff + tap * p.seg[s].C + ch * TC_BK,
+                               p.n_fixed > 0 ? ((int)blockIdx.x % p.n_fixed) * p.block_n : 0);
       }
       const int a_stages = p.a_stages, b_stages = p.b_stages;
       const bool stream_b = !p.b_resident;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int item = it_first; item < it_end; item += it_stride) {
         const int n_tile = item / p.n_mblocks, m_blk = item - n_tile * p.n_mblocks;   // neighbours share the weight tile
         const int m0 = m_blk * BM, n0 = n_tile * p.block_n;
         for (int s = 0; s < p.n_seg; ++s) {
@@ -312,7 +329,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   } else if (warp == TC_EPI_WARPS + 1) {
     // ===================== MMA issuer =====================
     if (ptx::elect_one()) {
-      MmaCtx mc{bar_afull, bar_aempty, bar_bfull, bar_bempty, bar_accfull, bar_accempty, ringA, ringB, b_bytes, tmem_base};
+      MmaCtx mc{bar_afull, bar_aempty, bar_bfull, bar_bempty, bar_accfull, bar_accempty, ringA, ringB, b_bytes, tmem_base, it_first, it_stride, it_end};
       const bool prof = kDbg && p.dbg_out != nullptr;
       // one instantiation per (row-tile count, weights resident?, cycle counters?): the loop body is a few scalar
       // instructions per tap so the tensor pipe, not this thread, sets the pace
@@ -345,7 +362,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     float* sm_bias = sm_bias_all;
     const uint32_t stg = ringB + (uint32_t)p.b_stages * b_bytes + (uint32_t)warp * 4096u;   // one 4 KB tile per warp
     uint8_t* stg_g = gbase + (stg - base);
-    const uint32_t rbar = base + 384 + (uint32_t)warp * 8;
+    const uint32_t rbar = base + 448 + (uint32_t)warp * 8;
     if (lane == 0) { ptx::mbar_init(rbar, 1); ptx::fence_barrier_init(); }
     __syncwarp();
     uint32_t res_phase = 0;
@@ -382,11 +399,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         tab_next[j] = v;
       }
     };
-    if (p.emb != nullptr && (int)blockIdx.x < p.n_items && !(dbg & 8)) load_table(blockIdx.x);
+    if (p.emb != nullptr && it_first < it_end && !(dbg & 8)) load_table(it_first);
     int tab_n_tile = -1;
     // (combining the GroupNorm sums per CTA in shared memory first was tried: shared-memory float atomics cost more than
     // the global REDs they save, 12 -> 31 kclk per CTA in the statistics section)
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++k_idx) {
+    for (int item = it_first; item < it_end; item += it_stride, ++k_idx) {
       const int set = k_idx & 1;
       const int n_tile = item / p.n_mblocks, m_blk = item - n_tile * p.n_mblocks;
       const int m0 = m_blk * BM, n0 = n_tile * p.block_n;
@@ -410,8 +427,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
         tab_n_tile = n_tile;
         if (p.emb != nullptr && !(dbg & 8)) {
-          const int item_next = item + gridDim.x;
-          if (item_next < p.n_items) load_table(item_next);
+          const int item_next = item + it_stride;
+          if (item_next < it_end) load_table(item_next);
         }
       }
       VF_EP_END(1);
@@ -713,7 +730,7 @@ void set_tc_debug_out(long long* p) { g_tc_dbg_out = p; }
 
 // ---- tiling choice -------------------------------------------------------------------------------------
 struct TcTiling {
-  int block_n = 0, G = 0, a_stages = 0, b_stages = 0, a_stage_bytes = 0, max_imgs = 0, b_resident = 0;
+  int block_n = 0, G = 0, a_stages = 0, b_stages = 0, a_stage_bytes = 0, max_imgs = 0, b_resident = 0, n_fixed = 0;
   size_t smem = 0;
   double cost = 0;
 };
@@ -721,7 +738,7 @@ struct TcTiling {
 static const double kIngestBytesPerClk = 42.5;   // L2 -> SM, per SM (B300_MICROARCH.md: ~6300 B/clk chip-wide / 148)
 static const size_t kSmemBudget = 227 * 1024;
 
-static bool pick_tiling(const TcParams& p, int cout_pad, int sms, bool epi_tma, TcTiling* best) {
+static bool pick_tiling(const TcParams& p, int cout_pad, int sms, bool epi_tma, bool light_epilogue, TcTiling* best) {
   bool found = false;
   const int rows_per_img = p.geo.in_padded ? p.geo.P : p.geo.HW;
   int halo_max = 0;
@@ -753,18 +770,35 @@ static bool pick_tiling(const TcParams& p, int cout_pad, int sms, bool epi_tma, 
       // pipeline depth is a hard requirement (both rings run across work items): >= 2 A slabs so the next slab
       // loads under the current one's MMAs, >= 4 weight tiles so a tap never waits for its own load
       c.a_stages = 2;
-      if (!(g_tc_dbg & 512) && t == 1 && taps <= 64 && fixed + 2 * (size_t)c.a_stage_bytes + (size_t)taps * bstage <= kSmemBudget) {
-        c.b_resident = 1;                        // weights-stationary: the whole [cout x K] tile lives in smem
+      // (a deeper activation ring — up to 8 slabs for the 1x1-only layers — was measured: no effect, scripts/sweep_1x1.py)
+      bool only_1x1 = true;
+      for (int s2 = 0; s2 < p.n_seg; ++s2) only_1x1 = only_1x1 && p.seg[s2].ntaps == 1;
+      const int a_want = 3;
+      const long mblocks = (p.geo.rows_total + BM - 1) / BM;
+      const bool fits_resident = taps <= 64 && fixed + 2 * (size_t)c.a_stage_bytes + (size_t)taps * bstage <= kSmemBudget;
+      const bool pin_tile = !(g_tc_dbg & 512) && !(g_tc_dbg & 4096) && t > 1 && t <= 8 && fits_resident && mblocks * t >= 4L * sms;
+      if ((!(g_tc_dbg & 512) && t == 1 && fits_resident) || pin_tile) {
+        // weights-stationary: the CTA's whole [block_n x K] tile lives in smem.  With several N tiles (pin_tile) every CTA keeps
+        // N tile (blockIdx % t) and strides over the M blocks only: the weights are fetched once per CTA instead of once per
+        // work item (1x1 projections: qkv)
+        c.b_resident = 1;
+        c.n_fixed = pin_tile ? t : 0;
         c.b_stages = (int)taps;
+        const size_t left = kSmemBudget - fixed - (size_t)taps * bstage;
+        c.a_stages = (int)(left / c.a_stage_bytes);
+        if (c.a_stages > a_want) c.a_stages = a_want;
       } else {
         const int b_min = taps < 4 ? (int)taps : 4;
         if (fixed + (size_t)c.a_stages * c.a_stage_bytes + (size_t)b_min * bstage > kSmemBudget) continue;
+        const int b_want = taps < 8 ? (int)taps : 8;                      // weight tiles in flight before A gets more than two slabs
+        if (fixed + (size_t)b_want * bstage + 2 * (size_t)c.a_stage_bytes <= kSmemBudget) {
+          c.a_stages = (int)((kSmemBudget - fixed - (size_t)b_want * bstage) / c.a_stage_bytes);
+          if (c.a_stages > a_want) c.a_stages = a_want;
+        }
         size_t left = kSmemBudget - fixed - (size_t)c.a_stages * c.a_stage_bytes;
         c.b_stages = (int)(left / bstage);
         if (c.b_stages > TC_MAX_STAGES) c.b_stages = TC_MAX_STAGES;
       }
-      // a third A slab when there is room
-      if (fixed + (size_t)3 * c.a_stage_bytes + (size_t)c.b_stages * bstage <= kSmemBudget) c.a_stages = 3;
       c.smem = fixed + (size_t)c.a_stages * c.a_stage_bytes + (size_t)c.b_stages * bstage;
       // cost model per work item
       double bytes = 0, cyc = 0;
@@ -782,13 +816,29 @@ static bool pick_tiling(const TcParams& p, int cout_pad, int sms, bool epi_tma, 
       }
       // the epilogue of an item overlaps the next item's main loop; the two warps of a TMEM lane quarter take alternate
       // (row tile, 64-column panel) units, ~2600 clk each with the GroupNorm sums
-      const double epi = 1500.0 + 2600.0 * ((G * ((bn + 63) / 64) + TC_NSUB - 1) / TC_NSUB);
+      double epi = 1500.0 + 2600.0 * ((G * ((bn + 63) / 64) + TC_NSUB - 1) / TC_NSUB);
+      if (only_1x1 && light_epilogue) {
+        // 1x1-only layers without bias / residual / statistics (qkv) have so few MMAs per item that the item time IS the epilogue's latency chain; measured per item at
+        // 168 view-images (scripts/sweep_1x1.py, qkv 192 -> 576): 1 / 2 / 3 / 4 units of (128 rows x 64 columns) = 5.2 / 6.2 /
+        // 6.8 / 10.8 kclk — three units of ONE 192-column accumulator cost barely more than two
+        static const double kEpi1x1[5] = {0.0, 5200.0, 6200.0, 6800.0, 10800.0};
+        epi = kEpi1x1[G * ((bn + 63) / 64)];
+      }
       double item = cyc > bytes / kIngestBytesPerClk ? cyc : bytes / kIngestBytesPerClk;
       if (epi > item) item = epi;
       const long items = (long)((p.geo.rows_total + BM - 1) / BM) * t;
-      const long rounds = (items + sms - 1) / sms;
+      long rounds = (items + sms - 1) / sms;
+      if (c.n_fixed) {                            // CTAs are split evenly over the N tiles; the one-off weight fetch is amortised over a CTA's items
+        const long per_tile = sms / t > 0 ? sms / t : 1;
+        rounds = (mblocks + per_tile - 1) / per_tile;
+        item += (double)taps * bstage / kIngestBytesPerClk / (double)rounds;
+      }
       // larger row groups shrink the weight ring and lengthen the drain of the last item: measured ~8 % per extra tile
       c.cost = rounds * item * (G > 2 ? 1.0 + 0.08 * (G - 2) : 1.0) + 3000.0;
+      {
+        static const double fixed_bias = [] { const char* e = getenv("VF_TC_FIXED_BIAS"); return e ? atof(e) : 1.0; }();   // A/B knob
+        if (c.n_fixed) c.cost *= fixed_bias;
+      }
       if (!found || c.cost < best->cost * 0.999 || (c.cost < best->cost * 1.001 && bn > best->block_n)) { *best = c; found = true; }
     }
   }
@@ -853,9 +903,11 @@ int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
   p.epi_tma = !out_f32 && (!a->qkv_split || ((2 * a->qkv_split) % 64 == 0 && !(g_tc_dbg & 1024))) && !p.geo.stride2 && layout_ok &&
               a->cout_pad % 64 == 0 && a->cout == a->cout_pad;
   TcTiling tl;
-  VF_REQUIRE(pick_tiling(p, a->cout_pad, sm_count(), p.epi_tma != 0, &tl), "vf_conv2d(tc): no tiling for cout_pad=%d W=%d", a->cout_pad, W);
+  const bool light_epilogue = !a->stats && !a->bias && !a->emb && !a->residual;
+  VF_REQUIRE(pick_tiling(p, a->cout_pad, sm_count(), p.epi_tma != 0, light_epilogue, &tl), "vf_conv2d(tc): no tiling for cout_pad=%d W=%d", a->cout_pad, W);
   p.block_n = tl.block_n; p.G = tl.G; p.a_stages = tl.a_stages; p.b_stages = tl.b_stages; p.a_stage_bytes = tl.a_stage_bytes;
   p.b_resident = tl.b_resident;
+  p.n_fixed = tl.n_fixed;
   p.max_imgs = tl.max_imgs;
   VF_REQUIRE(p.max_imgs * p.block_n <= 1024, "vf_conv2d(tc): bias table of %d x %d entries exceeds the epilogue's registers", p.max_imgs, p.block_n);
   p.n_tiles_n = a->cout_pad / p.block_n;
@@ -953,7 +1005,8 @@ int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
       if (rc) return rc;
     }
   }
-  const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
+  int grid = p.n_items < sm_count() ? p.n_items : sm_count();
+  if (p.n_fixed > 0 && grid < p.n_fixed) grid = p.n_fixed;
   if (g_tc_dbg & 256)
     fprintf(stderr, "[vf tc] rows %d W %d cout %d segs %d ktot %d | bn %d G %d a_stages %d (%d B) b_stages %d resident %d smem %zu items %d grid %d epi_tma %d a_lines %d epi_lines %d\n",
             p.geo.rows_total, W, a->cout, a->n_seg, k_total, p.block_n, p.G, p.a_stages, p.a_stage_bytes, p.b_stages, p.b_resident, tl.smem,

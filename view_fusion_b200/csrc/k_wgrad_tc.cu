@@ -14,6 +14,7 @@
 // stride / SBO = 1024, and start addresses shifted by whole rows.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "tc_ptx.cuh"
@@ -243,7 +244,11 @@ int conv2d_wgrad_tc(const vf_conv_args* a, const void* dy, int dy_ld, float* dwp
   if (p.acc_max > WG_MAX_ACC) p.acc_max = WG_MAX_ACC;
   // Few rows (the 16x16 and 8x8 levels): the reduction is short and the output large, so parallelism should come from
   // output tiles (one tap pair per job) rather than from row splits, whose partial sums all go through fp32 REDs
-  if (p.rows_total < 65536) p.acc_max = 1;
+  if (p.rows_total < 65536) {
+    static const int env_acc = [] { const char* e = getenv("VF_WG_ACC_SMALL"); return e ? atoi(e) : 0; }();     // A/B knob
+    const int small_acc = env_acc > 0 ? env_acc : 1;
+    if (p.acc_max > small_acc) p.acc_max = small_acc;
+  }
   p.n_seg = a->n_seg;
   int k_total = 0, halo_max = 0, jobs = 0, max_pairs = 0;
   for (int s = 0; s < a->n_seg; ++s) {
