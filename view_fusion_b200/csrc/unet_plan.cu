@@ -489,7 +489,7 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_create(const vf_un
   for (auto& b : u->blocks) {
     const int cin = b.c0 + b.c1;
     b.w1 = take((size_t)b.cout * 9 * cin * es);
-    const int k2 = 9 * b.cout + cin;        // conv2 taps + res_conv (or identity) columns: the residual rides in the GEMM
+    const int k2 = 9 * b.cout + (b.rs_w >= 0 ? cin : 0);   // conv2 taps + res_conv columns (the projection rides in the GEMM)
     b.w2 = take((size_t)b.cout * k2 * es);
     b.bias2 = take((size_t)b.cout * 4);
     if (b.attn) {
@@ -568,10 +568,9 @@ extern "C" __attribute__((visibility("default"))) int vf_unet_pack_weights(vf_un
   for (auto& b : u->blocks) {
     const int cin = b.c0 + b.c1;
     pl.conv(u->master[b.c1_w], b.cout, cin, 3, pk + b.w1, b.cout, 9 * cin, 0);
-    const int k2 = 9 * b.cout + cin;
+    const int k2 = 9 * b.cout + (b.rs_w >= 0 ? cin : 0);
     pl.conv(u->master[b.c2_w], b.cout, b.cout, 3, pk + b.w2, b.cout, k2, 0);
     if (b.rs_w >= 0) pl.conv(u->master[b.rs_w], b.cout, cin, 1, pk + b.w2, b.cout, k2, 9 * b.cout);
-    else pl.identity(pk + b.w2, b.cout, k2, 9 * b.cout);           // "h + x" (unet.py:245) as an exact 1x1 segment
     pl.bias(u->master[b.c2_b], b.rs_b >= 0 ? u->master[b.rs_b] : nullptr, b.cout, pk + b.bias2);
     if (b.attn) {
       pl.conv(u->master[b.qkv_w], 3 * b.cout, b.cout, 1, pk + b.wqkv, 3 * b.cout, b.cout, 0);
@@ -688,18 +687,25 @@ static Act run_resblock(Exec& ex, vf_unet* u, const uint8_t* pk, int images, con
     vf_conv_args a = conv_args_init();
     a.images = images; a.H = x.H; a.W = x.W;
     a.src[0] = a2.p; a.src_c[0] = b.cout; a.ksize[0] = 3; a.n_seg = 1;
-    // res_conv(x) — or x itself through identity columns — accumulates in the same TMEM tile: the residual is read
-    // by the TMA-fed main loop instead of by the (latency-bound) epilogue
-    a.src[1] = x.p; a.src_c[1] = x.C; a.ksize[1] = 1; a.n_seg = 2;
-    if (skip) { a.src[2] = skip->p; a.src_c[2] = skip->C; a.ksize[2] = 1; a.n_seg = 3; }
+    // res_conv(x) accumulates in the same TMEM tile (two extra K segments over x and the skip tensor).  An identity residual
+    // ("h + x", Cin == Cout) goes through the epilogue's TMA-fetched residual port instead: as a 1x1 K segment it cost a second
+    // activation slab per work item (64x64 64->64: 80 us against 58 us for the same layer without it)
+    if (b.rs_w >= 0) {
+      a.src[1] = x.p; a.src_c[1] = x.C; a.ksize[1] = 1; a.n_seg = 2;
+      if (skip) { a.src[2] = skip->p; a.src_c[2] = skip->C; a.ksize[2] = 1; a.n_seg = 3; }
+    } else {
+      a.residual = x.p;
+    }
     a.weight = pk + b.w2; a.cout = b.cout; a.cout_pad = b.cout;
     a.bias = reinterpret_cast<const float*>(pk + b.bias2);
     a.out = out.p; a.out_ld = b.cout; a.stats = out.stats;
     ConvMeta m;
     m.w_idx[0] = b.c2_w; m.cin_total[0] = b.cout; m.b_idx[0] = b.c2_b; m.b_idx[1] = b.rs_b; m.wt_off[0] = b.wt2;
-    // segments 1 (x) and 2 (skip): res_conv weight slices, or the identity (w_idx -1: gradient is a plain add)
-    m.w_idx[1] = b.rs_w; m.c_off[1] = 0; m.cin_total[1] = cin; m.wt_off[1] = b.rs_w >= 0 ? b.wtr0 : SIZE_MAX;
-    if (skip) { m.w_idx[2] = b.rs_w; m.c_off[2] = b.c0; m.cin_total[2] = cin; m.wt_off[2] = b.wtr1; }
+    // segments 1 (x) and 2 (skip): res_conv weight slices
+    if (b.rs_w >= 0) {
+      m.w_idx[1] = b.rs_w; m.c_off[1] = 0; m.cin_total[1] = cin; m.wt_off[1] = b.wtr0;
+      if (skip) { m.w_idx[2] = b.rs_w; m.c_off[2] = b.c0; m.cin_total[2] = cin; m.wt_off[2] = b.wtr1; }
+    }
     conv_call(ex, u, a, m);
   }
   if (!b.attn) return out;
