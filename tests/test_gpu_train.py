@@ -62,7 +62,8 @@ def test_train_bf16_mode_loss_and_gradient_direction(golden_dir):
 
 
 @pytest.mark.parametrize("case", [(3, 16, [(64, 3)], 64), (2, 32, [(128, 3)], 128), (3, 16, [(128, 3), (64, 1), (192, 1)], 192),
-                                  (5, 8, [(320, 3)], 320), (2, 64, [(64, 3), (64, 1)], 64)])
+                                  (5, 8, [(320, 3)], 320), (2, 64, [(64, 3), (64, 1)], 64), (3, 32, [(128, 3), (64, 1), (64, 1)], 64),
+                                  (40, 16, [(192, 3)], 64)])        # Cout <= 64: the kernel with the three kernel rows in N
 def test_wgrad_tcgen05_vs_cuda_cores(case):
     """tcgen05 MN-major weight-gradient GEMM vs the CUDA-core kernel and vs fp64 math on the same bf16 operands."""
     import ctypes as C
