@@ -44,21 +44,31 @@ def test_train_fp32_mode_loss_and_gradients(golden_dir, tag, cfg):
 
 
 def test_train_bf16_mode_loss_and_gradient_direction(golden_dir):
+    """bf16 tensor-core training step vs the reference's fp32 autograd (golden).  Per-tensor bars: every gradient tensor that
+    carries signal (norm > 1e-3 of the largest) within 3 % in norm (zero exceptions) and cos > 0.999 of the stored sample; the measured worst
+    cases go to the margins file (the kernels are pinned one by one, at tight bars, in tests/test_gpu_bwd_ops.py)."""
+    from gpu_util import margin
     g, loss, grads = _run(golden_dir, "small_n3", O.SMALL_V100, "bf16")
-    assert abs(loss - float(g["loss"])) < 1e-2 * abs(float(g["loss"]))
+    ok = margin("train small-v100 N=3 bf16: loss relative error vs reference", abs(loss - float(g["loss"])) / abs(float(g["loss"])), 1e-2)
     names = [str(n) for n in g["grad_names"]]
     norms = dict(zip(names, g["grad_norms"].tolist()))
     big = max(norms.values())
-    off = {n: (float(grads[n].norm()), r) for n, r in norms.items() if r > 1e-3 * big and not abs(float(grads[n].norm()) - r) < 0.1 * r}
-    assert len(off) <= 4, f"bf16 gradient norms off by > 10 %: {list(off.items())[:8]}"
+    live = {n: r for n, r in norms.items() if r > 1e-3 * big}
+    dev = {n: abs(float(grads[n].norm()) - r) / r for n, r in live.items()}
+    worst = max(dev, key=dev.get)
+    ok &= margin(f"train small-v100 N=3 bf16: worst per-tensor gradient-norm deviation ({worst})", dev[worst], 3e-2)
+    ok &= margin("train small-v100 N=3 bf16: mean per-tensor gradient-norm deviation", sum(dev.values()) / len(dev), 1e-2)
+    coss = {}
     for k in g:
         if k.startswith("grad:"):
             full = grads[k[5:]].reshape(-1)
             stride = max(1, (full.numel() + 8191) // 8192)
             a, b = full[::stride].double(), g[k].double()
             if float(b.norm()) > 1e-3 * big:
-                cos = float((a * b).sum() / (a.norm() * b.norm()))
-                assert cos > 0.98, (k, cos)
+                coss[k[5:]] = float((a * b).sum() / (a.norm() * b.norm()))
+    wc = min(coss, key=coss.get)
+    ok &= margin(f"train small-v100 N=3 bf16: worst gradient cosine vs reference ({wc})", coss[wc], 0.999, higher_is_better=True)
+    assert ok
 
 
 @pytest.mark.parametrize("case", [(3, 16, [(64, 3)], 64), (2, 32, [(128, 3)], 128), (3, 16, [(128, 3), (64, 1), (192, 1)], 192),
