@@ -508,14 +508,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               __syncwarp();
               if (eprof) ec[4] += clock64() - ts;
             }
-            // bias (+ embedding) of the first half of the slots is fetched from the table BEFORE the wait on the TMEM load, the
-            // second half right after it: the shared-memory latency (inflated by the MMA's own operand traffic) is then hidden
-            // behind the TMEM round trip / the first half's arithmetic instead of stalling every FADD
-            float4 bpre[SLOTS];
-            if (valid && has_tab && !has_res) {
-#pragma unroll
-              for (int q4 = 0; q4 < SLOTS; ++q4) bpre[q4] = *reinterpret_cast<const float4*>(brow + (hh * SLOTS) * 8 + q4 * 4);
-            }
             ptx::tmem_ld_wait();
             // one 16-byte slot = 8 channels; the residual / padding-row cases are separate straight-line loops so the
             // common path is (2 LDS + 8 FADD + 4 F2FP + 1 STS) per slot without selects or branches
@@ -539,13 +531,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 *slot = o;
               }
             } else if (has_tab) {
-              float4 bpost[SLOTS];
-#pragma unroll
-              for (int q4 = 0; q4 < SLOTS; ++q4) bpost[q4] = *reinterpret_cast<const float4*>(brow + (hh * SLOTS) * 8 + SLOTS * 4 + q4 * 4);
 #pragma unroll
               for (int jj = 0; jj < SLOTS; ++jj) {
                 const int j = hh * SLOTS + jj;
-                const float4 b0 = jj < SLOTS / 2 ? bpre[2 * jj] : bpost[2 * jj - SLOTS], b1 = jj < SLOTS / 2 ? bpre[2 * jj + 1] : bpost[2 * jj + 1 - SLOTS];
+                // (fetching the table entries before the wait on the TMEM load was measured: no effect on the 64x64 layers)
+                const float4 b0 = *reinterpret_cast<const float4*>(brow + j * 8), b1 = *reinterpret_cast<const float4*>(brow + j * 8 + 4);
                 const uint32_t* acc = &rr[jj >> 1][(jj & 1) * 8];
                 uint4 o;
                 o.x = pack_bf16x2(__uint_as_float(acc[0]) + b0.x, __uint_as_float(acc[1]) + b0.y);
