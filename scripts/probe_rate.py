@@ -19,3 +19,12 @@ for N in (64, 96):
         torch.cuda.synchronize()
         cyc = out.double().mean().item()
         print(f"N {N:3d} mode {ce:4d}: {cyc / (ng * 4):7.1f} cycles/MMA", flush=True)
+
+print("weight-stationary pattern (-300 plain G=2, -301 .ws G=2, -302 .ws fill/lastuse G=2, -303 plain G=4, -304 .ws G=4, -305 .ws fill/use/lastuse G=4):")
+for N in (64, 128):
+    for ce in (-300, -301, -302, -303, -304, -305):
+        ng = 1600
+        _lib.check(_lib.load_probes().vf_debug_umma_rate(N, 3, ng, ce, 148, out.data_ptr(), _lib.stream_handle()), "rate")
+        torch.cuda.synchronize()
+        cyc = out.double().mean().item()
+        print(f"N {N:3d} mode {ce:4d}: {cyc / (ng * 4):7.1f} cycles/MMA", flush=True)

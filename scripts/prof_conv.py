@@ -34,6 +34,10 @@ flops = 2 * R * S * S * cout * k_total
 variants = [("full", 0, True, True)]
 if len(sys.argv) > 2 and sys.argv[2] == "ablate":
     variants += [("no-res (typical)", 0, False, True), ("no-res dbg:no-table", 8, False, True), ("no-res-no-stats", 0, False, False), ("dbg:no-store", 2, True, True), ("dbg:no-unit-work", 4, True, True), ("dbg:no-unit-no-table", 12, True, True)]
+if len(sys.argv) > 2 and sys.argv[2] == "r02":
+    variants = [("conv1: no table", 0, False, True, False), ("bias only", 0, False, True, True), ("conv2: bias+residual", 0, True, True, True),
+                ("no table, no stats", 0, False, False, False)]
+variants = [v if len(v) == 5 else (*v, True) for v in variants]
 if len(sys.argv) > 2 and sys.argv[2] == "typical":
     variants = [("no-res (typical)", 0, False, True)]
 if len(sys.argv) > 2 and sys.argv[2] == "sweep":
@@ -43,10 +47,11 @@ if len(sys.argv) > 2 and sys.argv[2] == "sweep":
             for noresid in (0, 512):
                 variants.append((f"bn{bn} G{G} {'ring' if noresid else 'resident-ok'}", (bn // 16) << 20 | G << 16 | noresid | 256, True, True))
 lib = _lib.require_device()
-for name, dbg, use_res, use_stats in variants:
+variants = [v if len(v) == 5 else (*v, True) for v in variants]
+for name, dbg, use_res, use_stats, use_bias in variants:
     lib.vf_debug_flags(dbg)
     try:
-        ops.conv2d(srcs, [k for _, k in segs], w, R, S, S, cout, bias=bias, residual=res if use_res else None, want_stats=use_stats,
+        ops.conv2d(srcs, [k for _, k in segs], w, R, S, S, cout, bias=bias if use_bias else None, residual=res if use_res else None, want_stats=use_stats,
                    in_padded=not c["flat"], out=out, stats=stats)
         torch.cuda.synchronize()
     except RuntimeError as e:
@@ -60,7 +65,7 @@ for name, dbg, use_res, use_stats in variants:
         big = torch.empty(64 << 20, device="cuda").fill_(1.0)      # keeps the GPU busy while the launches are enqueued
         e0.record()
         for _ in range(NL):
-            ops.conv2d(srcs, [k for _, k in segs], w, R, S, S, cout, bias=bias, residual=res if use_res else None, want_stats=use_stats,
+            ops.conv2d(srcs, [k for _, k in segs], w, R, S, S, cout, bias=bias if use_bias else None, residual=res if use_res else None, want_stats=use_stats,
                        in_padded=not c["flat"], out=out, stats=stats)
         e1.record()
         torch.cuda.synchronize()
@@ -69,7 +74,7 @@ for name, dbg, use_res, use_stats in variants:
     cnt = torch.zeros(148 * 12 + 1 + 4 * 64, dtype=torch.int64, device="cuda")
     lib.vf_debug_counters(cnt.data_ptr())
     for _ in range(6):
-        ops.conv2d(srcs, [k for _, k in segs], w, R, S, S, cout, bias=bias, residual=res if use_res else None, want_stats=use_stats,
+        ops.conv2d(srcs, [k for _, k in segs], w, R, S, S, cout, bias=bias if use_bias else None, residual=res if use_res else None, want_stats=use_stats,
                    in_padded=not c["flat"], out=out, stats=stats)
     torch.cuda.synchronize()
     lib.vf_debug_counters(0)

@@ -183,7 +183,7 @@ def load() -> C.CDLL:
 
 
 PROBES_PATH = os.path.join(_HERE, "libviewfusion_b200_probes.so")
-PROBE_SYMBOLS = ["vf_debug_umma_shift", "vf_debug_umma_rate", "vf_debug_umma_mn"]      # include/viewfusion_b200_probes.h
+PROBE_SYMBOLS = ["vf_debug_umma_shift", "vf_debug_umma_rate", "vf_debug_umma_mn", "vf_debug_mufu_rate"]      # include/viewfusion_b200_probes.h
 _probes = None
 
 
@@ -195,7 +195,7 @@ def load_probes() -> C.CDLL:
             raise RuntimeError(f"{PROBES_PATH} is missing: build it with `python -m view_fusion_b200.build`")
         lib = C.CDLL(PROBES_PATH)
         p, i = C.c_void_p, C.c_int
-        for name, args in {"vf_debug_umma_rate": [i, i, i, i, i, p, p], "vf_debug_umma_mn": [p, i, p, i, i, i, i, p, p],
+        for name, args in {"vf_debug_mufu_rate": [i, i, i, p, p, p], "vf_debug_umma_rate": [i, i, i, i, i, p, p], "vf_debug_umma_mn": [p, i, p, i, i, i, i, p, p],
                            "vf_debug_umma_shift": [p, i, p, i, i, p, p]}.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = i, args

@@ -98,6 +98,31 @@ extern "C" __attribute__((visibility("default"))) int vf_debug_umma_shift(const 
 
 // ---- probe 2: sustained tcgen05.mma issue/execute rate from one thread (no loads; smem contents are irrelevant) ------
 namespace vf {
+// KIND 0: plain MMA, 1: .ws without collector hints, 2: .ws keeping the weight tile in collector buffer b0 across the G row tiles
+template <int KIND, int G>
+__device__ __forceinline__ void ws_pattern(uint32_t tmem_d, uint64_t ad, uint64_t bd, uint32_t idesc, int N, int n_groups, uint32_t sink_bar) {
+  for (int i = 0; i < n_groups; i += 4 * G) {
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) {
+      const uint64_t a_t = ad + (uint64_t)(tap * 67 * 8), b_t = bd + (uint64_t)(tap * N * 8);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const uint32_t d = tmem_d + (uint32_t)(g * N);
+          const uint64_t ag = a_t + (uint64_t)(2 * k + g * 1024), bk = b_t + (uint64_t)(2 * k);
+          if (KIND == 0) ptx::umma_f16(d, ag, bk, idesc, 1u);
+          else if (KIND == 1) ptx::umma_ws_f16<0>(d, ag, bk, idesc, 1u);
+          else if (g == 0) ptx::umma_ws_f16<1>(d, ag, bk, idesc, 1u);
+          else if (g == G - 1) ptx::umma_ws_f16<3>(d, ag, bk, idesc, 1u);
+          else ptx::umma_ws_f16<2>(d, ag, bk, idesc, 1u);
+        }
+      }
+      ptx::umma_commit(sink_bar);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128) umma_rate_probe(int N, int shift_rows, int n_groups, int commit_every, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -159,6 +184,21 @@ __global__ void __launch_bounds__(128) umma_rate_probe(int N, int shift_rows, in
             for (int k = kb; k < kb + chain; ++k)
               ptx::umma_f16(tmem_d + (uint32_t)(a * N), adp[a] + (uint64_t)(k * 128), bdm + (uint64_t)(k * 128), idm, 1u);
         ptx::umma_commit(sink_bar);
+      }
+    } else if (commit_every <= -300 && commit_every >= -309) {
+      // weight-stationary MMAs: G row tiles against the same weight tile, k-step outer / row tile inner.
+      // -300: plain MMA, G=2; -301: .ws without hints, G=2; -302: .ws fill/lastuse, G=2; -303: plain, G=4; -304: .ws no hints, G=4;
+      // -305: .ws fill/use/use/lastuse, G=4
+      const uint32_t sink_bar = base + 40;
+      ptx::mbar_init(sink_bar, 1);
+      ptx::fence_barrier_init();
+      switch (-300 - commit_every) {
+        case 0: ws_pattern<0, 2>(tmem_d, ad, bd, idesc, N, n_groups, sink_bar); break;
+        case 1: ws_pattern<1, 2>(tmem_d, ad, bd, idesc, N, n_groups, sink_bar); break;
+        case 2: ws_pattern<2, 2>(tmem_d, ad, bd, idesc, N, n_groups, sink_bar); break;
+        case 3: ws_pattern<0, 4>(tmem_d, ad, bd, idesc, N, n_groups, sink_bar); break;
+        case 4: ws_pattern<1, 4>(tmem_d, ad, bd, idesc, N, n_groups, sink_bar); break;
+        default: ws_pattern<2, 4>(tmem_d, ad, bd, idesc, N, n_groups, sink_bar); break;
       }
     } else if (commit_every >= 0) {
       for (int i = 0; i < n_groups; ++i) {
@@ -279,6 +319,76 @@ extern "C" __attribute__((visibility("default"))) int vf_debug_umma_mn(const voi
   const size_t smem = 1024 + 1024 + 2 * 8192 + 2 * 8192;
   VF_CUDA(cudaFuncSetAttribute(umma_mn_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   umma_mn_probe<<<1, 128, smem, as_stream(stream)>>>(mA, mB, shift_rows, lbo_bytes, sbo_bytes, out);
+  VF_LAUNCH_CHECK();
+  return VF_OK;
+}
+
+// ---- probe 4: special-function throughput (what bounds the SiLU of the GroupNorm pass) -------------------------------------
+namespace vf {
+// mode 0: tanh.approx.f32, 1: ex2.approx + rcp.approx (sigmoid), 2: tanh.approx.f16x2 (two elements per operation), 3: ex2 only,
+// 4: rcp only, 5: FMA only (baseline of the loop)
+template <int MODE>
+__global__ void __launch_bounds__(256) mufu_probe_kernel(int iters, float seed, float* out, long long* cyc) {
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = seed + 0.001f * (float)(threadIdx.x + j);
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      float a = v[j], b = v[j + 1];
+      if (MODE == 0) {
+        float ta, tb;
+        asm volatile("tanh.approx.f32 %0, %1;" : "=f"(ta) : "f"(a));
+        asm volatile("tanh.approx.f32 %0, %1;" : "=f"(tb) : "f"(b));
+        a = fmaf(a, ta, a); b = fmaf(b, tb, b);
+      } else if (MODE == 1) {
+        float ea, eb, ra, rb;
+        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(-a));
+        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(-b));
+        asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(1.f + ea));
+        asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(1.f + eb));
+        a = a * ra; b = b * rb;
+      } else if (MODE == 2) {
+        uint32_t h, t;
+        asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
+        asm volatile("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(h));
+        float ta, tb;
+        asm volatile("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %2; cvt.f32.f16 %0, lo; cvt.f32.f16 %1, hi;}" : "=f"(ta), "=f"(tb) : "r"(t));
+        a = fmaf(a, ta, a); b = fmaf(b, tb, b);
+      } else if (MODE == 3) {
+        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(a));
+        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(b) : "f"(b));
+      } else if (MODE == 4) {
+        asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(a));
+        asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(b) : "f"(b));
+      } else {
+        a = fmaf(a, 0.999f, 0.001f); b = fmaf(b, 0.999f, 0.001f);
+      }
+      v[j] = a * 0.9f + 0.05f; v[j + 1] = b * 0.9f + 0.05f;
+    }
+  }
+  const long long t1 = clock64();
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += v[j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+}  // namespace vf
+
+// cycles_out[grid] = cycles of `iters` x 8 elements per thread, 256 threads per CTA, `ctas_per_sm` x 148 CTAs
+extern "C" __attribute__((visibility("default"))) int vf_debug_mufu_rate(int mode, int iters, int grid, float* scratch, long long* cycles_out, vf_stream stream) {
+  using namespace vf;
+  cudaStream_t st = as_stream(stream);
+  switch (mode) {
+    case 0: mufu_probe_kernel<0><<<grid, 256, 0, st>>>(iters, 0.3f, scratch, cycles_out); break;
+    case 1: mufu_probe_kernel<1><<<grid, 256, 0, st>>>(iters, 0.3f, scratch, cycles_out); break;
+    case 2: mufu_probe_kernel<2><<<grid, 256, 0, st>>>(iters, 0.3f, scratch, cycles_out); break;
+    case 3: mufu_probe_kernel<3><<<grid, 256, 0, st>>>(iters, 0.3f, scratch, cycles_out); break;
+    case 4: mufu_probe_kernel<4><<<grid, 256, 0, st>>>(iters, 0.3f, scratch, cycles_out); break;
+    default: mufu_probe_kernel<5><<<grid, 256, 0, st>>>(iters, 0.3f, scratch, cycles_out); break;
+  }
   VF_LAUNCH_CHECK();
   return VF_OK;
 }

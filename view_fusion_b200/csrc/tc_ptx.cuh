@@ -142,6 +142,22 @@ __device__ __forceinline__ void umma_f16_k4(uint32_t tmem_d, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first)
       : "memory");
 }
+// Weight-stationary form: the B operand (N x 16 tile) can stay in one of the tensor core's collector buffers across
+// consecutive MMAs, so that MMAs of several row tiles against the same weight tile fetch it from shared memory once.
+// USE: 0 = no hint, 1 = fill (load B and keep it), 2 = use (reuse and keep), 3 = lastuse (reuse, then release).
+template <int USE>
+__device__ __forceinline__ void umma_ws_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+#define VF_WS_MMA(Q)                                                                                                   \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                                      \
+               "tcgen05.mma.ws.cta_group::1.kind::f16" Q " [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),                    \
+               "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)                                                     \
+               : "memory")
+  if (USE == 1) VF_WS_MMA(".collector::b0::fill");
+  else if (USE == 2) VF_WS_MMA(".collector::b0::use");
+  else if (USE == 3) VF_WS_MMA(".collector::b0::lastuse");
+  else VF_WS_MMA("");
+#undef VF_WS_MMA
+}
 // Arrives on `bar` once every previously issued tcgen05.mma of this thread has completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

@@ -161,15 +161,21 @@ __device__ __forceinline__ void store_vec(__nv_bfloat16* p, const float (&v)[8])
 }
 
 __device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+// silu(2h) = h + h*tanh(h)
+__device__ __forceinline__ float silu_half(float h) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 // x * sigmoid(x) with sigmoid = 0.5 * tanh(0.5 x) + 0.5: one MUFU op per element (tanh.approx, rel. error 2^-11, well
 // below the bf16 rounding of the stored result) instead of ex2 + rcp.  The SiLU pass is otherwise MUFU-bound.
 __device__ __forceinline__ float silu_fast(float x) {
 #ifdef VF_SILU_EXACT      // A/B build: 2 MUFU (ex2 + rcp), relative error ~1e-7 instead of 2^-11
   return __fdividef(x, 1.f + __expf(-x));
 #else
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
-  return x * fmaf(0.5f, t, 0.5f);
+  // h + h*tanh(h), h = x/2: three operations per element (the convolution's fused operand transform folds the halving into its
+  // coefficients and must produce the very same bits as vf_gn_apply)
+  return silu_half(0.5f * x);
 #endif
 }
 template <typename T> __device__ __forceinline__ float silu_for(float x);
