@@ -416,9 +416,11 @@ int vf_pack_conv_weight_t(const float* w_oihw, int cout, int cin, int ksize, int
 
 /* GroupNorm(+Swish) backward for dst = vf_gn_apply(src0 | src1): dy [images*P, C0+C1] PADDED.
  * dxK receives (accK == 0) or accumulates (accK != 0) the gradient of source K; dgamma/dbeta [C0+C1] fp32 are
- * accumulated; scratch: images*(C0+C1)*2 floats.  With swish != 0 the buffer behind dy is CONSUMED: the first pass
- * overwrites it with dy * swish'(z) so that the second pass is a pure FMA stream.  `shift` as in vf_gn_apply (dx0 is the
- * gradient w.r.t. src0 + s, which equals the gradient w.r.t. src0). */
+ * accumulated; scratch: images*(C0+C1)*2 floats.  Two implementations behind this entry point: when an (image, slab of whole
+ * groups) of x and dy fits in shared memory, ONE kernel reads x and dy once, keeps them on the SM between the reduction and
+ * the apply phase and writes dx (3 tensor passes); otherwise a reduce and an apply kernel (6 passes).  With swish != 0 the
+ * buffer behind dy MAY BE CONSUMED (the two-pass path overwrites it with dy * swish'(z) so that its second pass is a pure
+ * FMA stream).  `shift` as in vf_gn_apply (dx0 is the gradient w.r.t. src0 + s, which equals the gradient w.r.t. src0). */
 int vf_gn_backward(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1, const float* stats1,
                    int stats1_ld, int dtype, int images, int H, int W, int groups, const float* gamma, const float* beta, int swish,
                    const void* dy, float* scratch, float* dgamma, float* dbeta, void* dx0, int acc0, void* dx1, int acc1,

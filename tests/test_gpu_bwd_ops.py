@@ -34,7 +34,10 @@ def _dt(dtype):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("C0,C1,S,swish,acc", [(64, 0, 16, True, False), (192, 128, 8, True, True), (128, 64, 32, True, False),
                                                (320, 320, 8, True, False), (192, 0, 16, False, True), (64, 0, 64, True, False)])
-def test_groupnorm_swish_backward(lib, dtype, C0, C1, S, swish, acc):
+@pytest.mark.parametrize("one_pass", [True, False])
+def test_groupnorm_swish_backward(lib, dtype, C0, C1, S, swish, acc, one_pass):
+    """one_pass: the (image, slab of groups)-resident kernel where the slab fits in shared memory; False forces the two-pass
+    reduce + apply kernels (vf_debug_flags 0x2000), which otherwise only run for the shapes that do not fit."""
     from view_fusion_b200 import _lib, ops
     torch.manual_seed(C0 + C1 + S)
     R, groups = 3, 32
@@ -68,11 +71,16 @@ def test_groupnorm_swish_backward(lib, dtype, C0, C1, S, swish, acc):
     scratch = torch.empty(R * Cc * 2, device="cuda")
     dgm, dbt = torch.full((Cc,), 0.5, device="cuda"), torch.full((Cc,), -0.25, device="cuda")       # accumulated into
     gm, bt = gamma.cuda(), beta.cuda()
-    _lib.check(lib.vf_gn_backward(s0.data_ptr(), C0, st.data_ptr(), Cc, _lib.ptr(s1), C1, st.data_ptr() + 8 * C0 if C1 else 0, Cc, _dt(dtype),
-                                  R, S, S, groups, gm.data_ptr(), bt.data_ptr(), int(swish), dyp.data_ptr(), scratch.data_ptr(), dgm.data_ptr(),
-                                  dbt.data_ptr(), dx0.data_ptr(), int(acc), _lib.ptr(dx1), int(acc), None, _lib.stream_handle()), "vf_gn_backward")
-    torch.cuda.synchronize()
-    tag = f"gn_backward {'bf16' if dtype == torch.bfloat16 else 'fp32'} C={C0}+{C1} {S}x{S} swish={int(swish)} acc={int(acc)}"
+    lib.vf_debug_flags(0 if one_pass else 0x2000)
+    try:
+        _lib.check(lib.vf_gn_backward(s0.data_ptr(), C0, st.data_ptr(), Cc, _lib.ptr(s1), C1, st.data_ptr() + 8 * C0 if C1 else 0, Cc, _dt(dtype),
+                                      R, S, S, groups, gm.data_ptr(), bt.data_ptr(), int(swish), dyp.data_ptr(), scratch.data_ptr(), dgm.data_ptr(),
+                                      dbt.data_ptr(), dx0.data_ptr(), int(acc), _lib.ptr(dx1), int(acc), None, _lib.stream_handle()), "vf_gn_backward")
+        torch.cuda.synchronize()
+    finally:
+        lib.vf_debug_flags(0)
+    tag = (f"gn_backward {'bf16' if dtype == torch.bfloat16 else 'fp32'} C={C0}+{C1} {S}x{S} swish={int(swish)} acc={int(acc)} "
+           f"{'one-pass' if one_pass else 'two-pass'}")
     tol_x, tol_p = (1e-2, 5e-3) if dtype == torch.bfloat16 else (2e-5, 2e-5)
     ref0 = a0.grad.float() + (old0 if acc else 0)
     ok = margin(f"{tag}: dx0 rel-L2 vs fp64 autograd", rel(ops.from_padded(dx0, R, S, S), ref0), tol_x)

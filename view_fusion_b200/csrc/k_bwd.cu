@@ -274,7 +274,8 @@ __global__ void __launch_bounds__(kGbThreads, 2) gn_bwd_reduce_kernel(const GnBw
       load_vec(reinterpret_cast<const T*>(&gr[u]), g);
       if (p.swish) {
         // dz = dy * swish'(z) replaces dy in place (stored in the activation type): the apply pass then needs no
-        // transcendental at all
+        // transcendental at all.  (Recomputing dz in the apply pass instead of this 16-byte store was measured: one tensor
+        // pass less, but 131 -> 166 us per 64x64 x 64 layer, the tanh + FMAs cost the apply pass more than the store costs here.)
 #pragma unroll
         for (int j = 0; j < VEC; ++j) g[j] = dz_swish<T>(g[j], fmaf(x[j], cA[j], cD[j]));
         store_vec(const_cast<T*>(dy) + (size_t)(rb + u * PY) * C, g);
@@ -399,6 +400,216 @@ __global__ void __launch_bounds__(kGbThreads, 3) gn_bwd_apply_kernel(const GnBwd
         }
       }
       store_vec(dx + (size_t)r * ld, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One-pass GroupNorm (+Swish) backward: a CTA owns (image, slab of whole groups) and keeps the slab's x and dz in shared
+// memory between the reduction and the apply phase, so x and dy are read from HBM ONCE and nothing but dx is written
+// (3 tensor passes instead of the 6-7 of gn_bwd_reduce + gn_bwd_apply: dy is no longer rewritten with dz, and the second
+// read of x / dz never leaves the SM).  No cross-CTA reduction: groups are contiguous channel ranges, the slab holds whole
+// groups.  Used whenever the slab fits (gn_fused_slab); the two-pass kernels remain for the rest (64x64 x 192 channels).
+// Same arithmetic as the two-pass kernels (dz rounded to the activation type before the apply phase, sums taken in fp32
+// from the unrounded values); the partial sums are combined in a fixed order instead of by atomics.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kGfUnroll = 4;
+struct FlatWalk {          // (y, x) of pixel index i advancing by a constant stride, -> PADDED row (y+1)*W1 + x+1
+  int yy, xx, dy, dx, W;
+  __device__ __forceinline__ FlatWalk(int i, int stride, int w) : W(w) { yy = i / w; xx = i - yy * w; dy = stride / w; dx = stride - dy * w; }
+  __device__ __forceinline__ int prow(int W1) const { return (yy + 1) * W1 + xx + 1; }
+  __device__ __forceinline__ void step() { yy += dy; xx += dx; if (xx >= W) { xx -= W; ++yy; } }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(512) gn_bwd_fused_kernel(const GnBwdParams p, int SC) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int VEC = VecOf<T>::N;
+  constexpr int UN = kGfUnroll;
+  extern __shared__ __align__(16) uint8_t gf_smem[];
+  const int C = p.C0 + p.C1, gs = C / p.groups, W = p.W1 - 1, HW = p.HW;
+  const int img = p.img0 + blockIdx.y, c_lo = blockIdx.x * SC;
+  const int SCV = SC / VEC, PY = blockDim.x / SCV;           // blockDim = SCV * PY exactly
+  float* mr = reinterpret_cast<float*>(gf_smem);              // [SC][2] mean (of the stored x), rstd
+  float* tt = mr + 2 * SC;                                     // [SC][2] t1, t2
+  float* raw = tt + 2 * SC;                                    // [SC][2] staging
+  float* part2 = raw + 2 * SC;                                 // [blockDim + 2 SC] second reduction stage
+  float* part = part2 + blockDim.x + 2 * SC;                   // [PY][SC][2]
+  T* xs = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(part + (size_t)PY * SC * 2) + 15) & ~(uintptr_t)15);    // [HW][SC]
+  T* ds = xs + (size_t)HW * SC;                                // [HW][SC] dz in the activation type
+  const float inv_n = 1.f / ((float)gs * (float)HW);
+  const bool shifted = p.sh.bias != nullptr || p.sh.emb != nullptr;
+  const float* sh_emb = p.sh.emb ? p.sh.emb + (size_t)__ldg(p.sh.img_row + img) * p.sh.emb_ld : nullptr;
+  // ---- forward statistics of the slab's groups -> mean / rstd per channel (as gn_group_stats) ----
+  for (int i = threadIdx.x; i < SC; i += blockDim.x) {
+    const int ch = c_lo + i;
+    float S1, S2;
+    if (ch < p.C0) {
+      const float* sa = p.st0 + ((size_t)img * p.ld0 + ch) * 2;
+      S1 = __ldg(sa); S2 = __ldg(sa + 1);
+      if (shifted) {
+        const float sv = gn_shift_value(p.sh, sh_emb, ch);
+        S2 = fmaf(2.f * sv, S1, S2) + (float)HW * sv * sv;
+        S1 = fmaf((float)HW, sv, S1);
+      }
+    } else {
+      const float* sb = p.st1 + ((size_t)img * p.ld1 + (ch - p.C0)) * 2;
+      S1 = __ldg(sb); S2 = __ldg(sb + 1);
+    }
+    raw[2 * i] = S1; raw[2 * i + 1] = S2;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < SC; i += blockDim.x) {
+    const int g0 = i / gs * gs;
+    float s = 0.f, q = 0.f;
+    for (int j = 0; j < gs; ++j) { s += raw[2 * (g0 + j)]; q += raw[2 * (g0 + j) + 1]; }
+    float mean = s * inv_n;
+    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+    if (shifted && c_lo + i < p.C0) mean -= gn_shift_value(p.sh, sh_emb, c_lo + i);
+    mr[2 * i] = mean;
+    mr[2 * i + 1] = rsqrtf(var + 1e-5f);
+  }
+  __syncthreads();
+  // ---- phase 1: stream x, dy in; dz and the per-channel sums ----
+  const int cvl = threadIdx.x % SCV, py = threadIdx.x / SCV;
+  const int cl = cvl * VEC, c = c_lo + cl;                    // local / global first channel of the thread's vector
+  const bool first = c < p.C0;
+  const T* src = first ? (const T*)p.s0 + (size_t)img * p.P * p.C0 + c : (const T*)p.s1 + (size_t)img * p.P * p.C1 + (c - p.C0);
+  const int ld = first ? p.C0 : p.C1;
+  const T* dy = (const T*)p.dy + (size_t)img * p.P * C + c;
+  float cA[VEC], cD[VEC], sA[VEC], sB[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const float mu = mr[2 * (cl + j)], rs = mr[2 * (cl + j) + 1], ga = __ldg(p.gamma + c + j), be = __ldg(p.beta + c + j);
+    cA[j] = 0.5f * rs * ga; cD[j] = 0.5f * (be - mu * rs * ga);
+    sA[j] = sB[j] = 0.f;
+  }
+  {
+    FlatWalk fw(py, PY, W);
+    for (int ib = py; ib < HW; ib += UN * PY) {
+      uint4 xr[UN], gr[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        if (ib + u * PY < HW) {
+          const size_t r = (size_t)fw.prow(p.W1);
+          xr[u] = *reinterpret_cast<const uint4*>(src + r * ld);
+          gr[u] = *reinterpret_cast<const uint4*>(dy + r * C);
+        }
+        fw.step();
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int i = ib + u * PY;
+        if (i >= HW) continue;
+        float x[VEC], g[VEC];
+        load_vec(reinterpret_cast<const T*>(&xr[u]), x);
+        load_vec(reinterpret_cast<const T*>(&gr[u]), g);
+        if (p.swish) {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) g[j] = dz_swish<T>(g[j], fmaf(x[j], cA[j], cD[j]));
+        }
+        *reinterpret_cast<uint4*>(xs + (size_t)i * SC + cl) = xr[u];
+        store_vec(ds + (size_t)i * SC + cl, g);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { sA[j] += g[j]; sB[j] = fmaf(g[j], x[j], sB[j]); }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    part[(py * SC + cl + j) * 2] = sA[j];
+    part[(py * SC + cl + j) * 2 + 1] = sB[j];
+  }
+  __syncthreads();
+  // two-stage sum over the PY row lanes: (value i, chunk q) then chunks
+  const int nv = 2 * SC, nch = blockDim.x / nv > 0 ? blockDim.x / nv : 1;
+  for (int j = threadIdx.x; j < nv * nch; j += blockDim.x) {
+    const int i = j % nv, q = j / nv;
+    float t = 0.f;
+    for (int r = q; r < PY; r += nch) t += part[r * nv + i];
+    part2[q * nv + i] = t;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < SC; i += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int q = 0; q < nch; ++q) { a += part2[q * nv + 2 * i]; b += part2[q * nv + 2 * i + 1]; }
+    const int ch = c_lo + i;
+    const float mu = mr[2 * i], rs = mr[2 * i + 1], ga = __ldg(p.gamma + ch);
+    const float bx = rs * (b - mu * a);                        // sum(dz * xhat)
+    atomicAdd(p.dbeta + ch, a);
+    atomicAdd(p.dgamma + ch, bx);
+    raw[2 * i] = a * ga; raw[2 * i + 1] = bx * ga;
+    tt[2 * i] = a;                                             // kept for the closed-form column sums below
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < SC; i += blockDim.x) {
+    const int g0 = i / gs * gs;
+    float S1 = 0.f, S2 = 0.f;
+    for (int j = 0; j < gs; ++j) { S1 += raw[2 * (g0 + j)]; S2 += raw[2 * (g0 + j) + 1]; }
+    const float sum_dz = tt[2 * i];
+    const float rs = mr[2 * i + 1];
+    const float t1 = rs * S1 * inv_n, t2 = rs * S2 * inv_n;
+    tt[2 * i] = t1; tt[2 * i + 1] = t2;                        // (entry i is read and written by this thread only)
+    if (p.cs.db || p.cs.demb) {
+      const int ch = c_lo + i;
+      const float mu = mr[2 * i], ga = __ldg(p.gamma + ch);
+      const float sum_x = __ldg(p.st0 + ((size_t)img * p.ld0 + ch) * 2);
+      const float v = rs * ga * sum_dz - rs * t2 * sum_x + (mu * rs * t2 - t1) * (float)HW;
+      if (p.cs.db) atomicAdd(p.cs.db + ch, v);
+      if (p.cs.demb) atomicAdd(p.cs.demb + (size_t)__ldg(p.cs.img_row + img) * p.cs.emb_ld + p.cs.col + ch, v);
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: dx = cA*dz + cB*x + cC out of shared memory ----
+  T* dx = first ? (T*)p.dx0 + (size_t)img * p.P * p.C0 + c : (T*)p.dx1 + (size_t)img * p.P * p.C1 + (c - p.C0);
+  const bool accum = first ? p.acc0 : p.acc1;
+  float kA[VEC], kB[VEC], kC[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const float mu = mr[2 * (cl + j)], rs = mr[2 * (cl + j) + 1], ga = __ldg(p.gamma + c + j);
+    const float t1 = tt[2 * (cl + j)], t2 = tt[2 * (cl + j) + 1];
+    kA[j] = rs * ga; kB[j] = -rs * t2; kC[j] = mu * rs * t2 - t1;
+  }
+  {
+    FlatWalk fw(py, PY, W);
+    for (int ib = py; ib < HW; ib += UN * PY) {
+      uint4 orr[UN];
+      size_t rr[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        rr[u] = (size_t)fw.prow(p.W1);
+        if (accum && ib + u * PY < HW) orr[u] = *reinterpret_cast<const uint4*>(dx + rr[u] * ld);
+        fw.step();
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int i = ib + u * PY;
+        if (i >= HW) continue;
+        float x[VEC], g[VEC], o[VEC];
+        load_vec(xs + (size_t)i * SC + cl, x);
+        load_vec(ds + (size_t)i * SC + cl, g);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) o[j] = fmaf(kA[j], g[j], fmaf(x[j], kB[j], kC[j]));
+        if (accum) {
+          float old[VEC];
+          load_vec(reinterpret_cast<const T*>(&orr[u]), old);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) o[j] += old[j];
+        }
+        store_vec(dx + rr[u] * ld, o);
+      }
+    }
+  }
+  // gradients of padding rows are exact zeros (row 0 and column 0 of the PADDED image)
+  if (!accum) {
+    float z[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) z[j] = 0.f;
+    const int H = HW / W, npad = p.W1 + H;
+    for (int k = py; k < npad; k += PY) {
+      const int r = k < p.W1 ? k : (k - p.W1 + 1) * p.W1;
+      store_vec(dx + (size_t)r * ld, z);
     }
   }
 }
@@ -763,12 +974,47 @@ VF_API int vf_unpack_conv_wgrad(const float* dwp, int cout, int cin, int ksize, 
 namespace vf {
 // row splits per image of the two GroupNorm backward passes (one grid for both)
 static int gn_bwd_splits(int images, int P, int C, int PY) {
-  const int want = cdiv(148 * 8, images);
+  // the reduce pass runs 2 CTAs per SM: whole waves of 296 CTAs, ~6 CTAs per SM in total.  (64x64 x 64 channels, 168 view-images:
+  // 7 row splits 147 us, 13 splits 164 us, 26 splits 207 us — every CTA repeats the statistics prologue and the partial-sum epilogue)
+  const int want = cdiv(148 * 6, images);
   const int max_splits = P / (PY * 4) > 0 ? P / (PY * 4) : 1;
-  int splits = wave_splits(images, want, max_splits, 148 * 3);
-  if (latency_bound_layer(P, C) && !getenv("VF_GN_OLD_SPLITS"))
+  int splits = wave_splits(images, want, max_splits, 148 * 2);
+  // small layers by the latency model (the ones that still come here: most of them run the one-pass kernel)
+  if ((long)P * C <= 1089L * 128 && !getenv("VF_GN_OLD_SPLITS"))
     splits = latency_splits(images, P, kGbUnroll * PY, max_splits, 148 * 2, 3.0, 0.8);   // the reduce pass runs 2 CTAs per SM
   return splits;
+}
+
+// Slab (channels per CTA) of the one-pass kernel, 0 if it does not apply: a multiple of the group size and of the vector width
+// that divides C; the smallest one with >= 32-byte rows and >= 16 K elements per CTA that fits in shared memory (else the
+// largest that fits).  threads = (slab / vec) * row lanes; 512-thread CTAs when only one fits per SM.
+int tc_debug_flags();   // k_gemm_tc.cu (vf_debug_flags)
+static int gn_fused_slab(int C, int groups, int HW, int dtype, int* threads_out, size_t* smem_out) {
+  static const bool off = [] { const char* e = getenv("VF_GN_BWD_FUSED"); return e && e[0] == '0'; }();      // A/B knob
+  if (off || (tc_debug_flags() & 0x2000)) return 0;                                                        // test hook: two-pass kernels
+  const int vec = dtype == VF_BF16 ? 8 : 4, es = dtype == VF_BF16 ? 2 : 4;
+  const int gs = C / groups;
+  int unit = gs;
+  while (unit % vec) unit += gs;                 // lcm(gs, vec)
+  if (C % unit) return 0;
+  static const long min_elems = [] { const char* e = getenv("VF_GNF_MIN_ELEMS"); return e ? atol(e) : 16384L; }();      // A/B knobs
+  static const size_t limit = [] { const char* e = getenv("VF_GNF_SMEM_KB"); return (size_t)(e ? atol(e) : 90L) * 1024; }();
+  auto need = [&](int SC, int threads) { return (size_t)(8 * SC + threads) * 4 + (size_t)threads * vec * 8 + (size_t)2 * HW * SC * es + 16; };
+  int best = 0;
+  for (int SC = unit; SC <= C; SC += unit) {
+    if (C % SC || SC / vec > 512) continue;
+    if (need(SC, 256) > limit) break;
+    best = SC;
+    if (SC * es >= 32 && (long)HW * SC >= min_elems) break;
+  }
+  if (!best) return 0;
+  const int SCV = best / vec;
+  // (512-thread CTAs for wide slabs were measured slower: 8x8 x 192 channels 14.6 -> 22.7 us)
+  const int want = need(best, 256) > 100 * 1024 ? 512 : 256;
+  const int PY = want / SCV > 0 ? want / SCV : 1;
+  *threads_out = SCV * PY;
+  *smem_out = need(best, SCV * PY);
+  return best;
 }
 
 int gn_backward_impl(const void* src0, int C0, const float* stats0, int stats0_ld, const void* src1, int C1, const float* stats1,
@@ -794,6 +1040,25 @@ int gn_backward_impl(const void* src0, int C0, const float* stats0, int stats0_l
     VF_REQUIRE(!shift->emb || shift->img_row, "vf_gn_backward: shift.emb needs img_row");
     p.sh = *shift;
   }
+  {
+    // one-pass kernel when an (image, slab of whole groups) fits in shared memory
+    int threads = 0;
+    size_t smem = 0;
+    const int SC = gn_fused_slab(C, groups, H * W, dtype, &threads, &smem);
+    if (SC > 0) {
+      p.img0 = 0;
+      dim3 grid(C / SC, images);
+      if (dtype == VF_BF16) {
+        VF_SET_MAX_SMEM(gn_bwd_fused_kernel<__nv_bfloat16>, 227 * 1024);
+        VF_CUDA(launch_pdl(gn_bwd_fused_kernel<__nv_bfloat16>, grid, dim3(threads), smem, st, p, SC));
+      } else {
+        VF_SET_MAX_SMEM(gn_bwd_fused_kernel<float>, 227 * 1024);
+        VF_CUDA(launch_pdl(gn_bwd_fused_kernel<float>, grid, dim3(threads), smem, st, p, SC));
+      }
+      VF_LAUNCH_CHECK();
+      return VF_OK;
+    }
+  }
   if (!scratch_zeroed) VF_CUDA(cudaMemsetAsync(scratch, 0, (size_t)images * C * 2 * sizeof(float), st));
   const int CV = C / vec, PY = kGbThreads / CV > 0 ? kGbThreads / CV : 1;
   const int threads = CV * PY;
@@ -801,6 +1066,10 @@ int gn_backward_impl(const void* src0, int C0, const float* stats0, int stats0_l
   // 25 % slower than whole-batch launches: the smaller grids lose more than the L2 hits win.)
   const int group = images;
   int splits = gn_bwd_splits(group, p.P, C, PY);
+  {
+    static const int force = [] { const char* e = getenv("VF_GN_BWD_SPLITS"); return e ? atoi(e) : 0; }();      // A/B knob
+    if (force > 0) splits = force;
+  }
   p.rows_per_cta = cdiv(p.P, splits);
   splits = cdiv(p.P, p.rows_per_cta);
   const size_t smem_r = (size_t)(2 * C + 2 * C * PY) * sizeof(float), smem_a = (size_t)6 * C * sizeof(float);
