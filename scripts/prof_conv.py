@@ -38,6 +38,8 @@ if len(sys.argv) > 2 and sys.argv[2] == "r02":
     variants = [("conv1: no table", 0, False, True, False), ("bias only", 0, False, True, True), ("conv2: bias+residual", 0, True, True, True),
                 ("no table, no stats", 0, False, False, False)]
 variants = [v if len(v) == 5 else (*v, True) for v in variants]
+if len(sys.argv) > 2 and sys.argv[2] == "tail":
+    variants = [("short last box", 0, False, True, True), ("64-row boxes", 0x4000, False, True, True)]
 if len(sys.argv) > 2 and sys.argv[2] == "typical":
     variants = [("no-res (typical)", 0, False, True)]
 if len(sys.argv) > 2 and sys.argv[2] == "sweep":

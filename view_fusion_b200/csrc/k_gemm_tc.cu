@@ -49,6 +49,8 @@ struct TcSeg {
   int ntaps;     // 1 or 9
   int koff;      // first weight column of the segment
   int halo;      // rows loaded before/after the block: (W+1)+1 for 3x3, 0 for 1x1
+  int tail_rows; // >0: the last A box of a slab is this many rows (a second tensor map) instead of a full TC_ABOX: the slab is
+                 // 128*G + 2*halo rows rounded up to 8, not to 64 (12-15 % fewer activation bytes per work item)
 };
 
 struct TcParams {
@@ -197,6 +199,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap mapB,
                                                                 const __grid_constant__ CUtensorMap mapOut,
                                                                 const __grid_constant__ CUtensorMap mapRes,
+                                                                const __grid_constant__ CUtensorMap mapT0,
+                                                                const __grid_constant__ CUtensorMap mapT1,
+                                                                const __grid_constant__ CUtensorMap mapT2,
                                                                 const TcParams p) {
   // test hook: wall-clock stamps of CTA 0 (entry, after set-up + dependency wait, after the role loops, exit) per launch,
   // appended at dbg_out[grid*12 + 1 + 4*launch ..]; dbg_out[grid*12] counts the launches
@@ -249,6 +254,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     ptx::prefetch_tmap(&mapB);
     if (p.n_seg > 1) ptx::prefetch_tmap(&mapA1);
     if (p.n_seg > 2 || p.s2_cchunks) { ptx::prefetch_tmap(&mapA1); ptx::prefetch_tmap(&mapA2); }
+    for (int s = 0; s < p.n_seg; ++s)
+      if (p.seg[s].tail_rows) ptx::prefetch_tmap(s == 0 ? &mapT0 : (s == 1 ? &mapT1 : &mapT2));
     if (p.s2_cchunks) ptx::prefetch_tmap(&mapA3);
   }
   if (warp == TC_EPI_WARPS + 1) {
@@ -288,7 +295,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           for (int ch = 0; ch < sg.nchunks; ++ch) {
             ptx::mbar_wait(bar_aempty + 8 * as, a_par);
             const uint32_t fa = bar_afull + 8 * as;
-            ptx::mbar_arrive_expect_tx(fa, (uint32_t)nbox * TC_ABOX * 128);
+            ptx::mbar_arrive_expect_tx(fa, (uint32_t)((nbox - 1) * TC_ABOX + (sg.tail_rows ? sg.tail_rows : TC_ABOX)) * 128);
             const uint32_t sa = ringA + (uint32_t)as * (uint32_t)p.a_stage_bytes;
             if (p.s2_cchunks) {
               // output pixel (y, x), tap (kh, kw) reads input pixel (2y + kh - 1, 2x + kw - 1): phase (kh != 1, kw != 1),
@@ -308,8 +315,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 ptx::tma_load_3d(sa + b * (TC_ABOX * 128), mA, fa, ch * TC_BK, 0, img * (p.geo.H + 1) + y);
               }
             } else {
-              for (int b = 0; b < nbox; ++b)
+              const int nfull = sg.tail_rows ? nbox - 1 : nbox;
+              for (int b = 0; b < nfull; ++b)
                 ptx::tma_load_2d(sa + b * (TC_ABOX * 128), mA, fa, ch * TC_BK, m0 - sg.halo + b * TC_ABOX);
+              if (sg.tail_rows)
+                ptx::tma_load_2d(sa + nfull * (TC_ABOX * 128), s == 0 ? &mapT0 : (s == 1 ? &mapT1 : &mapT2), fa, ch * TC_BK, m0 - sg.halo + nfull * TC_ABOX);
             }
             if (++as == a_stages) { as = 0; a_par ^= 1u; }
             if (stream_b) {
@@ -739,6 +749,12 @@ struct TcTiling {
 static const double kIngestBytesPerClk = 42.5;   // L2 -> SM, per SM (B300_MICROARCH.md: ~6300 B/clk chip-wide / 148)
 static const size_t kSmemBudget = 227 * 1024;
 
+// the last box of an activation slab may be shorter than TC_ABOX rows: plain 2D maps only (PADDED -> PADDED and FLAT -> FLAT)
+static bool a_tail_boxes(const TcParams& p) {
+  static const bool off = [] { const char* e = getenv("VF_TC_TAIL"); return e && e[0] == '0'; }();      // A/B knob
+  return !off && !p.a_lines && !p.s2_cchunks && !(g_tc_dbg & 0x4000);
+}
+
 static bool pick_tiling(const TcParams& p, int cout_pad, int sms, bool epi_tma, bool light_epilogue, TcTiling* best) {
   bool found = false;
   const int rows_per_img = p.geo.in_padded ? p.geo.P : p.geo.HW;
@@ -749,6 +765,7 @@ static bool pick_tiling(const TcParams& p, int cout_pad, int sms, bool epi_tma, 
     chunks += p.seg[s].nchunks;
     taps += (long)p.seg[s].nchunks * p.seg[s].ntaps;
   }
+  const size_t a_unit = a_tail_boxes(p) ? 8 : TC_ABOX;      // granularity of an activation slab (TcSeg::tail_rows)
   for (int t = 1; t <= 32; ++t) {
     if (cout_pad % t) continue;
     const int bn = cout_pad / t;
@@ -763,7 +780,7 @@ static bool pick_tiling(const TcParams& p, int cout_pad, int sms, bool epi_tma, 
       const int BM = 128 * G;
       TcTiling c;
       c.block_n = bn; c.G = G;
-      c.a_stage_bytes = (int)align_up((size_t)BM + 2 * halo_max, TC_ABOX) * 128;
+      c.a_stage_bytes = (int)align_up((size_t)BM + 2 * halo_max, a_unit) * 128;
       c.max_imgs = (BM + rows_per_img - 1) / rows_per_img + 1;
       const size_t bias_bytes = align_up((size_t)c.max_imgs * bn * 4, 1024);
       const size_t fixed = 1024 + 1024 + 2 * bias_bytes + (epi_tma ? TC_EPI_WARPS * 4096 : 0);   // + staging tiles of the TMA epilogue
@@ -805,7 +822,7 @@ static bool pick_tiling(const TcParams& p, int cout_pad, int sms, bool epi_tma, 
       double bytes = 0, cyc = 0;
       for (int s = 0; s < p.n_seg; ++s) {
         const TcSeg& sg = p.seg[s];
-        const double arows = (double)align_up((size_t)BM + 2 * sg.halo, TC_ABOX);
+        const double arows = (double)align_up((size_t)BM + 2 * sg.halo, a_unit);
         bytes += sg.nchunks * (arows * 128.0 + (c.b_resident ? 0.0 : sg.ntaps * bn * 128.0));
         // measured (scripts/probe_rate.py, prof_conv.py): with two or more accumulators in rotation an MMA completes every
         // max(N/2, ~58) clk (the floor is the smem operand fetch); a single accumulator chains at ~91 clk; plus ~120 clk
@@ -959,6 +976,21 @@ int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
     }
     if (rc) return rc;
   }
+  CUtensorMap tails[3];
+  for (int s = 0; s < 3; ++s) tails[s] = maps[0];
+  if (a_tail_boxes(p)) {
+    for (int s = 0; s < a->n_seg; ++s) {
+      const int need = 128 * p.G + 2 * p.seg[s].halo, nbox = (need + TC_ABOX - 1) / TC_ABOX;
+      const int tail = (int)align_up((size_t)(need - (nbox - 1) * TC_ABOX), 8);
+      if (tail >= TC_ABOX) continue;
+      const uint64_t dims[2] = {(uint64_t)a->src_c[s], (uint64_t)p.geo.rows_total};
+      const uint64_t strides[1] = {(uint64_t)a->src_c[s] * 2};
+      const uint32_t box[2] = {TC_BK, (uint32_t)tail};
+      int rc = encode_bf16_map(&tails[s], a->src[s], 2, dims, strides, box);
+      if (rc) return rc;
+      p.seg[s].tail_rows = tail;
+    }
+  }
   for (int s = a->n_seg; s < 3 && !s2; ++s) maps[s] = maps[0];
   if (s2) { maps[0] = maps4[0]; maps[1] = maps4[1]; maps[2] = maps4[2]; } else maps4[3] = maps[0];
   CUtensorMap mapB;
@@ -1014,10 +1046,10 @@ int conv2d_tc(const vf_conv_args* a, cudaStream_t st) {
             p.n_items, grid, p.epi_tma, p.a_lines, p.epi_lines);
   if (g_tc_dbg != 0 || g_tc_dbg_out != nullptr) {          // a test hook is armed: the instrumented instantiation
     VF_SET_MAX_SMEM(conv_tc_kernel<true>, kSmemBudget);
-    VF_CUDA(launch_pdl(conv_tc_kernel<true>, dim3(grid), dim3(TC_THREADS), tl.smem, st, maps[0], maps[1], maps[2], maps4[3], mapB, mapOut, mapRes, p));
+    VF_CUDA(launch_pdl(conv_tc_kernel<true>, dim3(grid), dim3(TC_THREADS), tl.smem, st, maps[0], maps[1], maps[2], maps4[3], mapB, mapOut, mapRes, tails[0], tails[1], tails[2], p));
   } else {
     VF_SET_MAX_SMEM(conv_tc_kernel<false>, kSmemBudget);
-    VF_CUDA(launch_pdl(conv_tc_kernel<false>, dim3(grid), dim3(TC_THREADS), tl.smem, st, maps[0], maps[1], maps[2], maps4[3], mapB, mapOut, mapRes, p));
+    VF_CUDA(launch_pdl(conv_tc_kernel<false>, dim3(grid), dim3(TC_THREADS), tl.smem, st, maps[0], maps[1], maps[2], maps4[3], mapB, mapOut, mapRes, tails[0], tails[1], tails[2], p));
   }
   VF_LAUNCH_CHECK();
   return VF_OK;
