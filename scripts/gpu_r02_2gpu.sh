@@ -6,6 +6,6 @@ N=${1:-2}
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 --no-full-generate > gpurun_out/bench_r02_${N}gpu.json 2> gpurun_out/bench_r02_${N}gpu.err; echo "bench rc=$?"; tail -c 1500 gpurun_out/bench_r02_${N}gpu.err
 python - <<PY
 import json
-d=json.load(open('gpurun_out/bench_r02_${N}gpu.json'))
+d=json.loads(open('gpurun_out/bench_r02_${N}gpu.json').read().strip().splitlines()[-1])
 print({k:d[k] for k in ('value','ms_per_step','n_gpus')}, 'train', {k:d['train'][k] for k in ('ms_per_step','value')}, 'strong', d['train'].get('strong'))
 PY
