@@ -349,7 +349,10 @@ int vf_debug_gn_bwd_splits(int images, int H, int W, int C, int dtype);
 /* Test hook: route VF_BF16 vf_conv2d / vf_attention through the CUDA-core kernels (same bf16 storage, fp32
  * accumulation) so the tcgen05 kernels can be cross-checked on the device.  Never enabled by the product path. */
 void vf_debug_force_simt(int on);
-/* Test hook: ablation bits for the tcgen05 conv epilogue (timing studies only; results are wrong when set). */
+/* Test hook.  Bits 0-3: ablations of the tcgen05 conv epilogue (timing studies only; results are wrong when set).  Bits with
+ * correct results, used by the tests to reach the alternative code path: 0x100 print the plan, 0x200 / 0x1000 no resident / pinned
+ * weight tiles, 0x400 no TMA line maps, 0x800 no closed-form bias column sums, 0x2000 two-pass GroupNorm backward even where the
+ * one-pass kernel applies, 0x4000 64-row activation boxes only (no short last box); bits 16-27 force (G, block_n). */
 void vf_debug_flags(int flags);
 /* Test hook: device buffer [148*4] int64 receiving the tcgen05 conv's MMA-thread cycle counters (NULL = off). */
 void vf_debug_counters(long long* dev_buf);

@@ -19,18 +19,23 @@ cfgs = {
     "u16a": dict(S=16, segs=[(512, 3)], cout=192, flat=False),
     "u32a": dict(S=32, segs=[(320, 3)], cout=128, flat=False),
     "u64": dict(S=64, segs=[(64, 3), (64, 1), (64, 1)], cout=64, flat=False),
+    "d64": dict(S=64, segs=[(64, 3)], cout=64, flat=False, stride=2),
+    "d128": dict(S=32, segs=[(128, 3)], cout=128, flat=False, stride=2),
+    "d192": dict(S=16, segs=[(192, 3)], cout=192, flat=False, stride=2),
 }
 c = cfgs[case]
 S, segs, cout = c["S"], c["segs"], c["cout"]
+stride = c.get("stride", 1)
+So = S // stride
 rows = R * (S * S if c["flat"] else (S + 1) * (S + 1))
 srcs = [torch.randn(rows, ch, device="cuda").to(torch.bfloat16) for ch, _ in segs]
 k_total = sum(ch * k * k for ch, k in segs)
 w = (torch.randn(cout, k_total, device="cuda") / math.sqrt(k_total)).to(torch.bfloat16)
 bias = torch.randn(cout, device="cuda")
-res = torch.randn(R * (S + 1) * (S + 1), cout, device="cuda").to(torch.bfloat16)
-out = torch.empty(R * (S + 1) * (S + 1), cout, device="cuda", dtype=torch.bfloat16)
+res = torch.randn(R * (So + 1) * (So + 1), cout, device="cuda").to(torch.bfloat16)
+out = torch.empty(R * (So + 1) * (So + 1), cout, device="cuda", dtype=torch.bfloat16)
 stats = torch.zeros(R, cout, 2, device="cuda")
-flops = 2 * R * S * S * cout * k_total
+flops = 2 * R * So * So * cout * k_total
 variants = [("full", 0, True, True)]
 if len(sys.argv) > 2 and sys.argv[2] == "ablate":
     variants += [("no-res (typical)", 0, False, True), ("no-res dbg:no-table", 8, False, True), ("no-res-no-stats", 0, False, False), ("dbg:no-store", 2, True, True), ("dbg:no-unit-work", 4, True, True), ("dbg:no-unit-no-table", 12, True, True)]
@@ -40,6 +45,8 @@ if len(sys.argv) > 2 and sys.argv[2] == "r02":
 variants = [v if len(v) == 5 else (*v, True) for v in variants]
 if len(sys.argv) > 2 and sys.argv[2] == "tail":
     variants = [("short last box", 0, False, True, True), ("64-row boxes", 0x4000, False, True, True)]
+if len(sys.argv) > 2 and sys.argv[2] == "plain":
+    variants = [("bias + stats", 0, False, True, True)]
 if len(sys.argv) > 2 and sys.argv[2] == "typical":
     variants = [("no-res (typical)", 0, False, True)]
 if len(sys.argv) > 2 and sys.argv[2] == "sweep":
@@ -54,7 +61,7 @@ for name, dbg, use_res, use_stats, use_bias in variants:
     lib.vf_debug_flags(dbg)
     try:
         ops.conv2d(srcs, [k for _, k in segs], w, R, S, S, cout, bias=bias if use_bias else None, residual=res if use_res else None, want_stats=use_stats,
-                   in_padded=not c["flat"], out=out, stats=stats)
+                   in_padded=not c["flat"], out=out, stats=stats, stride=stride)
         torch.cuda.synchronize()
     except RuntimeError as e:
         continue
@@ -68,7 +75,7 @@ for name, dbg, use_res, use_stats, use_bias in variants:
         e0.record()
         for _ in range(NL):
             ops.conv2d(srcs, [k for _, k in segs], w, R, S, S, cout, bias=bias if use_bias else None, residual=res if use_res else None, want_stats=use_stats,
-                       in_padded=not c["flat"], out=out, stats=stats)
+                       in_padded=not c["flat"], out=out, stats=stats, stride=stride)
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3 / NL)
@@ -77,7 +84,7 @@ for name, dbg, use_res, use_stats, use_bias in variants:
     lib.vf_debug_counters(cnt.data_ptr())
     for _ in range(6):
         ops.conv2d(srcs, [k for _, k in segs], w, R, S, S, cout, bias=bias if use_bias else None, residual=res if use_res else None, want_stats=use_stats,
-                   in_padded=not c["flat"], out=out, stats=stats)
+                   in_padded=not c["flat"], out=out, stats=stats, stride=stride)
     torch.cuda.synchronize()
     lib.vf_debug_counters(0)
     st = cnt[148 * 12 + 1: 148 * 12 + 1 + 24].view(6, 4).cpu().double()

@@ -222,6 +222,22 @@ def test_conv_bf16_tcgen05(lib, case):
     assert rel(got, simt) < 3e-3
 
 
+@pytest.mark.parametrize("case", [CONV_CASES[0], CONV_CASES[2], CONV_CASES[7], CONV_CASES[8]])
+def test_conv_bf16_short_last_activation_box_is_bitwise_neutral(lib, case):
+    """The last TMA box of an activation slab is only as tall as the slab needs (a second tensor map per segment); with
+    vf_debug_flags(0x4000) every box is 64 rows as in round 1.  Same operands, same K order: identical bits."""
+    R, S, segs, cout, stride, ue, ur = case
+    _, *t = _conv_case(torch.bfloat16, R, S, segs, cout, stride, ue, ur)
+    a = _run_conv(torch.bfloat16, R, S, segs, cout, stride, *t)
+    lib.vf_debug_flags(0x4000)
+    try:
+        b = _run_conv(torch.bfloat16, R, S, segs, cout, stride, *t)
+    finally:
+        lib.vf_debug_flags(0)
+    from view_fusion_b200 import ops
+    assert torch.equal(ops.from_padded(a, R, S, S), ops.from_padded(b, R, S, S))
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_conv_flat_source_padded_output(lib, dtype):
     """1x1 conv over a FLAT source (attention output / packed first layer) into a PADDED output + PADDED residual."""
