@@ -12,6 +12,8 @@ WANT = [
     ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2_pct"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem_wavefronts"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy_pct"),
+    ("sm__inst_executed.avg.per_cycle_elapsed", "ipc"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
     ("launch__registers_per_thread", "regs"),
     ("launch__grid_size", "grid"),
     ("launch__block_size", "block"),
