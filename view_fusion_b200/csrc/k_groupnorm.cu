@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(kGnThreads, 4) gn_apply_kernel(const T* __rest
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, T* __restrict__ dst, const vf_gn_shift sh) {
   constexpr int VEC = VecOf<T>::N;
+  constexpr bool kHalved = kSwish && sizeof(T) == 2;
   pdl_launch_dependents();
   pdl_wait();                                        // the statistics and the sources come from the previous kernels
   extern __shared__ float ab[];                      // [C][2]: y = x*a + b, then [C][2] staging of the raw statistics
@@ -108,8 +109,8 @@ __global__ void __launch_bounds__(kGnThreads, 4) gn_apply_kernel(const T* __rest
         load_vec(reinterpret_cast<const T*>(&raw[u]), v);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-          const float y = v[j] * a[j] + b[j];
-          v[j] = kSwish ? silu_for<T>(y) : y;
+          const float y = fmaf(v[j], a[j], b[j]);
+          v[j] = kSwish ? (kHalved ? silu_half(y) : silu_for<T>(y)) : y;
         }
       }
       store_vec(out + (size_t)(pb + u * PY) * C, v);
@@ -156,8 +157,10 @@ __global__ void __launch_bounds__(kGnThreads, 4) gn_apply_kernel(const T* __rest
     ab[2 * ch + 1] = __ldg(beta + ch) - mean * a;
   }
   __syncthreads();
+  // bf16 + Swish: silu(z) = h + h*tanh(h) with h = z/2 — the halving is folded into the coefficients (scaling by 0.5 commutes with
+  // the rounding of the fma, so the bits are those of silu_fast(fmaf(x, a, b))) and the loop saves one multiply per element
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) { a[j] = ab[2 * (c + j)]; b[j] = ab[2 * (c + j) + 1]; }
+  for (int j = 0; j < VEC; ++j) { a[j] = (kHalved ? 0.5f : 1.f) * ab[2 * (c + j)]; b[j] = (kHalved ? 0.5f : 1.f) * ab[2 * (c + j) + 1]; }
   for (; pb < p1; pb += 2 * UN * PY) {
     fetch(pb + UN * PY, rb2, ib, pb2);
     emit(pb, ra, ia, pa);
