@@ -85,6 +85,11 @@ __global__ void __launch_bounds__(kGnThreads, 4) gn_apply_kernel(const T* __rest
   constexpr int UN = 2;
   int yy = (p0 + py) / W1, xx = (p0 + py) - yy * W1;
   const int dy = PY / W1, dx = PY - dy * W1;
+  // Rows are visited in order by both lambdas (every call takes the next UN rows of the thread), so the source / destination
+  // addresses are running pointers advanced by a constant stride instead of 64-bit products per row.
+  const T* fp = src + (size_t)(p0 + py) * ld;
+  T* ep = out + (size_t)(p0 + py) * C;
+  const size_t fstep = (size_t)PY * ld, estep = (size_t)PY * C;
   auto fetch = [&](int pb, uint4 (&raw)[UN], uint32_t& inm, uint32_t& padm) {
     inm = 0; padm = 0;
 #pragma unroll
@@ -92,7 +97,8 @@ __global__ void __launch_bounds__(kGnThreads, 4) gn_apply_kernel(const T* __rest
       const int p = pb + u * PY;
       const bool in = p < p1, pad = yy == 0 || xx == 0;
       inm |= (uint32_t)in << u; padm |= (uint32_t)pad << u;
-      if (in && !pad) raw[u] = *reinterpret_cast<const uint4*>(src + (size_t)p * ld);
+      if (in && !pad) raw[u] = *reinterpret_cast<const uint4*>(fp);
+      fp += fstep;
       yy += dy; xx += dx;
       if (xx >= W1) { xx -= W1; ++yy; }
     }
@@ -100,6 +106,8 @@ __global__ void __launch_bounds__(kGnThreads, 4) gn_apply_kernel(const T* __rest
   auto emit = [&](int pb, const uint4 (&raw)[UN], uint32_t inm, uint32_t padm) {
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
+      T* dstp = ep;
+      ep += estep;
       if (!((inm >> u) & 1u)) continue;
       float v[VEC];
       if ((padm >> u) & 1u) {
@@ -113,7 +121,7 @@ __global__ void __launch_bounds__(kGnThreads, 4) gn_apply_kernel(const T* __rest
           v[j] = kSwish ? (kHalved ? silu_half(y) : silu_for<T>(y)) : y;
         }
       }
-      store_vec(out + (size_t)(pb + u * PY) * C, v);
+      store_vec(dstp, v);
     }
   };
   uint4 ra[UN], rb2[UN];

@@ -141,12 +141,12 @@ __device__ __forceinline__ void load_vec(const float* p, float (&v)[4]) {
   v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 }
 __device__ __forceinline__ void load_vec(const __nv_bfloat16* p, float (&v)[8]) {
-  uint4 t = *reinterpret_cast<const uint4*>(p);
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 f = __bfloat1622float2(h[i]);
-    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  for (int i = 0; i < 4; ++i) {     // bf16 -> fp32 is a 16-bit shift: one SHL and one LOP per pair (the intrinsic costs PRMT + SHL for the high half)
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
   }
 }
 __device__ __forceinline__ void store_vec(float* p, const float (&v)[4]) {
