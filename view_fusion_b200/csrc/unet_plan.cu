@@ -1071,7 +1071,9 @@ __global__ void axpy_f32_kernel(float* __restrict__ dst, const float* __restrict
 //   embed_bwd_params_kernel  one thread per parameter-gradient element: sums the rank-1 contributions over the rows
 //                            dEw[e][i] = sum demb[e] t[i]; dEb[e] = sum demb[e]; dW2[o][i] = sum dt[o] h[i]; db2 = sum dt;
 //                            dW0[o][i] = sum da[o] pe[i]; db0 = sum da
-__global__ void __launch_bounds__(256) embed_bwd_rows_kernel(const float* __restrict__ level, const float* __restrict__ angle, int ic,
+constexpr int kEmbBwdThreads = 1024;   // the E-long reduction below is a chain of dependent L2 loads per thread: 16 thread groups instead of 4
+constexpr int kEmbBwdGroups = 16;
+__global__ void __launch_bounds__(kEmbBwdThreads) embed_bwd_rows_kernel(const float* __restrict__ level, const float* __restrict__ angle, int ic,
                                                              const float* __restrict__ w0, const float* __restrict__ b0,
                                                              const float* __restrict__ w2, const float* __restrict__ b2,
                                                              const float* __restrict__ ew, int E, const float* __restrict__ demb,
@@ -1081,7 +1083,7 @@ __global__ void __launch_bounds__(256) embed_bwd_rows_kernel(const float* __rest
   float* av = pe + ic;         // [4ic] pre-activation
   float* hid = av + 4 * ic;    // [4ic]
   float* dt = hid + 4 * ic;    // [ic]
-  float* part = dt + ic;       // [4][ic] partial dt
+  float* part = dt + ic;       // [kEmbBwdGroups][ic] partial dt
   const int row = blockIdx.x;
   const int half = ic / 2, cnt = ic / 4;
   float* out = rowbuf + (size_t)row * 11 * ic;
@@ -1111,14 +1113,15 @@ __global__ void __launch_bounds__(256) embed_bwd_rows_kernel(const float* __rest
   {
     const int ngrp = blockDim.x / ic > 0 ? (int)(blockDim.x / ic) : 1;
     const int grp = threadIdx.x / ic, i = threadIdx.x % ic;
-    if (grp < ngrp && grp < 4) {
-      const int gcount = ngrp < 4 ? ngrp : 4;
+    if (grp < ngrp && grp < kEmbBwdGroups) {
+      const int gcount = ngrp < kEmbBwdGroups ? ngrp : kEmbBwdGroups;
       float acc = 0.f;
+#pragma unroll 4
       for (int e = grp; e < E; e += gcount) acc += __ldg(g + e) * __ldg(ew + (size_t)e * ic + i);
       part[grp * ic + i] = acc;
     }
     __syncthreads();
-    const int gcount = ngrp < 4 ? ngrp : 4;
+    const int gcount = ngrp < kEmbBwdGroups ? ngrp : kEmbBwdGroups;
     for (int k = threadIdx.x; k < ic; k += blockDim.x) {
       float acc = 0.f;
       for (int q = 0; q < gcount; ++q) acc += part[q * ic + k];
@@ -1231,7 +1234,7 @@ struct UnpackList {
 static int embed_backward_launch(const float* level, const float* angle, int rows, int ic, const float* w0, const float* b0, const float* w2,
                                  const float* b2, const float* emb_w, int E, const float* demb, float* rowbuf, float* dew, float* deb, float* dw0,
                                  float* db0, float* dw2, float* db2, cudaStream_t st) {
-  embed_bwd_rows_kernel<<<rows, 256, (size_t)(14 * ic) * sizeof(float), st>>>(level, angle, ic, w0, b0, w2, b2, emb_w, E, demb, rowbuf);
+  embed_bwd_rows_kernel<<<rows, kEmbBwdThreads, (size_t)(10 + kEmbBwdGroups) * ic * sizeof(float), st>>>(level, angle, ic, w0, b0, w2, b2, emb_w, E, demb, rowbuf);
   const size_t total = (size_t)E * ic + E + (size_t)8 * ic * ic + 5 * ic;
   embed_bwd_params_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(rowbuf, demb, rows, ic, E, dew, deb, dw0, db0, dw2, db2);
   VF_LAUNCH_CHECK();
