@@ -1060,9 +1060,14 @@ __global__ void __launch_bounds__(256) grad8_to_padded_kernel(const float* __res
   }
 }
 
-__global__ void axpy_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] += src[i];
+// dst_j[i] += src_j[i] for up to 64 small (destination, source, count) jobs in ONE launch (grid.y = job): the per-block slices of the
+// embedding-table gradient go to the 30 FeatureWiseAffine weight / bias gradients (was 60 launches of axpy_f32_kernel per step)
+struct AxpyJobs { float* dst[64]; const float* src[64]; int n[64]; };
+__global__ void __launch_bounds__(256) multi_axpy_kernel(const AxpyJobs jobs) {
+  const int j = blockIdx.y;
+  float* __restrict__ d = jobs.dst[j];
+  const float* __restrict__ s = jobs.src[j];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < jobs.n[j]; i += gridDim.x * blockDim.x) d[i] += s[i];
 }
 
 // Backward of vf_embed in two launches (no atomics):
@@ -1603,11 +1608,23 @@ static void bw_finish(BwdCtx& cx, float* const* pg) {
     cx.rc = embed_backward_launch(u->last_level, u->last_angle, rows, ic, u->master[u->mlp_w0], u->master[u->mlp_b0], u->master[u->mlp_w2],
                                   u->master[u->mlp_b2], u->emb_w_dev, u->E, demb, emb_rows, dew, deb, pg[u->mlp_w0], pg[u->mlp_b0], pg[u->mlp_w2],
                                   pg[u->mlp_b2], cx.st);
+    AxpyJobs jobs{};
+    int nj = 0, nmax = 0;
+    auto flush = [&]() {
+      if (nj > 0) multi_axpy_kernel<<<dim3((unsigned)((nmax + 1023) / 1024 > 0 ? (nmax + 1023) / 1024 : 1), (unsigned)nj), 256, 0, cx.st>>>(jobs);
+      nj = 0; nmax = 0;
+    };
+    auto add = [&](float* d, const float* s2, int n) {
+      if (nj == 64) flush();
+      jobs.dst[nj] = d; jobs.src[nj] = s2; jobs.n[nj] = n;
+      nmax = n > nmax ? n : nmax;
+      ++nj;
+    };
     for (auto& b : u->blocks) {
-      const size_t nw = (size_t)b.cout * ic;
-      axpy_f32_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, cx.st>>>(pg[b.nf_w], dew + (size_t)b.emb_col * ic, nw);
-      axpy_f32_kernel<<<(unsigned)((b.cout + 255) / 256), 256, 0, cx.st>>>(pg[b.nf_b], deb + b.emb_col, (size_t)b.cout);
+      add(pg[b.nf_w], dew + (size_t)b.emb_col * ic, b.cout * ic);
+      add(pg[b.nf_b], deb + b.emb_col, b.cout);
     }
+    flush();
     if (cudaGetLastError() != cudaSuccess) { set_error("vf_unet_backward: embedding backward launch failed"); cx.rc = VF_ERR_CUDA; }
   }
 }
