@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_tc_kernel(const __grid
                                                                     const __grid_constant__ CUtensorMap mapDO,
                                                                     const __grid_constant__ CUtensorMap mapVT,
                                                                     const AttnBwdParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_tc_kernel(const __grid
   ptx::tc_fence_after();
   const uint32_t tm = *tmem_slot_ptr;
   const uint32_t tm_s = tm, tm_dp = tm + 128, tm_dq = tm + 256, tm_kv = tm;
+  pdl_wait();                                    // barrier / TMEM set-up above overlapped the previous kernel's tail
 
   if (warp == 4) {
     if (ptx::elect_one()) {
@@ -248,6 +250,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_tc_kernel(const __grid
 // dqkv[:, C:3C] = sum over the query-block slots of the fp32 partials
 __global__ void __launch_bounds__(256) attn_dkv_finish_kernel(const float* __restrict__ part, int nslots, size_t rows, int C,
                                                               __nv_bfloat16* __restrict__ dqkv) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t total = rows * (size_t)(2 * C / 8);
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
@@ -311,10 +315,10 @@ int attention_bwd_tc(const void* qkv, const void* vt, const void* out, const flo
   const size_t smem = 1024 + 1024 + 4 * (size_t)p.tile_bytes + 2 * 128 * 128;
   VF_REQUIRE(smem <= 227 * 1024, "vf_attention_backward(tc): L=%d C=%d need %zu B of shared memory", L, C, smem);
   VF_SET_MAX_SMEM(attn_bwd_tc_kernel, 227 * 1024);
-  attn_bwd_tc_kernel<<<images * p.nblk, AB_THREADS, smem, st>>>(mapQKV, mapDO, mapVT, p);
+  VF_CUDA(launch_pdl(attn_bwd_tc_kernel, dim3(images * p.nblk), dim3(AB_THREADS), smem, st, mapQKV, mapDO, mapVT, p));
   VF_LAUNCH_CHECK();
   const size_t total = rows * (size_t)(2 * C / 8);
-  attn_dkv_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(scratch, p.nblk, rows, C, p.dqkv);
+  VF_CUDA(launch_pdl(attn_dkv_finish_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, (const float*)scratch, p.nblk, rows, C, p.dqkv));
   VF_LAUNCH_CHECK();
   return VF_OK;
 }

@@ -836,6 +836,8 @@ __global__ void dkv_to_act_kernel(const float* __restrict__ dkv, int C, size_t r
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T* __restrict__ dy, int H, int W, int C, size_t total, T* __restrict__ dx, int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int VEC = VecOf<T>::N;
   const int CV = C / VEC;
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       // over PADDED low-res (row, vec)
@@ -876,6 +878,8 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T* __restrict
 // dst (PADDED 2H x 2W) = dy (PADDED H x W) at even pixels, zero elsewhere
 template <typename T>
 __global__ void __launch_bounds__(256) zero_insert2x_kernel(const T* __restrict__ dy, int H, int W, int C, size_t total, T* __restrict__ dst) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int VEC = VecOf<T>::N;
   const int CV = C / VEC;
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       // over PADDED full-res (row, vec)
@@ -894,6 +898,8 @@ __global__ void __launch_bounds__(256) zero_insert2x_kernel(const T* __restrict_
 
 template <typename T>
 __global__ void __launch_bounds__(256) add_inplace_kernel(T* __restrict__ dst, const T* __restrict__ src, size_t nvec) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int VEC = VecOf<T>::N;
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= nvec) return;
@@ -1149,8 +1155,8 @@ VF_API int vf_upsample2x_backward(const void* dy, int dtype, int images, int H, 
   VF_REQUIRE(C % vec == 0, "vf_upsample2x_backward: C=%d", C);
   const size_t total = (size_t)images * (H + 1) * (W + 1) * (C / vec);
   const unsigned grid = (unsigned)((total + 255) / 256);
-  if (dtype == VF_BF16) upsample2x_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)dy, H, W, C, total, (__nv_bfloat16*)dx, accumulate);
-  else upsample2x_bwd_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)dy, H, W, C, total, (float*)dx, accumulate);
+  if (dtype == VF_BF16) VF_CUDA(launch_pdl(upsample2x_bwd_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, as_stream(stream), (const __nv_bfloat16*)dy, H, W, C, total, (__nv_bfloat16*)dx, accumulate));
+  else VF_CUDA(launch_pdl(upsample2x_bwd_kernel<float>, dim3(grid), dim3(256), 0, as_stream(stream), (const float*)dy, H, W, C, total, (float*)dx, accumulate));
   VF_LAUNCH_CHECK();
   return VF_OK;
 }
@@ -1161,8 +1167,8 @@ VF_API int vf_zero_insert2x(const void* dy, int dtype, int images, int H, int W,
   VF_REQUIRE(C % vec == 0, "vf_zero_insert2x: C=%d", C);
   const size_t total = (size_t)images * (2 * H + 1) * (2 * W + 1) * (C / vec);
   const unsigned grid = (unsigned)((total + 255) / 256);
-  if (dtype == VF_BF16) zero_insert2x_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)dy, H, W, C, total, (__nv_bfloat16*)dst);
-  else zero_insert2x_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)dy, H, W, C, total, (float*)dst);
+  if (dtype == VF_BF16) VF_CUDA(launch_pdl(zero_insert2x_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, as_stream(stream), (const __nv_bfloat16*)dy, H, W, C, total, (__nv_bfloat16*)dst));
+  else VF_CUDA(launch_pdl(zero_insert2x_kernel<float>, dim3(grid), dim3(256), 0, as_stream(stream), (const float*)dy, H, W, C, total, (float*)dst));
   VF_LAUNCH_CHECK();
   return VF_OK;
 }
@@ -1173,8 +1179,8 @@ VF_API int vf_add_inplace(void* dst, const void* src, int dtype, size_t n_elems,
   VF_REQUIRE(n_elems % vec == 0, "vf_add_inplace: n_elems not a multiple of %zu", vec);
   const size_t nvec = n_elems / vec;
   const unsigned grid = (unsigned)((nvec + 255) / 256);
-  if (dtype == VF_BF16) add_inplace_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((__nv_bfloat16*)dst, (const __nv_bfloat16*)src, nvec);
-  else add_inplace_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((float*)dst, (const float*)src, nvec);
+  if (dtype == VF_BF16) VF_CUDA(launch_pdl(add_inplace_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, as_stream(stream), (__nv_bfloat16*)dst, (const __nv_bfloat16*)src, nvec));
+  else VF_CUDA(launch_pdl(add_inplace_kernel<float>, dim3(grid), dim3(256), 0, as_stream(stream), (float*)dst, (const float*)src, nvec));
   VF_LAUNCH_CHECK();
   return VF_OK;
 }

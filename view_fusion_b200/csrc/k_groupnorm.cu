@@ -223,6 +223,8 @@ __global__ void __launch_bounds__(256) zero_padding_kernel(T* __restrict__ dst, 
 // FLAT <-> PADDED copies (tests / taps); one thread per PADDED (row, 16-byte vector)
 template <typename T, bool kToPadded>
 __global__ void __launch_bounds__(256) repad_kernel(const T* __restrict__ src, int H, int W, int C, size_t total, T* __restrict__ dst) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int VEC = VecOf<T>::N;
   const int CV = C / VEC;
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -356,11 +358,11 @@ static int repad(const void* src, int dtype, int images, int H, int W, int C, vo
   const unsigned grid = (unsigned)((total + 255) / 256);
   cudaStream_t st = as_stream(stream);
   if (dtype == VF_BF16) {
-    if (to_padded) repad_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, H, W, C, total, (__nv_bfloat16*)dst);
-    else repad_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, H, W, C, total, (__nv_bfloat16*)dst);
+    if (to_padded) VF_CUDA(launch_pdl(repad_kernel<__nv_bfloat16, true>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)src, H, W, C, total, (__nv_bfloat16*)dst));
+    else VF_CUDA(launch_pdl(repad_kernel<__nv_bfloat16, false>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)src, H, W, C, total, (__nv_bfloat16*)dst));
   } else {
-    if (to_padded) repad_kernel<float, true><<<grid, 256, 0, st>>>((const float*)src, H, W, C, total, (float*)dst);
-    else repad_kernel<float, false><<<grid, 256, 0, st>>>((const float*)src, H, W, C, total, (float*)dst);
+    if (to_padded) VF_CUDA(launch_pdl(repad_kernel<float, true>, dim3(grid), dim3(256), 0, st, (const float*)src, H, W, C, total, (float*)dst));
+    else VF_CUDA(launch_pdl(repad_kernel<float, false>, dim3(grid), dim3(256), 0, st, (const float*)src, H, W, C, total, (float*)dst));
   }
   VF_LAUNCH_CHECK();
   return VF_OK;

@@ -1033,6 +1033,8 @@ __global__ void __launch_bounds__(256) colsum_bias_kernel(const T* __restrict__ 
 // One thread per (padded row, group of 8 channels): 32-byte read, 16/32-byte write.
 template <typename T>
 __global__ void __launch_bounds__(256) grad8_to_padded_kernel(const float* __restrict__ g8, int H, int W, int ld, size_t total, T* __restrict__ dst) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // over (padded row, channel octet)
   if (gid >= total) return;
   const int oct = ld / 8;
@@ -1470,8 +1472,8 @@ static void bw_begin(BwdCtx& cx, const float* g8) {
   if (!cx.dry) {
     const size_t total = (size_t)images * (S + 1) * (S + 1) * (np / 8);
     const unsigned grid = (unsigned)((total + 255) / 256);
-    if (dt == VF_BF16) grad8_to_padded_kernel<__nv_bfloat16><<<grid, 256, 0, cx.st>>>(g8, S, S, np, total, (__nv_bfloat16*)g_out);
-    else grad8_to_padded_kernel<float><<<grid, 256, 0, cx.st>>>(g8, S, S, np, total, (float*)g_out);
+    if (dt == VF_BF16) launch_pdl(grad8_to_padded_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, cx.st, g8, S, S, np, total, (__nv_bfloat16*)g_out);
+    else launch_pdl(grad8_to_padded_kernel<float>, dim3(grid), dim3(256), 0, cx.st, g8, S, S, np, total, (float*)g_out);
   }
   cx.dwp_cur = dwp;
   cx.gn_cur = gn_scratch;
