@@ -345,6 +345,9 @@ int vf_debug_gn_splits(int images, int H, int W, int C, int dtype, int* threads_
  * (Cin/64), GEMM rows, bias-table images, K. */
 int vf_debug_conv_tiling(const vf_conv_args* a, int* out16);
 int vf_debug_gn_bwd_splits(int images, int H, int W, int C, int dtype);
+/* Same for the one-pass GroupNorm backward: channels per CTA (a slab of whole groups; 0 = the layer takes the two-pass kernels,
+ * negative = unsupported shape), CTA threads and dynamic shared memory through the out parameters. */
+int vf_debug_gn_bwd_slab(int C, int groups, int H, int W, int dtype, int* threads_out, int* smem_out);
 
 /* Test hook: route VF_BF16 vf_conv2d / vf_attention through the CUDA-core kernels (same bf16 storage, fp32
  * accumulation) so the tcgen05 kernels can be cross-checked on the device.  Never enabled by the product path. */

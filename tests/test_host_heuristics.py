@@ -52,6 +52,35 @@ def test_large_layers_keep_the_wave_filling_rule():
         assert _bwd(168, S, Cc) >= 3
 
 
+def _slab(Cc, S, dtype=BF16):
+    th, sm = C.c_int(0), C.c_int(0)
+    sc = _lib.load().vf_debug_gn_bwd_slab(Cc, 32, S, S, dtype, C.byref(th), C.byref(sm))
+    return sc, th.value, sm.value
+
+
+@pytest.mark.parametrize("S,Cc", [(8, 192), (8, 320), (8, 512), (8, 640), (16, 128), (16, 192), (16, 320), (16, 384), (16, 512), (32, 64), (32, 128),
+                                  (32, 256)])
+def test_one_pass_groupnorm_backward_takes_the_layers_whose_slab_fits(S, Cc):
+    """(image, slab of whole groups) resident in shared memory: every layer up to 32x32 x 256 channels of the benchmark UNet."""
+    sc, threads, smem = _slab(Cc, S)
+    gs = Cc // 32
+    assert sc > 0 and Cc % sc == 0 and sc % gs == 0 and sc % 8 == 0, (sc, gs)          # whole groups, whole 16-byte vectors, covers C exactly
+    assert sc * 2 >= 32, "rows of at least one 32-byte sector"
+    assert 0 < threads <= 512 and threads % (sc // 8) == 0
+    assert smem <= 90 * 1024 and smem >= 2 * S * S * sc * 2                             # x and dz of the slab live in shared memory
+
+
+@pytest.mark.parametrize("S,Cc", [(64, 64), (64, 128), (64, 192), (32, 320), (32, 192)])
+def test_one_pass_groupnorm_backward_leaves_the_large_layers_to_two_passes(S, Cc):
+    assert _slab(Cc, S)[0] == 0
+
+
+def test_one_pass_groupnorm_backward_fp32_and_bad_shapes():
+    sc, threads, smem = _slab(192, 16, _lib.VF_F32)
+    assert sc > 0 and sc % 6 == 0 and sc % 4 == 0 and smem <= 90 * 1024
+    assert _lib.load().vf_debug_gn_bwd_slab(100, 32, 16, 16, BF16, None, None) < 0
+
+
 def test_unsupported_shapes_are_rejected():
     assert _fwd(168, 16, 100)[0] < 0                    # channels not a multiple of the 16-byte vector
     assert _bwd(0, 16, 192) < 0

@@ -27,7 +27,7 @@ SYMBOLS = [
     "vf_unet_packed_t_bytes", "vf_unet_pack_weights_t", "vf_unet_backward_workspace_bytes", "vf_unet_backward", "vf_unet_backward_plan", "vf_unet_backward_phase",
     "vf_conv2d_wgrad", "vf_unpack_conv_wgrad", "vf_pack_conv_weight_t", "vf_gn_backward", "vf_attention_backward",
     "vf_upsample2x_backward", "vf_zero_insert2x", "vf_add_inplace", "vf_grad8_to_act", "vf_colsum_bias", "vf_embed_backward",
-    "vf_adam_chunk_elems", "vf_adam_step", "vf_eval_metrics", "vf_prepare_batch_u8", "vf_debug_gn_splits", "vf_debug_gn_bwd_splits", "vf_debug_conv_tiling",
+    "vf_adam_chunk_elems", "vf_adam_step", "vf_eval_metrics", "vf_prepare_batch_u8", "vf_debug_gn_splits", "vf_debug_gn_bwd_splits", "vf_debug_gn_bwd_slab", "vf_debug_conv_tiling",
 ]
 
 
@@ -127,6 +127,7 @@ def load() -> C.CDLL:
         "vf_prepare_batch_u8": (i, [p, p, i, i, i, i, i, p, p, p, p]),
         "vf_debug_gn_splits": (i, [i, i, i, i, i, C.POINTER(i)]),
         "vf_debug_gn_bwd_splits": (i, [i, i, i, i, i]),
+        "vf_debug_gn_bwd_slab": (i, [i, i, i, i, i, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "vf_debug_conv_tiling": (i, [p, C.POINTER(i)]),
         "vf_unet_profile_launches": (i, [p, C.POINTER(C.c_float), C.POINTER(i), C.POINTER(i), i]),
         "vf_unet_read_tap": (i, [p, p, C.c_char_p, p, C.POINTER(C.c_int64), p]),

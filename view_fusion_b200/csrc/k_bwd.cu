@@ -1097,6 +1097,19 @@ int gn_backward_impl(const void* src0, int C0, const float* stats0, int stats0_l
 }
 }  // namespace vf
 
+// Test hook (host only): the one-pass GroupNorm backward's plan for C channels in `groups` groups over H x W pixels: channels per
+// CTA (0 = the layer takes the two-pass kernels), threads and dynamic shared memory through the out parameters.
+VF_API int vf_debug_gn_bwd_slab(int C, int groups, int H, int W, int dtype, int* threads_out, int* smem_out) {
+  const int vec = dtype == VF_BF16 ? 8 : 4;
+  if (C <= 0 || groups <= 0 || C % groups || C % vec || H <= 0 || W <= 0) return -1;
+  int threads = 0;
+  size_t smem = 0;
+  const int sc = vf::gn_fused_slab(C, groups, H * W, dtype, &threads, &smem);
+  if (threads_out) *threads_out = threads;
+  if (smem_out) *smem_out = (int)smem;
+  return sc;
+}
+
 // Test hook (host only): row splits the GroupNorm backward would launch with.
 VF_API int vf_debug_gn_bwd_splits(int images, int H, int W, int C, int dtype) {
   const int vec = dtype == VF_BF16 ? 8 : 4;
