@@ -46,6 +46,38 @@ def test_graph_replay_equals_eager_loop(prec, cfg, tol):
     assert ret_g.shape == ret_e.shape
 
 
+@pytest.mark.parametrize("prec,cfg,tol", [("fp32", O.TINY, 2e-5), ("bf16", TOY64, 1e-2)])
+def test_p_sample_graph_path_equals_eager_path(prec, cfg, tol):
+    """p_sample(want_weights=False) replays the captured step (inputs copied into the plan's loop buffers, time-steps and seed
+    into the device-resident state); with weights requested it runs eagerly.  Same injected noise -> same y_{t-1}, for ragged view
+    counts, t > 0 and the noise-free t = 0 step; the caller's y_t must not be modified."""
+    m, _ = build_model(cfg, 3, prec)
+    S = cfg["image_size"]
+    y_cond, y_T, angle = _inputs(3, 4, S, 4)
+    vc = torch.tensor([4, 1, 3])
+    z = torch.randn(3, 3, S, S, generator=torch.Generator().manual_seed(3)).cuda()
+    for tval in (1500, 1, 0):
+        t = torch.full((3,), tval, dtype=torch.long)
+        keep = y_T.clone()
+        y_e, logits, weights = m.p_sample(y_T, y_cond, vc, angle, t, noise=z)                      # eager (weights wanted); warms the plan
+        assert logits is not None and weights is not None
+        y_g, lg, wg = m.p_sample(y_T, y_cond, vc, angle, t, noise=z, want_weights=False)           # graph
+        torch.cuda.synchronize()
+        assert lg is None and wg is None and torch.equal(y_T, keep)
+        assert margin(f"p_sample graph vs eager, {prec}, t={tval}: y_prev rel-L2", rel(y_g, y_e), tol)
+    assert m._graph_error is None, m._graph_error
+    plan = next(iter(m._plans.values()))
+    assert len(plan.graphs) == 1, "p_sample must have captured / replayed a CUDA graph"
+    # in-kernel noise: two calls draw different noise, re-seeding torch reproduces them
+    t = torch.full((3,), 1000, dtype=torch.long)
+    torch.manual_seed(11)
+    a1 = m.p_sample(y_T, y_cond, vc, angle, t, want_weights=False)[0]
+    a2 = m.p_sample(y_T, y_cond, vc, angle, t, want_weights=False)[0]
+    torch.manual_seed(11)
+    b1 = m.p_sample(y_T, y_cond, vc, angle, t, want_weights=False)[0]
+    assert rel(a2, a1) > 1e-3 and rel(b1, a1) < 2e-5
+
+
 def test_philox_noise_follows_torch_manual_seed():
     m, _ = build_model(O.TINY, 3, "fp32")
     y_cond, y_T, angle = _inputs(2, 3, 16, 2)

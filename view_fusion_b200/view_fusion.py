@@ -268,13 +268,37 @@ class ViewFusion(nn.Module):
             w = self.weighting_inference
             weights = torch.empty(plan.B, plan.max_v, 3, H, W, device=y_t.device) if (w and want_weights) else None
             logits = torch.empty(plan.images, 3, H, W, device=y_t.device) if (w and want_weights) else None
-            y_prev = torch.empty_like(y_t)
             if not add_noise:
                 noise = None
+            if self._p_sample_graph(plan, y_t, y_cond, angle, t, noise, clip_denoised, w, weights is not None or logits is not None
+                                    or _eps_out is not None):
+                return plan.y.clone(), None, None
+            y_prev = torch.empty_like(y_t)
             self._step(plan, y_t, y_cond, angle, t, y_prev, z=None if noise is None else noise.to(y_t.device).contiguous().float(),
                        add_noise=add_noise, clip=clip_denoised, weighting=w, eps_out=_eps_out, weights_out=weights,
                        logits_out=logits)
+            plan.warm = True
         return y_prev, logits, weights
+
+    def _p_sample_graph(self, plan: _Plan, y_t, y_cond, angle, t, noise, clip, w, wants_extras: bool) -> bool:
+        """p_sample through the captured step of generate(): the inputs are copied into the plan's loop buffers (device to
+        device), the time-steps and the Philox seed into the device-resident loop state, and ONE graph replay runs the
+        169 kernels; y_{t-1} is left in plan.y.  Taken when the caller wants nothing but y_{t-1} (no weights / logits /
+        eps), clipping is on, and the plan has already run one eager step (lazy initialisations happen outside a capture).
+        `any(t > 0)` is then decided on the device like in generate().  Returns False when the eager path must run."""
+        unet = self.denoise_fn
+        if wants_extras or not clip or not self.use_cuda_graph or unet._profiling or not plan.warm:
+            return False
+        with_z = noise is not None
+        plan.loop_buffers(y_cond, angle, y_t)
+        if with_z:
+            if plan.z is None:
+                plan.z = torch.empty_like(plan.y)
+            plan.z.copy_(noise.to(y_t.device).float())
+        plan.t_state.copy_(t)
+        plan.noise_ctr.copy_(torch.tensor([0, 0 if with_z else self._fresh_seed()], dtype=torch.int64), non_blocking=True)
+        gkey = (unet.packed_weights().data_ptr(), unet.workspace(plan.images).data_ptr(), with_z, w)
+        return self._replay(plan, gkey, with_z, w)
 
     # ---------------------------------------------------------------- generate (:179-214)
     def _replay(self, plan: _Plan, key, with_z: bool, w: bool):
